@@ -1,0 +1,141 @@
+"""Generate the golden fixtures under ``tests/golden/`` by running the UNMODIFIED reference
+(``/root/reference/pyNeuralEMPC`` imported through ``oracle.shim``) on seeded inputs.
+
+Run once in the build container:  ``python tests/golden/make_golden.py``.
+The GPU box has no ``/root/reference``; tests there only read the committed ``.npz`` files.
+
+What is recorded (all float64 unless noted):
+  lv_mlp_weights.npz      weights of examples/lotka_volterra/nn_model.h5 (float32, by offset)
+  ref_<kind>_H6.npz       full dense integrator outputs (forward, jacobian (m,n), hessian (m,n,n),
+                          hessianstructure (n,n)) + IpoptProblem callbacks, LV fixture net, H=6
+  ref_<kind>_H25.npz      IpoptProblem callbacks at the shipped problem size (C1: H=25)
+  ref_discrete_d5_H5.npz  x_dim=4,u_dim=1 network through Discret/Unity (RK4 of the reference
+                          crashes unless x_dim+u_dim == 3 -- recorded as ``rk4_d5_error``)
+  ref_rk4_f32_H6.npz      RK4 with the network evaluated in float32 (TensorFlow numerics mimic)
+The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
+reference's ``Model`` (TensorFlow is not installed), so these files pin the integrator / IPOPT
+glue of the oracle, not TensorFlow's autodiff.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from oracle import shim  # noqa: E402
+from oracle.mlp_np import MLP, read_lv_fixture_h5  # noqa: E402
+from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
+
+DT_RK4 = 0.1  # examples/lotka_volterra/run.py:77
+
+
+def ref_objective(ref, sep):
+    class Obj(ref.objective.base.ObjectiveFunc):
+        def forward(self, states, u, p=None, tvp=None):
+            return sep.forward(states, u)
+
+        def gradient(self, states, u, p=None, tvp=None):
+            return sep.gradient(states, u)
+
+        def hessian(self, states, u, p=None, tvp=None):
+            return sep.hessian(states, u)
+
+        def hessianstructure(self, H, model):
+            return sep.hessianstructure(H, model)
+
+    return Obj()
+
+
+def make_integrator(ref, kind, model, H):
+    if kind == "discrete":
+        return ref.integrator.discret.DiscretIntegrator(model, H)
+    if kind == "unity":
+        return ref.integrator.unity.UnityIntegrator(model, H)
+    return ref.integrator.rk4.RK4Integrator(model, H, DT_RK4)
+
+
+def record(ref, mlp, kind, H, seed, objective_kind, full_dense):
+    rng = np.random.default_rng(seed)
+    xd, ud = mlp.x_dim, mlp.u_dim
+    n, m = H * (xd + ud), H * xd
+    z = rng.uniform(-1, 1, size=n)
+    x0 = rng.uniform(-1, 1, size=xd)
+    lam = rng.standard_normal(m)
+    sigma = 0.7
+    if objective_kind == "linear":
+        sep = SeparableQuadraticObjective.linear_in_u(H, xd, ud, 1.1)          # run.py:83-87
+    elif objective_kind == "setpoint":
+        sep = SeparableQuadraticObjective.control_setpoint(H, xd, ud, 2.0)     # test.py:59-60
+    else:
+        sep = SeparableQuadraticObjective.tracking(H, xd, ud, rng.uniform(0.5, 2, xd), rng.uniform(0.1, 1, ud),
+                                                   x_ref=rng.uniform(-1, 1, (H, xd)))
+    model = shim.make_reference_model(mlp)
+    integ = make_integrator(ref, kind, model, H)
+    np.random.seed(seed)                                   # integrator/base.py:96 uses the global RNG
+    pb = ref.optimizer.ipopt.IpoptProblem(x0, ref_objective(ref, sep), [], integ, use_hessian=True)
+    out = dict(kind=kind, H=H, x_dim=xd, u_dim=ud, DT=DT_RK4, z=z, x0=x0, lam=lam, sigma=sigma,
+               obj_lin=sep.lin, obj_quad=sep.quad, obj_ref=sep.ref, net_dtype=str(mlp.dtype))
+    out["objective"] = pb.objective(z)
+    out["gradient"] = pb.gradient(z)
+    out["constraints"] = pb.constraints(z)
+    out["jacobian"] = pb.jacobian(z)
+    r, c = pb.hessianstructure()
+    out["hes_rows"], out["hes_cols"] = r, c
+    out["hessian_values"] = pb.hessian(z, lam, sigma)
+    out["integrator_structure"] = integ.hessianstructure()
+    if full_dense:
+        states, u = z[:H * xd].reshape(H, xd), z[H * xd:].reshape(H, ud)
+        out["integrator_forward"] = integ.forward(states, u, x0)
+        out["integrator_jacobian"] = integ.jacobian(states, u, x0)
+        out["integrator_hessian"] = integ.hessian(states, u, x0)
+    return out
+
+
+def main():
+    ref = shim.load_reference()
+    h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
+    weights = read_lv_fixture_h5(h5)
+    np.savez(os.path.join(HERE, "lv_mlp_weights.npz"),
+             **{f"W{i}": W for i, (W, _) in enumerate(weights)},
+             **{f"b{i}": b for i, (_, b) in enumerate(weights)})
+    lv = MLP(weights, 2, 1, dtype=np.float64)
+    objective_of = {"discrete": "setpoint", "unity": "tracking", "rk4": "linear"}
+    for i, kind in enumerate(("discrete", "unity", "rk4")):
+        np.savez_compressed(os.path.join(HERE, f"ref_{kind}_H6.npz"),
+                            **record(ref, lv, kind, 6, 100 + i, "tracking", True))
+        np.savez_compressed(os.path.join(HERE, f"ref_{kind}_H25.npz"),
+                            **record(ref, lv, kind, 25, 200 + i, objective_of[kind], False))
+    # float32 network arithmetic (what Keras / tf.hessians do, model/tensorflow.py:51,91)
+    np.savez_compressed(os.path.join(HERE, "ref_rk4_f32_H6.npz"),
+                        **record(ref, lv.astype(np.float32), "rk4", 6, 300, "linear", True))
+    # a d = 5 network: Discret / Unity work, the reference RK4 Hessian does not (rk4.py:246)
+    net5 = MLP.glorot([5, 8, 8, 4], 4, 1, seed=7)
+    out = record(ref, net5, "discrete", 5, 400, "tracking", True)
+    out.update({f"net_W{i}": W for i, (W, _) in enumerate(net5.weights)})
+    out.update({f"net_b{i}": b for i, (_, b) in enumerate(net5.weights)})
+    uni = record(ref, net5, "unity", 5, 400, "tracking", True)
+    out.update({f"unity_{k}": v for k, v in uni.items() if k.startswith(("integrator_", "hessian_values", "jacobian", "constraints"))})
+    try:
+        model = shim.make_reference_model(net5)
+        integ = ref.integrator.rk4.RK4Integrator(model, 5, DT_RK4)
+        rng = np.random.default_rng(1)
+        integ.hessian(rng.uniform(size=(5, 4)), rng.uniform(size=(5, 1)), rng.uniform(size=4))
+        out["rk4_d5_error"] = "none"
+    except Exception as e:  # noqa: BLE001 -- the reference's own failure is the datum
+        out["rk4_d5_error"] = f"{type(e).__name__}: {e}"
+    # ... but its RK4 forward/jacobian are dimension-generic: record them for d = 5
+    rng = np.random.default_rng(401)
+    xs, us, x0 = rng.uniform(-1, 1, (5, 4)), rng.uniform(-1, 1, (5, 1)), rng.uniform(-1, 1, 4)
+    integ = ref.integrator.rk4.RK4Integrator(shim.make_reference_model(net5), 5, DT_RK4)
+    out.update(rk4_x=xs, rk4_u=us, rk4_x0=x0, rk4_forward=integ.forward(xs, us, x0),
+               rk4_jacobian=integ.jacobian(xs, us, x0))
+    np.savez_compressed(os.path.join(HERE, "ref_discrete_d5_H5.npz"), **out)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
