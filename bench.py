@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the NLP-evaluation hot path (BASELINE.json metric: Jacobian+Hessian NLP evals/s in horizon-steps/s).
+
+One "step" of this bench = ONE NLP evaluation of the whole batch at one iterate: constraint residual + sparse
+Jacobian values + lambda-contracted sparse Lagrangian-Hessian values + objective value/gradient for B independent
+problems (2 kernel launches).  Workload at N=1 is BASELINE.json configs[1] ("C2"): Lotka-Volterra-shaped MLP
+3->30->30->2 (tanh), RK4 integrator DT=0.1, horizon 50, batch 4096 problems PER GPU (weak scaling, no collective on
+the data path -- problems are independent).
+
+  python bench.py [--gpus N --steps K --warmup W]            # this framework (CUDA kernels)
+  python bench.py --impl reference [...]                     # the reference CPU algorithm (oracle port) on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the host-buffer
+plug-in call (pinned host -> device -> host inside the timed region); `roofline` = dominant kernel vs the measured
+FP32 FMA peak (the path is compute bound: ~560 flop/byte); `cpu_baseline` = the dense reference-literal port timed
+on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "jac_hess_nlp_eval_horizon_steps_per_s"
+UNIT = "horizon-steps/s"
+
+WORKLOADS = {
+    # name: (layer dims, x, u, integrator, DT, H, B per GPU)
+    "C2": dict(dims=[3, 30, 30, 2], x=2, u=1, integ="rk4", DT=0.1, H=50, B=4096,
+               desc="Lotka-Volterra MLP 3-30-30-2 tanh, RK4 DT=0.1, H=50, B=4096 problems/GPU (BASELINE configs[1])"),
+    "C1": dict(dims=[3, 30, 30, 2], x=2, u=1, integ="discrete", DT=None, H=25, B=1,
+               desc="examples/lotka_volterra: discrete integrator, H=25, single problem (BASELINE configs[0])"),
+    "C3": dict(dims=[5, 128, 128, 128, 4], x=4, u=1, integ="rk4", DT=0.1, H=100, B=16384,
+               desc="cart-pole MLP 5-128-128-128-4 tanh, RK4, H=100, B=16384 (BASELINE configs[2])"),
+    "C4": dict(dims=[16, 256, 256, 256, 256, 12], x=12, u=4, integ="discrete", DT=None, H=200, B=65536,
+               desc="quadrotor MLP 16-256x4-12, discrete, H=200, B=65536 (BASELINE configs[3])"),
+}
+
+
+def make_problem(wl, B, seed=1234):
+    """synthetic weights (Glorot-uniform, seed 0) and iterates: z,x0 ~ U(-1,1), lambda ~ N(0,1), sigma=1."""
+    from oracle.mlp_np import MLP
+    from oracle.objectives_np import SeparableQuadraticObjective
+    mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+    H, xd, ud = wl["H"], wl["x"], wl["u"]
+    n, m = H * (xd + ud), H * xd
+    rng = np.random.default_rng(seed)
+    Z = rng.uniform(-1, 1, (B, n))
+    X0 = rng.uniform(-1, 1, (B, xd))
+    lam = rng.standard_normal((B, m))
+    obj = SeparableQuadraticObjective.tracking(H, xd, ud, np.linspace(1.0, 2.0, xd), np.linspace(0.1, 0.2, ud))
+    return mlp, obj, Z, X0, lam
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the dense reference-literal port (oracle/dense_ref.py) on host cores
+# ------------------------------------------------------------------------------------------------------
+def _cpu_problem_eval(args):
+    """one problem, one iterate: objective, gradient, constraints, dense Jacobian, Lagrangian Hessian
+    (reference optimizer/ipopt.py callbacks over the dense O(H^3) integrator arrays)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    wl, z, x0, lam = args
+    from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem
+    from oracle.mlp_np import MLP, DenseModelView
+    from oracle.objectives_np import SeparableQuadraticObjective
+    cache = _cpu_problem_eval.__dict__.setdefault("cache", {})
+    key = json.dumps(wl, sort_keys=True)
+    if key not in cache:
+        mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+        obj = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
+        integ = DenseIntegrator(DenseModelView(mlp), wl["H"], "discrete" if wl["integ"] == "discrete" else wl["integ"], DT=wl["DT"])
+        integ.hessianstructure()            # structure probing is a one-off in the reference too (cached)
+        cache[key] = (obj, integ)
+    obj, integ = cache[key]
+    pb = DenseIpoptProblem(x0, obj, integ)
+    pb.objective(z); pb.gradient(z); pb.constraints(z); pb.jacobian(z)
+    return float(pb.hessian(z, lam, 1.0).sum())
+
+
+def cpu_reference_run(wl_name, sample, steps, warmup, procs=None):
+    """times `steps` evaluations of a bounded sample of `sample` problems on `procs` worker processes."""
+    import multiprocessing as mp
+    wl = {k: v for k, v in WORKLOADS[wl_name].items() if k != "desc"}
+    procs = procs or os.cpu_count() or 1
+    _, _, Z, X0, lam = make_problem(wl, sample)
+    jobs = [(wl, Z[i], X0[i], lam[i]) for i in range(sample)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        chunk = max(1, sample // (procs * 4))
+        for _ in range(max(1, warmup)):
+            pool.map(_cpu_problem_eval, jobs[:procs], chunksize=1)      # builds the per-process caches
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_problem_eval, jobs, chunksize=chunk)
+        dt = time.perf_counter() - t0
+    ms = dt / steps * 1e3
+    return dict(value=sample * wl["H"] / (dt / steps), ms_per_step=ms, cores=procs,
+                sample=f"{sample} of {wl['B']} problems per step ({sample * wl['H']} horizon-steps), dense reference-literal port "
+                       f"(oracle/dense_ref.py: O(H^3) dense Jacobian/Hessian like integrator/rk4.py + optimizer/ipopt.py), float32 network")
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def gpu_run(args):
+    import torch
+    import torch.distributed as dist
+    from pyneuralempc_b200 import NlpEvaluator
+    from pyneuralempc_b200.engine import measure_fma_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["B"]
+    mlp, obj, Z, X0, lam = make_problem(wl, B, seed=1234 + rank)        # every rank owns different problems
+    ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"], compute_dtype=args.dtype,
+                      io_dtype=args.io_dtype, device=local, kernel=args.kernel)
+    ev.set_objective(obj.lin, obj.quad, obj.ref)
+    dev = ev.tdevice
+    tdt = ev.tdtype
+    # rotating input/output sets so successive steps never re-read an L2-resident set (inputs+outputs of all sets >> 126 MB L2)
+    nsets = args.sets
+    zs = [torch.as_tensor(np.roll(Z, s, axis=0), dtype=tdt, device=dev) for s in range(nsets)]
+    x0s = [torch.as_tensor(np.roll(X0, s, axis=0), dtype=tdt, device=dev) for s in range(nsets)]
+    lams = [torch.as_tensor(np.roll(lam, s, axis=0), dtype=tdt, device=dev) for s in range(nsets)]
+    outs = [ev.alloc_outputs(B) for _ in range(nsets)]
+    set_bytes = sum(t.numel() * t.element_size() for t in (zs[0], x0s[0], lams[0])) + sum(t.numel() * t.element_size() for t in outs[0].values())
+
+    def step(i, want=("resid", "jac", "hes", "obj", "grad")):
+        s = i % nsets
+        ev.eval(zs[s], x0s[s], lams[s], 1.0, want=want, out=outs[s])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ev.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = ev.launch_count - l0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    steps_per_eval = B * wl["H"]
+    value = world * steps_per_eval / (ms_step * 1e-3)
+
+    # ---- dominant kernel alone (residual+Jacobian+Hessian kernel), per-launch CUDA events --------------------------------
+    kt = []
+    for i in range(max(5, min(args.steps, 20))):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(i, want=("resid", "jac", "hes")); b_.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b_))
+    k_ms = statistics.mean(kt)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through the plug-in call, H2D + D2H inside the timed region -----------------------------------
+    npdt = np.float64 if args.io_dtype == "float64" else np.float32
+    Zh, X0h, lamh = Z.astype(npdt), X0.astype(npdt), lam.astype(npdt)
+    for _ in range(3):
+        ev.eval_host(Zh, X0h, lamh, 1.0)
+    barrier()
+    t0 = time.perf_counter()
+    chk = 0.0
+    for _ in range(args.steps):
+        o = ev.eval_host(Zh, X0h, lamh, 1.0)
+        chk += float(o["obj"][0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps_per_eval / (float(te.item()) / args.steps)
+    h2d, d2h = ev.host_io_bytes(B)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    fma_peak = measure_fma_peak(local, args.dtype, 300)
+    flops = ev.flops_per_step * steps_per_eval
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = ev.bytes_per_step() * steps_per_eval
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+    if os.path.exists(tr_path):
+        try:
+            traffic = json.load(open(tr_path)).get(args.workload)
+        except (OSError, ValueError):
+            traffic = None
+    roofline = {"bound": "fp32-fma" if args.dtype == "float32" else "fp64-fma",
+                "note": "compute bound on the CUDA-core FMA pipe (arithmetic intensity %.0f flop/B); neither HBM nor tensor cores bound this kernel" % (flops / alg_bytes),
+                "kernel": ev.kernel_name, "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                "peak_source": "measured live: register-resident FMA loop (nempc_measure_fma_peak)",
+                "kernel_ms": k_ms, "flops_per_horizon_step": ev.flops_per_step, "bytes_per_horizon_step": ev.bytes_per_step(),
+                "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "traffic": traffic}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--workload", args.workload,
+                            "--cpu-sample", str(args.cpu_sample)], capture_output=True, text=True)
+        try:
+            c = json.loads(r.stdout.strip().splitlines()[-1])
+            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+        except (ValueError, IndexError):
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "batch_per_gpu": B, "horizon": wl["H"], "io_dtype": args.io_dtype,
+                       "horizon_steps_per_eval_per_gpu": steps_per_eval, "parallelism": f"independent problems sharded over {world} GPU(s), no data-path collective",
+                       "l2": f"{nsets} rotating input/output sets, {set_bytes * nsets / 1e6:.0f} MB total > 126 MB L2",
+                       "eval": "residual + sparse Jacobian + lambda-contracted sparse Lagrangian Hessian + objective value/gradient"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(te.item()) / args.steps * 1e3, "api": "NlpEvaluator.eval_host -> nempc_eval_host (pinned host buffers)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_run(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    r = cpu_reference_run(args.workload, args.cpu_sample, max(1, args.steps), max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "note": "reference CPU algorithm (oracle port; TensorFlow/JAX/cyipopt are not installable here), bounded sample per step"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's)")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"], help="arithmetic type of the network/chain rule")
+    ap.add_argument("--io-dtype", default="float64", choices=["float32", "float64"], help="element type of z/lambda/values (reference: float64)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--sets", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=128, help="problems per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_baseline_worker:
+        print(json.dumps(cpu_reference_run(args.workload, args.cpu_sample, 2, 1)))
+        return
+    if args.impl == "reference":
+        reference_run(args)
+    else:
+        gpu_run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+/*
+ * nempc.h -- C ABI of the B200-native NLP-evaluation hot path of pyNeuralEMPC.
+ *
+ * The reference has no FFI: its boundary for this path is four duck-typed Python classes plus the
+ * cyipopt callback protocol.  Each entry point below states which reference
+ * interface it replaces (paths relative to /root/reference/pyNeuralEMPC/).  The Python mirror of those
+ * classes lives in pyneuralempc_b200/ and binds this library with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 (NEMPC_OK) or a negative NEMPC_E* code; nothing throws across the ABI;
+ *     nempc_last_error() gives the message (pass NULL for errors of nempc_create itself).
+ *   - the caller owns all I/O buffers; the handle owns device weights, index tables and staging.
+ *   - one CUDA stream per call; calls on ONE handle are not re-entrant (the reference's callbacks are
+ *     single-threaded: optimizer/ipopt.py:189); independent handles may be used from different threads/GPUs.
+ *   - there is NO CPU fallback: every compute entry point fails with NEMPC_ECUDA when no device is usable.
+ *
+ * Problem layout (identical to the reference)
+ *   decision vector z = [x_1 .. x_H | u_0 .. u_{H-1}], n = H*(x_dim+u_dim)      optimizer/ipopt.py:20-28
+ *   constraint row r = t*x_dim + p,  c_t = Phi(x_{t-1}, u_t) - x_t,  m = H*x_dim  integrator/discret.py:13-30
+ *   batches are row-major: z (B,n), x0 (B,x_dim), lambda (B,m), resid (B,m), jac_vals (B,nnz_jac),
+ *   hes_vals (B,nnz_hes), obj (B), grad (B,n); element type = desc.io_dtype.
+ *   Jacobian values follow nempc_structure() (row-major order of the non-zeros of the dense matrix of
+ *   integrator/discret.py:32-58 / rk4.py:113-178); Hessian values follow
+ *   np.nonzero(np.tril(objective_map + integrator_map)) of optimizer/ipopt.py:55-62.
+ */
+#ifndef NEMPC_H_
+#define NEMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEMPC_MAX_LAYERS 8   /* dense layers including the linear output layer */
+#define NEMPC_MAX_D 16       /* x_dim + u_dim */
+
+enum { NEMPC_OK = 0, NEMPC_EINVAL = -1, NEMPC_ECUDA = -2, NEMPC_ENOMEM = -3, NEMPC_ESTATE = -4, NEMPC_EUNSUPPORTED = -5 };
+enum { NEMPC_F32 = 0, NEMPC_F64 = 1 };
+enum { NEMPC_INTEG_DISCRETE = 0,   /* x_{t-1} + f - x_t        integrator/discret.py:13-30 */
+       NEMPC_INTEG_UNITY = 1,      /* f - x_t                  integrator/unity.py:15-32   */
+       NEMPC_INTEG_RK4 = 2 };      /* classical RK4, ZOH on u  integrator/rk4.py:57-83      */
+enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2 };
+enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2 };
+
+typedef struct nempc_desc {
+    int32_t x_dim, u_dim;                /* model/base.py:4-9 */
+    int32_t horizon;                     /* H, integrator/base.py:19 */
+    int32_t n_layers;                    /* Keras Dense layers, hidden (activation) + 1 linear output */
+    int32_t widths[NEMPC_MAX_LAYERS];    /* fan-out of each layer; widths[n_layers-1] == x_dim */
+    int32_t activation;                  /* NEMPC_ACT_* of the hidden layers */
+    int32_t integrator;                  /* NEMPC_INTEG_* */
+    double  dt;                          /* RK4 step (integrator/rk4.py:48); ignored otherwise */
+    int32_t compute_dtype;               /* network + chain-rule arithmetic: NEMPC_F32 (reference: Keras f32) or F64 */
+    int32_t io_dtype;                    /* element type of every I/O buffer (reference: f64, ipopt.py) */
+    int32_t device;                      /* CUDA ordinal */
+    int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO picks the register-resident kernel when it applies) */
+} nempc_desc;
+
+typedef struct nempc_handle nempc_handle;
+
+const char* nempc_version(void);
+const char* nempc_last_error(const nempc_handle* h);
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+/* replaces the construction chain Model -> Integrator -> ObjectiveFunc -> IpoptProblem
+ * (model/tensorflow.py:9-29, integrator/rk4.py:48-54, optimizer/ipopt.py:8-18). */
+int nempc_create(const nempc_desc* desc, nempc_handle** out);
+int nempc_destroy(nempc_handle* h);
+
+/* Keras kernel layout W[in][out] row-major, y = x @ W + b (examples/lotka_volterra/nn_model.h5); HOST pointers,
+ * always double (float32 weights are exactly representable). */
+int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const double* b);
+
+/* separable cost f(z) = sum_i lin_i z_i + quad_i (z_i - ref_i)^2 -- the families used with
+ * objective/jax.py:28-57 (run.py:83-84 linear in u, test.py:59-60 squared set-point, diagonal tracking).
+ * HOST pointers of length n, NULL = zeros.  Changes the Hessian pattern where quad != 0 on x_H. */
+int nempc_set_objective(nempc_handle* h, const double* lin, const double* quad, const double* ref);
+
+/* ---- sparsity (host only, no device needed) ----------------------------------------------------------- */
+/* replaces Integrator.hessianstructure / JAXObjectifFunc.hessianstructure / IpoptProblem.hessianstructure
+ * (integrator/base.py:83-115, objective/jax.py:59-90, optimizer/ipopt.py:55-62) with the analytic pattern,
+ * and adds the Jacobian pattern the reference leaves dense (optimizer/ipopt.py:88-96).
+ * quad_mask: n bytes, non-zero where the objective has a diagonal Hessian entry (NULL = none). */
+int nempc_structure_counts(int32_t horizon, int32_t x_dim, int32_t u_dim, const uint8_t* quad_mask,
+                           int64_t* nnz_jac, int64_t* nnz_hes);
+int nempc_structure_fill(int32_t horizon, int32_t x_dim, int32_t u_dim, const uint8_t* quad_mask,
+                         int32_t* jac_row, int32_t* jac_col, int32_t* hes_row, int32_t* hes_col);
+int nempc_dims(const nempc_handle* h, int64_t* n, int64_t* m, int64_t* nnz_jac, int64_t* nnz_hes);
+int nempc_structure(const nempc_handle* h, int32_t* jac_row, int32_t* jac_col, int32_t* hes_row, int32_t* hes_col);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+/* One NLP evaluation of B independent problems at one iterate; replaces, per problem,
+ *   IpoptProblem.constraints (ipopt.py:44-52)  -> resid      Integrator.forward  (discret.py:13-30, rk4.py:57-83)
+ *   IpoptProblem.jacobian    (ipopt.py:88-96)  -> jac_vals   Integrator.jacobian (discret.py:32-58, rk4.py:113-178)
+ *   IpoptProblem.hessian     (ipopt.py:66-86)  -> hes_vals   Integrator.hessian  (discret.py:61-81, rk4.py:181-285)
+ *                                                            + obj_factor * ObjectiveFunc.hessian (objective/jax.py:43-57)
+ *   IpoptProblem.objective / gradient (ipopt.py:30-42) -> obj, grad
+ * DEVICE pointers, element type io_dtype.  Any output may be NULL (skipped); hes_vals needs lambda.
+ * obj_factor: device array of B values, or NULL to use obj_factor_scalar for every problem.
+ * stream: a cudaStream_t (NULL = default stream).  Asynchronous. */
+int nempc_eval(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda,
+               const void* obj_factor, double obj_factor_scalar,
+               void* resid, void* jac_vals, void* hes_vals, void* obj, void* grad, void* stream);
+
+/* Same call with HOST buffers (the cyipopt callback situation): copies inputs to the handle's device staging,
+ * evaluates, copies the requested outputs back and synchronises.  Pinned host memory makes the copies async DMA. */
+int nempc_eval_host(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda,
+                    const void* obj_factor, double obj_factor_scalar,
+                    void* resid, void* jac_vals, void* hes_vals, void* obj, void* grad);
+
+/* Per-step blocks before sparse assembly: pred (B,H,x) = Phi(x_{t-1},u_t) without the -x_t term,
+ * AB (B,H,x,d) = d Phi / d(x_{t-1},u_t), Hblk (B,H,x,d,d) per-output second derivatives (not lambda-contracted):
+ * what Integrator.jacobian / Integrator.hessian scatter densely (rk4.py:159-176, 266-283).  DEVICE pointers. */
+int nempc_eval_blocks(nempc_handle* h, int64_t B, const void* z, const void* x0,
+                      void* pred, void* AB, void* Hblk, void* stream);
+
+/* Raw network value / Jacobian / per-output Hessian of N stacked inputs zin (N,d):
+ * replaces KerasTFModel.forward / .jacobian / .hessian per sample (model/tensorflow.py:49-109),
+ * f (N,x), jac (N,x,d), hes (N,x,d,d).  DEVICE pointers; jac / hes may be NULL. */
+int nempc_model_eval(nempc_handle* h, int64_t N, const void* zin, void* f, void* jac, void* hes, void* stream);
+
+/* Stand-alone objective value / gradient of the separable cost (no handle needed):
+ * replaces JAXObjectifFunc.forward / .gradient (objective/jax.py:28-41).  z (B,n) and obj (B) / grad (B,n) are
+ * DEVICE arrays of io_dtype; lin / quad / ref are DEVICE arrays of n doubles.  obj or grad may be NULL. */
+int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const double* lin, const double* quad,
+                         const double* ref, void* obj, void* grad, void* stream);
+
+/* ---- introspection -------------------------------------------------------------------------------------- */
+int64_t nempc_launch_count(const nempc_handle* h);   /* kernels launched by this handle so far */
+const char* nempc_kernel_name(const nempc_handle* h); /* "fast_mlp2<...>" or "generic<...>" */
+/* algorithmic FLOP per horizon step (SURVEY 8d formula) for the roofline report */
+double nempc_flops_per_step(const nempc_handle* h);
+/* sustained FMA throughput of the device's FP32 / FP64 pipe (TFLOP/s), measured with a register-resident
+ * FMA loop for about `millis` ms: the denominator of the compute roofline. */
+int nempc_measure_fma_peak(int32_t device, int32_t dtype, int32_t millis, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEMPC_H_ */

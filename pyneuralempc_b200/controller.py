@@ -1,0 +1,70 @@
+"""MPC controller entry point -- the contract of ``/root/reference/pyNeuralEMPC/controller.py:7-113``:
+``NMPC(integrator, objective_func, constraint_list, H, DT, optimizer, use_hessian)`` and
+``next(x0, p, tvp, init_x, init_u) -> (x_pred (H, x_dim), u (H, u_dim))`` or ``(None, None)`` on solver failure.
+Unlike the reference (controller.py:86-105 never calls ``set_use_hessian``), ``use_hessian`` is forwarded to the
+problem factory so the Lagrangian-Hessian path is actually reachable."""
+from __future__ import annotations
+
+import numpy as np
+
+from .constraints import DomainConstraint
+from .optimizer import Optimizer
+from .optimizer.slsqp import Slsqp
+
+
+class NMPC:
+    def __init__(self, integrator, objective_func, constraint_list, H, DT, optimizer=None, use_hessian=True):
+        self.integrator = integrator
+        self.objective_func = objective_func
+        self.constraint_list = list(constraint_list)
+        domain = [c for c in self.constraint_list if isinstance(c, DomainConstraint)]
+        if not domain:
+            raise ValueError("constraint_list must contain a DomainConstraint")
+        self.domain_constraint = domain[0]
+        self.constraint_list.remove(self.domain_constraint)
+        self.H = H
+        self.DT = DT
+        self.optimizer = optimizer if optimizer is not None else Slsqp(verbose=0)
+        self.use_hessian = use_hessian
+
+    def _check(self, x0, p, tvp, init_x, init_u):
+        m = self.integrator.model
+        assert len(x0.shape) == 1, "x0 must be a vector"
+        assert x0.shape[0] == m.x_dim, "x0 dim must set according to your model !"
+        if p is not None:
+            assert len(p.shape) == 1, "p must be a vector"
+            assert p.shape[0] == m.p_dim, "p dim must set according to your model !"
+        if tvp is not None:
+            assert len(tvp.shape) == 2, "tvp must be a vector"
+            assert tvp.shape[1] == m.tvp_dim, "tvp dim must set according to your model !"
+            assert tvp.shape[0] == self.H, "tvp first dim must set according to the horizon size !"
+        assert (init_x is None) == (init_u is None), "you must give both init values"
+        if init_x is not None:
+            assert init_x.shape[1] == m.x_dim, f"init_x dim must have the good feature size (expected {m.x_dim})"
+            assert init_u.shape[1] == m.u_dim, f"init_u dim mist have the good feature size (expected {m.u_dim})"
+
+    def get_pb(self, x0, p=None, tvp=None, init_x=None, init_u=None):
+        self._check(x0, p, tvp, init_x, init_u)
+        f = self.optimizer.get_factory()
+        f.set_x0(x0)
+        f.set_objective(self.objective_func)
+        f.set_integrator(self.integrator)
+        f.set_constraints(self.constraint_list)
+        if hasattr(f, "set_use_hessian") and type(f).__name__.startswith("Ipopt"):
+            f.set_use_hessian(self.use_hessian)
+        if init_x is not None:
+            f.set_init_values(init_x, init_u)
+        if tvp is not None:
+            f.set_tvp(tvp)
+        if p is not None:
+            f.set_p(p)
+        return f.getProblemInterface()
+
+    def next(self, x0, p=None, tvp=None, init_x=None, init_u=None):
+        pb = self.get_pb(x0, p, tvp, init_x, init_u)
+        res = self.optimizer.solve(pb, self.domain_constraint)
+        if res == Optimizer.SUCCESS:
+            nx = self.integrator.model.x_dim * self.integrator.H
+            sol = self.optimizer.prev_result
+            return sol[:nx].reshape(self.integrator.H, -1), sol[nx:].reshape(self.integrator.H, -1)
+        return None, None

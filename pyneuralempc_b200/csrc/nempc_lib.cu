@@ -1,0 +1,644 @@
+// libnempc: CUDA kernels (sm_100a) + C ABI (include/nempc.h) of the pyNeuralEMPC NLP-evaluation hot path.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nempc.h"
+#include "nempc_fast.cuh"
+#include "nempc_generic.cuh"
+#include "nempc_layout.h"
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+extern __shared__ __align__(16) unsigned char nempc_smem[];
+
+template <typename T, typename TIO, int DMAX>
+__global__ void __launch_bounds__(256)
+nempc_generic_kernel(const NetView<T> net, const StageTable<T> st, const NlpLayout L, const SlotLayout sl,
+                     const EvalArgs<TIO> ar, const int tps, T* __restrict__ gws) {
+    const int slots = blockDim.x / tps;
+    const int slot = threadIdx.x / tps;
+    const int lt = threadIdx.x - slot * tps;
+    T* ws = gws ? gws + ((long long)blockIdx.x * slots + slot) * sl.total
+                : reinterpret_cast<T*>(nempc_smem) + (long long)slot * sl.total;
+    const int bar_id = 1 + slot;
+    for (long long tile = blockIdx.x; tile * slots < ar.nsteps; tile += gridDim.x) {
+        const long long step = tile * slots + slot;
+        if (step < ar.nsteps) {
+            generic_step<T, TIO, DMAX>(net, st, L, sl, ar, step, ws, lt, tps, bar_id);
+            slot_barrier(bar_id, tps);      // workspace is reused by the next step of this slot
+        }
+    }
+}
+
+template <int X, int U, int H1, int H2, int MODE, typename TIO>
+__global__ void __launch_bounds__(128)
+nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2> w, const StageTable<float> st,
+                  const NlpLayout L, const EvalArgs<TIO> ar) {
+    // cold per-thread state (layer-1 activations, per-output Hessian accumulators): [element][thread], bank = thread
+    float* scr = reinterpret_cast<float*>(nempc_smem) + threadIdx.x;
+    for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps;
+         step += (long long)gridDim.x * blockDim.x)
+        fast_step<X, U, H1, H2, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+}
+
+// objective value + gradient of f(z) = sum lin_i z_i + quad_i (z_i - ref_i)^2 : one warp per problem,
+// fixed summation order (deterministic).  Replaces JAXObjectifFunc.forward / .gradient (objective/jax.py:28-41).
+template <typename TIO>
+__global__ void nempc_objective_kernel(const TIO* __restrict__ z, const double* __restrict__ lin,
+                                       const double* __restrict__ quad, const double* __restrict__ ref,
+                                       TIO* __restrict__ obj, TIO* __restrict__ grad, int n, long long B) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = warp; b < B; b += nwarps) {
+        double acc = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double zi = (double)z[b * n + i];
+            const double dz = zi - ref[i];
+            acc += lin[i] * zi + quad[i] * dz * dz;
+            if (grad) grad[b * n + i] = (TIO)(lin[i] + 2.0 * quad[i] * dz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (obj && lane == 0) obj[b] = (TIO)acc;
+    }
+}
+
+// register-resident FMA loop: sustained FP32 / FP64 FMA-pipe throughput (the compute-roofline denominator)
+template <typename T>
+__global__ void nempc_fma_peak_kernel(T* out, int iters, T seed) {
+    T a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (T)(threadIdx.x + i);
+    const T m = (T)0.999, c = (T)1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = a[i] * m + c;
+    }
+    T s = (T)0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == (T)123456789) out[0] = s;      // never true; keeps the loop alive
+}
+
+// ======================================================================================================
+// handle
+// ======================================================================================================
+static thread_local std::string g_err;
+
+struct FastShape { int x, u, h1, h2; };
+
+struct nempc_handle {
+    nempc_desc desc{};
+    int d = 0, L = 0;
+    std::vector<int> dims;                       // d, widths...
+    std::vector<std::vector<double>> W, bvec;
+    std::vector<bool> wset;
+    std::vector<double> lin, quad, ref;
+    bool has_objective = false;
+    NlpLayout lay{};
+    // device state
+    void* dW[NEMPC_MAXL] = {}; void* dWT[NEMPC_MAXL] = {}; void* db[NEMPC_MAXL] = {};
+    double *dlin = nullptr, *dquad = nullptr, *dref = nullptr;
+    int use_fast = 0; int fast_id = -1;
+    std::vector<unsigned char> fastw;            // FastWeights<...> blob
+    SlotLayout sl{};
+    int tps = 32, slots = 1, dmax = 4;
+    size_t smem_bytes = 0; bool global_ws = false; void* gws = nullptr; size_t gws_bytes = 0;
+    int sm_count = 0; int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;               // own stream for *_host calls
+    // staging for eval_host
+    void* st_buf[10] = {}; size_t st_cap[10] = {};
+    long long launches = 0;
+    std::string err, kname;
+};
+
+#define SET_ERR(h, ...)                                   \
+    do {                                                  \
+        char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \
+        if (h) (h)->err = _b; g_err = _b;                 \
+    } while (0)
+#define CU(h, call)                                                                   \
+    do {                                                                              \
+        cudaError_t _e = (call);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            SET_ERR(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return NEMPC_ECUDA;                                                       \
+        }                                                                             \
+    } while (0)
+
+static size_t dsize(int dt) { return dt == NEMPC_F64 ? 8 : 4; }
+
+static const FastShape kFastShapes[] = {{2, 1, 30, 30}, {2, 1, 32, 32}, {2, 1, 16, 16}};
+static const int kNumFastShapes = sizeof(kFastShapes) / sizeof(kFastShapes[0]);
+
+static int fast_shape_id(const nempc_desc& d) {
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.n_layers != 3) return -1;
+    for (int i = 0; i < kNumFastShapes; ++i)
+        if (d.x_dim == kFastShapes[i].x && d.u_dim == kFastShapes[i].u && d.widths[0] == kFastShapes[i].h1 &&
+            d.widths[1] == kFastShapes[i].h2)
+            return i;
+    return -1;
+}
+
+extern "C" const char* nempc_version(void) { return "nempc 0.1 (sm_100a)"; }
+extern "C" const char* nempc_last_error(const nempc_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+// ---- structure (host only) -----------------------------------------------------------------------------
+static int check_dims(int H, int x, int u) {
+    if (H < 1 || x < 1 || u < 1 || x + u > NEMPC_MAX_D || x > NEMPC_LAYOUT_MAX_X) return NEMPC_EINVAL;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_structure_counts(int32_t H, int32_t x, int32_t u, const uint8_t* quad_mask, int64_t* nnz_jac,
+                                      int64_t* nnz_hes) {
+    if (check_dims(H, x, u)) { SET_ERR((nempc_handle*)nullptr, "bad dims H=%d x=%d u=%d", H, x, u); return NEMPC_EINVAL; }
+    NlpLayout L; nlp_layout_init(L, H, x, u, quad_mask);
+    if (nnz_jac) *nnz_jac = L.nnz_jac;
+    if (nnz_hes) *nnz_hes = L.nnz_hes;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_structure_fill(int32_t H, int32_t x, int32_t u, const uint8_t* quad_mask, int32_t* jr, int32_t* jc,
+                                    int32_t* hr, int32_t* hc) {
+    if (check_dims(H, x, u)) { SET_ERR((nempc_handle*)nullptr, "bad dims H=%d x=%d u=%d", H, x, u); return NEMPC_EINVAL; }
+    NlpLayout L; nlp_layout_init(L, H, x, u, quad_mask);
+    if (jr && jc) {
+        for (int t = 0; t < H; ++t)
+            for (int p = 0; p < x; ++p) {
+                const int r = t * x + p;
+                if (t > 0) for (int q = 0; q < x; ++q) { int s = jac_slot_A(L, t, p, q); jr[s] = r; jc[s] = (t - 1) * x + q; }
+                { int s = jac_slot_minus1(L, t, p); jr[s] = r; jc[s] = r; }
+                for (int q = 0; q < u; ++q) { int s = jac_slot_B(L, t, p, q); jr[s] = r; jc[s] = H * x + t * u + q; }
+            }
+    }
+    if (hr && hc) {
+        for (int t = 0; t < H; ++t) {
+            if (t > 0)
+                for (int p = 0; p < x; ++p)
+                    for (int q = 0; q <= p; ++q) { int s = hes_slot_xx(L, t, p, q); hr[s] = (t - 1) * x + p; hc[s] = (t - 1) * x + q; }
+            for (int q = 0; q < u; ++q) {
+                const int r = H * x + t * u + q;
+                if (t > 0) for (int p = 0; p < x; ++p) { int s = hes_slot_ux(L, t, q, p); hr[s] = r; hc[s] = (t - 1) * x + p; }
+                for (int r2 = 0; r2 <= q; ++r2) { int s = hes_slot_uu(L, t, q, r2); hr[s] = r; hc[s] = H * x + t * u + r2; }
+            }
+        }
+        for (int p = 0; p < x; ++p)
+            if (L.hes_last_slot[p] >= 0) { hr[L.hes_last_slot[p]] = (H - 1) * x + p; hc[L.hes_last_slot[p]] = (H - 1) * x + p; }
+    }
+    return NEMPC_OK;
+}
+
+static void rebuild_layout(nempc_handle* h) {
+    std::vector<uint8_t> mask;
+    if (h->has_objective) {
+        mask.resize(h->lay.n);
+        for (size_t i = 0; i < mask.size(); ++i) mask[i] = h->quad[i] != 0.0;
+    }
+    nlp_layout_init(h->lay, h->desc.horizon, h->desc.x_dim, h->desc.u_dim, mask.empty() ? nullptr : mask.data());
+}
+
+extern "C" int nempc_dims(const nempc_handle* h, int64_t* n, int64_t* m, int64_t* nnz_jac, int64_t* nnz_hes) {
+    if (!h) return NEMPC_EINVAL;
+    if (n) *n = h->lay.n;
+    if (m) *m = h->lay.m;
+    if (nnz_jac) *nnz_jac = h->lay.nnz_jac;
+    if (nnz_hes) *nnz_hes = h->lay.nnz_hes;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, int32_t* hr, int32_t* hc) {
+    if (!h) return NEMPC_EINVAL;
+    std::vector<uint8_t> mask;
+    if (h->has_objective) { mask.resize(h->lay.n); for (int i = 0; i < h->lay.n; ++i) mask[i] = h->quad[i] != 0.0; }
+    return nempc_structure_fill(h->desc.horizon, h->desc.x_dim, h->desc.u_dim, mask.empty() ? nullptr : mask.data(), jr, jc, hr, hc);
+}
+
+// ---- lifetime ------------------------------------------------------------------------------------------------
+static void free_device(nempc_handle* h) {
+    for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
+    cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws);
+    for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
+    if (!desc || !out) { SET_ERR((nempc_handle*)nullptr, "null argument"); return NEMPC_EINVAL; }
+    *out = nullptr;
+    const nempc_desc& D = *desc;
+    if (check_dims(D.horizon, D.x_dim, D.u_dim)) {
+        SET_ERR((nempc_handle*)nullptr, "unsupported dims: H=%d x_dim=%d u_dim=%d (need H>=1, x_dim+u_dim<=%d)", D.horizon, D.x_dim, D.u_dim, NEMPC_MAX_D);
+        return NEMPC_EINVAL;
+    }
+    if (D.n_layers < 2 || D.n_layers > NEMPC_MAX_LAYERS) { SET_ERR((nempc_handle*)nullptr, "n_layers must be in [2,%d]", NEMPC_MAX_LAYERS); return NEMPC_EINVAL; }
+    if (D.widths[D.n_layers - 1] != D.x_dim) { SET_ERR((nempc_handle*)nullptr, "last layer width %d != x_dim %d", D.widths[D.n_layers - 1], D.x_dim); return NEMPC_EINVAL; }
+    for (int l = 0; l < D.n_layers; ++l) if (D.widths[l] < 1 || D.widths[l] > 4096) { SET_ERR((nempc_handle*)nullptr, "bad width"); return NEMPC_EINVAL; }
+    if (D.activation < 0 || D.activation > NEMPC_ACT_SOFTPLUS || D.integrator < 0 || D.integrator > NEMPC_INTEG_RK4) { SET_ERR((nempc_handle*)nullptr, "bad activation/integrator"); return NEMPC_EINVAL; }
+    if (D.integrator == NEMPC_INTEG_RK4 && !(D.dt > 0.0)) { SET_ERR((nempc_handle*)nullptr, "RK4 needs dt > 0"); return NEMPC_EINVAL; }
+    if ((D.compute_dtype != NEMPC_F32 && D.compute_dtype != NEMPC_F64) || (D.io_dtype != NEMPC_F32 && D.io_dtype != NEMPC_F64) ||
+        (D.compute_dtype == NEMPC_F64 && D.io_dtype == NEMPC_F32)) { SET_ERR((nempc_handle*)nullptr, "unsupported dtype combination"); return NEMPC_EINVAL; }
+
+    nempc_handle* h = new nempc_handle();
+    h->desc = D; h->d = D.x_dim + D.u_dim; h->L = D.n_layers;
+    h->dims.push_back(h->d);
+    for (int l = 0; l < D.n_layers; ++l) h->dims.push_back(D.widths[l]);
+    h->W.resize(h->L); h->bvec.resize(h->L); h->wset.assign(h->L, false);
+    nlp_layout_init(h->lay, D.horizon, D.x_dim, D.u_dim, nullptr);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= D.device || D.device < 0) {
+        SET_ERR((nempc_handle*)nullptr, "no usable CUDA device %d (%s); libnempc has no CPU path", D.device, e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
+        delete h; return NEMPC_ECUDA;
+    }
+    if ((e = cudaSetDevice(D.device)) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "cudaSetDevice: %s", cudaGetErrorString(e)); delete h; return NEMPC_ECUDA; }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, D.device);
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, D.device);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "stream: %s", cudaGetErrorString(e)); delete h; return NEMPC_ECUDA; }
+
+    // kernel choice
+    h->fast_id = fast_shape_id(D);
+    if (D.kernel == NEMPC_KERNEL_FAST && h->fast_id < 0) {
+        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_FAST requested but no register-resident instantiation matches this network");
+        free_device(h); delete h; return NEMPC_EUNSUPPORTED;
+    }
+    h->use_fast = (h->fast_id >= 0 && D.kernel != NEMPC_KERNEL_GENERIC) ? 1 : 0;
+
+    // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
+    int sum_h = 0, hmax = 0;
+    for (int l = 0; l + 1 < h->L; ++l) { sum_h += D.widths[l]; hmax = std::max(hmax, D.widths[l]); }
+    h->sl = make_slot_layout(D.x_dim, h->d, sum_h, hmax);
+    h->dmax = h->d <= 4 ? 4 : (h->d <= 8 ? 8 : 16);
+    h->tps = std::min(256, std::max(32, (hmax + 31) / 32 * 32));
+    const size_t per_slot = (size_t)h->sl.total * dsize(D.compute_dtype);
+    int slots = std::max(1, 256 / h->tps);
+    if (h->tps > 32) slots = std::min(slots, 15);
+    const size_t budget = (size_t)std::max(0, h->max_smem_optin - 1024);
+    while (slots > 1 && per_slot * slots > budget / 2) --slots;    // keep >= 2 CTAs/SM when possible
+    if (per_slot * slots > budget) { h->global_ws = true; h->smem_bytes = 0; }
+    else h->smem_bytes = per_slot * slots;
+    h->slots = slots;
+
+    char nm[160];
+    if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank)", D.x_dim, D.u_dim, D.widths[0], D.widths[1]);
+    else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
+    h->kname = nm;
+    *out = h;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_destroy(nempc_handle* h) {
+    if (!h) return NEMPC_OK;
+    cudaSetDevice(h->desc.device);
+    free_device(h);
+    delete h;
+    return NEMPC_OK;
+}
+
+template <typename T> static int upload_layer(nempc_handle* h, int l, int fin, int fout) {
+    std::vector<T> w(fin * (size_t)fout), wt(fin * (size_t)fout), b(fout);
+    for (int i = 0; i < fin; ++i)
+        for (int j = 0; j < fout; ++j) { w[i * (size_t)fout + j] = (T)h->W[l][i * (size_t)fout + j]; wt[j * (size_t)fin + i] = (T)h->W[l][i * (size_t)fout + j]; }
+    for (int j = 0; j < fout; ++j) b[j] = (T)h->bvec[l][j];
+    if (!h->dW[l]) {
+        CU(h, cudaMalloc(&h->dW[l], w.size() * sizeof(T)));
+        CU(h, cudaMalloc(&h->dWT[l], w.size() * sizeof(T)));
+        CU(h, cudaMalloc(&h->db[l], b.size() * sizeof(T)));
+    }
+    CU(h, cudaMemcpy(h->dW[l], w.data(), w.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->dWT[l], wt.data(), wt.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->db[l], b.data(), b.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return NEMPC_OK;
+}
+
+template <int X, int U, int H1, int H2> static void fill_fast(nempc_handle* h) {
+    typedef FastWeights<X, U, H1, H2> FW;
+    h->fastw.assign(sizeof(FW), 0);
+    fill_fast_weights<X, U, H1, H2>(*reinterpret_cast<FW*>(h->fastw.data()), h->W[0].data(), h->bvec[0].data(),
+                                    h->W[1].data(), h->bvec[1].data(), h->W[2].data(), h->bvec[2].data());
+}
+
+extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const double* b) {
+    if (!h || !W || !b || layer < 0 || layer >= h->L) { SET_ERR(h, "nempc_set_weights: bad argument"); return NEMPC_EINVAL; }
+    const int fin = h->dims[layer], fout = h->dims[layer + 1];
+    h->W[layer].assign(W, W + (size_t)fin * fout);
+    h->bvec[layer].assign(b, b + fout);
+    CU(h, cudaSetDevice(h->desc.device));
+    int rc = h->desc.compute_dtype == NEMPC_F64 ? upload_layer<double>(h, layer, fin, fout) : upload_layer<float>(h, layer, fin, fout);
+    if (rc) return rc;
+    h->wset[layer] = true;
+    bool all = true; for (bool s : h->wset) all = all && s;
+    if (all && h->fast_id >= 0) {
+        switch (h->fast_id) {
+            case 0: fill_fast<2, 1, 30, 30>(h); break;
+            case 1: fill_fast<2, 1, 32, 32>(h); break;
+            case 2: fill_fast<2, 1, 16, 16>(h); break;
+        }
+    }
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_set_objective(nempc_handle* h, const double* lin, const double* quad, const double* ref) {
+    if (!h) return NEMPC_EINVAL;
+    const int n = h->lay.n;
+    h->lin.assign(n, 0.0); h->quad.assign(n, 0.0); h->ref.assign(n, 0.0);
+    if (lin) h->lin.assign(lin, lin + n);
+    if (quad) h->quad.assign(quad, quad + n);
+    if (ref) h->ref.assign(ref, ref + n);
+    h->has_objective = true;
+    rebuild_layout(h);
+    CU(h, cudaSetDevice(h->desc.device));
+    if (!h->dlin) {
+        CU(h, cudaMalloc(&h->dlin, n * sizeof(double)));
+        CU(h, cudaMalloc(&h->dquad, n * sizeof(double)));
+        CU(h, cudaMalloc(&h->dref, n * sizeof(double)));
+    }
+    CU(h, cudaMemcpy(h->dlin, h->lin.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->dquad, h->quad.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->dref, h->ref.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    return NEMPC_OK;
+}
+
+// ---- launches ------------------------------------------------------------------------------------------------
+static int ready(nempc_handle* h) {
+    if (!h) return NEMPC_EINVAL;
+    for (size_t l = 0; l < h->wset.size(); ++l)
+        if (!h->wset[l]) { SET_ERR(h, "weights of layer %zu not set", l); return NEMPC_ESTATE; }
+    return NEMPC_OK;
+}
+
+template <typename T> static NetView<T> make_net(const nempc_handle* h) {
+    NetView<T> n{};
+    n.L = h->L; n.act = h->desc.activation;
+    int off = 0, hm = 0;
+    for (int l = 0; l <= h->L; ++l) n.dims[l] = h->dims[l];
+    for (int l = 0; l + 1 < h->L; ++l) { n.hoff[l] = off; off += h->dims[l + 1]; hm = std::max(hm, h->dims[l + 1]); }
+    n.sum_h = off; n.hmax = hm;
+    for (int l = 0; l < h->L; ++l) { n.W[l] = (const T*)h->dW[l]; n.WT[l] = (const T*)h->dWT[l]; n.b[l] = (const T*)h->db[l]; }
+    return n;
+}
+
+template <typename T, typename TIO, int DMAX>
+static int launch_generic_t(nempc_handle* h, const EvalArgs<TIO>& ar, bool model_mode, cudaStream_t s) {
+    auto kern = nempc_generic_kernel<T, TIO, DMAX>;
+    const int threads = h->tps * h->slots;
+    if (h->smem_bytes > 48 * 1024) CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    int occ = 1;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, h->smem_bytes));
+    occ = std::max(1, occ);
+    const long long tiles = (ar.nsteps + h->slots - 1) / h->slots;
+    const long long grid = std::max(1LL, std::min(tiles, (long long)h->sm_count * occ));
+    T* gws = nullptr;
+    if (h->global_ws) {
+        const size_t need = (size_t)grid * h->slots * h->sl.total * sizeof(T);
+        if (need > h->gws_bytes) {
+            CU(h, cudaStreamSynchronize(s));
+            cudaFree(h->gws); h->gws = nullptr; h->gws_bytes = 0;
+            CU(h, cudaMalloc(&h->gws, need));
+            h->gws_bytes = need;
+        }
+        gws = (T*)h->gws;
+    }
+    NetView<T> net = make_net<T>(h);
+    StageTable<T> st = make_stage_table<T>(h->desc.integrator == NEMPC_INTEG_RK4 && !model_mode, h->desc.dt);
+    kern<<<(unsigned)grid, threads, h->smem_bytes, s>>>(net, st, h->lay, h->sl, ar, h->tps, gws);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+
+template <typename T, typename TIO>
+static int launch_generic_d(nempc_handle* h, const EvalArgs<TIO>& ar, bool model_mode, cudaStream_t s) {
+    switch (h->dmax) {
+        case 4: return launch_generic_t<T, TIO, 4>(h, ar, model_mode, s);
+        case 8: return launch_generic_t<T, TIO, 8>(h, ar, model_mode, s);
+        default: return launch_generic_t<T, TIO, 16>(h, ar, model_mode, s);
+    }
+}
+
+template <typename TIO> static int launch_generic(nempc_handle* h, const EvalArgs<TIO>& ar, bool model_mode, cudaStream_t s);
+template <> int launch_generic<float>(nempc_handle* h, const EvalArgs<float>& ar, bool model_mode, cudaStream_t s) {
+    return launch_generic_d<float, float>(h, ar, model_mode, s);
+}
+template <> int launch_generic<double>(nempc_handle* h, const EvalArgs<double>& ar, bool model_mode, cudaStream_t s) {
+    return h->desc.compute_dtype == NEMPC_F64 ? launch_generic_d<double, double>(h, ar, model_mode, s)
+                                              : launch_generic_d<float, double>(h, ar, model_mode, s);
+}
+
+template <int X, int U, int H1, int H2, typename TIO>
+static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    typedef FastWeights<X, U, H1, H2> FW;
+    const FW& w = *reinterpret_cast<const FW*>(h->fastw.data());
+    StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
+    const int threads = 128;
+    const long long blocks = std::max(1LL, (ar.nsteps + threads - 1) / threads);
+    const unsigned grid = (unsigned)std::min(blocks, (long long)h->sm_count * 64);
+    const size_t smem = mode >= 2 ? (size_t)FastScratch<X, U, H1, H2>::COUNT * threads * sizeof(float) : 0;
+    switch (mode) {
+        case 0: nempc_fast_kernel<X, U, H1, H2, 0, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        case 1: nempc_fast_kernel<X, U, H1, H2, 1, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        default: nempc_fast_kernel<X, U, H1, H2, 2, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+    }
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+
+template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    switch (h->fast_id) {
+        case 0: return launch_fast_shape<2, 1, 30, 30, TIO>(h, ar, mode, s);
+        case 1: return launch_fast_shape<2, 1, 32, 32, TIO>(h, ar, mode, s);
+        case 2: return launch_fast_shape<2, 1, 16, 16, TIO>(h, ar, mode, s);
+    }
+    SET_ERR(h, "internal: bad fast_id");
+    return NEMPC_EINVAL;
+}
+
+template <typename TIO>
+static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda, const void* obj_factor,
+                  double sigma, void* resid, void* jac, void* hes, void* obj, void* grad, cudaStream_t s) {
+    if (resid || jac || hes) {
+        EvalArgs<TIO> ar{};
+        ar.z = (const TIO*)z; ar.x0 = (const TIO*)x0; ar.lam = (const TIO*)lambda; ar.sigma = (const TIO*)obj_factor;
+        ar.sigma_scalar = sigma; ar.quad = h->has_objective ? h->dquad : nullptr;
+        ar.resid = (TIO*)resid; ar.jac = (TIO*)jac; ar.hes = (TIO*)hes;
+        ar.nsteps = (long long)B * h->desc.horizon;
+        const int mode = hes ? 2 : (jac ? 1 : 0);
+        ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
+                   (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
+        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s);
+        if (rc) return rc;
+    }
+    if (obj || grad) {
+        if (!h->has_objective) { SET_ERR(h, "obj/grad requested but nempc_set_objective was never called"); return NEMPC_ESTATE; }
+        const int threads = 256;
+        const long long warps_needed = B;
+        const unsigned grid = (unsigned)std::max(1LL, std::min((warps_needed * 32 + threads - 1) / threads, (long long)h->sm_count * 16));
+        nempc_objective_kernel<TIO><<<grid, threads, 0, s>>>((const TIO*)z, h->dlin, h->dquad, h->dref, (TIO*)obj, (TIO*)grad, h->lay.n, B);
+        CU(h, cudaGetLastError());
+        h->launches++;
+    }
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_eval(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda,
+                          const void* obj_factor, double sigma, void* resid, void* jac, void* hes, void* obj, void* grad,
+                          void* stream) {
+    int rc = ready(h);
+    if (rc) return rc;
+    if (B < 0 || !z || !x0) { SET_ERR(h, "nempc_eval: bad argument"); return NEMPC_EINVAL; }
+    if (hes && !lambda) { SET_ERR(h, "nempc_eval: hes_vals needs lambda"); return NEMPC_EINVAL; }
+    if (B == 0) return NEMPC_OK;
+    CU(h, cudaSetDevice(h->desc.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    return h->desc.io_dtype == NEMPC_F64 ? eval_t<double>(h, B, z, x0, lambda, obj_factor, sigma, resid, jac, hes, obj, grad, s)
+                                         : eval_t<float>(h, B, z, x0, lambda, obj_factor, sigma, resid, jac, hes, obj, grad, s);
+}
+
+static int stage_reserve(nempc_handle* h, int i, size_t bytes) {
+    if (bytes <= h->st_cap[i]) return NEMPC_OK;
+    cudaFree(h->st_buf[i]); h->st_buf[i] = nullptr; h->st_cap[i] = 0;
+    const size_t cap = bytes + bytes / 4;
+    CU(h, cudaMalloc(&h->st_buf[i], cap));
+    h->st_cap[i] = cap;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_eval_host(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda,
+                               const void* obj_factor, double sigma, void* resid, void* jac, void* hes, void* obj,
+                               void* grad) {
+    int rc = ready(h);
+    if (rc) return rc;
+    if (B < 0 || !z || !x0) { SET_ERR(h, "nempc_eval_host: bad argument"); return NEMPC_EINVAL; }
+    if (hes && !lambda) { SET_ERR(h, "nempc_eval_host: hes_vals needs lambda"); return NEMPC_EINVAL; }
+    if (B == 0) return NEMPC_OK;
+    CU(h, cudaSetDevice(h->desc.device));
+    const size_t es = dsize(h->desc.io_dtype);
+    const NlpLayout& L = h->lay;
+    const size_t sz[10] = {(size_t)B * L.n * es, (size_t)B * L.x * es, lambda ? (size_t)B * L.m * es : 0, obj_factor ? (size_t)B * es : 0,
+                           resid ? (size_t)B * L.m * es : 0, jac ? (size_t)B * L.nnz_jac * es : 0, hes ? (size_t)B * L.nnz_hes * es : 0,
+                           obj ? (size_t)B * es : 0, grad ? (size_t)B * L.n * es : 0, 0};
+    for (int i = 0; i < 9; ++i) if (sz[i]) { rc = stage_reserve(h, i, sz[i]); if (rc) return rc; }
+    cudaStream_t s = h->stream;
+    const void* in[4] = {z, x0, lambda, obj_factor};
+    for (int i = 0; i < 4; ++i) if (sz[i]) CU(h, cudaMemcpyAsync(h->st_buf[i], in[i], sz[i], cudaMemcpyHostToDevice, s));
+    void* d[5] = {sz[4] ? h->st_buf[4] : nullptr, sz[5] ? h->st_buf[5] : nullptr, sz[6] ? h->st_buf[6] : nullptr,
+                  sz[7] ? h->st_buf[7] : nullptr, sz[8] ? h->st_buf[8] : nullptr};
+    rc = nempc_eval(h, B, h->st_buf[0], h->st_buf[1], sz[2] ? h->st_buf[2] : nullptr, sz[3] ? h->st_buf[3] : nullptr, sigma,
+                    d[0], d[1], d[2], d[3], d[4], (void*)s);
+    if (rc) return rc;
+    void* outp[5] = {resid, jac, hes, obj, grad};
+    for (int i = 0; i < 5; ++i) if (sz[4 + i]) CU(h, cudaMemcpyAsync(outp[i], d[i], sz[4 + i], cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return NEMPC_OK;
+}
+
+template <typename TIO>
+static int blocks_t(nempc_handle* h, long long N, const void* z, const void* x0, void* pred, void* AB, void* Hblk, bool model_mode, cudaStream_t s) {
+    EvalArgs<TIO> ar{};
+    ar.z = (const TIO*)z; ar.x0 = (const TIO*)x0; ar.pred = (TIO*)pred; ar.AB = (TIO*)AB; ar.Hblk = (TIO*)Hblk;
+    ar.nsteps = N;
+    ar.flags = (model_mode ? NEMPC_MODE_MODEL : NEMPC_MODE_BLOCKS) | (AB || Hblk ? NEMPC_WANT_JAC : 0) | (Hblk ? NEMPC_WANT_HES : 0) |
+               (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
+    return launch_generic<TIO>(h, ar, model_mode, s);
+}
+
+extern "C" int nempc_eval_blocks(nempc_handle* h, int64_t B, const void* z, const void* x0, void* pred, void* AB, void* Hblk, void* stream) {
+    int rc = ready(h);
+    if (rc) return rc;
+    if (B < 0 || !z || !x0) { SET_ERR(h, "nempc_eval_blocks: bad argument"); return NEMPC_EINVAL; }
+    if (B == 0) return NEMPC_OK;
+    CU(h, cudaSetDevice(h->desc.device));
+    const long long N = (long long)B * h->desc.horizon;
+    return h->desc.io_dtype == NEMPC_F64 ? blocks_t<double>(h, N, z, x0, pred, AB, Hblk, false, (cudaStream_t)stream)
+                                         : blocks_t<float>(h, N, z, x0, pred, AB, Hblk, false, (cudaStream_t)stream);
+}
+
+extern "C" int nempc_model_eval(nempc_handle* h, int64_t N, const void* zin, void* f, void* jac, void* hes, void* stream) {
+    int rc = ready(h);
+    if (rc) return rc;
+    if (N < 0 || !zin) { SET_ERR(h, "nempc_model_eval: bad argument"); return NEMPC_EINVAL; }
+    if (N == 0) return NEMPC_OK;
+    CU(h, cudaSetDevice(h->desc.device));
+    return h->desc.io_dtype == NEMPC_F64 ? blocks_t<double>(h, N, zin, nullptr, f, jac, hes, true, (cudaStream_t)stream)
+                                         : blocks_t<float>(h, N, zin, nullptr, f, jac, hes, true, (cudaStream_t)stream);
+}
+
+extern "C" int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const double* lin, const double* quad,
+                                    const double* ref, void* obj, void* grad, void* stream) {
+    if (B < 0 || n < 1 || !z || !lin || !quad || !ref || (io_dtype != NEMPC_F32 && io_dtype != NEMPC_F64)) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_objective_eval: bad argument");
+        return NEMPC_EINVAL;
+    }
+    if (B == 0 || (!obj && !grad)) return NEMPC_OK;
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((B * 32 + threads - 1) / threads, 148 * 16));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (io_dtype == NEMPC_F64) nempc_objective_kernel<double><<<grid, threads, 0, s>>>((const double*)z, lin, quad, ref, (double*)obj, (double*)grad, (int)n, B);
+    else nempc_objective_kernel<float><<<grid, threads, 0, s>>>((const float*)z, lin, quad, ref, (float*)obj, (float*)grad, (int)n, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "objective kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------------------------
+extern "C" int64_t nempc_launch_count(const nempc_handle* h) { return h ? h->launches : 0; }
+extern "C" const char* nempc_kernel_name(const nempc_handle* h) { return h ? h->kname.c_str() : ""; }
+
+extern "C" double nempc_flops_per_step(const nempc_handle* h) {
+    if (!h) return 0.0;
+    const double d = h->d, x = h->desc.x_dim;
+    double sumW = 0, sumh = 0;
+    for (int l = 0; l < h->L; ++l) sumW += (double)h->dims[l] * h->dims[l + 1];
+    for (int l = 0; l + 1 < h->L; ++l) sumh += h->dims[l + 1];
+    const double stage = 2 * sumW + 2 * d * (sumW - d * h->dims[1]) + 2 * sumW + d * (d + 1) * sumh;
+    const int S = h->desc.integrator == NEMPC_INTEG_RK4 ? 4 : 1;
+    return S * stage + (S == 4 ? 6 * x * d * d + 6 * x * x : 0.0);
+}
+
+template <typename T> static int fma_peak_t(int millis, double* tflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    T* out = nullptr;
+    if (cudaMalloc(&out, sizeof(T)) != cudaSuccess) return NEMPC_ECUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int threads = 256, blocks = sms * 8;
+    int iters = 2000;
+    double best = 0.0;
+    float total_ms = 0.f;
+    nempc_fma_peak_kernel<T><<<blocks, threads>>>(out, 200, (T)1);   // warm-up
+    cudaDeviceSynchronize();
+    while (total_ms < (float)millis) {
+        cudaEventRecord(e0);
+        nempc_fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)1);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return NEMPC_ECUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total_ms += ms;
+        const double flops = 2.0 * 16 * 8 * (double)iters * threads * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < 5.f) iters *= 2;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_measure_fma_peak(int32_t device, int32_t dtype, int32_t millis, double* tflops) {
+    if (!tflops) return NEMPC_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "no usable CUDA device %d", device); return NEMPC_ECUDA; }
+    return dtype == NEMPC_F64 ? fma_peak_t<double>(millis, tflops) : fma_peak_t<float>(millis, tflops);
+}

@@ -1,0 +1,247 @@
+"""Batched device evaluator: one ``nempc_handle`` (C ABI, include/nempc.h) wrapped for Python.
+
+This is the object every drop-in class shares.  One ``eval`` = residual + sparse Jacobian values + sparse
+Lagrangian-Hessian values (+ objective value / gradient) of ``B`` independent transcription NLPs at one iterate,
+i.e. what IPOPT asks of ``IpoptProblem.constraints / jacobian / hessian / objective / gradient``
+(reference optimizer/ipopt.py:30-96) -- for a whole batch, in one or two kernel launches.
+
+torch is used for device memory, streams and pinned host buffers only; all arithmetic is in libnempc.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_NP = {"float32": np.float32, "float64": np.float64}
+
+
+def _vp(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class NlpEvaluator:
+    def __init__(self, weights, x_dim, u_dim, H, integrator="discrete", DT=None, activation="tanh",
+                 compute_dtype="float32", io_dtype="float64", device=0, kernel="auto"):
+        import torch
+        self._torch = torch
+        self.lib = _lib.load()
+        self.x_dim, self.u_dim, self.H = int(x_dim), int(u_dim), int(H)
+        self.d = self.x_dim + self.u_dim
+        self.integrator, self.DT, self.activation = integrator, DT, activation
+        self.compute_dtype, self.io_dtype = str(compute_dtype), str(io_dtype)
+        self.device = int(device)
+        if integrator not in _lib.INTEGRATORS:
+            raise ValueError(f"integrator must be one of {sorted(_lib.INTEGRATORS)}")
+        if integrator == "rk4" and DT is None:
+            raise ValueError("rk4 needs DT")
+        weights = [(np.ascontiguousarray(W, np.float64), np.ascontiguousarray(b, np.float64)) for W, b in weights]
+        if len(weights) > _lib.MAX_LAYERS:
+            raise ValueError("too many layers")
+        desc = _lib.NempcDesc()
+        desc.x_dim, desc.u_dim, desc.horizon, desc.n_layers = self.x_dim, self.u_dim, self.H, len(weights)
+        fan_in = self.d
+        for l, (W, b) in enumerate(weights):
+            if W.ndim != 2 or W.shape[0] != fan_in or b.shape != (W.shape[1],):
+                raise ValueError(f"layer {l}: expected kernel ({fan_in}, out) and bias (out,), got {W.shape} {b.shape}")
+            desc.widths[l] = W.shape[1]
+            fan_in = W.shape[1]
+        desc.activation = _lib.ACTIVATIONS[activation]
+        desc.integrator = _lib.INTEGRATORS[integrator]
+        desc.dt = 0.0 if DT is None else float(DT)
+        desc.compute_dtype = _lib.F64 if self.compute_dtype == "float64" else _lib.F32
+        desc.io_dtype = _lib.F64 if self.io_dtype == "float64" else _lib.F32
+        desc.device = self.device
+        desc.kernel = _lib.KERNELS[kernel]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.nempc_create(ctypes.byref(desc), ctypes.byref(h)), None, "nempc_create")
+        self._h = h
+        for l, (W, b) in enumerate(weights):
+            self._check(self.lib.nempc_set_weights(h, l, W.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)),
+                        "nempc_set_weights")
+        self.weights = weights
+        self.tdtype = torch.float64 if self.io_dtype == "float64" else torch.float32
+        self.tdevice = torch.device("cuda", self.device)
+        self._objective = None
+        self._refresh_dims()
+        self._pinned = {}
+
+    # ---- lifetime / errors ------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        _lib.check(rc, self._h, what)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.nempc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+    # ---- static information -------------------------------------------------------------------------------
+    def _refresh_dims(self):
+        n, m, nj, nh = (ctypes.c_int64() for _ in range(4))
+        self._check(self.lib.nempc_dims(self._h, ctypes.byref(n), ctypes.byref(m), ctypes.byref(nj), ctypes.byref(nh)), "nempc_dims")
+        self.n, self.m, self.nnz_jac, self.nnz_hes = n.value, m.value, nj.value, nh.value
+        jr, jc = np.empty(self.nnz_jac, np.int32), np.empty(self.nnz_jac, np.int32)
+        hr, hc = np.empty(self.nnz_hes, np.int32), np.empty(self.nnz_hes, np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self._check(self.lib.nempc_structure(self._h, p(jr), p(jc), p(hr), p(hc)), "nempc_structure")
+        self.jac_rows, self.jac_cols, self.hes_rows, self.hes_cols = jr, jc, hr, hc
+
+    def set_objective(self, lin=None, quad=None, ref=None):
+        """separable cost ``sum lin*z + quad*(z-ref)^2`` (see objective.py); arrays of length n or None."""
+        arrs = []
+        for a in (lin, quad, ref):
+            arrs.append(None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64).ravel(), (self.n,))))
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        self._check(self.lib.nempc_set_objective(self._h, p(arrs[0]), p(arrs[1]), p(arrs[2])), "nempc_set_objective")
+        self._objective = arrs
+        self._refresh_dims()
+
+    @property
+    def has_objective(self):
+        return self._objective is not None
+
+    @property
+    def kernel_name(self):
+        return self.lib.nempc_kernel_name(self._h).decode()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.nempc_launch_count(self._h))
+
+    @property
+    def flops_per_step(self):
+        return float(self.lib.nempc_flops_per_step(self._h))
+
+    def bytes_per_step(self):
+        """algorithmic bytes per horizon step: inputs z_t, lambda_t, x_t in; resid, A|B, tril Hessian block out."""
+        s = 8 if self.io_dtype == "float64" else 4
+        x, d = self.x_dim, self.d
+        return s * (d + x + x + x * d + d * (d + 1) // 2)
+
+    # ---- device-resident evaluation ---------------------------------------------------------------------------
+    def _as_dev(self, a, shape):
+        torch = self._torch
+        if a is None:
+            return None
+        if not isinstance(a, torch.Tensor):
+            a = torch.as_tensor(np.asarray(a), dtype=self.tdtype)
+        a = a.to(device=self.tdevice, dtype=self.tdtype).contiguous()
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+        return a
+
+    def alloc_outputs(self, B, want=("resid", "jac", "hes", "obj", "grad")):
+        torch = self._torch
+        shapes = {"resid": (B, self.m), "jac": (B, self.nnz_jac), "hes": (B, self.nnz_hes), "obj": (B,), "grad": (B, self.n)}
+        return {k: torch.empty(shapes[k], dtype=self.tdtype, device=self.tdevice) for k in want}
+
+    def eval(self, z, x0, lam=None, obj_factor=1.0, want=("resid", "jac", "hes", "obj", "grad"), out=None, stream=None):
+        """z (B,n), x0 (B,x), lam (B,m) CUDA tensors of io dtype -> dict of CUDA tensors (asynchronous)."""
+        torch = self._torch
+        B = int(z.shape[0])
+        z = self._as_dev(z, (B, self.n))
+        x0 = self._as_dev(x0, (B, self.x_dim))
+        lam = self._as_dev(lam, (B, self.m))
+        want = tuple(w for w in want if not (w in ("obj", "grad") and not self.has_objective))
+        if "hes" in want and lam is None:
+            raise ValueError("'hes' needs lam")
+        sig_t, sig_s = None, 1.0
+        if isinstance(obj_factor, torch.Tensor) or np.ndim(obj_factor) > 0:
+            sig_t = self._as_dev(obj_factor, (B,))
+        else:
+            sig_s = float(obj_factor)
+        if out is None:
+            out = self.alloc_outputs(B, want)
+        s = torch.cuda.current_stream(self.tdevice).cuda_stream if stream is None else stream
+        g = lambda k: _vp(out[k]) if k in want else None
+        self._check(self.lib.nempc_eval(self._h, B, _vp(z), _vp(x0), _vp(lam), _vp(sig_t), sig_s,
+                                        g("resid"), g("jac"), g("hes"), g("obj"), g("grad"), ctypes.c_void_p(s)), "nempc_eval")
+        return out
+
+    def eval_blocks(self, z, x0, want_hessian=True):
+        """per-step blocks before sparse assembly: Phi (B,H,x), dPhi/d(x_prev,u) (B,H,x,d), per-output Hessians (B,H,x,d,d)."""
+        torch = self._torch
+        B = int(z.shape[0])
+        z = self._as_dev(z, (B, self.n))
+        x0 = self._as_dev(x0, (B, self.x_dim))
+        pred = torch.empty((B, self.H, self.x_dim), dtype=self.tdtype, device=self.tdevice)
+        AB = torch.empty((B, self.H, self.x_dim, self.d), dtype=self.tdtype, device=self.tdevice)
+        Hb = torch.empty((B, self.H, self.x_dim, self.d, self.d), dtype=self.tdtype, device=self.tdevice) if want_hessian else None
+        s = torch.cuda.current_stream(self.tdevice).cuda_stream
+        self._check(self.lib.nempc_eval_blocks(self._h, B, _vp(z), _vp(x0), _vp(pred), _vp(AB), _vp(Hb), ctypes.c_void_p(s)), "nempc_eval_blocks")
+        return pred, AB, Hb
+
+    def model_eval(self, zin, want_jac=True, want_hes=True):
+        """raw network value (N,x), Jacobian (N,x,d), per-output Hessian (N,x,d,d) of stacked inputs zin (N,d)."""
+        torch = self._torch
+        N = int(zin.shape[0])
+        zin = self._as_dev(zin, (N, self.d))
+        f = torch.empty((N, self.x_dim), dtype=self.tdtype, device=self.tdevice)
+        J = torch.empty((N, self.x_dim, self.d), dtype=self.tdtype, device=self.tdevice) if (want_jac or want_hes) else None
+        Hs = torch.empty((N, self.x_dim, self.d, self.d), dtype=self.tdtype, device=self.tdevice) if want_hes else None
+        s = torch.cuda.current_stream(self.tdevice).cuda_stream
+        self._check(self.lib.nempc_model_eval(self._h, N, _vp(zin), _vp(f), _vp(J), _vp(Hs), ctypes.c_void_p(s)), "nempc_model_eval")
+        return f, J, Hs
+
+    # ---- host-buffer evaluation (the solver-callback situation) ---------------------------------------------------
+    def _pin(self, key, shape):
+        torch = self._torch
+        t = self._pinned.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=self.tdtype).pin_memory()
+            self._pinned[key] = t
+        return t
+
+    def eval_host(self, z, x0, lam=None, obj_factor=1.0, want=("resid", "jac", "hes", "obj", "grad")):
+        """numpy in -> numpy out through ``nempc_eval_host``: inputs are copied into persistent pinned buffers, the
+        library DMA-copies them to the device, evaluates, DMA-copies the results into pinned buffers and
+        synchronises; the returned arrays are views of those pinned buffers (valid until the next call)."""
+        npdt = _NP[self.io_dtype]
+        z = np.asarray(z, npdt)
+        if z.ndim == 1:
+            z = z[None]
+        B = z.shape[0]
+        x0 = np.asarray(x0, npdt).reshape(B, self.x_dim)
+        want = tuple(w for w in want if not (w in ("obj", "grad") and not self.has_objective))
+        if "hes" in want and lam is None:
+            raise ValueError("'hes' needs lam")
+        pz = self._pin("z", (B, self.n)); pz.numpy()[...] = z
+        px = self._pin("x0", (B, self.x_dim)); px.numpy()[...] = x0
+        pl = None
+        if lam is not None and "hes" in want:
+            pl = self._pin("lam", (B, self.m)); pl.numpy()[...] = np.asarray(lam, npdt).reshape(B, self.m)
+        ps, sig_s = None, 1.0
+        if np.ndim(obj_factor) > 0:
+            ps = self._pin("sig", (B,)); ps.numpy()[...] = np.asarray(obj_factor, npdt)
+        else:
+            sig_s = float(obj_factor)
+        shapes = {"resid": (B, self.m), "jac": (B, self.nnz_jac), "hes": (B, self.nnz_hes), "obj": (B,), "grad": (B, self.n)}
+        outs = {k: self._pin("o_" + k, shapes[k]) for k in want}
+        g = lambda k: _vp(outs[k]) if k in want else None
+        self._check(self.lib.nempc_eval_host(self._h, B, _vp(pz), _vp(px), _vp(pl), _vp(ps), sig_s,
+                                             g("resid"), g("jac"), g("hes"), g("obj"), g("grad")), "nempc_eval_host")
+        return {k: v.numpy() for k, v in outs.items()}
+
+    def host_io_bytes(self, B, want=("resid", "jac", "hes", "obj", "grad"), with_lambda=True):
+        s = 8 if self.io_dtype == "float64" else 4
+        h2d = B * (self.n + self.x_dim + (self.m if with_lambda else 0)) * s
+        sizes = {"resid": self.m, "jac": self.nnz_jac, "hes": self.nnz_hes, "obj": 1, "grad": self.n}
+        d2h = B * sum(sizes[k] for k in want) * s
+        return h2d, d2h
+
+
+def measure_fma_peak(device=0, dtype="float32", millis=300):
+    """sustained FMA-pipe throughput (TFLOP/s) of the device: the compute-roofline denominator."""
+    lib = _lib.load()
+    out = ctypes.c_double()
+    _lib.check(lib.nempc_measure_fma_peak(int(device), _lib.F64 if dtype == "float64" else _lib.F32, int(millis), ctypes.byref(out)),
+               None, "nempc_measure_fma_peak")
+    return out.value

@@ -1,0 +1,168 @@
+"""Integrator layer: equality constraints ``c_t = Phi(x_{t-1}, u_t) - x_t`` evaluated by CUDA kernels.
+
+Mirrors ``/root/reference/pyNeuralEMPC/integrator/``: ``Integrator`` (base.py:5-123), ``DiscretIntegrator``
+(discret.py), ``UnityIntegrator`` (unity.py) and ``RK4Integrator`` (rk4.py) -- same constructors, attributes
+(``H``, ``model``, ``nb_contraints`` [sic]), call signatures, assertion behaviour and dense return layouts, so a
+reference ``IpoptProblem`` / ``SlsqpProblem`` can drive them unchanged:
+
+* ``forward(x, u, x0)``  -> (m,)            discret.py:13-30, unity.py:15-32, rk4.py:57-83
+* ``jacobian(x, u, x0)`` -> dense (m, n)     discret.py:32-58, rk4.py:113-178
+* ``hessian(x, u, x0)``  -> dense (m, n, n)  discret.py:61-81, rk4.py:181-285 (any x_dim+u_dim, not only 3)
+* ``hessianstructure()`` -> (n, n) 0/1 map   base.py:83-115 (analytic instead of numerically probed)
+
+The dense arrays exist for drop-in compatibility only (O(H^3) like the reference).  The scalable interface is
+``.evaluator`` (sparse values in the structure order; see ``optimizer.ipopt.CudaIpoptProblem``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import NlpEvaluator
+from .model import CudaMLPModel, Model
+
+
+class Integrator:
+    """Abstract integrator (reference integrator/base.py:5-123)."""
+
+    def __init__(self, model, H: int, nb_contraints: int):
+        if not isinstance(model, (Model,)):
+            raise ValueError("The model provided isn't a Model object !")
+        self.H = H
+        self.model = model
+        self.nb_contraints = nb_contraints
+        self.hessian_structure_cache = None
+
+    def forward(self, x, u, x0, p=None, tvp=None):
+        raise NotImplementedError("")
+
+    def jacobian(self, x, u, x0, p=None, tvp=None):
+        raise NotImplementedError("")
+
+    def hessian(self, x, u, x0, p=None, tvp=None):
+        raise NotImplementedError("")
+
+    def hessianstructure(self):
+        if self.hessian_structure_cache is None:
+            self.hessian_structure_cache = self._compute_hessianstructure()
+        return self.hessian_structure_cache
+
+    def get_lower_bounds(self, _):
+        return [0.0, ] * self.nb_contraints
+
+    def get_upper_bounds(self, _):
+        return [0.0, ] * self.nb_contraints
+
+
+class _CudaIntegrator(Integrator):
+    KIND = None
+
+    def __init__(self, model, H, DT=None, cache_mode=False, cache_size=2):
+        super().__init__(model, H, model.x_dim * H)
+        if not isinstance(model, CudaMLPModel):
+            raise ValueError("CUDA integrators need a CudaMLPModel (the network is fused into the integrator kernel)")
+        self.DT = DT
+        self.cache_mode = cache_mode
+        self._cache, self._cache_size = [], max(1, int(cache_size))
+        self.evaluator = NlpEvaluator(model.weights, model.x_dim, model.u_dim, H, self.KIND, DT=DT,
+                                      activation=model.activation, compute_dtype=model.dtype, io_dtype="float64",
+                                      device=model.device, kernel=model.kernel)
+
+    # ---- helpers --------------------------------------------------------------------------------------------
+    def _pack(self, x, u, x0):
+        assert len(x.shape) == 2 and len(u.shape) == 2, "x and u tensor must have dim 2"       # discret.py:15
+        x0 = np.asarray(x0, np.float64)
+        z = np.concatenate([np.asarray(x, np.float64).reshape(-1), np.asarray(u, np.float64).reshape(-1)])
+        return z, x0.reshape(-1)
+
+    def _first_order(self, x, u, x0, want):
+        """residual (+ Jacobian values) at one iterate; with ``cache_mode`` the pair is computed together and
+        memoised on the exact input bytes (the reference memoises k1..k4 on a str() hash, rk4.py:20-43)."""
+        z, x0v = self._pack(x, u, x0)
+        if not self.cache_mode:
+            return self.evaluator.eval_host(z, x0v, want=want)
+        key = z.tobytes() + x0v.tobytes()
+        for k, v in self._cache:
+            if k == key:
+                return v
+        out = {k: v.copy() for k, v in self.evaluator.eval_host(z, x0v, want=("resid", "jac")).items()}
+        self._cache.append((key, out))
+        del self._cache[:-self._cache_size]
+        return out
+
+    # ---- reference interface ------------------------------------------------------------------------------------
+    def forward(self, x, u, x0, p=None, tvp=None):
+        assert len(np.shape(x0)) == 1, "x0 shape must have dim 1"                            # discret.py:17
+        return self._first_order(x, u, x0, ("resid",))["resid"][0].copy()
+
+    def jacobian(self, x, u, x0, p=None, tvp=None):
+        ev = self.evaluator
+        vals = self._first_order(x, u, x0, ("jac",))["jac"][0]
+        J = np.zeros((ev.m, ev.n))
+        J[ev.jac_rows, ev.jac_cols] = vals
+        return J
+
+    def hessian_blocks(self, x, u, x0):
+        """per-step, per-output second derivatives (H, x_dim, d, d) -- what rk4.py:266 calls ``model_H``."""
+        z, x0v = self._pack(x, u, x0)
+        _, _, Hb = self.evaluator.eval_blocks(z[None], x0v[None])
+        return Hb[0].cpu().numpy()
+
+    def hessian(self, x, u, x0, p=None, tvp=None):
+        H, xd, ud = self.H, self.model.x_dim, self.model.u_dim
+        n = H * (xd + ud)
+        blk = self.hessian_blocks(x, u, x0)
+        out = np.zeros((H, xd, n, n))
+        off = xd * H
+        for t in range(H):                                   # same scatter as rk4.py:270-283 / discret.py:70-78
+            cu = slice(off + t * ud, off + (t + 1) * ud)
+            out[t, :, cu, cu] = blk[t, :, xd:, xd:]
+            if t > 0:
+                cx = slice(xd * (t - 1), xd * t)
+                out[t, :, cx, cx] = blk[t, :, :xd, :xd]
+                out[t, :, cx, cu] = blk[t, :, :xd, xd:]
+                out[t, :, cu, cx] = blk[t, :, xd:, :xd]
+        return out.reshape(-1, n, n)
+
+    def _compute_hessianstructure(self):
+        H, xd, ud = self.H, self.model.x_dim, self.model.u_dim
+        n = H * (xd + ud)
+        m = np.zeros((n, n))
+        for t in range(H):
+            cu = slice(H * xd + t * ud, H * xd + (t + 1) * ud)
+            m[cu, cu] = 1.0
+            if t > 0:
+                cx = slice((t - 1) * xd, t * xd)
+                m[cx, cx] = 1.0
+                m[cx, cu] = 1.0
+                m[cu, cx] = 1.0
+        return m
+
+
+class CudaDiscretIntegrator(_CudaIntegrator):
+    """``x_{t-1} + f(x_{t-1}, u_t) - x_t`` (reference integrator/discret.py:8-81)."""
+    KIND = "discrete"
+
+    def __init__(self, model, H):
+        super().__init__(model, H)
+
+
+class CudaUnityIntegrator(_CudaIntegrator):
+    """``f(x_{t-1}, u_t) - x_t`` (reference integrator/unity.py:9-81)."""
+    KIND = "unity"
+
+    def __init__(self, model, H):
+        super().__init__(model, H)
+
+
+class CudaRK4Integrator(_CudaIntegrator):
+    """classical RK4 on ``xdot = f(x, u)``, zero-order hold on u (reference integrator/rk4.py:46-285)."""
+    KIND = "rk4"
+
+    def __init__(self, model, H, DT, cache_mode=False, cache_size=2):
+        super().__init__(model, H, DT=DT, cache_mode=cache_mode, cache_size=cache_size)
+
+
+# reference spellings
+DiscretIntegrator = CudaDiscretIntegrator
+UnityIntegrator = CudaUnityIntegrator
+RK4Integrator = CudaRK4Integrator

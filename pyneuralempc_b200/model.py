@@ -1,0 +1,134 @@
+"""Dynamics-model layer: the reference's ``Model`` contract with the network evaluated by CUDA kernels.
+
+Mirrors ``/root/reference/pyNeuralEMPC/model/base.py:3-18`` (``Model``) and the behaviour of
+``model/tensorflow.py:8-109`` (``KerasTFModel``): same constructor checks, same call signature as the
+integrators use it (``forward(x, u, p=, tvp=)``), same dense output layouts:
+
+* ``forward``  -> (N, x_dim)
+* ``jacobian`` -> (N*x_dim, N*(x_dim+u_dim)), columns ``[x_0..x_{N-1} | u_0..u_{N-1}]`` (tensorflow.py:68-73)
+* ``hessian``  -> (N, x_dim, N*d, N*d), same ordering on both trailing axes (tensorflow.py:101-107)
+
+The per-sample blocks behind those dense arrays (``blocks``) come from ``nempc_model_eval``; the dense scatter is
+only there for drop-in compatibility with reference-style integrators -- the CUDA integrators never use it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import NlpEvaluator
+
+
+class Model:
+    """Abstract dynamics model (reference model/base.py:3-18)."""
+
+    def __init__(self, x_dim: int, u_dim: int, p_dim=None, tvp_dim=None):
+        self.x_dim = x_dim
+        self.u_dim = u_dim
+        self.p_dim = p_dim
+        self.tvp_dim = tvp_dim
+
+    def forward(self, x, u, p=None, tvp=None):
+        raise NotImplementedError("")
+
+    def jacobian(self, x, u, p=None, tvp=None):
+        raise NotImplementedError("")
+
+    def hessian(self, x, u, p=None, tvp=None):
+        raise NotImplementedError("")
+
+
+class CudaMLPModel(Model):
+    """Feed-forward network (Keras ``Sequential`` of ``Dense`` layers, linear last layer) on the GPU.
+
+    ``weights``: list of ``(kernel[in, out], bias[out])`` in Keras layout.  ``dtype`` is the arithmetic type of the
+    network ('float32' = what Keras/TensorFlow computes in, 'float64' for the 1e-10 parity mode); inputs and
+    outputs are float64 like the reference's numpy arrays."""
+
+    def __init__(self, weights, x_dim: int, u_dim: int, p_dim=0, tvp_dim=0, activation="tanh", dtype="float32",
+                 device=0, kernel="auto", standardScaler=None):
+        if standardScaler is not None:
+            raise NotImplementedError("This feature isn't supported yet !")        # tensorflow.py:11-12
+        if p_dim or tvp_dim:
+            raise NotImplementedError("p / tvp inputs are not supported on the CUDA path yet")
+        weights = [(np.asarray(W, np.float64), np.asarray(b, np.float64)) for W, b in weights]
+        if weights[-1][0].shape[1] != x_dim:                                       # tensorflow.py:20-21
+            raise ValueError("Your model do not provide a suitable output dim ! \n It must get the same dim as the state dim.")
+        if weights[0][0].shape[0] != x_dim + u_dim:                                # tensorflow.py:23-24
+            raise ValueError("Your model do not provide a suitable input dim ! \n It must get the same dim as the sum of all input vars (x, u, p, tvp).")
+        super().__init__(x_dim, u_dim, p_dim, tvp_dim)
+        self.weights = weights
+        self.activation, self.dtype, self.device, self.kernel = activation, dtype, device, kernel
+        self._ev = None
+
+    # ---- constructors -------------------------------------------------------------------------------------
+    @classmethod
+    def from_npz(cls, path, x_dim, u_dim, **kw):
+        """weights stored as W0,b0,W1,b1,... (tests/golden/lv_mlp_weights.npz has this layout)."""
+        d = np.load(path)
+        n = len([k for k in d.files if k.startswith("W")])
+        return cls([(d[f"W{i}"], d[f"b{i}"]) for i in range(n)], x_dim, u_dim, **kw)
+
+    @classmethod
+    def from_torch_sequential(cls, seq, x_dim, u_dim, **kw):
+        """``torch.nn.Sequential`` of ``Linear`` (+ Tanh/Sigmoid/Softplus) modules; Linear stores ``[out, in]``."""
+        import torch
+        ws, act = [], kw.pop("activation", None)
+        names = {torch.nn.Tanh: "tanh", torch.nn.Sigmoid: "sigmoid", torch.nn.Softplus: "softplus"}
+        for mod in seq:
+            if isinstance(mod, torch.nn.Linear):
+                b = mod.bias.detach().cpu().double().numpy() if mod.bias is not None else np.zeros(mod.out_features)
+                ws.append((mod.weight.detach().cpu().double().numpy().T.copy(), b))
+            elif type(mod) in names:
+                if act not in (None, names[type(mod)]):
+                    raise ValueError("mixed activations are not supported")
+                act = names[type(mod)]
+            else:
+                raise ValueError(f"unsupported module {type(mod).__name__}")
+        return cls(ws, x_dim, u_dim, activation=act or "tanh", **kw)
+
+    def __getstate__(self):                      # picklable without the device handle (tensorflow.py:31-37)
+        st = dict(self.__dict__)
+        st["_ev"] = None
+        return st
+
+    # ---- evaluation ----------------------------------------------------------------------------------------------
+    def evaluator(self):
+        if self._ev is None:
+            self._ev = NlpEvaluator(self.weights, self.x_dim, self.u_dim, 1, "unity", activation=self.activation,
+                                    compute_dtype=self.dtype, io_dtype="float64", device=self.device, kernel=self.kernel)
+        return self._ev
+
+    def _gather_input(self, x, u, p=None, tvp=None):          # tensorflow.py:39-47
+        if p is not None or tvp is not None:
+            raise NotImplementedError("p / tvp inputs are not supported on the CUDA path yet")
+        return np.concatenate([np.asarray(x, np.float64), np.asarray(u, np.float64)], axis=1)
+
+    def blocks(self, x, u, p=None, tvp=None, want_jac=True, want_hes=True):
+        """per-sample value (N,x), Jacobian (N,x,d), per-output Hessian (N,x,d,d) as numpy arrays."""
+        f, J, Hs = self.evaluator().model_eval(self._gather_input(x, u, p, tvp), want_jac, want_hes)
+        c = lambda t: None if t is None else t.cpu().numpy()
+        return c(f), c(J), c(Hs)
+
+    def forward(self, x, u, p=None, tvp=None):
+        return self.blocks(x, u, p, tvp, False, False)[0]
+
+    def jacobian(self, x, u, p=None, tvp=None):
+        N, xd, ud = x.shape[0], self.x_dim, self.u_dim
+        _, J, _ = self.blocks(x, u, p, tvp, True, False)
+        out = np.zeros((N * xd, N * (xd + ud)))
+        for i in range(N):
+            out[i * xd:(i + 1) * xd, i * xd:(i + 1) * xd] = J[i, :, :xd]
+            out[i * xd:(i + 1) * xd, N * xd + i * ud:N * xd + (i + 1) * ud] = J[i, :, xd:]
+        return out
+
+    def hessian(self, x, u, p=None, tvp=None):
+        N, xd, ud = x.shape[0], self.x_dim, self.u_dim
+        _, _, Hs = self.blocks(x, u, p, tvp, True, True)
+        out = np.zeros((N, xd, N * (xd + ud), N * (xd + ud)))
+        for i in range(N):
+            sx, su = slice(i * xd, (i + 1) * xd), slice(N * xd + i * ud, N * xd + (i + 1) * ud)
+            out[i, :, sx, sx] = Hs[i, :, :xd, :xd]
+            out[i, :, sx, su] = Hs[i, :, :xd, xd:]
+            out[i, :, su, sx] = Hs[i, :, xd:, :xd]
+            out[i, :, su, su] = Hs[i, :, xd:, xd:]
+        return out

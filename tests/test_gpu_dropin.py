@@ -1,0 +1,186 @@
+"""The drop-in classes (Model / Integrator / ObjectiveFunc / IpoptProblem / NMPC mirrors) against the dense
+reference-literal oracle and the golden files, plus closed-loop parity of SciPy solvers driven by CUDA vs oracle
+callbacks (IPOPT / cyipopt are not installed in this image: SURVEY 8c)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem  # noqa: E402
+from oracle.mlp_np import MLP, DenseModelView  # noqa: E402
+from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a) - b).max()) / max(1.0, float(np.abs(b).max()))
+
+
+def test_model_dense_layouts(lv_weights):
+    from pyneuralempc_b200.model import CudaMLPModel
+    rng = np.random.default_rng(0)
+    x, u = rng.uniform(-1, 1, (6, 2)), rng.uniform(-1, 1, (6, 1))
+    view = DenseModelView(MLP(lv_weights, 2, 1))
+    for dtype, tol in (("float32", 1e-5), ("float64", 1e-10)):
+        m = CudaMLPModel(lv_weights, 2, 1, dtype=dtype)
+        assert _rel(m.forward(x, u), view.forward(x, u)) < tol
+        assert _rel(m.jacobian(x, u), view.jacobian(x, u)) < tol
+        assert _rel(m.hessian(x, u), view.hessian(x, u)) < tol
+        assert m.hessian(x, u).shape == (6, 2, 18, 18)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert _rel(m2.forward(x, u), view.forward(x, u)) < 1e-10
+    with pytest.raises(ValueError):
+        CudaMLPModel(lv_weights, 3, 1)
+    with pytest.raises(NotImplementedError):
+        CudaMLPModel(lv_weights, 2, 1, standardScaler=object())
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+def test_integrators_dense_interface_vs_reference_goldens(golden_dir, lv_weights, kind):
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.model import CudaMLPModel
+    g = np.load(os.path.join(golden_dir, f"ref_{kind}_H6.npz"))
+    H = 6
+    z, x0 = g["z"], g["x0"]
+    s, u = z[:12].reshape(H, 2), z[12:].reshape(H, 1)
+    for dtype, tol in (("float32", 1e-5), ("float64", 1e-10)):
+        model = CudaMLPModel(lv_weights, 2, 1, dtype=dtype)
+        integ = {"discrete": lambda: I.DiscretIntegrator(model, H), "unity": lambda: I.UnityIntegrator(model, H),
+                 "rk4": lambda: I.RK4Integrator(model, H, 0.1, cache_mode=True)}[kind]()
+        assert integ.nb_contraints == 12
+        assert _rel(integ.forward(s, u, x0), g["integrator_forward"]) < tol
+        assert _rel(integ.jacobian(s, u, x0), g["integrator_jacobian"]) < tol
+        assert _rel(integ.hessian(s, u, x0), g["integrator_hessian"]) < tol
+        np.testing.assert_array_equal(integ.hessianstructure(), g["integrator_structure"])
+        assert integ.get_lower_bounds(H) == [0.0] * 12
+    with pytest.raises(ValueError):
+        I.DiscretIntegrator(object(), H)
+    with pytest.raises(AssertionError):
+        integ.forward(s, u, x0.reshape(1, -1))
+
+
+def test_rk4_hessian_for_d5_where_reference_crashes(golden_dir):
+    """reference RK4Integrator.hessian only runs for x_dim+u_dim == 3 (rk4.py:246); the CUDA one is generic."""
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.model import CudaMLPModel
+    g = np.load(os.path.join(golden_dir, "ref_discrete_d5_H5.npz"))
+    weights = [(g[f"net_W{i}"], g[f"net_b{i}"]) for i in range(3)]
+    model = CudaMLPModel(weights, 4, 1, dtype="float64")
+    integ = I.RK4Integrator(model, 5, 0.1)
+    assert _rel(integ.forward(g["rk4_x"], g["rk4_u"], g["rk4_x0"]), g["rk4_forward"]) < 1e-10
+    assert _rel(integ.jacobian(g["rk4_x"], g["rk4_u"], g["rk4_x0"]), g["rk4_jacobian"]) < 1e-10
+    dense = DenseIntegrator(DenseModelView(MLP(weights, 4, 1)), 5, "rk4", DT=0.1)
+    assert _rel(integ.hessian(g["rk4_x"], g["rk4_u"], g["rk4_x0"]), dense.hessian(g["rk4_x"], g["rk4_u"], g["rk4_x0"])) < 1e-10
+    di = I.DiscretIntegrator(model, 5)
+    z, x0 = g["z"], g["x0"]
+    assert _rel(di.hessian(z[:20].reshape(5, 4), z[20:].reshape(5, 1), x0), g["integrator_hessian"]) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+def test_ipopt_problem_callbacks_vs_reference_goldens(golden_dir, lv_weights, kind):
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaSeparableObjective
+    from pyneuralempc_b200.optimizer import CudaIpoptProblem, ProblemInterfaceHessianFree
+    g = np.load(os.path.join(golden_dir, f"ref_{kind}_H25.npz"))
+    H = 25
+    model = CudaMLPModel(lv_weights, 2, 1, dtype="float64")
+    integ = {"discrete": lambda: I.DiscretIntegrator(model, H), "unity": lambda: I.UnityIntegrator(model, H),
+             "rk4": lambda: I.RK4Integrator(model, H, 0.1)}[kind]()
+    obj = CudaSeparableObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+    z = g["z"]
+    assert abs(obj.forward(z[:50].reshape(H, 2), z[50:].reshape(H, 1)) - float(g["objective"])) < 1e-10
+    assert _rel(obj.gradient(z[:50].reshape(H, 2), z[50:].reshape(H, 1)), g["gradient"]) < 1e-10
+    pb = CudaIpoptProblem(g["x0"], obj, [], integ, use_hessian=True)
+    n_before = pb.ev.launch_count
+    assert abs(pb.objective(z) - float(g["objective"])) < 1e-10
+    assert _rel(pb.gradient(z), g["gradient"]) < 1e-10
+    assert _rel(pb.constraints(z), g["constraints"]) < 1e-10
+    jr, jc = pb.jacobianstructure()
+    J = np.zeros((50, 75)); J[jr, jc] = pb.jacobian(z)
+    assert _rel(J, g["jacobian"]) < 1e-10
+    assert pb.ev.launch_count - n_before == 2            # ONE evaluation (2 kernels) served all four callbacks
+    r, c = pb.hessianstructure()
+    np.testing.assert_array_equal(r, g["hes_rows"]); np.testing.assert_array_equal(c, g["hes_cols"])
+    assert _rel(pb.hessian(z, g["lam"], float(g["sigma"])), g["hessian_values"]) < 1e-10
+    dense = CudaIpoptProblem(g["x0"], obj, [], integ, use_hessian=False, sparse_jacobian=False)
+    assert _rel(dense.jacobian(z), g["jacobian"]) < 1e-10      # literal dense (m, n) drop-in
+    assert not hasattr(ProblemInterfaceHessianFree(dense), "hessian")
+    assert (pb.get_constraint_lower_bounds() == 0).all() and len(pb.get_constraint_upper_bounds()) == 50
+
+
+def _lv_setup(lv_weights, H, dtype="float64"):
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.constraints import DomainConstraint
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaQuadraticObjective
+    model = CudaMLPModel(lv_weights, 2, 1, dtype=dtype)
+    integ = I.RK4Integrator(model, H, 0.1, cache_mode=True)
+    obj = CudaQuadraticObjective(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.3, -0.2]))
+    dom = DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])   # run.py:72-74
+    return model, integ, obj, dom
+
+
+def test_closed_loop_slsqp_and_trust_constr_match_oracle(lv_weights):
+    """same solver, CUDA callbacks vs oracle callbacks: identical iteration counts, final cost within 1e-6."""
+    from scipy.optimize import Bounds, NonlinearConstraint, minimize
+    from scipy.sparse import coo_matrix
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import Slsqp, TrustConstr
+    H = 10
+    x0 = np.array([0.66, -0.9])                               # run.py:54
+    model, integ, obj, dom = _lv_setup(lv_weights, H)
+    # --- oracle side
+    o_obj = SeparableQuadraticObjective(obj.lin, obj.quad, obj.ref)
+    o_pb = DenseIpoptProblem(x0, o_obj, DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "rk4", DT=0.1))
+    x_init = np.concatenate([np.tile(x0, H), np.zeros(H)])
+    bounds = Bounds(dom.get_lower_bounds(H), dom.get_upper_bounds(H))
+    ref = minimize(o_pb.objective, x_init, method="SLSQP", jac=o_pb.gradient, bounds=bounds,
+                   constraints=[{"type": "eq", "fun": o_pb.constraints, "jac": o_pb.jacobian}],
+                   options={"maxiter": 200, "ftol": 0.5e-6})
+    # --- CUDA side through the controller
+    opt = Slsqp(verbose=0)
+    mpc = NMPC(integ, obj, [dom], H, 0.1, optimizer=opt)
+    xs, us = mpc.next(x0)
+    assert xs.shape == (H, 2) and us.shape == (H, 1)
+    assert opt.last_result.nit == ref.nit
+    assert abs(opt.last_result.fun - ref.fun) < 1e-6
+    assert np.abs(np.concatenate([xs.ravel(), us.ravel()]) - ref.x).max() < 1e-6
+    # --- trust-constr consumes the sparse Jacobian and the Lagrangian Hessian
+    n, m = 3 * H, 2 * H
+    hr, hc = o_pb.hessianstructure()
+    off = hr != hc
+
+    def sym(vals):
+        return coo_matrix((np.concatenate([vals, vals[off]]), (np.concatenate([hr, hc[off]]), np.concatenate([hc, hr[off]]))), shape=(n, n)).tocsr()
+
+    con = NonlinearConstraint(o_pb.constraints, 0.0, 0.0, jac=lambda x: coo_matrix(o_pb.jacobian(x)).tocsr(),
+                              hess=lambda x, v: sym(o_pb.hessian(x, v, 0.0)))
+    ref2 = minimize(o_pb.objective, x_init, method="trust-constr", jac=o_pb.gradient, hess=lambda x: sym(o_pb.hessian(x, np.zeros(m), 1.0)),
+                    constraints=[con], bounds=bounds, options={"maxiter": 200, "gtol": 1e-8, "xtol": 1e-10})
+    opt2 = TrustConstr()
+    mpc2 = NMPC(integ, obj, [dom], H, 0.1, optimizer=opt2)
+    xs2, us2 = mpc2.next(x0)
+    assert xs2 is not None
+    assert opt2.last_result.nit == ref2.nit
+    assert abs(opt2.last_result.fun - ref2.fun) < 1e-6
+    assert np.abs(opt2.last_result.x - ref2.x).max() < 1e-5
+
+
+def test_nmpc_failure_convention_and_asserts(lv_weights):
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import Optimizer, Slsqp
+
+    class AlwaysFail(Slsqp):
+        def solve(self, problem, domain_constraint):
+            return Optimizer.FAIL
+
+    model, integ, obj, dom = _lv_setup(lv_weights, 5, "float32")
+    mpc = NMPC(integ, obj, [dom], 5, 0.1, optimizer=AlwaysFail(verbose=0))
+    assert mpc.next(np.array([0.1, 0.2])) == (None, None)        # controller.py:109-113
+    with pytest.raises(AssertionError):
+        mpc.next(np.array([[0.1, 0.2]]))
+    with pytest.raises(AssertionError):
+        mpc.next(np.array([0.1, 0.2, 0.3]))

@@ -1,0 +1,214 @@
+"""Parity of the CUDA path (through the C ABI, libnempc.so) with the CPU oracle and the golden files recorded
+from the unmodified reference.  Tolerances: network arithmetic float32 -> 1e-5 relative to the largest magnitude of
+the compared array; float64 -> 1e-10 (BASELINE.json north_star).  Sparsity indices are compared bit-exactly."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.blocks_np import BlockEvaluator, step_blocks  # noqa: E402
+from oracle.mlp_np import MLP  # noqa: E402
+from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
+
+TOL32, TOL64 = 1e-5, 1e-10
+KEYS = (("resid", "resid"), ("jac_vals", "jac"), ("hes_vals", "hes"), ("obj", "obj"), ("grad", "grad"))
+
+
+def _relerr(got, ref):
+    return float(np.abs(np.asarray(got) - ref).max()) / max(1.0, float(np.abs(ref).max()))
+
+
+def _evaluator(mlp, kind, H, compute, kernel="auto", obj=None, io="float64"):
+    from pyneuralempc_b200 import NlpEvaluator
+    ev = NlpEvaluator(mlp.weights, mlp.x_dim, mlp.u_dim, H, kind, DT=0.1, activation=mlp.activation,
+                      compute_dtype=compute, io_dtype=io, kernel=kernel)
+    if obj is not None:
+        ev.set_objective(obj.lin, obj.quad, obj.ref)
+    return ev
+
+
+def _problem(dims, xd, ud, H, B, act="tanh", seed=0):
+    rng = np.random.default_rng(seed)
+    mlp = MLP.glorot(dims, xd, ud, seed=seed + 1, activation=act)
+    n, m = H * (xd + ud), H * xd
+    obj = SeparableQuadraticObjective.tracking(H, xd, ud, rng.uniform(0.5, 2, xd), rng.uniform(0.1, 1, ud),
+                                               x_ref=rng.uniform(-1, 1, (H, xd)))
+    obj.lin[:] = rng.uniform(-1, 1, n)
+    return mlp, obj, rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, xd)), rng.standard_normal((B, m)), rng.uniform(0.5, 1.5, B)
+
+
+def _run(ev, Z, X0, lam, sig):
+    import torch
+    t = lambda a: torch.as_tensor(a, dtype=ev.tdtype).cuda()
+    out = ev.eval(t(Z), t(X0), t(lam), t(sig))
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+CASES = [("discrete", [3, 30, 30, 2], 2, 1, 25, "tanh"), ("unity", [3, 30, 30, 2], 2, 1, 25, "tanh"),
+         ("rk4", [3, 30, 30, 2], 2, 1, 50, "tanh"), ("rk4", [5, 12, 9, 7, 4], 4, 1, 10, "tanh"),
+         ("rk4", [6, 40, 3], 3, 3, 5, "tanh"), ("discrete", [16, 24, 12], 12, 4, 4, "tanh"),
+         ("rk4", [2, 6, 1], 1, 1, 1, "tanh"), ("rk4", [3, 9, 8, 2], 2, 1, 3, "sigmoid"),
+         ("unity", [4, 6, 6, 6, 2], 2, 2, 2, "softplus"), ("rk4", [5, 128, 128, 128, 4], 4, 1, 6, "tanh"),
+         ("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 3, "tanh"), ("rk4", [16, 64, 64, 12], 12, 4, 3, "tanh")]
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,act", CASES)
+@pytest.mark.parametrize("compute", ("float64", "float32"))
+def test_generic_kernel_vs_oracle(kind, dims, xd, ud, H, act, compute):
+    B = 5
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, act)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, compute, "generic", obj)
+    np.testing.assert_array_equal(ev.hes_rows, BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).hes_rows)
+    got = _run(ev, Z, X0, lam, sig)
+    tol = TOL64 if compute == "float64" else TOL32
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < tol, (kg, _relerr(got[kg], ref[kr]))
+    assert ev.launch_count == 2
+    ev.close()
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+@pytest.mark.parametrize("h", (30, 32, 16))
+def test_fast_kernel_vs_oracle(kind, h, lv_weights):
+    H, B = 50, 300                      # 15000 steps: several CTAs, ragged last block
+    mlp = MLP(lv_weights, 2, 1) if h == 30 else MLP.glorot([3, h, h, 2], 2, 1, seed=h)
+    rng = np.random.default_rng(h)
+    obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 0.5], [0.3], x_ref=rng.uniform(-1, 1, (H, 2)))
+    Z, X0 = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2))
+    lam, sig = rng.standard_normal((B, H * 2)), rng.uniform(0.5, 1.5, B)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "fast", obj)
+    assert "fast" in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < TOL32, (kg, _relerr(got[kg], ref[kr]))
+    # reduced request sets run the cheaper kernel instantiations and must agree
+    import torch
+    t = lambda a: torch.as_tensor(a).cuda()
+    o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+    o0 = ev.eval(t(Z), t(X0), want=("resid",))
+    torch.cuda.synchronize()
+    assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL32
+    assert _relerr(o1["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    assert _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    ev.close()
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+@pytest.mark.parametrize("H", (6, 25))
+def test_against_reference_goldens(golden_dir, lv_weights, kind, H):
+    """values recorded from the unmodified reference (IpoptProblem callbacks) -- both kernels."""
+    g = np.load(os.path.join(golden_dir, f"ref_{kind}_H{H}.npz"))
+    mlp = MLP(lv_weights, 2, 1)
+    obj = SeparableQuadraticObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+    jr, jc = np.nonzero(g["jacobian"])
+    for kernel, compute, tol in (("fast", "float32", TOL32), ("generic", "float32", TOL32), ("generic", "float64", TOL64)):
+        ev = _evaluator(mlp, kind, H, compute, kernel, obj)
+        np.testing.assert_array_equal(ev.hes_rows, g["hes_rows"])
+        np.testing.assert_array_equal(ev.hes_cols, g["hes_cols"])
+        np.testing.assert_array_equal(ev.jac_rows, jr)
+        np.testing.assert_array_equal(ev.jac_cols, jc)
+        got = _run(ev, g["z"][None], g["x0"][None], g["lam"][None], np.asarray([float(g["sigma"])]))
+        assert _relerr(got["resid"][0], g["constraints"]) < tol
+        assert _relerr(got["jac"][0], g["jacobian"][jr, jc]) < tol
+        assert _relerr(got["hes"][0], g["hessian_values"]) < tol
+        assert _relerr(got["grad"][0], g["gradient"]) < tol
+        assert abs(got["obj"][0] - float(g["objective"])) < tol * max(1.0, abs(float(g["objective"])))
+        ev.close()
+
+
+def test_float32_io_and_host_call(lv_weights):
+    H, B = 25, 64
+    mlp = MLP(lv_weights, 2, 1)
+    rng = np.random.default_rng(5)
+    obj = SeparableQuadraticObjective.control_setpoint(H, 2, 1, 2.0)
+    Z, X0 = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2))
+    lam, sig = rng.standard_normal((B, H * 2)), rng.uniform(0.5, 1.5, B)
+    ref = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    for io in ("float32", "float64"):
+        ev = _evaluator(mlp, "rk4", H, "float32", "auto", obj, io=io)
+        got = _run(ev, Z, X0, lam, sig)
+        host = ev.eval_host(Z, X0, lam, sig)
+        for kr, kg in KEYS:
+            assert _relerr(got[kg], ref[kr]) < 2e-5, kg
+            np.testing.assert_array_equal(host[kg], got[kg])          # host-buffer call == device call, bit for bit
+        # scalar objective factor and single-problem (1-D) input
+        one = ev.eval_host(Z[0], X0[0], lam[0], 0.25)
+        r1 = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Z[:1], X0[:1], lam[:1], 0.25)
+        assert _relerr(one["hes"], r1["hes_vals"]) < 2e-5
+        ev.close()
+
+
+def test_blocks_and_model_entry_points():
+    import torch
+    mlp, _, Z, X0, _, _ = _problem([5, 12, 9, 4], 4, 1, 4, 3)
+    ev_o = BlockEvaluator(mlp, "rk4", 4, DT=0.1)
+    _, _, xprev = ev_o.split(Z, X0)
+    zz = np.concatenate([xprev, Z[:, 16:].reshape(3, 4, 1)], axis=2).reshape(-1, 5)
+    pred, AB, Hb = step_blocks(mlp, "rk4", 0.1, zz)
+    ev = _evaluator(mlp, "rk4", 4, "float64", "generic")
+    p2, AB2, Hb2 = ev.eval_blocks(torch.as_tensor(Z).cuda(), torch.as_tensor(X0).cuda())
+    assert _relerr(p2.cpu().numpy().reshape(-1, 4), pred + zz[:, :4]) < TOL64
+    assert _relerr(AB2.cpu().numpy().reshape(-1, 4, 5), AB + np.eye(4, 5)[None]) < TOL64
+    assert _relerr(Hb2.cpu().numpy().reshape(-1, 4, 5, 5), Hb) < TOL64
+    f, J, Hs = mlp.blocks(zz)
+    f2, J2, Hs2 = ev.model_eval(torch.as_tensor(zz).cuda())
+    assert _relerr(f2.cpu().numpy(), f) < TOL64 and _relerr(J2.cpu().numpy(), J) < TOL64 and _relerr(Hs2.cpu().numpy(), Hs) < TOL64
+    ev.close()
+
+
+def test_edge_cases(lv_weights):
+    import torch
+    from pyneuralempc_b200 import NlpEvaluator
+    from pyneuralempc_b200._lib import NempcError
+    mlp = MLP(lv_weights, 2, 1)
+    ev = _evaluator(mlp, "rk4", 1, "float32")                  # H = 1: no state-state block at all
+    assert ev.nnz_hes == 1 and ev.nnz_jac == 2 * 2
+    z = torch.zeros((0, 3), dtype=torch.float64).cuda()        # empty batch is a no-op
+    out = ev.eval(z, torch.zeros((0, 2), dtype=torch.float64).cuda(), torch.zeros((0, 2), dtype=torch.float64).cuda())
+    assert out["resid"].shape == (0, 2)
+    with pytest.raises(ValueError):
+        ev.eval(torch.zeros((1, 3), dtype=torch.float64).cuda(), torch.zeros((1, 2), dtype=torch.float64).cuda(), want=("hes",))
+    ev.close()
+    with pytest.raises(NempcError):                             # fast kernel requested for a shape it does not cover
+        NlpEvaluator(MLP.glorot([3, 7, 7, 2], 2, 1).weights, 2, 1, 5, "rk4", DT=0.1, kernel="fast")
+    with pytest.raises(ValueError):
+        NlpEvaluator(mlp.weights, 2, 1, 5, "rk4")               # RK4 without DT
+
+
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size (B=4096, H=50: 204800 steps), size-independent checks:
+    fast == generic kernel; Hessian linear in lambda and in the objective factor; batch-permutation equivariance;
+    a random subsample equals the oracle."""
+    import torch
+    H, B = 50, 4096
+    rng = np.random.default_rng(1234)
+    mlp = MLP.glorot([3, 30, 30, 2], 2, 1, seed=0)
+    obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 2.0], [0.1])
+    Z, X0 = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2))
+    l1, l2 = rng.standard_normal((B, H * 2)), rng.standard_normal((B, H * 2))
+    fast = _evaluator(mlp, "rk4", H, "float32", "fast", obj)
+    gen = _evaluator(mlp, "rk4", H, "float32", "generic", obj)
+    ones, zeros = np.ones(B), np.zeros(B)
+    a = _run(fast, Z, X0, l1, ones)
+    g = _run(gen, Z, X0, l1, ones)
+    for k in ("resid", "jac", "hes", "obj", "grad"):
+        assert _relerr(a[k], g[k]) < TOL32, k
+    b = _run(fast, Z, X0, l2, zeros)
+    c = _run(fast, Z, X0, l1 + l2, ones)
+    assert _relerr(c["hes"], a["hes"] + b["hes"]) < TOL32
+    perm = rng.permutation(B)
+    p = _run(fast, Z[perm], X0[perm], l1[perm], ones)
+    for k in ("resid", "jac", "hes", "obj", "grad"):
+        np.testing.assert_array_equal(p[k], a[k][perm])
+    idx = rng.choice(B, 16, replace=False)
+    ref = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Z[idx], X0[idx], l1[idx], 1.0)
+    for kr, kg in KEYS:
+        assert _relerr(a[kg][idx], ref[kr]) < TOL32, kg
+    # constant structural entries
+    assert (a["jac"][:, fast.jac_rows == fast.jac_cols] == -1.0).all()
+    fast.close(); gen.close()
