@@ -1,14 +1,20 @@
 // Register-resident kernel body for small two-hidden-layer networks (the Lotka-Volterra class of
 // BASELINE configs C1/C2: 3 -> 30 tanh -> 30 tanh -> 2): ONE THREAD PER HORIZON STEP.
 //
-// Design (B200): the whole weight set (a few KB) is passed as a __grid_constant__ kernel parameter, so every
-// weight is an immediate constant-bank operand of an FFMA -- no shared-memory staging, no load instructions,
-// no barriers.  All loops are fully unrolled with compile-time indices, activations / tangents live in
-// registers, and the layer-2 pre-activation (value + d tangent rows) is accumulated input-stationary so that
-// layer 1 is produced one neuron at a time and never stored.  The last hidden layer is consumed on the fly
-// (output value, local Jacobian, curvature, adjoint seed), then one more sweep over W2 gives the layer-1
-// adjoint and curvature.  Per-output ("forward-only") second-order chain through the RK4 stages as in
-// nempc_generic.cuh, which needs no reverse sweep over stages and therefore no stored stage state.
+// Design (B200):
+//  * the whole weight set (~13 KB incl. padding and pre-multiplied products) is a __grid_constant__ kernel
+//    parameter; every loop over neurons is warp-uniform, so weights arrive as LDCU.128 (uniform constant loads
+//    into UNIFORM registers) and feed FFMA as a uniform operand -- no per-thread registers, no shared-memory
+//    staging, no barriers;
+//  * loops over INPUT neurons are real loops (compact code: the round-1 profile profiles/r1a showed the fully
+//    unrolled variant stalled 3.9 cycles/issue on instruction fetch), loops over the register-resident OUTPUT
+//    chunk are unrolled (compile-time register indices);
+//  * layer-2 pre-activations (value + D tangent rows) are accumulated in registers for a chunk of H2/NCHUNK
+//    output neurons at a time and consumed on the fly (output value, local Jacobian, curvature, adjoint seed);
+//  * cold per-thread state (layer-1 activations, s'(a2), per-output Hessian accumulators) lives in a
+//    [element][thread] shared-memory scratch: bank = thread, conflict-free;
+//  * per-output ("forward-only") second-order chain through the RK4 stages as in nempc_generic.cuh: no reverse
+//    sweep over stages, hence no stored stage state.
 //
 // Same maths and references as nempc_generic.cuh (integrator/rk4.py:113-285, model/tensorflow.py:49-109).
 #pragma once
@@ -16,55 +22,70 @@
 
 #include "nempc_generic.cuh"
 
-template <int X, int U, int H1, int H2> struct FastWeights {
+template <int X, int U, int H1, int H2, int NCHUNK> struct FastWeights {
     static constexpr int D = X + U;
     static constexpr int NS = D * (D + 1) / 2;
-    float W1[D][H1];
-    float b1[H1];
-    float W2[H1][H2];
-    float b2[H2];
-    float W3[H2][X];
-    float b3[X];
-    float P1[NS][H1];   // W1[c][i] * W1[c2][i], packed lower triangle e = c(c+1)/2 + c2: layer-1 tangents are constant
-    float W23[X][H1][H2];   // W2[i][j] * W3[j][p]: the per-output layer-1 adjoint is sum_j W23[p][i][j] * s'(a2_j)
+    static constexpr int DP = (D + 1 + 3) / 4 * 4;        // W1 column + bias, padded to 128 bit
+    static constexpr int JC = H2 / NCHUNK;                // output neurons per register chunk
+    static constexpr int JCP = (JC + 3) / 4 * 4;
+    static constexpr int H2P = (H2 + 3) / 4 * 4;
+    static constexpr int NSP = (NS + 3) / 4 * 4;
+    static_assert(H2 % NCHUNK == 0, "H2 must be divisible by NCHUNK");
+    static_assert(X <= 4, "W3T packs x_dim into one 128-bit slot");
+    alignas(16) float W1T[H1][DP];          // [i][c] = W1[c][i], [i][D] = b1[i]
+    alignas(16) float W2C[NCHUNK][H1][JCP]; // [jc][i][jj] = W2[i][jc*JC+jj]
+    alignas(16) float b2[NCHUNK][JCP];
+    alignas(16) float W3T[NCHUNK][JC][4];   // [jc][jj][p] = W3[j][p]
+    alignas(16) float b3[4];
+    alignas(16) float W23[X][H1][H2P];      // W2[i][j] * W3[j][p]: layer-1 adjoint of output p = sum_j W23[p][i][j] s'(a2_j)
+    alignas(16) float P1T[H1][NSP];         // W1[c][i] * W1[c2][i], e = c(c+1)/2 + c2: layer-1 tangents are constant
 };
 
 // host-side fill from Keras-layout double arrays (W[in][out])
-template <int X, int U, int H1, int H2>
-inline void fill_fast_weights(FastWeights<X, U, H1, H2>& f, const double* W1, const double* b1, const double* W2,
+template <int X, int U, int H1, int H2, int NCHUNK>
+inline void fill_fast_weights(FastWeights<X, U, H1, H2, NCHUNK>& f, const double* W1, const double* b1, const double* W2,
                               const double* b2, const double* W3, const double* b3) {
-    constexpr int D = X + U;
-    for (int c = 0; c < D; ++c) for (int i = 0; i < H1; ++i) f.W1[c][i] = (float)W1[c * H1 + i];
-    for (int i = 0; i < H1; ++i) f.b1[i] = (float)b1[i];
-    for (int i = 0; i < H1; ++i) for (int j = 0; j < H2; ++j) f.W2[i][j] = (float)W2[i * H2 + j];
-    for (int j = 0; j < H2; ++j) f.b2[j] = (float)b2[j];
-    for (int j = 0; j < H2; ++j) for (int p = 0; p < X; ++p) f.W3[j][p] = (float)W3[j * X + p];
+    typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
+    constexpr int D = X + U, JC = FW::JC;
+    for (int i = 0; i < H1; ++i) {
+        for (int c = 0; c < D; ++c) f.W1T[i][c] = (float)W1[c * H1 + i];
+        f.W1T[i][D] = (float)b1[i];
+        for (int c = 0; c < D; ++c)
+            for (int c2 = 0; c2 <= c; ++c2) f.P1T[i][c * (c + 1) / 2 + c2] = f.W1T[i][c] * f.W1T[i][c2];
+    }
+    for (int jc = 0; jc < NCHUNK; ++jc)
+        for (int jj = 0; jj < JC; ++jj) {
+            const int j = jc * JC + jj;
+            f.b2[jc][jj] = (float)b2[j];
+            for (int i = 0; i < H1; ++i) f.W2C[jc][i][jj] = (float)W2[i * H2 + j];
+            for (int p = 0; p < X; ++p) f.W3T[jc][jj][p] = (float)W3[j * X + p];
+        }
     for (int p = 0; p < X; ++p) f.b3[p] = (float)b3[p];
-    for (int c = 0; c < D; ++c) for (int c2 = 0; c2 <= c; ++c2) for (int i = 0; i < H1; ++i)
-        f.P1[c * (c + 1) / 2 + c2][i] = f.W1[c][i] * f.W1[c2][i];
-    for (int p = 0; p < X; ++p) for (int i = 0; i < H1; ++i) for (int j = 0; j < H2; ++j)
-        f.W23[p][i][j] = f.W2[i][j] * f.W3[j][p];
+    for (int p = 0; p < X; ++p)
+        for (int i = 0; i < H1; ++i)
+            for (int j = 0; j < H2; ++j) f.W23[p][i][j] = (float)W2[i * H2 + j] * (float)W3[j * X + p];
 }
 
-// per-thread scratch in shared memory for COLD state (touched once per stage, not in the FMA loops):
-// element e of thread tid lives at scr[e * stride] with stride = blockDim.x -> bank = tid, conflict-free.
+// per-thread scratch in shared memory for COLD state: element e of thread tid lives at scr[e * stride] with
+// stride = blockDim.x -> bank = tid, conflict-free.
 template <int X, int U, int H1, int H2> struct FastScratch {
     static constexpr int NS = (X + U) * (X + U + 1) / 2;
-    static constexpr int H1_OFF = 0;                 // layer-1 activations, written in phase A, read in phase C
-    static constexpr int HPREV_OFF = H1;             // h_{s-1}[p] packed
-    static constexpr int HACC_OFF = H1 + X * NS;     // sum_s c_s h_s[p]
-    static constexpr int COUNT = H1 + 2 * X * NS;
+    static constexpr int H1_OFF = 0;                     // layer-1 activations
+    static constexpr int SP2_OFF = H1;                   // s'(a2_j)
+    static constexpr int HPREV_OFF = H1 + H2;            // h_{s-1}[p] packed
+    static constexpr int HACC_OFF = H1 + H2 + X * NS;    // sum_s c_s h_s[p]
+    static constexpr int COUNT = H1 + H2 + 2 * X * NS;
+    static constexpr int count(int mode) { return mode >= 2 ? COUNT : H1; }
 };
 
-NEMPC_HD constexpr int tri_index(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
-
 // MODE: 0 residual only, 1 + Jacobian, 2 + Hessian
-template <int X, int U, int H1, int H2, int MODE, typename TIO>
-NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2>& w, const StageTable<float>& st, const NlpLayout& L,
+template <int X, int U, int H1, int H2, int NCHUNK, int MODE, typename TIO>
+NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageTable<float>& st, const NlpLayout& L,
                         const EvalArgs<TIO>& ar, long long step, float* scr, const int sstride) {
-    constexpr int D = X + U, NS = D * (D + 1) / 2;
-    constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
+    typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
     typedef FastScratch<X, U, H1, H2> SC;
+    constexpr int D = X + U, NS = D * (D + 1) / 2, JC = FW::JC, NR = (MODE >= 1) ? 1 + D : 1;
+    constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
     typedef typename WideOf<float, TIO>::type TW;
     const bool unity = (ar.flags & NEMPC_UNITY) != 0;
     const long long b = step / L.H;
@@ -97,40 +118,16 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2>& w, const StageTable<flo
 #pragma unroll
         for (int c = 0; c < D; ++c) zs[c] = (c < X) ? fmaf(a_s, kprev[c < X ? c : 0], z[c]) : z[c];
 
-        // ---- phase A: layer 1 neuron by neuron, accumulated straight into the layer-2 pre-activations ------------
-        float av[H2], at[JAC ? D : 1][H2];
-#pragma unroll
-        for (int j = 0; j < H2; ++j) {
-            av[j] = w.b2[j];
-            if (JAC) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) at[c][j] = 0.f;
-            }
-        }
-#pragma unroll
+        // ---- layer 1: activations to scratch -------------------------------------------------------------------
+#pragma unroll 2
         for (int i = 0; i < H1; ++i) {
-            float a1 = w.b1[i];
+            float a1 = w.W1T[i][D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) a1 = fmaf(w.W1[c][i], zs[c], a1);
-            const float t1 = tanhf(a1);
-            if (HES) scr[(SC::H1_OFF + i) * sstride] = t1;
-            float v[D];
-            if (JAC) {
-                const float sp = fmaf(-t1, t1, 1.f);
-#pragma unroll
-                for (int c = 0; c < D; ++c) v[c] = sp * w.W1[c][i];
-            }
-#pragma unroll
-            for (int j = 0; j < H2; ++j) {
-                av[j] = fmaf(w.W2[i][j], t1, av[j]);
-                if (JAC) {
-#pragma unroll
-                    for (int c = 0; c < D; ++c) at[c][j] = fmaf(w.W2[i][j], v[c], at[c][j]);
-                }
-            }
+            for (int c = 0; c < D; ++c) a1 = fmaf(w.W1T[i][c], zs[c], a1);
+            scr[(SC::H1_OFF + i) * sstride] = tanhf(a1);
         }
-        // ---- phase B: consume layer 2 on the fly ----------------------------------------------------------------------
-        float k[X], J[X][D], M[X][NS], sp2[HES ? H2 : 1];
+
+        float k[X], J[X][D], M[X][NS];
 #pragma unroll
         for (int p = 0; p < X; ++p) {
             k[p] = w.b3[p];
@@ -139,51 +136,89 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2>& w, const StageTable<flo
 #pragma unroll
             for (int e = 0; e < NS; ++e) M[p][e] = 0.f;
         }
+        // ---- layer 2, one register chunk of JC output neurons at a time ---------------------------------------------
+#pragma unroll 1
+        for (int jc = 0; jc < NCHUNK; ++jc) {
+            float acc[NR][JC];
 #pragma unroll
-        for (int j = 0; j < H2; ++j) {
-            const float t2 = tanhf(av[j]);
+            for (int jj = 0; jj < JC; ++jj) {
+                acc[0][jj] = w.b2[jc][jj];
 #pragma unroll
-            for (int p = 0; p < X; ++p) k[p] = fmaf(w.W3[j][p], t2, k[p]);
-            if (JAC) {
-                const float sp = fmaf(-t2, t2, 1.f);
+                for (int r = 1; r < NR; ++r) acc[r][jj] = 0.f;
+            }
+#pragma unroll 2
+            for (int i = 0; i < H1; ++i) {
+                const float t1 = scr[(SC::H1_OFF + i) * sstride];
+                float v[D];
+                if (JAC) {
+                    const float sp = fmaf(-t1, t1, 1.f);
 #pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const float vt = sp * at[c][j];
-#pragma unroll
-                    for (int p = 0; p < X; ++p) J[p][c] = fmaf(w.W3[j][p], vt, J[p][c]);
+                    for (int c = 0; c < D; ++c) v[c] = sp * w.W1T[i][c];      // post-activation tangent of layer 1
                 }
-                if (HES) {
-                    const float spp = -2.f * t2 * sp;
-                    float pp[NS];
 #pragma unroll
-                    for (int c = 0; c < D; ++c)
+                for (int jj = 0; jj < JC; ++jj) {
+                    const float wij = w.W2C[jc][i][jj];
+                    acc[0][jj] = fmaf(wij, t1, acc[0][jj]);
+                    if (JAC) {
 #pragma unroll
-                        for (int c2 = 0; c2 <= c; ++c2) pp[c * (c + 1) / 2 + c2] = at[c][j] * at[c2][j];
-#pragma unroll
-                    for (int p = 0; p < X; ++p) {
-                        const float q = spp * w.W3[j][p];
-#pragma unroll
-                        for (int e = 0; e < NS; ++e) M[p][e] = fmaf(q, pp[e], M[p][e]);
+                        for (int c = 0; c < D; ++c) acc[JAC ? 1 + c : 0][jj] = fmaf(wij, v[c], acc[JAC ? 1 + c : 0][jj]);
                     }
-                    sp2[j] = sp;
+                }
+            }
+            // consume the chunk: output value, local Jacobian, layer-2 curvature, adjoint seed
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) {
+                const float t2 = tanhf(acc[0][jj]);
+#pragma unroll
+                for (int p = 0; p < X; ++p) k[p] = fmaf(w.W3T[jc][jj][p], t2, k[p]);
+                if (JAC) {
+                    const float sp = fmaf(-t2, t2, 1.f);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const float vt = sp * acc[JAC ? 1 + c : 0][jj];
+#pragma unroll
+                        for (int p = 0; p < X; ++p) J[p][c] = fmaf(w.W3T[jc][jj][p], vt, J[p][c]);
+                    }
+                    if (HES) {
+                        const float spp = -2.f * t2 * sp;
+                        float pp[NS];
+#pragma unroll
+                        for (int c = 0; c < D; ++c)
+#pragma unroll
+                            for (int c2 = 0; c2 <= c; ++c2) pp[c * (c + 1) / 2 + c2] = acc[JAC ? 1 + c : 0][jj] * acc[JAC ? 1 + c2 : 0][jj];
+#pragma unroll
+                        for (int p = 0; p < X; ++p) {
+                            const float q = spp * w.W3T[jc][jj][p];
+#pragma unroll
+                            for (int e = 0; e < NS; ++e) M[p][e] = fmaf(q, pp[e], M[p][e]);
+                        }
+                        scr[(SC::SP2_OFF + jc * JC + jj) * sstride] = sp;
+                    }
                 }
             }
         }
-        // ---- phase C: layer-1 adjoint (per output) and its curvature ------------------------------------------------------
+        // ---- layer-1 adjoint (per output) and its curvature ---------------------------------------------------------------
         if (HES) {
+            float sp2[H2];
 #pragma unroll
+            for (int j = 0; j < H2; ++j) sp2[j] = scr[(SC::SP2_OFF + j) * sstride];
+#pragma unroll 1
             for (int i = 0; i < H1; ++i) {
                 const float t1 = scr[(SC::H1_OFF + i) * sstride];
                 const float sp = fmaf(-t1, t1, 1.f);
                 const float spp = -2.f * t1 * sp;
 #pragma unroll
                 for (int p = 0; p < X; ++p) {
-                    float g = 0.f;
+                    float g0 = 0.f, g1 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < H2; ++j) g = fmaf(w.W23[p][i][j], sp2[j], g);
-                    const float cf = spp * g;
+                    for (int j = 0; j + 1 < H2; j += 2) {
+                        g0 = fmaf(w.W23[p][i][j], sp2[j], g0);
+                        g1 = fmaf(w.W23[p][i][j + 1], sp2[j + 1], g1);
+                    }
+                    if (H2 & 1) g0 = fmaf(w.W23[p][i][H2 - 1], sp2[H2 - 1], g0);
+                    const float cf = spp * (g0 + g1);
 #pragma unroll
-                    for (int e = 0; e < NS; ++e) M[p][e] = fmaf(cf, w.P1[e][i], M[p][e]);
+                    for (int e = 0; e < NS; ++e) M[p][e] = fmaf(cf, w.P1T[i][e], M[p][e]);
                 }
             }
         }
@@ -195,11 +230,11 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2>& w, const StageTable<flo
             for (int p = 0; p < X; ++p)
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    float acc = (c >= X) ? J[p][c] : 0.f;
+                    float a = (c >= X) ? J[p][c] : 0.f;
 #pragma unroll
-                    for (int kk = 0; kk < X; ++kk) acc = fmaf(J[p][kk], Rt[kk][c], acc);
-                    dk[p][c] = acc;
-                    dkacc[p][c] = fmaf(c_s, acc, dkacc[p][c]);
+                    for (int kk = 0; kk < X; ++kk) a = fmaf(J[p][kk], Rt[kk][c], a);
+                    dk[p][c] = a;
+                    dkacc[p][c] = fmaf(c_s, a, dkacc[p][c]);
                 }
         }
         if (HES) {
@@ -211,31 +246,41 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2>& w, const StageTable<flo
                 for (int kk = 0; kk < D; ++kk)
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
-                        float acc = 0.f;
+                        float a = 0.f;
 #pragma unroll
-                        for (int l2 = 0; l2 < D; ++l2) acc = fmaf(M[p][tri_index(kk, l2)], NEMPC_RF(l2, c), acc);
-                        tm[kk][c] = acc;
+                        for (int l2 = 0; l2 < D; ++l2) a = fmaf(M[p][l2 <= kk ? kk * (kk + 1) / 2 + l2 : l2 * (l2 + 1) / 2 + kk], NEMPC_RF(l2, c), a);
+                        tm[kk][c] = a;
                     }
 #pragma unroll
-                for (int a = 0; a < D; ++a)
+                for (int a2 = 0; a2 < D; ++a2)
 #pragma unroll
-                    for (int c = 0; c <= a; ++c) {
-                        float acc = 0.f;
+                    for (int c = 0; c <= a2; ++c) {
+                        float a = 0.f;
 #pragma unroll
-                        for (int kk = 0; kk < D; ++kk) acc = fmaf(NEMPC_RF(kk, a), tm[kk][c], acc);
-#pragma unroll
-                        for (int kk = 0; kk < X; ++kk) acc = fmaf(a_s * J[p][kk], scr[(SC::HPREV_OFF + kk * NS + a * (a + 1) / 2 + c) * sstride], acc);
-                        hs[p][a * (a + 1) / 2 + c] = acc;
+                        for (int kk = 0; kk < D; ++kk) a = fmaf(NEMPC_RF(kk, a2), tm[kk][c], a);
+                        hs[p][a2 * (a2 + 1) / 2 + c] = a;
                     }
             }
+            // + a_s sum_k J[p][k] h_{s-1}[k]   (h_{s-1} is read from scratch BEFORE it is overwritten)
 #pragma unroll
-            for (int p = 0; p < X; ++p)
+            for (int e = 0; e < NS; ++e) {
+                float hp[X];
 #pragma unroll
-                for (int e = 0; e < NS; ++e) {
+                for (int kk = 0; kk < X; ++kk) hp[kk] = scr[(SC::HPREV_OFF + kk * NS + e) * sstride];
+#pragma unroll
+                for (int p = 0; p < X; ++p) {
+                    float a = hs[p][e];
+#pragma unroll
+                    for (int kk = 0; kk < X; ++kk) a = fmaf(a_s * J[p][kk], hp[kk], a);
+                    hs[p][e] = a;
+                }
+#pragma unroll
+                for (int p = 0; p < X; ++p) {
                     scr[(SC::HPREV_OFF + p * NS + e) * sstride] = hs[p][e];
                     float* ha = scr + (SC::HACC_OFF + p * NS + e) * sstride;
                     *ha = fmaf(c_s, hs[p][e], *ha);
                 }
+            }
         }
 #undef NEMPC_RF
 #pragma unroll

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -38,15 +39,22 @@ nempc_generic_kernel(const NetView<T> net, const StageTable<T> st, const NlpLayo
     }
 }
 
-template <int X, int U, int H1, int H2, int MODE, typename TIO>
-__global__ void __launch_bounds__(128)
-nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2> w, const StageTable<float> st,
+#ifndef NEMPC_FAST_THREADS
+#define NEMPC_FAST_THREADS 128
+#endif
+#ifndef NEMPC_FAST_MINBLOCKS
+#define NEMPC_FAST_MINBLOCKS 4
+#endif
+
+template <int X, int U, int H1, int H2, int NCHUNK, int MODE, typename TIO>
+__global__ void __launch_bounds__(NEMPC_FAST_THREADS, NEMPC_FAST_MINBLOCKS)
+nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2, NCHUNK> w, const StageTable<float> st,
                   const NlpLayout L, const EvalArgs<TIO> ar) {
     // cold per-thread state (layer-1 activations, per-output Hessian accumulators): [element][thread], bank = thread
     float* scr = reinterpret_cast<float*>(nempc_smem) + threadIdx.x;
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps;
          step += (long long)gridDim.x * blockDim.x)
-        fast_step<X, U, H1, H2, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+        fast_step<X, U, H1, H2, NCHUNK, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
 }
 
 // objective value + gradient of f(z) = sum lin_i z_i + quad_i (z_i - ref_i)^2 : one warp per problem,
@@ -305,6 +313,11 @@ extern "C" int nempc_destroy(nempc_handle* h) {
     return NEMPC_OK;
 }
 
+template <typename FW> static FW* fast_blob(nempc_handle* h) {       // 16-byte aligned view into the byte blob
+    uintptr_t a = reinterpret_cast<uintptr_t>(h->fastw.data());
+    return reinterpret_cast<FW*>((a + 15) & ~uintptr_t(15));
+}
+
 template <typename T> static int upload_layer(nempc_handle* h, int l, int fin, int fout) {
     std::vector<T> w(fin * (size_t)fout), wt(fin * (size_t)fout), b(fout);
     for (int i = 0; i < fin; ++i)
@@ -321,11 +334,11 @@ template <typename T> static int upload_layer(nempc_handle* h, int l, int fin, i
     return NEMPC_OK;
 }
 
-template <int X, int U, int H1, int H2> static void fill_fast(nempc_handle* h) {
-    typedef FastWeights<X, U, H1, H2> FW;
-    h->fastw.assign(sizeof(FW), 0);
-    fill_fast_weights<X, U, H1, H2>(*reinterpret_cast<FW*>(h->fastw.data()), h->W[0].data(), h->bvec[0].data(),
-                                    h->W[1].data(), h->bvec[1].data(), h->W[2].data(), h->bvec[2].data());
+template <int X, int U, int H1, int H2, int NCHUNK> static void fill_fast(nempc_handle* h) {
+    typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
+    h->fastw.assign(sizeof(FW) + 16, 0);
+    fill_fast_weights<X, U, H1, H2, NCHUNK>(*fast_blob<FW>(h), h->W[0].data(), h->bvec[0].data(),
+                                            h->W[1].data(), h->bvec[1].data(), h->W[2].data(), h->bvec[2].data());
 }
 
 extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const double* b) {
@@ -340,9 +353,9 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
     bool all = true; for (bool s : h->wset) all = all && s;
     if (all && h->fast_id >= 0) {
         switch (h->fast_id) {
-            case 0: fill_fast<2, 1, 30, 30>(h); break;
-            case 1: fill_fast<2, 1, 32, 32>(h); break;
-            case 2: fill_fast<2, 1, 16, 16>(h); break;
+            case 0: fill_fast<2, 1, 30, 30, 2>(h); break;
+            case 1: fill_fast<2, 1, 32, 32, 2>(h); break;
+            case 2: fill_fast<2, 1, 16, 16, 1>(h); break;
         }
     }
     return NEMPC_OK;
@@ -435,19 +448,19 @@ template <> int launch_generic<double>(nempc_handle* h, const EvalArgs<double>& 
                                               : launch_generic_d<float, double>(h, ar, model_mode, s);
 }
 
-template <int X, int U, int H1, int H2, typename TIO>
+template <int X, int U, int H1, int H2, int NCHUNK, typename TIO>
 static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    typedef FastWeights<X, U, H1, H2> FW;
-    const FW& w = *reinterpret_cast<const FW*>(h->fastw.data());
+    typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
+    const FW& w = *fast_blob<FW>(h);
     StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
-    const int threads = 128;
+    const int threads = NEMPC_FAST_THREADS;
     const long long blocks = std::max(1LL, (ar.nsteps + threads - 1) / threads);
     const unsigned grid = (unsigned)std::min(blocks, (long long)h->sm_count * 64);
-    const size_t smem = mode >= 2 ? (size_t)FastScratch<X, U, H1, H2>::COUNT * threads * sizeof(float) : 0;
+    const size_t smem = (size_t)FastScratch<X, U, H1, H2>::count(mode) * threads * sizeof(float);
     switch (mode) {
-        case 0: nempc_fast_kernel<X, U, H1, H2, 0, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
-        case 1: nempc_fast_kernel<X, U, H1, H2, 1, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
-        default: nempc_fast_kernel<X, U, H1, H2, 2, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        case 0: nempc_fast_kernel<X, U, H1, H2, NCHUNK, 0, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        case 1: nempc_fast_kernel<X, U, H1, H2, NCHUNK, 1, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        default: nempc_fast_kernel<X, U, H1, H2, NCHUNK, 2, TIO><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
     }
     CU(h, cudaGetLastError());
     h->launches++;
@@ -456,9 +469,9 @@ static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode,
 
 template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
     switch (h->fast_id) {
-        case 0: return launch_fast_shape<2, 1, 30, 30, TIO>(h, ar, mode, s);
-        case 1: return launch_fast_shape<2, 1, 32, 32, TIO>(h, ar, mode, s);
-        case 2: return launch_fast_shape<2, 1, 16, 16, TIO>(h, ar, mode, s);
+        case 0: return launch_fast_shape<2, 1, 30, 30, 2, TIO>(h, ar, mode, s);
+        case 1: return launch_fast_shape<2, 1, 32, 32, 2, TIO>(h, ar, mode, s);
+        case 2: return launch_fast_shape<2, 1, 16, 16, 1, TIO>(h, ar, mode, s);
     }
     SET_ERR(h, "internal: bad fast_id");
     return NEMPC_EINVAL;
@@ -496,9 +509,9 @@ extern "C" int nempc_eval(nempc_handle* h, int64_t B, const void* z, const void*
                           void* stream) {
     int rc = ready(h);
     if (rc) return rc;
+    if (B == 0) return NEMPC_OK;
     if (B < 0 || !z || !x0) { SET_ERR(h, "nempc_eval: bad argument"); return NEMPC_EINVAL; }
     if (hes && !lambda) { SET_ERR(h, "nempc_eval: hes_vals needs lambda"); return NEMPC_EINVAL; }
-    if (B == 0) return NEMPC_OK;
     CU(h, cudaSetDevice(h->desc.device));
     cudaStream_t s = (cudaStream_t)stream;
     return h->desc.io_dtype == NEMPC_F64 ? eval_t<double>(h, B, z, x0, lambda, obj_factor, sigma, resid, jac, hes, obj, grad, s)
@@ -519,9 +532,9 @@ extern "C" int nempc_eval_host(nempc_handle* h, int64_t B, const void* z, const 
                                void* grad) {
     int rc = ready(h);
     if (rc) return rc;
+    if (B == 0) return NEMPC_OK;
     if (B < 0 || !z || !x0) { SET_ERR(h, "nempc_eval_host: bad argument"); return NEMPC_EINVAL; }
     if (hes && !lambda) { SET_ERR(h, "nempc_eval_host: hes_vals needs lambda"); return NEMPC_EINVAL; }
-    if (B == 0) return NEMPC_OK;
     CU(h, cudaSetDevice(h->desc.device));
     const size_t es = dsize(h->desc.io_dtype);
     const NlpLayout& L = h->lay;

@@ -57,6 +57,8 @@ class _CudaIntegrator(Integrator):
     KIND = None
 
     def __init__(self, model, H, DT=None, cache_mode=False, cache_size=2):
+        if not isinstance(model, (Model,)):
+            raise ValueError("The model provided isn't a Model object !")
         super().__init__(model, H, model.x_dim * H)
         if not isinstance(model, CudaMLPModel):
             raise ValueError("CUDA integrators need a CudaMLPModel (the network is fused into the integrator kernel)")

@@ -57,21 +57,22 @@ void run_generic_d(const HostNet<T>& hn, const StageTable<T>& st, const NlpLayou
     else run_generic<T, 16>(hn, st, L, ar);
 }
 
-template <int X, int U, int H1, int H2>
+template <int X, int U, int H1, int H2, int NCHUNK>
 void run_fast(const double* wflat, const StageTable<float>& st, const NlpLayout& L, const EvalArgs<double>& ar, int mode) {
-    typedef FastWeights<X, U, H1, H2> FW;
-    std::vector<unsigned char> blob(sizeof(FW));
-    FW& f = *reinterpret_cast<FW*>(blob.data());
+    typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
+    FW* fp = new FW();
+    FW& f = *fp;
     constexpr int D = X + U;
     const double* W1 = wflat; const double* b1 = W1 + D * H1; const double* W2 = b1 + H1; const double* b2 = W2 + H1 * H2;
     const double* W3 = b2 + H2; const double* b3 = W3 + H2 * X;
-    fill_fast_weights<X, U, H1, H2>(f, W1, b1, W2, b2, W3, b3);
+    fill_fast_weights<X, U, H1, H2, NCHUNK>(f, W1, b1, W2, b2, W3, b3);
     std::vector<float> scr(FastScratch<X, U, H1, H2>::COUNT);
     for (long long s = 0; s < ar.nsteps; ++s) {
-        if (mode == 0) fast_step<X, U, H1, H2, 0, double>(f, st, L, ar, s, scr.data(), 1);
-        else if (mode == 1) fast_step<X, U, H1, H2, 1, double>(f, st, L, ar, s, scr.data(), 1);
-        else fast_step<X, U, H1, H2, 2, double>(f, st, L, ar, s, scr.data(), 1);
+        if (mode == 0) fast_step<X, U, H1, H2, NCHUNK, 0, double>(f, st, L, ar, s, scr.data(), 1);
+        else if (mode == 1) fast_step<X, U, H1, H2, NCHUNK, 1, double>(f, st, L, ar, s, scr.data(), 1);
+        else fast_step<X, U, H1, H2, NCHUNK, 2, double>(f, st, L, ar, s, scr.data(), 1);
     }
+    delete fp;
 }
 
 }  // namespace
@@ -103,9 +104,9 @@ extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths,
         if (what != 0 || compute_f64 || act != 0 || n_layers != 3 || x != 2 || u != 1) return -1;
         StageTable<float> st = make_stage_table<float>(rk4, dt);
         const int mode = out2 ? 2 : (out1 ? 1 : 0);
-        if (widths[0] == 30 && widths[1] == 30) run_fast<2, 1, 30, 30>(wflat, st, L, ar, mode);
-        else if (widths[0] == 32 && widths[1] == 32) run_fast<2, 1, 32, 32>(wflat, st, L, ar, mode);
-        else if (widths[0] == 16 && widths[1] == 16) run_fast<2, 1, 16, 16>(wflat, st, L, ar, mode);
+        if (widths[0] == 30 && widths[1] == 30) run_fast<2, 1, 30, 30, 2>(wflat, st, L, ar, mode);
+        else if (widths[0] == 32 && widths[1] == 32) run_fast<2, 1, 32, 32, 2>(wflat, st, L, ar, mode);
+        else if (widths[0] == 16 && widths[1] == 16) run_fast<2, 1, 16, 16, 1>(wflat, st, L, ar, mode);
         else return -1;
         return 0;
     }

@@ -112,13 +112,15 @@ def test_ipopt_problem_callbacks_vs_reference_goldens(golden_dir, lv_weights, ki
 
 
 def _lv_setup(lv_weights, H, dtype="float64"):
+    """the fixture network predicts the NEXT state (f(0.66,-0.9,0) ~ (0.69,-0.82)), so the physically meaningful
+    transcription for it is the unity integrator."""
     from pyneuralempc_b200 import integrator as I
     from pyneuralempc_b200.constraints import DomainConstraint
     from pyneuralempc_b200.model import CudaMLPModel
     from pyneuralempc_b200.objective import CudaQuadraticObjective
     model = CudaMLPModel(lv_weights, 2, 1, dtype=dtype)
-    integ = I.RK4Integrator(model, H, 0.1, cache_mode=True)
-    obj = CudaQuadraticObjective(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.3, -0.2]))
+    integ = I.UnityIntegrator(model, H)
+    obj = CudaQuadraticObjective(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.5, -0.7]))
     dom = DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])   # run.py:72-74
     return model, integ, obj, dom
 
@@ -134,7 +136,7 @@ def test_closed_loop_slsqp_and_trust_constr_match_oracle(lv_weights):
     model, integ, obj, dom = _lv_setup(lv_weights, H)
     # --- oracle side
     o_obj = SeparableQuadraticObjective(obj.lin, obj.quad, obj.ref)
-    o_pb = DenseIpoptProblem(x0, o_obj, DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "rk4", DT=0.1))
+    o_pb = DenseIpoptProblem(x0, o_obj, DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "unity"))
     x_init = np.concatenate([np.tile(x0, H), np.zeros(H)])
     bounds = Bounds(dom.get_lower_bounds(H), dom.get_upper_bounds(H))
     ref = minimize(o_pb.objective, x_init, method="SLSQP", jac=o_pb.gradient, bounds=bounds,
@@ -144,6 +146,7 @@ def test_closed_loop_slsqp_and_trust_constr_match_oracle(lv_weights):
     opt = Slsqp(verbose=0)
     mpc = NMPC(integ, obj, [dom], H, 0.1, optimizer=opt)
     xs, us = mpc.next(x0)
+    assert ref.success and xs is not None
     assert xs.shape == (H, 2) and us.shape == (H, 1)
     assert opt.last_result.nit == ref.nit
     assert abs(opt.last_result.fun - ref.fun) < 1e-6
