@@ -7,7 +7,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB_PATH = os.path.join(CSRC, "libnempc.so")
+LIB_PATH = os.environ.get("NEMPC_LIB_PATH") or os.path.join(CSRC, "libnempc.so")   # env override: kernel-variant experiments
 SOURCES = ["nempc_lib.cu"]
 HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -22,6 +22,8 @@ def find_nvcc():
 
 
 def is_stale():
+    if os.environ.get("NEMPC_LIB_PATH"):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

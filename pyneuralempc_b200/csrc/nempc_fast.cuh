@@ -22,6 +22,36 @@
 
 #include "nempc_generic.cuh"
 
+// ---- packed f32x2 arithmetic (sm_100a FFMA2 / FMUL2) --------------------------------------------------------------
+// On the device an f2 is a 64-bit register pair and fma2 is `fma.rn.f32x2`; ptxas folds pk(s, s) into the scalar-
+// broadcast operand form and takes constant-bank pairs as a uniform-register operand
+// (`FFMA2 R, R.F32, UR.F32x2, R.F32x2`), so a packed FMA costs ONE issue slot for two FMAs per lane.
+// On the host (tests/hostsim) the same names are plain float pairs.
+#if defined(__CUDA_ARCH__)
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float f2lo(f2 a) { float lo, hi; asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return lo; }
+__device__ __forceinline__ float f2hi(f2 a) { float lo, hi; asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return hi; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v)); return d; }
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU pipe (EX2 + RCP): absolute error ~1e-7 (same size as f32 rounding of the
+// activations), saturates correctly to +-1; 5 instructions instead of ~20 for libdevice tanhf.
+__device__ __forceinline__ float fast_tanh(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+#else
+struct f2 { float lo, hi; };
+inline f2 pk(float lo, float hi) { f2 r; r.lo = lo; r.hi = hi; return r; }
+inline float f2lo(f2 a) { return a.lo; }
+inline float f2hi(f2 a) { return a.hi; }
+inline f2 fma2(f2 a, f2 b, f2 c) { return pk(fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)); }
+inline f2 mul2(f2 a, f2 b) { return pk(a.lo * b.lo, a.hi * b.hi); }
+inline float fast_tanh(float x) { const float e = exp2f(x * 2.885390081777927f); return fmaf(-2.0f, 1.0f / (e + 1.0f), 1.0f); }
+#endif
+
 template <int X, int U, int H1, int H2, int NCHUNK> struct FastWeights {
     static constexpr int D = X + U;
     static constexpr int NS = D * (D + 1) / 2;
@@ -37,7 +67,8 @@ template <int X, int U, int H1, int H2, int NCHUNK> struct FastWeights {
     alignas(16) float b2[NCHUNK][JCP];
     alignas(16) float W3T[NCHUNK][JC][4];   // [jc][jj][p] = W3[j][p]
     alignas(16) float b3[4];
-    alignas(16) float W23[X][H1][H2P];      // W2[i][j] * W3[j][p]: layer-1 adjoint of output p = sum_j W23[p][i][j] s'(a2_j)
+    static constexpr int XQ = (X + 1) / 2 * 2;            // outputs padded to an even count (packed pairs over p)
+    alignas(16) float W23T[H1][H2P][XQ];    // [i][j][p] = W2[i][j] * W3[j][p]: layer-1 adjoint of output p = sum_j W23T[i][j][p] s'(a2_j)
     alignas(16) float P1T[H1][NSP];         // W1[c][i] * W1[c2][i], e = c(c+1)/2 + c2: layer-1 tangents are constant
 };
 
@@ -63,7 +94,7 @@ inline void fill_fast_weights(FastWeights<X, U, H1, H2, NCHUNK>& f, const double
     for (int p = 0; p < X; ++p) f.b3[p] = (float)b3[p];
     for (int p = 0; p < X; ++p)
         for (int i = 0; i < H1; ++i)
-            for (int j = 0; j < H2; ++j) f.W23[p][i][j] = (float)W2[i * H2 + j] * (float)W3[j * X + p];
+            for (int j = 0; j < H2; ++j) f.W23T[i][j][p] = (float)W2[i * H2 + j] * (float)W3[j * X + p];
 }
 
 // per-thread scratch in shared memory for COLD state: element e of thread tid lives at scr[e * stride] with
@@ -124,27 +155,31 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
             float a1 = w.W1T[i][D];
 #pragma unroll
             for (int c = 0; c < D; ++c) a1 = fmaf(w.W1T[i][c], zs[c], a1);
-            scr[(SC::H1_OFF + i) * sstride] = tanhf(a1);
+            scr[(SC::H1_OFF + i) * sstride] = fast_tanh(a1);
         }
 
-        float k[X], J[X][D], M[X][NS];
+        // packed state: k2 = (k[0],k[1]), J2[c] = (J[0][c],J[1][c]) [pairs over outputs p], M2[p][e/2] [pairs over e]
+        constexpr int XP = (X + 1) / 2, NSH = (NS + 1) / 2, JCH = FW::JCP / 2;
+        f2 k2[XP], J2[XP][D], M2[X][NSH];
 #pragma unroll
-        for (int p = 0; p < X; ++p) {
-            k[p] = w.b3[p];
+        for (int q = 0; q < XP; ++q) {
+            k2[q] = pk(w.b3[2 * q], w.b3[2 * q + 1]);
 #pragma unroll
-            for (int c = 0; c < D; ++c) J[p][c] = 0.f;
-#pragma unroll
-            for (int e = 0; e < NS; ++e) M[p][e] = 0.f;
+            for (int c = 0; c < D; ++c) J2[q][c] = pk(0.f, 0.f);
         }
+#pragma unroll
+        for (int p = 0; p < X; ++p)
+#pragma unroll
+            for (int e = 0; e < NSH; ++e) M2[p][e] = pk(0.f, 0.f);
         // ---- layer 2, one register chunk of JC output neurons at a time ---------------------------------------------
 #pragma unroll 1
         for (int jc = 0; jc < NCHUNK; ++jc) {
-            float acc[NR][JC];
+            f2 acc[NR][JCH];                       // acc[r][h] = rows (value, tangents) x neuron pair (2h, 2h+1)
 #pragma unroll
-            for (int jj = 0; jj < JC; ++jj) {
-                acc[0][jj] = w.b2[jc][jj];
+            for (int h = 0; h < JCH; ++h) {
+                acc[0][h] = pk(w.b2[jc][2 * h], w.b2[jc][2 * h + 1]);
 #pragma unroll
-                for (int r = 1; r < NR; ++r) acc[r][jj] = 0.f;
+                for (int r = 1; r < NR; ++r) acc[r][h] = pk(0.f, 0.f);
             }
 #pragma unroll 2
             for (int i = 0; i < H1; ++i) {
@@ -156,41 +191,49 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
                     for (int c = 0; c < D; ++c) v[c] = sp * w.W1T[i][c];      // post-activation tangent of layer 1
                 }
 #pragma unroll
-                for (int jj = 0; jj < JC; ++jj) {
-                    const float wij = w.W2C[jc][i][jj];
-                    acc[0][jj] = fmaf(wij, t1, acc[0][jj]);
+                for (int h = 0; h < JCH; ++h) {
+                    const f2 wp = pk(w.W2C[jc][i][2 * h], w.W2C[jc][i][2 * h + 1]);
+                    acc[0][h] = fma2(pk(t1, t1), wp, acc[0][h]);
                     if (JAC) {
 #pragma unroll
-                        for (int c = 0; c < D; ++c) acc[JAC ? 1 + c : 0][jj] = fmaf(wij, v[c], acc[JAC ? 1 + c : 0][jj]);
+                        for (int c = 0; c < D; ++c) acc[JAC ? 1 + c : 0][h] = fma2(pk(v[c], v[c]), wp, acc[JAC ? 1 + c : 0][h]);
                     }
                 }
             }
             // consume the chunk: output value, local Jacobian, layer-2 curvature, adjoint seed
 #pragma unroll
             for (int jj = 0; jj < JC; ++jj) {
-                const float t2 = tanhf(acc[0][jj]);
+                const float a2 = (jj & 1) ? f2hi(acc[0][jj / 2]) : f2lo(acc[0][jj / 2]);
+                const float t2 = fast_tanh(a2);
+                f2 w3[XP];
 #pragma unroll
-                for (int p = 0; p < X; ++p) k[p] = fmaf(w.W3T[jc][jj][p], t2, k[p]);
+                for (int q = 0; q < XP; ++q) {
+                    w3[q] = pk(w.W3T[jc][jj][2 * q], w.W3T[jc][jj][2 * q + 1]);
+                    k2[q] = fma2(pk(t2, t2), w3[q], k2[q]);
+                }
                 if (JAC) {
                     const float sp = fmaf(-t2, t2, 1.f);
+                    float tg[D];
 #pragma unroll
                     for (int c = 0; c < D; ++c) {
-                        const float vt = sp * acc[JAC ? 1 + c : 0][jj];
+                        tg[c] = (jj & 1) ? f2hi(acc[JAC ? 1 + c : 0][jj / 2]) : f2lo(acc[JAC ? 1 + c : 0][jj / 2]);
+                        const float vt = sp * tg[c];
 #pragma unroll
-                        for (int p = 0; p < X; ++p) J[p][c] = fmaf(w.W3T[jc][jj][p], vt, J[p][c]);
+                        for (int q = 0; q < XP; ++q) J2[q][c] = fma2(pk(vt, vt), w3[q], J2[q][c]);
                     }
                     if (HES) {
                         const float spp = -2.f * t2 * sp;
-                        float pp[NS];
+                        float pp[2 * NSH];
 #pragma unroll
                         for (int c = 0; c < D; ++c)
 #pragma unroll
-                            for (int c2 = 0; c2 <= c; ++c2) pp[c * (c + 1) / 2 + c2] = acc[JAC ? 1 + c : 0][jj] * acc[JAC ? 1 + c2 : 0][jj];
+                            for (int c2 = 0; c2 <= c; ++c2) pp[c * (c + 1) / 2 + c2] = tg[c] * tg[c2];
+                        if (NS & 1) pp[NS] = 0.f;
 #pragma unroll
                         for (int p = 0; p < X; ++p) {
                             const float q = spp * w.W3T[jc][jj][p];
 #pragma unroll
-                            for (int e = 0; e < NS; ++e) M[p][e] = fmaf(q, pp[e], M[p][e]);
+                            for (int e = 0; e < NSH; ++e) M2[p][e] = fma2(pk(q, q), pk(pp[2 * e], pp[2 * e + 1]), M2[p][e]);
                         }
                         scr[(SC::SP2_OFF + jc * JC + jj) * sstride] = sp;
                     }
@@ -198,6 +241,8 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
             }
         }
         // ---- layer-1 adjoint (per output) and its curvature ---------------------------------------------------------------
+        // g2[q] = (g[2q], g[2q+1])[i] = sum_j s'(a2_j) * W23T[i][j][2q..2q+1]: scalar-broadcast x uniform pair (the FFMA2 form
+        // of the layer-2 loop), four independent chains; s'(a2) stays in registers for the whole loop.
         if (HES) {
             float sp2[H2];
 #pragma unroll
@@ -208,19 +253,34 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
                 const float sp = fmaf(-t1, t1, 1.f);
                 const float spp = -2.f * t1 * sp;
 #pragma unroll
-                for (int p = 0; p < X; ++p) {
-                    float g0 = 0.f, g1 = 0.f;
+                for (int q = 0; q < XP; ++q) {
+                    f2 g[4];
 #pragma unroll
-                    for (int j = 0; j + 1 < H2; j += 2) {
-                        g0 = fmaf(w.W23[p][i][j], sp2[j], g0);
-                        g1 = fmaf(w.W23[p][i][j + 1], sp2[j + 1], g1);
+                    for (int r = 0; r < 4; ++r) g[r] = pk(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < H2; ++j)
+                        g[j & 3] = fma2(pk(sp2[j], sp2[j]), pk(w.W23T[i][j][2 * q], w.W23T[i][j][2 * q + 1]), g[j & 3]);
+                    const float glo = (f2lo(g[0]) + f2lo(g[1])) + (f2lo(g[2]) + f2lo(g[3]));
+                    const float ghi = (f2hi(g[0]) + f2hi(g[1])) + (f2hi(g[2]) + f2hi(g[3]));
+                    const float cf0 = spp * glo, cf1 = spp * ghi;
+#pragma unroll
+                    for (int e = 0; e < NSH; ++e) {
+                        const f2 p1 = pk(w.P1T[i][2 * e], w.P1T[i][2 * e + 1]);
+                        M2[2 * q][e] = fma2(pk(cf0, cf0), p1, M2[2 * q][e]);
+                        if (2 * q + 1 < X) M2[2 * q + 1 < X ? 2 * q + 1 : 0][e] = fma2(pk(cf1, cf1), p1, M2[2 * q + 1 < X ? 2 * q + 1 : 0][e]);
                     }
-                    if (H2 & 1) g0 = fmaf(w.W23[p][i][H2 - 1], sp2[H2 - 1], g0);
-                    const float cf = spp * (g0 + g1);
-#pragma unroll
-                    for (int e = 0; e < NS; ++e) M[p][e] = fmaf(cf, w.P1T[i][e], M[p][e]);
                 }
             }
+        }
+        // unpack for the (small) stage algebra
+        float k[X], J[X][D], M[X][NS];
+#pragma unroll
+        for (int p = 0; p < X; ++p) {
+            k[p] = (p & 1) ? f2hi(k2[p / 2]) : f2lo(k2[p / 2]);
+#pragma unroll
+            for (int c = 0; c < D; ++c) J[p][c] = (p & 1) ? f2hi(J2[p / 2][c]) : f2lo(J2[p / 2][c]);
+#pragma unroll
+            for (int e = 0; e < NS; ++e) M[p][e] = (e & 1) ? f2hi(M2[p][e / 2]) : f2lo(M2[p][e / 2]);
         }
         // ---- stage algebra -------------------------------------------------------------------------------------------------
 #define NEMPC_RF(kk, cc) ((kk) < X ? Rt[(kk) < X ? (kk) : 0][cc] : ((kk) == (cc) ? 1.f : 0.f))

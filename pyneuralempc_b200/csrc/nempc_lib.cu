@@ -42,12 +42,15 @@ nempc_generic_kernel(const NetView<T> net, const StageTable<T> st, const NlpLayo
 #ifndef NEMPC_FAST_THREADS
 #define NEMPC_FAST_THREADS 128
 #endif
-#ifndef NEMPC_FAST_MINBLOCKS
-#define NEMPC_FAST_MINBLOCKS 4
+#ifndef NEMPC_FAST_NCHUNK30        // register chunks of the 30-wide second layer: 3 chunks x 10 neurons = 5 packed pairs each
+#define NEMPC_FAST_NCHUNK30 3      // (sweep profiles/r1d: 3 chunks @ 5 CTAs/SM 0.299 ms, 2 @ 4 0.307, 2 @ 3 0.475, 1 @ 2 0.551)
+#endif
+#ifndef NEMPC_FAST_MINBLOCKS       // CTAs/SM the register allocator must allow: occupancy is the main lever of this kernel
+#define NEMPC_FAST_MINBLOCKS(JC) ((JC) <= 10 ? 5 : 4)
 #endif
 
 template <int X, int U, int H1, int H2, int NCHUNK, int MODE, typename TIO>
-__global__ void __launch_bounds__(NEMPC_FAST_THREADS, NEMPC_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(NEMPC_FAST_THREADS, NEMPC_FAST_MINBLOCKS(H2 / NCHUNK))
 nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2, NCHUNK> w, const StageTable<float> st,
                   const NlpLayout L, const EvalArgs<TIO> ar) {
     // cold per-thread state (layer-1 activations, per-output Hessian accumulators): [element][thread], bank = thread
@@ -99,6 +102,24 @@ __global__ void nempc_fma_peak_kernel(T* out, int iters, T seed) {
     if (s == (T)123456789) out[0] = s;      // never true; keeps the loop alive
 }
 
+// packed variant (fma.rn.f32x2 -> FFMA2): two FMAs per lane per issued instruction
+__global__ void nempc_fma2_peak_kernel(float* out, int iters, float seed) {
+    f2 a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = pk(seed + (float)(threadIdx.x + i), seed - (float)i);
+    const f2 m = pk(0.999f, 0.998f), c = pk(1e-3f, 2e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fma2(a[i], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += f2lo(a[i]) + f2hi(a[i]);
+    if (s == 123456789.f) out[0] = s;
+}
+
 // ======================================================================================================
 // handle
 // ======================================================================================================
@@ -125,6 +146,7 @@ struct nempc_handle {
     size_t smem_bytes = 0; bool global_ws = false; void* gws = nullptr; size_t gws_bytes = 0;
     int sm_count = 0; int max_smem_optin = 0;
     cudaStream_t stream = nullptr;               // own stream for *_host calls
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunk pipeline of nempc_eval_host (H2D | kernels | D2H overlap)
     // staging for eval_host
     void* st_buf[10] = {}; size_t st_cap[10] = {};
     long long launches = 0;
@@ -238,6 +260,7 @@ static void free_device(nempc_handle* h) {
     cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 3; ++i) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
 }
 
 extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
@@ -273,6 +296,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, D.device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, D.device);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "stream: %s", cudaGetErrorString(e)); delete h; return NEMPC_ECUDA; }
+    for (int i = 0; i < 3; ++i)
+        if ((e = cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking)) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "stream: %s", cudaGetErrorString(e)); free_device(h); delete h; return NEMPC_ECUDA; }
 
     // kernel choice
     h->fast_id = fast_shape_id(D);
@@ -353,7 +378,7 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
     bool all = true; for (bool s : h->wset) all = all && s;
     if (all && h->fast_id >= 0) {
         switch (h->fast_id) {
-            case 0: fill_fast<2, 1, 30, 30, 2>(h); break;
+            case 0: fill_fast<2, 1, 30, 30, NEMPC_FAST_NCHUNK30>(h); break;
             case 1: fill_fast<2, 1, 32, 32, 2>(h); break;
             case 2: fill_fast<2, 1, 16, 16, 1>(h); break;
         }
@@ -469,7 +494,7 @@ static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode,
 
 template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
     switch (h->fast_id) {
-        case 0: return launch_fast_shape<2, 1, 30, 30, 2, TIO>(h, ar, mode, s);
+        case 0: return launch_fast_shape<2, 1, 30, 30, NEMPC_FAST_NCHUNK30, TIO>(h, ar, mode, s);
         case 1: return launch_fast_shape<2, 1, 32, 32, 2, TIO>(h, ar, mode, s);
         case 2: return launch_fast_shape<2, 1, 16, 16, 1, TIO>(h, ar, mode, s);
     }
@@ -542,17 +567,36 @@ extern "C" int nempc_eval_host(nempc_handle* h, int64_t B, const void* z, const 
                            resid ? (size_t)B * L.m * es : 0, jac ? (size_t)B * L.nnz_jac * es : 0, hes ? (size_t)B * L.nnz_hes * es : 0,
                            obj ? (size_t)B * es : 0, grad ? (size_t)B * L.n * es : 0, 0};
     for (int i = 0; i < 9; ++i) if (sz[i]) { rc = stage_reserve(h, i, sz[i]); if (rc) return rc; }
-    cudaStream_t s = h->stream;
+    // Chunk pipeline: the batch is cut along B and chunk c runs H2D -> kernels -> D2H on stream c % 3, so the
+    // upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap (separate copy engines;
+    // PCIe is full duplex).  Small batches and the global-workspace fallback use a single chunk.
+    const size_t per_problem = ((size_t)2 * L.n + L.x + 2 * L.m + L.nnz_jac + L.nnz_hes + 2) * es;
+    int64_t chunk = B;
+    if (!h->global_ws && B >= 512) {
+        chunk = std::max<int64_t>(256, (int64_t)((size_t)(8u << 20) / per_problem));     // ~8 MB of traffic per chunk
+        chunk = std::min<int64_t>(chunk, (B + 2) / 3);                                    // at least 3 chunks in flight
+    }
+    const size_t in_w[4] = {(size_t)L.n * es, (size_t)L.x * es, (size_t)L.m * es, es};
+    const size_t out_w[5] = {(size_t)L.m * es, (size_t)L.nnz_jac * es, (size_t)L.nnz_hes * es, es, (size_t)L.n * es};
     const void* in[4] = {z, x0, lambda, obj_factor};
-    for (int i = 0; i < 4; ++i) if (sz[i]) CU(h, cudaMemcpyAsync(h->st_buf[i], in[i], sz[i], cudaMemcpyHostToDevice, s));
-    void* d[5] = {sz[4] ? h->st_buf[4] : nullptr, sz[5] ? h->st_buf[5] : nullptr, sz[6] ? h->st_buf[6] : nullptr,
-                  sz[7] ? h->st_buf[7] : nullptr, sz[8] ? h->st_buf[8] : nullptr};
-    rc = nempc_eval(h, B, h->st_buf[0], h->st_buf[1], sz[2] ? h->st_buf[2] : nullptr, sz[3] ? h->st_buf[3] : nullptr, sigma,
-                    d[0], d[1], d[2], d[3], d[4], (void*)s);
-    if (rc) return rc;
     void* outp[5] = {resid, jac, hes, obj, grad};
-    for (int i = 0; i < 5; ++i) if (sz[4 + i]) CU(h, cudaMemcpyAsync(outp[i], d[i], sz[4 + i], cudaMemcpyDeviceToHost, s));
-    CU(h, cudaStreamSynchronize(s));
+    int ci = 0;
+    for (int64_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
+        const int64_t nb = std::min(chunk, B - c0);
+        cudaStream_t s = (chunk == B) ? h->stream : h->pipe[ci % 3];
+        void* din[4]; void* dout[5];
+        for (int i = 0; i < 4; ++i) {
+            din[i] = sz[i] ? (char*)h->st_buf[i] + c0 * in_w[i] : nullptr;
+            if (sz[i]) CU(h, cudaMemcpyAsync(din[i], (const char*)in[i] + c0 * in_w[i], nb * in_w[i], cudaMemcpyHostToDevice, s));
+        }
+        for (int i = 0; i < 5; ++i) dout[i] = sz[4 + i] ? (char*)h->st_buf[4 + i] + c0 * out_w[i] : nullptr;
+        rc = nempc_eval(h, nb, din[0], din[1], din[2], din[3], sigma, dout[0], dout[1], dout[2], dout[3], dout[4], (void*)s);
+        if (rc) return rc;
+        for (int i = 0; i < 5; ++i)
+            if (sz[4 + i]) CU(h, cudaMemcpyAsync((char*)outp[i] + c0 * out_w[i], dout[i], nb * out_w[i], cudaMemcpyDeviceToHost, s));
+    }
+    if (chunk == B) CU(h, cudaStreamSynchronize(h->stream));
+    else for (int i = 0; i < 3; ++i) CU(h, cudaStreamSynchronize(h->pipe[i]));
     return NEMPC_OK;
 }
 
@@ -619,7 +663,7 @@ extern "C" double nempc_flops_per_step(const nempc_handle* h) {
     return S * stage + (S == 4 ? 6 * x * d * d + 6 * x * x : 0.0);
 }
 
-template <typename T> static int fma_peak_t(int millis, double* tflops) {
+template <typename T> static int fma_peak_t(int millis, double* tflops, bool packed = false) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -631,17 +675,21 @@ template <typename T> static int fma_peak_t(int millis, double* tflops) {
     int iters = 2000;
     double best = 0.0;
     float total_ms = 0.f;
-    nempc_fma_peak_kernel<T><<<blocks, threads>>>(out, 200, (T)1);   // warm-up
+    auto launch = [&](int it) {
+        if (packed) nempc_fma2_peak_kernel<<<blocks, threads>>>((float*)out, it, 1.f);
+        else nempc_fma_peak_kernel<T><<<blocks, threads>>>(out, it, (T)1);
+    };
+    launch(200);   // warm-up
     cudaDeviceSynchronize();
     while (total_ms < (float)millis) {
         cudaEventRecord(e0);
-        nempc_fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)1);
+        launch(iters);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return NEMPC_ECUDA; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         total_ms += ms;
-        const double flops = 2.0 * 16 * 8 * (double)iters * threads * blocks;
+        const double flops = 2.0 * 16 * 8 * (double)iters * threads * blocks * (packed ? 2.0 : 1.0);
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
         if (ms < 5.f) iters *= 2;
     }
@@ -653,5 +701,12 @@ template <typename T> static int fma_peak_t(int millis, double* tflops) {
 extern "C" int nempc_measure_fma_peak(int32_t device, int32_t dtype, int32_t millis, double* tflops) {
     if (!tflops) return NEMPC_EINVAL;
     if (cudaSetDevice(device) != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "no usable CUDA device %d", device); return NEMPC_ECUDA; }
-    return dtype == NEMPC_F64 ? fma_peak_t<double>(millis, tflops) : fma_peak_t<float>(millis, tflops);
+    if (dtype == NEMPC_F64) return fma_peak_t<double>(millis, tflops);
+    double scalar = 0.0, packed = 0.0;       // FP32: best of scalar FFMA and packed FFMA2 issue
+    int rc = fma_peak_t<float>(millis / 2 + 1, &scalar);
+    if (rc) return rc;
+    rc = fma_peak_t<float>(millis / 2 + 1, &packed, true);
+    if (rc) return rc;
+    *tflops = scalar > packed ? scalar : packed;
+    return NEMPC_OK;
 }

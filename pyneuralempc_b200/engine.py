@@ -200,35 +200,56 @@ class NlpEvaluator:
             self._pinned[key] = t
         return t
 
+    def pinned_buffers(self, B, want=("resid", "jac", "hes", "obj", "grad"), with_lambda=True, per_problem_factor=False):
+        """persistent page-locked host buffers (numpy views) for a batch of B problems: write the iterate into
+        ``z / x0 / lam (/ sig)``, call :meth:`eval_pinned`, read the results from the output views -- no staging copy."""
+        want = tuple(w for w in want if not (w in ("obj", "grad") and not self.has_objective))
+        shapes = {"z": (B, self.n), "x0": (B, self.x_dim), "resid": (B, self.m), "jac": (B, self.nnz_jac),
+                  "hes": (B, self.nnz_hes), "obj": (B,), "grad": (B, self.n)}
+        keys = ["z", "x0"] + list(want)
+        if with_lambda:
+            shapes["lam"] = (B, self.m); keys.append("lam")
+        if per_problem_factor:
+            shapes["sig"] = (B,); keys.append("sig")
+        return {k: self._pin(k, shapes[k]).numpy() for k in keys}
+
+    def eval_pinned(self, B, obj_factor=1.0, want=("resid", "jac", "hes", "obj", "grad"), per_problem_factor=False):
+        """``nempc_eval_host`` on the buffers of :meth:`pinned_buffers`: chunk-pipelined H2D -> kernels -> D2H, then
+        a synchronise.  Returns the dict of output views."""
+        want = tuple(w for w in want if not (w in ("obj", "grad") and not self.has_objective))
+        pz, px = self._pinned["z"], self._pinned["x0"]
+        if tuple(pz.shape) != (B, self.n):
+            raise ValueError("call pinned_buffers(B, ...) first")
+        pl = self._pinned.get("lam") if "hes" in want else None
+        if "hes" in want and (pl is None or tuple(pl.shape) != (B, self.m)):
+            raise ValueError("'hes' needs the lam buffer")
+        ps = self._pinned.get("sig") if per_problem_factor else None
+        outs = {k: self._pinned[k] for k in want}
+        g = lambda k: _vp(outs[k]) if k in want else None
+        self._check(self.lib.nempc_eval_host(self._h, B, _vp(pz), _vp(px), _vp(pl), _vp(ps), float(obj_factor),
+                                             g("resid"), g("jac"), g("hes"), g("obj"), g("grad")), "nempc_eval_host")
+        return {k: v.numpy() for k, v in outs.items()}
+
     def eval_host(self, z, x0, lam=None, obj_factor=1.0, want=("resid", "jac", "hes", "obj", "grad")):
-        """numpy in -> numpy out through ``nempc_eval_host``: inputs are copied into persistent pinned buffers, the
-        library DMA-copies them to the device, evaluates, DMA-copies the results into pinned buffers and
-        synchronises; the returned arrays are views of those pinned buffers (valid until the next call)."""
+        """numpy in -> numpy out (the solver-callback situation): the arrays are copied into the persistent pinned
+        buffers, then :meth:`eval_pinned`.  The returned arrays are views of pinned buffers, valid until the next call."""
         npdt = _NP[self.io_dtype]
         z = np.asarray(z, npdt)
         if z.ndim == 1:
             z = z[None]
         B = z.shape[0]
-        x0 = np.asarray(x0, npdt).reshape(B, self.x_dim)
         want = tuple(w for w in want if not (w in ("obj", "grad") and not self.has_objective))
         if "hes" in want and lam is None:
             raise ValueError("'hes' needs lam")
-        pz = self._pin("z", (B, self.n)); pz.numpy()[...] = z
-        px = self._pin("x0", (B, self.x_dim)); px.numpy()[...] = x0
-        pl = None
-        if lam is not None and "hes" in want:
-            pl = self._pin("lam", (B, self.m)); pl.numpy()[...] = np.asarray(lam, npdt).reshape(B, self.m)
-        ps, sig_s = None, 1.0
-        if np.ndim(obj_factor) > 0:
-            ps = self._pin("sig", (B,)); ps.numpy()[...] = np.asarray(obj_factor, npdt)
-        else:
-            sig_s = float(obj_factor)
-        shapes = {"resid": (B, self.m), "jac": (B, self.nnz_jac), "hes": (B, self.nnz_hes), "obj": (B,), "grad": (B, self.n)}
-        outs = {k: self._pin("o_" + k, shapes[k]) for k in want}
-        g = lambda k: _vp(outs[k]) if k in want else None
-        self._check(self.lib.nempc_eval_host(self._h, B, _vp(pz), _vp(px), _vp(pl), _vp(ps), sig_s,
-                                             g("resid"), g("jac"), g("hes"), g("obj"), g("grad")), "nempc_eval_host")
-        return {k: v.numpy() for k, v in outs.items()}
+        per_problem = np.ndim(obj_factor) > 0
+        buf = self.pinned_buffers(B, want, with_lambda="hes" in want, per_problem_factor=per_problem)
+        buf["z"][...] = z
+        buf["x0"][...] = np.asarray(x0, npdt).reshape(B, self.x_dim)
+        if "hes" in want:
+            buf["lam"][...] = np.asarray(lam, npdt).reshape(B, self.m)
+        if per_problem:
+            buf["sig"][...] = np.asarray(obj_factor, npdt)
+        return self.eval_pinned(B, 1.0 if per_problem else float(obj_factor), want, per_problem)
 
     def host_io_bytes(self, B, want=("resid", "jac", "hes", "obj", "grad"), with_lambda=True):
         s = 8 if self.io_dtype == "float64" else 4
