@@ -19,6 +19,7 @@
 // Same maths and references as nempc_generic.cuh (integrator/rk4.py:113-285, model/tensorflow.py:49-109).
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "nempc_generic.cuh"
 
@@ -52,6 +53,9 @@ inline f2 mul2(f2 a, f2 b) { return pk(a.lo * b.lo, a.hi * b.hi); }
 inline float fast_tanh(float x) { const float e = exp2f(x * 2.885390081777927f); return fmaf(-2.0f, 1.0f / (e + 1.0f), 1.0f); }
 #endif
 
+// 16-byte weight quad: read as ONE uniform 128-bit constant load (LDCU.128) and consumed as two FFMA2 operand pairs
+struct alignas(16) nf4 { float x, y, z, w; };
+
 template <int X, int U, int H1, int H2, int NCHUNK> struct FastWeights {
     static constexpr int D = X + U;
     static constexpr int NS = D * (D + 1) / 2;
@@ -62,14 +66,15 @@ template <int X, int U, int H1, int H2, int NCHUNK> struct FastWeights {
     static constexpr int NSP = (NS + 3) / 4 * 4;
     static_assert(H2 % NCHUNK == 0, "H2 must be divisible by NCHUNK");
     static_assert(X <= 4, "W3T packs x_dim into one 128-bit slot");
-    alignas(16) float W1T[H1][DP];          // [i][c] = W1[c][i], [i][D] = b1[i]
-    alignas(16) float W2C[NCHUNK][H1][JCP]; // [jc][i][jj] = W2[i][jc*JC+jj]
+    static_assert(DP == 4 && X == 2, "the register-resident kernel is instantiated for x_dim = 2, x_dim+u_dim = 3");
+    nf4 W1T[H1];                            // (W1[0][i], W1[1][i], W1[2][i], b1[i])
+    nf4 W2C[NCHUNK][H1][JCP / 4];           // [jc][i][q] = W2[i][jc*JC + 4q .. 4q+3]  (zero padded)
     alignas(16) float b2[NCHUNK][JCP];
     alignas(16) float W3T[NCHUNK][JC][4];   // [jc][jj][p] = W3[j][p]
     alignas(16) float b3[4];
     static constexpr int XQ = (X + 1) / 2 * 2;            // outputs padded to an even count (packed pairs over p)
-    alignas(16) float W23T[H1][H2P][XQ];    // [i][j][p] = W2[i][j] * W3[j][p]: layer-1 adjoint of output p = sum_j W23T[i][j][p] s'(a2_j)
-    alignas(16) float P1T[H1][NSP];         // W1[c][i] * W1[c2][i], e = c(c+1)/2 + c2: layer-1 tangents are constant
+    nf4 W23T[H1][H2P / 2];                  // [i][h] = (W2[i][2h]W3[2h][0], W2[i][2h]W3[2h][1], W2[i][2h+1]W3[2h+1][0], W2[i][2h+1]W3[2h+1][1])
+    nf4 P1T[H1][NSP / 4];                   // W1[c][i] * W1[c2][i], e = c(c+1)/2 + c2 (zero padded): layer-1 tangents are constant
 };
 
 // host-side fill from Keras-layout double arrays (W[in][out])
@@ -78,23 +83,26 @@ inline void fill_fast_weights(FastWeights<X, U, H1, H2, NCHUNK>& f, const double
                               const double* b2, const double* W3, const double* b3) {
     typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
     constexpr int D = X + U, JC = FW::JC;
+    memset(&f, 0, sizeof(FW));
+    auto at = [](nf4* base, int idx) -> float& { return (&base[idx / 4].x)[idx % 4]; };
     for (int i = 0; i < H1; ++i) {
-        for (int c = 0; c < D; ++c) f.W1T[i][c] = (float)W1[c * H1 + i];
-        f.W1T[i][D] = (float)b1[i];
+        float w1[D];
+        for (int c = 0; c < D; ++c) { w1[c] = (float)W1[c * H1 + i]; at(&f.W1T[i], c) = w1[c]; }
+        at(&f.W1T[i], D) = (float)b1[i];
         for (int c = 0; c < D; ++c)
-            for (int c2 = 0; c2 <= c; ++c2) f.P1T[i][c * (c + 1) / 2 + c2] = f.W1T[i][c] * f.W1T[i][c2];
+            for (int c2 = 0; c2 <= c; ++c2) at(f.P1T[i], c * (c + 1) / 2 + c2) = w1[c] * w1[c2];
     }
     for (int jc = 0; jc < NCHUNK; ++jc)
         for (int jj = 0; jj < JC; ++jj) {
             const int j = jc * JC + jj;
             f.b2[jc][jj] = (float)b2[j];
-            for (int i = 0; i < H1; ++i) f.W2C[jc][i][jj] = (float)W2[i * H2 + j];
+            for (int i = 0; i < H1; ++i) at(f.W2C[jc][i], jj) = (float)W2[i * H2 + j];
             for (int p = 0; p < X; ++p) f.W3T[jc][jj][p] = (float)W3[j * X + p];
         }
     for (int p = 0; p < X; ++p) f.b3[p] = (float)b3[p];
-    for (int p = 0; p < X; ++p)
-        for (int i = 0; i < H1; ++i)
-            for (int j = 0; j < H2; ++j) f.W23T[i][j][p] = (float)W2[i * H2 + j] * (float)W3[j * X + p];
+    for (int i = 0; i < H1; ++i)
+        for (int j = 0; j < H2; ++j)
+            for (int p = 0; p < X; ++p) at(f.W23T[i], 2 * j + p) = (float)W2[i * H2 + j] * (float)W3[j * X + p];
 }
 
 // per-thread scratch in shared memory for COLD state: element e of thread tid lives at scr[e * stride] with
@@ -152,9 +160,8 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
         // ---- layer 1: activations to scratch -------------------------------------------------------------------
 #pragma unroll 2
         for (int i = 0; i < H1; ++i) {
-            float a1 = w.W1T[i][D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) a1 = fmaf(w.W1T[i][c], zs[c], a1);
+            const nf4 w1 = w.W1T[i];
+            const float a1 = fmaf(w1.x, zs[0], fmaf(w1.y, zs[1], fmaf(w1.z, zs[2], w1.w)));
             scr[(SC::H1_OFF + i) * sstride] = fast_tanh(a1);
         }
 
@@ -187,12 +194,14 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
                 float v[D];
                 if (JAC) {
                     const float sp = fmaf(-t1, t1, 1.f);
-#pragma unroll
-                    for (int c = 0; c < D; ++c) v[c] = sp * w.W1T[i][c];      // post-activation tangent of layer 1
+                    const nf4 w1 = w.W1T[i];
+                    v[0] = sp * w1.x; v[1] = sp * w1.y; v[2] = sp * w1.z;     // post-activation tangent of layer 1
                 }
 #pragma unroll
                 for (int h = 0; h < JCH; ++h) {
-                    const f2 wp = pk(w.W2C[jc][i][2 * h], w.W2C[jc][i][2 * h + 1]);
+                    if (2 * h >= JC) continue;                                // padding pair of the last quad
+                    const nf4 wq = w.W2C[jc][i][h / 2];
+                    const f2 wp = (h & 1) ? pk(wq.z, wq.w) : pk(wq.x, wq.y);
                     acc[0][h] = fma2(pk(t1, t1), wp, acc[0][h]);
                     if (JAC) {
 #pragma unroll
@@ -258,14 +267,17 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
 #pragma unroll
                     for (int r = 0; r < 4; ++r) g[r] = pk(0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < H2; ++j)
-                        g[j & 3] = fma2(pk(sp2[j], sp2[j]), pk(w.W23T[i][j][2 * q], w.W23T[i][j][2 * q + 1]), g[j & 3]);
+                    for (int j = 0; j < H2; ++j) {
+                        const nf4 wq = w.W23T[i][j / 2];
+                        g[j & 3] = fma2(pk(sp2[j], sp2[j]), (j & 1) ? pk(wq.z, wq.w) : pk(wq.x, wq.y), g[j & 3]);
+                    }
                     const float glo = (f2lo(g[0]) + f2lo(g[1])) + (f2lo(g[2]) + f2lo(g[3]));
                     const float ghi = (f2hi(g[0]) + f2hi(g[1])) + (f2hi(g[2]) + f2hi(g[3]));
                     const float cf0 = spp * glo, cf1 = spp * ghi;
 #pragma unroll
                     for (int e = 0; e < NSH; ++e) {
-                        const f2 p1 = pk(w.P1T[i][2 * e], w.P1T[i][2 * e + 1]);
+                        const nf4 pq = w.P1T[i][e / 2];
+                        const f2 p1 = (e & 1) ? pk(pq.z, pq.w) : pk(pq.x, pq.y);
                         M2[2 * q][e] = fma2(pk(cf0, cf0), p1, M2[2 * q][e]);
                         if (2 * q + 1 < X) M2[2 * q + 1 < X ? 2 * q + 1 : 0][e] = fma2(pk(cf1, cf1), p1, M2[2 * q + 1 < X ? 2 * q + 1 : 0][e]);
                     }
