@@ -87,18 +87,25 @@ def _cpu_problem_eval(args):
     return float(pb.hessian(z, lam, 1.0).sum())
 
 
-def cpu_reference_run(wl_name, sample, steps, warmup, procs=None):
-    """times `steps` evaluations of a bounded sample of `sample` problems on `procs` worker processes."""
+def cpu_reference_run(wl_name, sample, steps, warmup, procs=None, budget_s=None):
+    """times `steps` evaluations of a bounded sample of problems on `procs` worker processes.  With `budget_s` the
+    sample size is chosen so that the whole run lasts about that long (the per-problem cost is measured first)."""
     import multiprocessing as mp
     wl = {k: v for k, v in WORKLOADS[wl_name].items() if k != "desc"}
     procs = procs or os.cpu_count() or 1
-    _, _, Z, X0, lam = make_problem(wl, sample)
-    jobs = [(wl, Z[i], X0[i], lam[i]) for i in range(sample)]
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
+        _, _, Z, X0, lam = make_problem(wl, max(sample, 4 * procs))
+        for _ in range(max(1, min(warmup, 3))):
+            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i]) for i in range(procs)], chunksize=1)   # per-process caches
+        if budget_s:
+            t0 = time.perf_counter()
+            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i]) for i in range(2 * procs)], chunksize=1)
+            per_problem = (time.perf_counter() - t0) / (2 * procs)          # wall seconds per problem with all workers busy
+            sample = int(max(procs, min(wl["B"], 512, budget_s / max(1, steps) / per_problem)))
+            _, _, Z, X0, lam = make_problem(wl, sample)
+        jobs = [(wl, Z[i], X0[i], lam[i]) for i in range(sample)]
         chunk = max(1, sample // (procs * 4))
-        for _ in range(max(1, warmup)):
-            pool.map(_cpu_problem_eval, jobs[:procs], chunksize=1)      # builds the per-process caches
         t0 = time.perf_counter()
         for _ in range(steps):
             pool.map(_cpu_problem_eval, jobs, chunksize=chunk)
@@ -315,7 +322,7 @@ def reference_run(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    r = cpu_reference_run(args.workload, args.cpu_sample, max(1, args.steps), max(1, args.warmup))
+    r = cpu_reference_run(args.workload, args.cpu_sample, max(1, args.steps), max(1, args.warmup), budget_s=args.cpu_budget)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -338,6 +345,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--sets", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=128, help="problems per CPU-baseline step")
+    ap.add_argument("--cpu-budget", type=float, default=90.0, help="--impl reference: target wall seconds of the timed loop (sets the sample size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
