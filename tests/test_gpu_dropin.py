@@ -187,3 +187,62 @@ def test_nmpc_failure_convention_and_asserts(lv_weights):
         mpc.next(np.array([[0.1, 0.2]]))
     with pytest.raises(AssertionError):
         mpc.next(np.array([0.1, 0.2, 0.3]))
+
+
+def test_ipopt_solve_wiring_with_stub_cyipopt(lv_weights, monkeypatch):
+    """cyipopt/IPOPT are not installable here: a stub `cyipopt.Problem` that drives the callbacks the way
+    cyipopt does (objective, gradient, constraints, jacobian[structure], hessian[structure]) and delegates the actual
+    optimisation to SciPy checks the glue of optimizer/ipopt.py:138-195: initial guess, bounds, options, sparse
+    structures, status mapping and the (x_pred, u) reshaping of NMPC.next."""
+    import sys
+    import types
+    from scipy.optimize import Bounds, NonlinearConstraint, minimize
+    from scipy.sparse import coo_matrix
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import Ipopt
+
+    seen = {}
+
+    class Problem:
+        def __init__(self, n, m, problem_obj, lb, ub, cl, cu):
+            self.n, self.m, self.obj, self.lb, self.ub, self.cl, self.cu = n, m, problem_obj, lb, ub, cl, cu
+            self.options = {}
+
+        def add_option(self, k, v):
+            self.options[k] = v
+
+        def solve(self, x_init):
+            seen["options"] = dict(self.options)
+            seen["x_init"] = np.array(x_init)
+            o = self.obj
+            jr, jc = o.jacobianstructure()
+            hr, hc = o.hessianstructure()
+            assert len(o.constraints(x_init)) == self.m and len(o.gradient(x_init)) == self.n
+            assert o.jacobian(x_init).shape == jr.shape and o.hessian(x_init, np.ones(self.m), 1.0).shape == hr.shape
+            assert (hr >= hc).all()
+            off = hr != hc
+            sym = lambda v: coo_matrix((np.concatenate([v, v[off]]), (np.concatenate([hr, hc[off]]), np.concatenate([hc, hr[off]]))),
+                                       shape=(self.n, self.n)).tocsr()
+            con = NonlinearConstraint(o.constraints, self.cl, self.cu, jac=lambda x: coo_matrix((o.jacobian(x), (jr, jc)), shape=(self.m, self.n)).tocsr(),
+                                      hess=lambda x, v: sym(o.hessian(x, v, 0.0)))
+            r = minimize(o.objective, x_init, method="trust-constr", jac=o.gradient, hess=lambda x: sym(o.hessian(x, np.zeros(self.m), 1.0)),
+                         constraints=[con], bounds=Bounds(self.lb, self.ub), options={"maxiter": self.options["max_iter"], "gtol": 1e-8})
+            return r.x, {"status": 0 if r.constr_violation < 1e-6 else -1, "obj_val": r.fun}
+
+    monkeypatch.setitem(sys.modules, "cyipopt", types.SimpleNamespace(Problem=Problem))
+    H = 10
+    x0 = np.array([0.66, -0.9])
+    model, integ, obj, dom = _lv_setup(lv_weights, H)
+    opt = Ipopt(max_iteration=150)
+    xs, us = NMPC(integ, obj, [dom], H, 0.1, optimizer=opt, use_hessian=True).next(x0)
+    assert xs.shape == (H, 2) and us.shape == (H, 1)
+    assert seen["options"] == {"max_iter": 150, "tol": 1e-1, "acceptable_tol": 1e-4, "print_level": 0}     # ipopt.py:172,184-186
+    np.testing.assert_array_equal(seen["x_init"], np.concatenate([np.tile(x0, H), np.zeros(H)]))            # ipopt.py:149
+    o_obj = SeparableQuadraticObjective(obj.lin, obj.quad, obj.ref)
+    o_pb = DenseIpoptProblem(x0, o_obj, DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "unity"))
+    z = np.concatenate([xs.ravel(), us.ravel()])
+    assert np.abs(o_pb.constraints(z)).max() < 1e-6 and (us <= 0.2 + 1e-9).all() and (us >= -1 - 1e-9).all()
+    assert abs(o_pb.objective(z) - 1.2449937) < 1e-4            # optimum found by SLSQP / trust-constr on the oracle
+    # Hessian-free mode hides hessian* but keeps the sparse Jacobian structure (ipopt.py:159-160)
+    xs2, _ = NMPC(integ, obj, [dom], H, 0.1, optimizer=Ipopt(), use_hessian=False).get_pb(x0).use_hessian, None
+    assert xs2 is False
