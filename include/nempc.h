@@ -126,6 +126,24 @@ int nempc_model_eval(nempc_handle* h, int64_t N, const void* zin, void* f, void*
 int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const double* lin, const double* quad,
                          const double* ref, void* obj, void* grad, void* stream);
 
+/* ---- batched on-device NMPC solver ----------------------------------------------------------
+ * Replaces, for a batch of B independent problems, the solver call of Ipopt.solve / Slsqp.solve
+ * (optimizer/ipopt.py:162-189, optimizer/slsqp.py:172-173): a primal-dual interior-point method whose Newton step is a
+ * Riccati sweep over the block-tridiagonal KKT system, consuming the Jacobian / Hessian value arrays of nempc_eval in
+ * place.  Needs io_dtype = F64 and nempc_set_objective.  lb / ub: HOST arrays of n doubles in DomainConstraint order
+ * (constraints.py:26-30), +-inf = unbounded.  x0 (B,x), z (B,n), lambda (B,m), kkt_error (B): DEVICE doubles;
+ * status / iterations (B): DEVICE int32.  z is the initial guess when use_init != 0 (else [x0 tiled | zeros],
+ * optimizer/ipopt.py:149) and receives the solution.  status: 0 converged, 1 iteration limit, 2 failed (non-finite step:
+ * the problem is infeasible or unbounded; the reference returns Optimizer.FAIL there).  Synchronises the stream. */
+typedef struct nempc_solver_opts {
+    int32_t max_iter, max_backtrack;
+    double tol, mu_init, mu_min, kappa_eps, kappa_mu, theta_mu, tau_min, bound_push, eta, reg_init, reg_max;
+} nempc_solver_opts;
+int nempc_solver_defaults(nempc_solver_opts* opts);
+int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const double* lb, const double* ub, void* z, int32_t use_init,
+                void* lambda, int32_t* status, int32_t* iterations, double* kkt_error, const nempc_solver_opts* opts,
+                int32_t* outer_iterations, void* stream);
+
 /* ---- introspection -------------------------------------------------------------------------------------- */
 int64_t nempc_launch_count(const nempc_handle* h);   /* kernels launched by this handle so far */
 const char* nempc_kernel_name(const nempc_handle* h); /* "fast_mlp2<...>" or "generic<...>" */

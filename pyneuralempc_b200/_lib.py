@@ -17,7 +17,7 @@ KERNELS = {"auto": 0, "generic": 1, "fast": 2}
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",
            "nempc_set_objective", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
            "nempc_eval", "nempc_eval_host", "nempc_eval_blocks", "nempc_model_eval", "nempc_launch_count",
-           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval")
+           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve")
 
 
 class NempcDesc(ctypes.Structure):
@@ -26,6 +26,12 @@ class NempcDesc(ctypes.Structure):
                 ("activation", ctypes.c_int32), ("integrator", ctypes.c_int32), ("dt", ctypes.c_double),
                 ("compute_dtype", ctypes.c_int32), ("io_dtype", ctypes.c_int32), ("device", ctypes.c_int32),
                 ("kernel", ctypes.c_int32)]
+
+
+class SolverOpts(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int32), ("max_backtrack", ctypes.c_int32)] + \
+               [(k, ctypes.c_double) for k in ("tol", "mu_init", "mu_min", "kappa_eps", "kappa_mu", "theta_mu", "tau_min",
+                                               "bound_push", "eta", "reg_init", "reg_max")]
 
 
 class NempcError(RuntimeError):
@@ -68,6 +74,8 @@ def load():
     lib.nempc_flops_per_step.restype = dbl
     lib.nempc_measure_fma_peak.argtypes = [i32, i32, i32, ctypes.POINTER(dbl)]
     lib.nempc_objective_eval.argtypes = [i32, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.nempc_solver_defaults.argtypes = [ctypes.POINTER(SolverOpts)]
+    lib.nempc_solve.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.POINTER(SolverOpts), ctypes.POINTER(i32), vp]
     for name in EXPORTS:
         getattr(lib, name)                  # AttributeError here = the .so does not match include/nempc.h
     _lib = lib

@@ -9,6 +9,7 @@ import numpy as np
 
 from .constraints import DomainConstraint
 from .optimizer import Optimizer
+from .optimizer.ipm import CudaIpm
 from .optimizer.slsqp import Slsqp
 
 
@@ -68,3 +69,49 @@ class NMPC:
             sol = self.optimizer.prev_result
             return sol[:nx].reshape(self.integrator.H, -1), sol[nx:].reshape(self.integrator.H, -1)
         return None, None
+
+
+class BatchedNMPC:
+    """``NMPC`` for B independent problems (scenarios or closed-loop replicas) solved together on the device.
+
+    The reference has no batch axis (one ``NMPC`` = one problem); this is its batched sibling:
+    ``next(X0 (B, x_dim)) -> (x_pred (B, H, x_dim), u (B, H, u_dim), ok (B,))`` with ``ok[b] = False`` where the
+    single-problem controller would have returned ``(None, None)`` (controller.py:109-113)."""
+
+    def __init__(self, integrator, objective_func, constraint_list, H, DT, optimizer=None, warm_start=True):
+        from .objective import CudaSeparableObjective
+        if not isinstance(objective_func, CudaSeparableObjective):
+            raise ValueError("BatchedNMPC needs a CudaSeparableObjective")
+        domain = [c for c in constraint_list if isinstance(c, DomainConstraint)]
+        if not domain:
+            raise ValueError("constraint_list must contain a DomainConstraint")
+        if len(domain) != len(constraint_list):
+            raise NotImplementedError("extra constraints are not supported by the on-device solver")
+        self.integrator, self.objective_func, self.domain_constraint = integrator, objective_func, domain[0]
+        self.H, self.DT = H, DT
+        self.optimizer = optimizer if optimizer is not None else CudaIpm()
+        self.warm_start = warm_start
+        self.ev = integrator.evaluator
+        self.ev.set_objective(objective_func.lin, objective_func.quad, objective_func.ref)
+        self._prev = None
+        self.last_info = None
+
+    def _shifted(self, Z):
+        """previous solution shifted by one step (the batch version of optimizer/ipopt.py:141-147)."""
+        import torch
+        H, xd, ud = self.H, self.ev.x_dim, self.ev.u_dim
+        nx = xd * H
+        return torch.cat([Z[:, xd:nx], Z[:, nx - xd:nx], Z[:, nx + ud:], Z[:, nx + ud * (H - 1):nx + ud * H]], dim=1)
+
+    def next(self, X0):
+        X0 = np.asarray(X0, np.float64) if not hasattr(X0, "device") else X0
+        assert X0.ndim == 2 and X0.shape[1] == self.ev.x_dim, "X0 must be (B, x_dim)"
+        z0 = None
+        if self.warm_start and self._prev is not None and self._prev.shape[0] == X0.shape[0]:
+            z0 = self._shifted(self._prev)
+        out = self.optimizer.solve_batch(self.ev, X0, self.domain_constraint, Z_init=z0)
+        ok = out["status"] == 0
+        self._prev = out["z"] if bool(ok.all()) else None
+        self.last_info = out
+        B, H, xd = X0.shape[0], self.H, self.ev.x_dim
+        return out["z"][:, :H * xd].reshape(B, H, xd), out["z"][:, H * xd:].reshape(B, H, -1), ok

@@ -14,6 +14,7 @@
 #include "nempc_fast.cuh"
 #include "nempc_generic.cuh"
 #include "nempc_layout.h"
+#include "nempc_solver.cuh"
 
 // ======================================================================================================
 // kernels
@@ -120,6 +121,36 @@ __global__ void nempc_fma2_peak_kernel(float* out, int iters, float seed) {
     if (s == 123456789.f) out[0] = s;
 }
 
+// ---- interior-point solver kernels: one thread per problem ------------------------------------------------------------
+__global__ void nempc_ipm_init_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int has_init) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ipm_init_problem(L, w, b, o, has_init != 0);
+}
+template <int XM, int UM>
+__global__ void nempc_ipm_kkt_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ipm_kkt_problem<XM, UM>(L, w, b, o);
+    if (w.status[b] == NEMPC_ST_RUNNING) { atomicAdd(&counts[0], 1); if (!w.accepted[b]) atomicAdd(&counts[1], 1); }
+}
+__global__ void nempc_ipm_linesearch_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ipm_linesearch_problem(L, w, b, o);
+    if (w.status[b] == NEMPC_ST_RUNNING && !w.accepted[b]) atomicAdd(&counts[1], 1);
+}
+__global__ void nempc_ipm_update_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ipm_update_problem(L, w, b, o);
+}
+__global__ void nempc_ipm_finish_kernel(const SolverWs w, long long B, int* status, int* iters, double* err) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    status[b] = w.status[b] == NEMPC_ST_RUNNING ? NEMPC_ST_MAXITER : w.status[b];
+    if (iters) iters[b] = w.iters[b];
+    if (err) err[b] = w.err[b];
+}
+
 // ======================================================================================================
 // handle
 // ======================================================================================================
@@ -150,6 +181,8 @@ struct nempc_handle {
     // staging for eval_host
     void* st_buf[10] = {}; size_t st_cap[10] = {};
     long long launches = 0;
+    // solver workspace
+    void* sv_buf = nullptr; size_t sv_cap = 0; double *sv_lb = nullptr, *sv_ub = nullptr; int* sv_counts = nullptr; int* sv_counts_host = nullptr;
     std::string err, kname;
 };
 
@@ -258,6 +291,7 @@ extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, 
 static void free_device(nempc_handle* h) {
     for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
     cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws);
+    cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 3; ++i) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
@@ -645,6 +679,99 @@ extern "C" int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, cons
     else nempc_objective_kernel<float><<<grid, threads, 0, s>>>((const float*)z, lin, quad, ref, (float*)obj, (float*)grad, (int)n, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "objective kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+// ---- batched interior-point solver ---------------------------------------------------------------------------------------
+extern "C" int nempc_solver_defaults(nempc_solver_opts* o) {
+    if (!o) return NEMPC_EINVAL;
+    const SolverOpts d = solver_defaults();
+    o->max_iter = d.max_iter; o->max_backtrack = d.max_backtrack; o->tol = d.tol; o->mu_init = d.mu_init; o->mu_min = d.mu_min;
+    o->kappa_eps = d.kappa_eps; o->kappa_mu = d.kappa_mu; o->theta_mu = d.theta_mu; o->tau_min = d.tau_min;
+    o->bound_push = d.bound_push; o->eta = d.eta; o->reg_init = d.reg_init; o->reg_max = d.reg_max;
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const double* lb, const double* ub, void* z, int32_t use_init,
+                           void* lambda, int32_t* status, int32_t* iterations, double* kkt_error, const nempc_solver_opts* opts,
+                           int32_t* outer_iterations, void* stream) {
+    int rc = ready(h);
+    if (rc) return rc;
+    if (outer_iterations) *outer_iterations = 0;
+    if (B == 0) return NEMPC_OK;
+    if (B < 0 || !x0 || !lb || !ub || !z || !status) { SET_ERR(h, "nempc_solve: bad argument"); return NEMPC_EINVAL; }
+    if (h->desc.io_dtype != NEMPC_F64) { SET_ERR(h, "nempc_solve needs io_dtype = F64"); return NEMPC_EUNSUPPORTED; }
+    if (!h->has_objective) { SET_ERR(h, "nempc_solve: nempc_set_objective was never called"); return NEMPC_ESTATE; }
+    CU(h, cudaSetDevice(h->desc.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const NlpLayout& L = h->lay;
+    SolverOpts o = solver_defaults();
+    if (opts) {
+        o.max_iter = opts->max_iter; o.max_backtrack = opts->max_backtrack; o.tol = opts->tol; o.mu_init = opts->mu_init; o.mu_min = opts->mu_min;
+        o.kappa_eps = opts->kappa_eps; o.kappa_mu = opts->kappa_mu; o.theta_mu = opts->theta_mu; o.tau_min = opts->tau_min;
+        o.bound_push = opts->bound_push; o.eta = opts->eta; o.reg_init = opts->reg_init; o.reg_max = opts->reg_max;
+    }
+    // ---- workspace -------------------------------------------------------------------------------------------------------
+    const size_t n = L.n, m = L.m, nj = (size_t)L.nnz_jac, nh = (size_t)L.nnz_hes, Hux = (size_t)L.H * L.u * L.x, Hu = (size_t)L.H * L.u;
+    const size_t per = 9 * n + 4 * m + nj + nh + Hux + Hu + 2 /*obj, objt*/ + 7 /*scalars*/ + 2 /*3 ints, padded*/;
+    const size_t need = per * (size_t)B * sizeof(double);
+    if (need > h->sv_cap) {
+        CU(h, cudaStreamSynchronize(s));
+        cudaFree(h->sv_buf); h->sv_buf = nullptr; h->sv_cap = 0;
+        CU(h, cudaMalloc(&h->sv_buf, need));
+        h->sv_cap = need;
+    }
+    if (!h->sv_lb) {
+        CU(h, cudaMalloc(&h->sv_lb, n * sizeof(double))); CU(h, cudaMalloc(&h->sv_ub, n * sizeof(double)));
+        CU(h, cudaMalloc(&h->sv_counts, 2 * sizeof(int))); CU(h, cudaMallocHost(&h->sv_counts_host, 2 * sizeof(int)));
+    }
+    CU(h, cudaMemcpyAsync(h->sv_lb, lb, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->sv_ub, ub, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    double* p = (double*)h->sv_buf;
+    auto take = [&](size_t cnt) { double* r = p; p += cnt * (size_t)B; return r; };
+    SolverWs w{};
+    w.x0 = (const double*)x0; w.lb = h->sv_lb; w.ub = h->sv_ub;
+    w.z = (double*)z; w.lam = take(m); w.zL = take(n); w.zU = take(n);
+    w.dz = take(n); w.lamn = take(m); w.dzL = take(n); w.dzU = take(n);
+    w.grad = take(n); w.resid = take(m); w.jac = take(nj); w.hes = take(nh); w.obj = take(1);
+    w.zt = take(n); w.residt = take(m); w.objt = take(1);
+    w.K = take(Hux); w.kf = take(Hu);
+    w.mu = take(1); w.nu = take(1); w.alpha = take(1); w.alphaD = take(1); w.phi0 = take(1); w.dphi = take(1); w.err = take(1);
+    int* ip = (int*)take(2);
+    w.status = ip; w.iters = ip + B; w.accepted = ip + 2 * B;
+    const int threads = 128;
+    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    const bool small = L.x <= 4 && L.u <= 2;
+    nempc_ipm_init_kernel<<<grid, threads, 0, s>>>(L, w, o, B, use_init);
+    CU(h, cudaGetLastError()); h->launches++;
+    int it = 0;
+    for (; it < o.max_iter; ++it) {
+        rc = nempc_eval(h, B, w.z, x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)s);
+        if (rc) return rc;
+        CU(h, cudaMemsetAsync(h->sv_counts, 0, 2 * sizeof(int), s));
+        if (small) nempc_ipm_kkt_kernel<4, 2><<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+        else nempc_ipm_kkt_kernel<NEMPC_SOLVER_XM, NEMPC_SOLVER_UM><<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+        CU(h, cudaGetLastError()); h->launches++;
+        CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        if (h->sv_counts_host[0] == 0) break;                      // every problem converged or failed
+        for (int t = 0; t < o.max_backtrack && h->sv_counts_host[1] > 0; ++t) {
+            rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
+            if (rc) return rc;
+            CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
+            nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+            CU(h, cudaGetLastError()); h->launches++;
+            CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CU(h, cudaStreamSynchronize(s));
+        }
+        nempc_ipm_update_kernel<<<grid, threads, 0, s>>>(L, w, o, B);
+        CU(h, cudaGetLastError()); h->launches++;
+    }
+    nempc_ipm_finish_kernel<<<grid, threads, 0, s>>>(w, B, status, iterations, kkt_error);
+    CU(h, cudaGetLastError()); h->launches++;
+    if (lambda) CU(h, cudaMemcpyAsync(lambda, w.lam, (size_t)B * m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (outer_iterations) *outer_iterations = it;
     return NEMPC_OK;
 }
 

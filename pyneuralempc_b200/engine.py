@@ -251,6 +251,48 @@ class NlpEvaluator:
             buf["sig"][...] = np.asarray(obj_factor, npdt)
         return self.eval_pinned(B, 1.0 if per_problem else float(obj_factor), want, per_problem)
 
+    # ---- batched on-device solver ------------------------------------------------------------------
+    def solve(self, x0, lb, ub, z_init=None, stream=None, **options):
+        """Solve ``B`` independent NMPC problems ``min f(z) s.t. c(z)=0, lb<=z<=ub`` on the device (``nempc_solve``:
+        primal-dual interior point, Riccati KKT solves on the block-banded values of ``eval``).
+
+        x0: (B, x_dim) initial states (numpy or CUDA tensor); lb / ub: length-n bound vectors in ``DomainConstraint``
+        order (``get_lower_bounds(H)``), +-inf allowed; z_init: optional (B, n) warm start.  options: fields of
+        ``nempc_solver_opts`` (max_iter, tol, mu_init, ...).  Returns a dict of CUDA tensors ``z`` (B,n), ``lam`` (B,m),
+        ``status`` (0 converged / 1 iteration limit / 2 failed), ``iterations``, ``kkt_error`` and ``outer_iterations``."""
+        torch = self._torch
+        if self.io_dtype != "float64":
+            raise ValueError("solve() needs io_dtype='float64'")
+        if not self.has_objective:
+            raise ValueError("solve() needs set_objective(...)")
+        x0 = torch.as_tensor(np.asarray(x0, np.float64)) if not isinstance(x0, torch.Tensor) else x0
+        x0 = x0.to(device=self.tdevice, dtype=torch.float64).reshape(-1, self.x_dim).contiguous()
+        B = int(x0.shape[0])
+        lb = np.ascontiguousarray(np.asarray(lb, np.float64).ravel())
+        ub = np.ascontiguousarray(np.asarray(ub, np.float64).ravel())
+        if lb.shape != (self.n,) or ub.shape != (self.n,):
+            raise ValueError(f"lb / ub must have length n = {self.n}")
+        if z_init is None:
+            z = torch.empty((B, self.n), dtype=torch.float64, device=self.tdevice)
+        else:
+            z = self._as_dev(z_init, (B, self.n)).clone()
+        lam = torch.empty((B, self.m), dtype=torch.float64, device=self.tdevice)
+        status = torch.empty(B, dtype=torch.int32, device=self.tdevice)
+        iters = torch.empty(B, dtype=torch.int32, device=self.tdevice)
+        kkt = torch.empty(B, dtype=torch.float64, device=self.tdevice)
+        opts = _lib.SolverOpts()
+        self._check(self.lib.nempc_solver_defaults(ctypes.byref(opts)), "nempc_solver_defaults")
+        for k, v in options.items():
+            if not hasattr(opts, k):
+                raise TypeError(f"unknown solver option {k!r}")
+            setattr(opts, k, v)
+        outer = ctypes.c_int32()
+        s = torch.cuda.current_stream(self.tdevice).cuda_stream if stream is None else stream
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self._check(self.lib.nempc_solve(self._h, B, _vp(x0), p(lb), p(ub), _vp(z), int(z_init is not None), _vp(lam), _vp(status),
+                                         _vp(iters), _vp(kkt), ctypes.byref(opts), ctypes.byref(outer), ctypes.c_void_p(s)), "nempc_solve")
+        return dict(z=z, lam=lam, status=status, iterations=iters, kkt_error=kkt, outer_iterations=outer.value)
+
     def host_io_bytes(self, B, want=("resid", "jac", "hes", "obj", "grad"), with_lambda=True):
         s = 8 if self.io_dtype == "float64" else 4
         h2d = B * (self.n + self.x_dim + (self.m if with_lambda else 0)) * s

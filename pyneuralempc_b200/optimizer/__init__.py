@@ -2,3 +2,4 @@
 from .base import Optimizer, ProblemFactory, ProblemInterface, ProblemInterfaceHessianFree  # noqa: F401
 from .ipopt import CudaIpoptProblem, Ipopt, IpoptProblem, IpoptProblemFactory  # noqa: F401
 from .slsqp import Slsqp, SlsqpProblem, TrustConstr  # noqa: F401
+from .ipm import CudaIpm  # noqa: F401

@@ -11,6 +11,7 @@
 #include "../../pyneuralempc_b200/csrc/nempc_fast.cuh"
 #include "../../pyneuralempc_b200/csrc/nempc_generic.cuh"
 #include "../../pyneuralempc_b200/csrc/nempc_layout.h"
+#include "../../pyneuralempc_b200/csrc/nempc_solver.cuh"
 
 namespace {
 
@@ -118,4 +119,73 @@ extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths,
         run_generic_d<float>(hn, make_stage_table<float>(rk4, dt), L, ar);
     }
     return 0;
+}
+
+// Host emulation of nempc_solve: same per-problem bodies (nempc_solver.cuh), evaluations by the generic f64 kernel body.
+// lb/ub: n doubles; z (B,n) in/out; lam (B,m) out; status/iters (B) out; kkt (B) out.  Returns outer iterations.
+extern "C" int hostsim_solve(int x, int u, int H, int n_layers, const int* widths, int act, int integ, double dt,
+                             const double* wflat, const double* lin, const double* quad, const double* ref, long long B,
+                             const double* x0, const double* lb, const double* ub, double* z, int use_init, double* lam_out,
+                             int* status, int* iters, double* kkt, int max_iter, double tol) {
+    const int d = x + u;
+    const size_t n = (size_t)H * d, m = (size_t)H * x;
+    std::vector<uint8_t> mask(n);
+    for (size_t i = 0; i < n; ++i) mask[i] = quad[i] != 0.0;
+    NlpLayout L; nlp_layout_init(L, H, x, u, mask.data());
+    HostNet<double> hn; build_net(hn, d, n_layers, widths, act, wflat);
+    StageTable<double> st = make_stage_table<double>(integ == 2, dt);
+    SolverOpts o = solver_defaults();
+    o.max_iter = max_iter; o.tol = tol;
+    const size_t nj = (size_t)L.nnz_jac, nh = (size_t)L.nnz_hes;
+    auto vec = [&](size_t per) { return std::vector<double>(per * (size_t)B, 0.0); };
+    std::vector<double> lam = vec(m), zL = vec(n), zU = vec(n), dz = vec(n), lamn = vec(m), dzL = vec(n), dzU = vec(n), grad = vec(n),
+                        resid = vec(m), jac = vec(nj), hes = vec(nh), obj = vec(1), zt = vec(n), residt = vec(m), objt = vec(1),
+                        K = vec((size_t)H * u * x), kf = vec((size_t)H * u), mu = vec(1), nu = vec(1), alpha = vec(1), alphaD = vec(1),
+                        phi0 = vec(1), dphi = vec(1), err = vec(1);
+    std::vector<int> stv(B), itv(B), acc(B);
+    SolverWs w{};
+    w.x0 = x0; w.lb = lb; w.ub = ub; w.z = z; w.lam = lam.data(); w.zL = zL.data(); w.zU = zU.data(); w.dz = dz.data(); w.lamn = lamn.data();
+    w.dzL = dzL.data(); w.dzU = dzU.data(); w.grad = grad.data(); w.resid = resid.data(); w.jac = jac.data(); w.hes = hes.data(); w.obj = obj.data();
+    w.zt = zt.data(); w.residt = residt.data(); w.objt = objt.data(); w.K = K.data(); w.kf = kf.data(); w.mu = mu.data(); w.nu = nu.data();
+    w.alpha = alpha.data(); w.alphaD = alphaD.data(); w.phi0 = phi0.data(); w.dphi = dphi.data(); w.err = err.data();
+    w.status = stv.data(); w.iters = itv.data(); w.accepted = acc.data();
+    auto evaluate = [&](const double* zz, const double* lm, double* r, double* jv, double* hv, double* ob, double* gr) {
+        EvalArgs<double> ar{};
+        ar.z = zz; ar.x0 = x0; ar.lam = lm; ar.sigma = nullptr; ar.sigma_scalar = 1.0; ar.quad = quad;
+        ar.resid = r; ar.jac = jv; ar.hes = hv; ar.nsteps = B * (long long)H;
+        ar.flags = (jv || hv ? NEMPC_WANT_JAC : 0) | (hv ? NEMPC_WANT_HES : 0) | (integ == 1 ? NEMPC_UNITY : 0);
+        run_generic_d<double>(hn, st, L, ar);
+        for (long long b = 0; b < B; ++b) {
+            double a = 0.0;
+            for (size_t i = 0; i < n; ++i) {
+                const double zi = zz[b * n + i], dd = zi - ref[i];
+                a += lin[i] * zi + quad[i] * dd * dd;
+                if (gr) gr[b * n + i] = lin[i] + 2.0 * quad[i] * dd;
+            }
+            ob[b] = a;
+        }
+    };
+    for (long long b = 0; b < B; ++b) ipm_init_problem(L, w, b, o, use_init != 0);
+    int it = 0;
+    for (; it < o.max_iter; ++it) {
+        evaluate(z, lam.data(), resid.data(), jac.data(), hes.data(), obj.data(), grad.data());
+        int running = 0, pending = 0;
+        for (long long b = 0; b < B; ++b) {
+            if (x <= 4 && u <= 2) ipm_kkt_problem<4, 2>(L, w, b, o); else ipm_kkt_problem<NEMPC_SOLVER_XM, NEMPC_SOLVER_UM>(L, w, b, o);
+            if (stv[b] == NEMPC_ST_RUNNING) { ++running; if (!acc[b]) ++pending; }
+        }
+        if (running == 0) break;
+        for (int t = 0; t < o.max_backtrack && pending > 0; ++t) {
+            evaluate(zt.data(), nullptr, residt.data(), nullptr, nullptr, objt.data(), nullptr);
+            pending = 0;
+            for (long long b = 0; b < B; ++b) { ipm_linesearch_problem(L, w, b, o); if (stv[b] == NEMPC_ST_RUNNING && !acc[b]) ++pending; }
+        }
+        for (long long b = 0; b < B; ++b) ipm_update_problem(L, w, b, o);
+    }
+    for (long long b = 0; b < B; ++b) {
+        status[b] = stv[b] == NEMPC_ST_RUNNING ? NEMPC_ST_MAXITER : stv[b];
+        iters[b] = itv[b]; kkt[b] = err[b];
+    }
+    if (lam_out) memcpy(lam_out, lam.data(), sizeof(double) * m * (size_t)B);
+    return it;
 }

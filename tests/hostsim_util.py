@@ -11,7 +11,7 @@ SRC = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
 OUT_DIR = os.path.join(ROOT, "tests", "_hostsim")
 LIB = os.path.join(OUT_DIR, "libnempc_hostsim.so")
 _DEPS = [SRC] + [os.path.join(ROOT, "pyneuralempc_b200", "csrc", f)
-                 for f in ("nempc_generic.cuh", "nempc_fast.cuh", "nempc_layout.h")]
+                 for f in ("nempc_generic.cuh", "nempc_fast.cuh", "nempc_layout.h", "nempc_solver.cuh")]
 INTEG = {"discrete": 0, "unity": 1, "rk4": 2}
 ACT = {"tanh": 0, "sigmoid": 1, "softplus": 2}
 
@@ -82,3 +82,23 @@ def run(mlp, kind, H, DT, Z, X0, lam=None, sigma=1.0, quad=None, compute_f64=Tru
     if what == "eval":
         return {"resid": o0, "jac_vals": o1, "hes_vals": o2}
     return o0, o1, o2
+
+
+def solve(mlp, kind, H, DT, obj, X0, lb, ub, Z_init=None, max_iter=60, tol=1e-6):
+    """host emulation of nempc_solve (float64 arithmetic).  Returns Z, lam, dict(status, iterations, kkt_error, outer)."""
+    xd, ud = mlp.x_dim, mlp.u_dim
+    n, m = H * (xd + ud), H * xd
+    widths = np.asarray([W.shape[1] for W, _ in mlp.weights], np.int32)
+    wflat = np.concatenate([np.concatenate([np.asarray(W, np.float64).ravel(), np.asarray(b, np.float64).ravel()]) for W, b in mlp.weights])
+    X0 = np.ascontiguousarray(np.atleast_2d(X0), np.float64)
+    B = X0.shape[0]
+    Z = np.zeros((B, n)) if Z_init is None else np.ascontiguousarray(Z_init, np.float64).copy()
+    lam = np.zeros((B, m)); status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32); kkt = np.zeros(B)
+    lin, quad, ref = (np.ascontiguousarray(a, np.float64) for a in (obj.lin, obj.quad, obj.ref))
+    lb, ub = np.ascontiguousarray(lb, np.float64), np.ascontiguousarray(ub, np.float64)
+    fn = lib().hostsim_solve
+    fn.restype = ctypes.c_int
+    outer = fn(xd, ud, int(H), len(widths), _p(widths), ACT[mlp.activation], INTEG[kind], ctypes.c_double(0.0 if DT is None else DT),
+               _p(wflat), _p(lin), _p(quad), _p(ref), ctypes.c_longlong(B), _p(X0), _p(lb), _p(ub), _p(Z), int(Z_init is not None),
+               _p(lam), _p(status), _p(iters), _p(kkt), int(max_iter), ctypes.c_double(tol))
+    return Z, lam, dict(status=status, iterations=iters, kkt_error=kkt, outer=outer)

@@ -1,0 +1,112 @@
+"""nempc_solve on the GPU: same iterates as the host emulation / numpy statement (float64 network arithmetic), the SLSQP
+optimum of the oracle problem, failure convention, warm start, the Optimizer / NMPC / BatchedNMPC drop-ins, float32 network."""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.blocks_np import BlockEvaluator  # noqa: E402
+from oracle.mlp_np import MLP  # noqa: E402
+from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
+from oracle.solver_np import BatchedIPM  # noqa: E402
+
+CASES = [("unity", "lv", 2, 1, 10, None, 1e9), ("rk4", [3, 30, 30, 2], 2, 1, 20, 0.1, 5.0), ("rk4", [5, 32, 32, 4], 4, 1, 15, 0.05, 5.0),
+         ("discrete", [16, 24, 24, 12], 12, 4, 6, None, 5.0)]
+
+
+def _setup(kind, dims, x, u, H, DT, xb, lv_weights, seed=1, B=5):
+    rng = np.random.default_rng(seed)
+    if dims == "lv":
+        mlp = MLP(lv_weights, 2, 1)
+        obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.5, -0.7]))
+        lb = np.array([-np.inf, -np.inf] * H + [-1.0] * H); ub = np.array([1.0, np.inf] * H + [0.2] * H)
+        X0 = np.vstack([[0.66, -0.9], rng.uniform(-0.8, 0.8, (B - 1, 2))])
+    else:
+        mlp = MLP.glorot(dims, x, u, seed=3)
+        W, b = mlp.weights[-1]; mlp.weights[-1] = (W * 0.5, b * 0.5)
+        obj = SeparableQuadraticObjective.tracking(H, x, u, np.ones(x), 0.05 * np.ones(u), x_ref=rng.uniform(-0.3, 0.3, (H, x)))
+        lb = np.array([-xb] * (H * x) + [-0.3] * (H * u)); ub = np.array([xb] * (H * x) + [0.3] * (H * u))
+        X0 = rng.uniform(-0.8, 0.8, (B, x))
+    return mlp, obj, lb, ub, X0
+
+
+def _ev(mlp, kind, H, DT, obj, compute="float64"):
+    from pyneuralempc_b200 import NlpEvaluator
+    ev = NlpEvaluator(mlp.weights, mlp.x_dim, mlp.u_dim, H, kind, DT=DT, compute_dtype=compute, io_dtype="float64")
+    ev.set_objective(obj.lin, obj.quad, obj.ref)
+    return ev
+
+
+@pytest.mark.parametrize("kind,dims,x,u,H,DT,xb", CASES)
+def test_device_solver_matches_numpy_statement(kind, dims, x, u, H, DT, xb, lv_weights):
+    mlp, obj, lb, ub, X0 = _setup(kind, dims, x, u, H, DT, xb, lv_weights)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Zr, lr, info = BatchedIPM(BlockEvaluator(mlp, kind, H, DT=DT, objective=obj), lb, ub).solve(X0)
+    out = _ev(mlp, kind, H, DT, obj).solve(X0, lb, ub)
+    assert (out["status"].cpu().numpy() == 0).all() and info["converged"].all()
+    np.testing.assert_array_equal(out["iterations"].cpu().numpy(), info["iterations"])
+    np.testing.assert_allclose(out["z"].cpu().numpy(), Zr, atol=1e-7)
+    np.testing.assert_allclose(out["lam"].cpu().numpy(), lr, atol=1e-5)
+    assert (out["kkt_error"].cpu().numpy() <= 1e-6).all()
+
+
+def test_float32_network_and_large_batch(lv_weights):
+    """float32 network arithmetic (the reference's Keras precision) with the reference's acceptable tolerance 1e-4
+    (optimizer/ipopt.py:185); 2048 problems at once; every solution is feasible and within 1e-4 of the float64 optimum."""
+    mlp, obj, lb, ub, X0 = _setup("unity", "lv", 2, 1, 10, None, 0, lv_weights, B=2048)
+    o32 = _ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=1e-4)
+    o64 = _ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-8)
+    assert (o32["status"].cpu().numpy() == 0).all() and (o64["status"].cpu().numpy() == 0).all()
+    assert np.abs(o32["z"].cpu().numpy() - o64["z"].cpu().numpy()).max() < 1e-3
+    ref = BlockEvaluator(mlp, "unity", 10, objective=obj).evaluate(o32["z"].cpu().numpy()[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
+    assert np.abs(ref["resid"]).max() < 1e-4
+    assert int(o32["iterations"].max()) <= 30
+
+
+def test_infeasible_problems_fail_cleanly_on_device():
+    rng = np.random.default_rng(1)
+    H, x, u = 25, 2, 1
+    mlp = MLP.glorot([3, 30, 30, 2], x, u, seed=3)
+    W, b = mlp.weights[-1]; mlp.weights[-1] = (W * 0.5, b * 0.5)
+    obj = SeparableQuadraticObjective.tracking(H, x, u, np.ones(x), 0.05 * np.ones(u), x_ref=rng.uniform(-0.3, 0.3, (H, x)))
+    lb = np.array([-1.0] * (H * x) + [-0.3] * (H * u)); ub = np.array([1.0] * (H * x) + [0.3] * (H * u))
+    X0 = rng.uniform(-0.8, 0.8, (6, x))
+    out = _ev(mlp, "discrete", H, None, obj).solve(X0, lb, ub, max_iter=80)
+    st = out["status"].cpu().numpy()
+    assert np.isfinite(out["z"].cpu().numpy()).all() and (st != 0).any() and (st == 0).any()
+
+
+def test_optimizer_and_controllers(lv_weights):
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.constraints import DomainConstraint
+    from pyneuralempc_b200.controller import NMPC, BatchedNMPC
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaQuadraticObjective
+    from pyneuralempc_b200.optimizer import CudaIpm, Slsqp
+    H = 10
+    model = CudaMLPModel(lv_weights, 2, 1, dtype="float64")
+    integ = I.UnityIntegrator(model, H)
+    obj = CudaQuadraticObjective(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.5, -0.7]))
+    dom = DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])
+    x0 = np.array([0.66, -0.9])
+    xs, us = NMPC(integ, obj, [dom], H, 0.1, optimizer=CudaIpm()).next(x0)
+    xs2, us2 = NMPC(integ, obj, [dom], H, 0.1, optimizer=Slsqp(verbose=0, tolerance=1e-12)).next(x0)
+    assert xs.shape == (H, 2) and us.shape == (H, 1)
+    assert np.abs(xs - xs2).max() < 1e-4 and np.abs(us - us2).max() < 1e-4
+    # batched closed loop: 64 replicas, 3 MPC steps with the shifted warm start, plant = the network itself (unity model)
+    rng = np.random.default_rng(0)
+    mpc = BatchedNMPC(integ, obj, [dom], H, 0.1)
+    X = np.vstack([x0, rng.uniform(-0.8, 0.8, (63, 2))])
+    its = []
+    for _ in range(3):
+        xp, up, ok = mpc.next(X)
+        assert bool(ok.all()) and xp.shape == (64, H, 2) and up.shape == (64, H, 1)
+        its.append(int(mpc.last_info["iterations"].sum()))
+        X = xp[:, 0].cpu().numpy()                       # the model predicts the next state exactly
+    assert its[1] < its[0]                               # warm start pays off
+    np.testing.assert_allclose(xp[0, 0].cpu().numpy(), X[0])
+    with pytest.raises(ValueError):
+        model.evaluator().solve(X, np.zeros(3), np.zeros(3))   # no objective / wrong bounds
