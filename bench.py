@@ -87,6 +87,48 @@ def _cpu_problem_eval(args):
     return float(pb.hessian(z, lam, 1.0).sum())
 
 
+def solver_bounds(wl):
+    """control bounds of the shipped example (u in [-1, 0.2], examples/lotka_volterra/run.py:72-74 after normalisation),
+    states unbounded."""
+    H, xd, ud = wl["H"], wl["x"], wl["u"]
+    return np.array([-np.inf] * (H * xd) + [-1.0] * (H * ud)), np.array([np.inf] * (H * xd) + [0.2] * (H * ud))
+
+
+def _cpu_problem_solve(args):
+    """one MPC solve the reference way: SciPy SLSQP (the reference's own Slsqp optimizer, optimizer/slsqp.py:172-173,
+    default ftol 0.5e-6, maxiter 200) on the dense reference-literal callbacks."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import warnings
+    from scipy.optimize import Bounds, minimize
+    wl, x0 = args
+    from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem
+    from oracle.mlp_np import MLP, DenseModelView
+    from oracle.objectives_np import SeparableQuadraticObjective
+    mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+    obj = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
+    pb = DenseIpoptProblem(x0, obj, DenseIntegrator(DenseModelView(mlp), wl["H"], wl["integ"], DT=wl["DT"]))
+    lb, ub = solver_bounds(wl)
+    x_init = np.concatenate([np.tile(x0, wl["H"]), np.zeros(wl["H"] * wl["u"])])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = minimize(pb.objective, x_init, method="SLSQP", jac=pb.gradient, bounds=Bounds(lb, ub),
+                     constraints=[{"type": "eq", "fun": pb.constraints, "jac": pb.jacobian}], options={"maxiter": 200, "ftol": 0.5e-6})
+    return bool(r.success), int(r.nit), float(r.fun)
+
+
+def cpu_solver_run(wl_name, procs=None):
+    import multiprocessing as mp
+    wl = {k: v for k, v in WORKLOADS[wl_name].items() if k != "desc"}
+    procs = procs or os.cpu_count() or 1
+    _, _, _, X0, _ = make_problem(wl, procs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_problem_solve, [(wl, X0[i]) for i in range(procs)], chunksize=1)
+        dt = time.perf_counter() - t0
+    return dict(value=procs / dt, unit="solves/s", cores=procs, kind="port", converged=sum(r[0] for r in res), iterations_mean=float(np.mean([r[1] for r in res])),
+                sample=f"{procs} problems (one per core), SciPy SLSQP = the reference's Slsqp optimizer on the dense reference-literal callbacks")
+
+
 def cpu_reference_run(wl_name, sample, steps, warmup, procs=None, budget_s=None):
     """times `steps` evaluations of a bounded sample of problems on `procs` worker processes.  With `budget_s` the
     sample size is chosen so that the whole run lasts about that long (the per-problem cost is measured first)."""
@@ -262,6 +304,29 @@ def gpu_run(args):
     h2d, d2h = ev.host_io_bytes(B)
     clocks = sampler.stop() if rank == 0 else None     # sampled across the timed loop, the kernel-only loop and the e2e loop
 
+    # ---- MPC solves/s: the batched on-device interior-point solver (nempc_solve) on the same B problems --------------------------
+    solves = None
+    if args.io_dtype == "float64" and not args.no_solver:
+        lb, ub = solver_bounds(wl)
+        x0d = torch.as_tensor(X0, dtype=torch.float64, device=dev)
+        sopt = dict(tol=1e-4, max_iter=40)          # the reference's IPOPT acceptable_tol (optimizer/ipopt.py:185)
+        ev.solve(x0d, lb, ub, **sopt)
+        barrier()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            so = ev.solve(x0d, lb, ub, **sopt)
+        torch.cuda.synchronize()
+        ts = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        conv = torch.tensor([float((so["status"] == 0).sum().item())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            dist.all_reduce(conv, op=dist.ReduceOp.SUM)
+        solves = {"metric": "mpc_solves_per_s", "value": world * B / float(ts.item()), "unit": "solves/s", "batch_per_gpu": B,
+                  "ms_per_batch": float(ts.item()) * 1e3, "converged_frac": float(conv.item()) / (world * B),
+                  "ipm_iterations_mean": float(so["iterations"].double().mean().item()), "outer_iterations": so["outer_iterations"],
+                  "tol": sopt["tol"], "solver": "nempc_solve: primal-dual interior point, Riccati KKT sweep on the block-banded values, x0 device-resident",
+                  "bounds": "u in [-1, 0.2] (run.py:72-74), states free"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,10 +360,12 @@ def gpu_run(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--workload", args.workload,
-                            "--cpu-sample", str(args.cpu_sample)], capture_output=True, text=True)
+                            "--cpu-sample", str(args.cpu_sample)] + (["--no-solver"] if args.no_solver else []), capture_output=True, text=True)
         try:
             c = json.loads(r.stdout.strip().splitlines()[-1])
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+            if solves is not None and "solver" in c:
+                solves["cpu_baseline"] = c["solver"]
         except (ValueError, IndexError):
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -311,7 +378,7 @@ def gpu_run(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te.item()) / args.steps * 1e3, "api": "NlpEvaluator.eval_pinned -> nempc_eval_host (pinned host buffers, chunk-pipelined H2D|kernels|D2H)",
                     "numpy_callback_ms_per_step": cb_ms},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mpc_solves": solves}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -347,10 +414,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128, help="problems per CPU-baseline step")
     ap.add_argument("--cpu-budget", type=float, default=90.0, help="--impl reference: target wall seconds of the timed loop (sets the sample size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver", action="store_true", help="skip the MPC-solves/s leg")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_worker:
-        print(json.dumps(cpu_reference_run(args.workload, args.cpu_sample, 2, 1)))
+        out = cpu_reference_run(args.workload, args.cpu_sample, 2, 1)
+        if not args.no_solver:
+            out["solver"] = cpu_solver_run(args.workload)
+        print(json.dumps(out))
         return
     if args.impl == "reference":
         reference_run(args)
