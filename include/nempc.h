@@ -41,7 +41,8 @@ enum { NEMPC_INTEG_DISCRETE = 0,   /* x_{t-1} + f - x_t        integrator/discre
        NEMPC_INTEG_UNITY = 1,      /* f - x_t                  integrator/unity.py:15-32   */
        NEMPC_INTEG_RK4 = 2 };      /* classical RK4, ZOH on u  integrator/rk4.py:57-83      */
 enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2 };
-enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2 };
+enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2,
+       NEMPC_KERNEL_TC = 3 };      /* tcgen05 tensor-core kernel: f32 tanh networks whose hidden layers are all 128 wide */
 
 typedef struct nempc_desc {
     int32_t x_dim, u_dim;                /* model/base.py:4-9 */
@@ -54,7 +55,7 @@ typedef struct nempc_desc {
     int32_t compute_dtype;               /* network + chain-rule arithmetic: NEMPC_F32 (reference: Keras f32) or F64 */
     int32_t io_dtype;                    /* element type of every I/O buffer (reference: f64, ipopt.py) */
     int32_t device;                      /* CUDA ordinal */
-    int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO picks the register-resident kernel when it applies) */
+    int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO: register-resident kernel for the small LV class, tensor-core kernel for 128-wide nets, else generic) */
 } nempc_desc;
 
 typedef struct nempc_handle nempc_handle;

@@ -12,7 +12,7 @@ OK = 0
 F32, F64 = 0, 1
 INTEGRATORS = {"discrete": 0, "unity": 1, "rk4": 2}
 ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2}
-KERNELS = {"auto": 0, "generic": 1, "fast": 2}
+KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
 
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",
            "nempc_set_objective", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",

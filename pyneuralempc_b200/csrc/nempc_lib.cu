@@ -15,6 +15,7 @@
 #include "nempc_generic.cuh"
 #include "nempc_layout.h"
 #include "nempc_solver.cuh"
+#include "nempc_tc.cuh"
 
 // ======================================================================================================
 // kernels
@@ -171,6 +172,7 @@ struct nempc_handle {
     void* dW[NEMPC_MAXL] = {}; void* dWT[NEMPC_MAXL] = {}; void* db[NEMPC_MAXL] = {};
     double *dlin = nullptr, *dquad = nullptr, *dref = nullptr;
     int use_fast = 0; int fast_id = -1;
+    int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr;   // tensor-core kernel: f16 weight images, f32 constants
     std::vector<unsigned char> fastw;            // FastWeights<...> blob
     SlotLayout sl{};
     int tps = 32, slots = 1, dmax = 4;
@@ -211,6 +213,19 @@ static int fast_shape_id(const nempc_desc& d) {
         if (d.x_dim == kFastShapes[i].x && d.u_dim == kFastShapes[i].u && d.widths[0] == kFastShapes[i].h1 &&
             d.widths[1] == kFastShapes[i].h2)
             return i;
+    return -1;
+}
+
+// tensor-core kernel instantiations: (x, u, hidden layers), every hidden layer NEMPC_TC_HW wide
+struct TcShape { int x, u, nhid; };
+static const TcShape kTcShapes[] = {{4, 1, 3}, {4, 1, 2}, {2, 1, 3}, {2, 1, 2}, {3, 1, 3}, {3, 1, 2}, {4, 2, 3}, {4, 2, 2}};
+static const int kNumTcShapes = sizeof(kTcShapes) / sizeof(kTcShapes[0]);
+
+static int tc_shape_id(const nempc_desc& d) {
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH) return -1;
+    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_TC_HW) return -1;
+    for (int i = 0; i < kNumTcShapes; ++i)
+        if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid) return i;
     return -1;
 }
 
@@ -290,7 +305,7 @@ extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, 
 // ---- lifetime ------------------------------------------------------------------------------------------------
 static void free_device(nempc_handle* h) {
     for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
-    cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws);
+    cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws); cudaFree(h->d_tcimg); cudaFree(h->d_tccb);
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -339,7 +354,13 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
         SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_FAST requested but no register-resident instantiation matches this network");
         free_device(h); delete h; return NEMPC_EUNSUPPORTED;
     }
-    h->use_fast = (h->fast_id >= 0 && D.kernel != NEMPC_KERNEL_GENERIC) ? 1 : 0;
+    h->use_fast = (h->fast_id >= 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST)) ? 1 : 0;
+    h->tc_id = tc_shape_id(D);
+    if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0) {
+        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d)", NEMPC_TC_HW);
+        free_device(h); delete h; return NEMPC_EUNSUPPORTED;
+    }
+    h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
 
     // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
     int sum_h = 0, hmax = 0;
@@ -358,6 +379,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
 
     char nm[160];
     if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank)", D.x_dim, D.u_dim, D.widths[0], D.widths[1]);
+    else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, NEMPC_TC_HW);
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
     h->kname = nm;
     *out = h;
@@ -400,6 +422,38 @@ template <int X, int U, int H1, int H2, int NCHUNK> static void fill_fast(nempc_
                                             h->W[1].data(), h->bvec[1].data(), h->W[2].data(), h->bvec[2].data());
 }
 
+// f16 hi/lo operand images of the hidden-to-hidden layers + the f32 constant block of nempc_tc_kernel
+static int upload_tc(nempc_handle* h) {
+    const int nhid = h->L - 1, HW = NEMPC_TC_HW, x = h->desc.x_dim, d = h->d, xp = (x + 3) / 4 * 4, nmm = nhid - 1;
+    std::vector<__half> img((size_t)nmm * 2 * 128 * HW);
+    for (int l = 0; l < nmm; ++l) {
+        const std::vector<double>& W = h->W[l + 1];                       // [in][out]
+        __half* hi = img.data() + (size_t)l * 2 * 128 * HW;
+        __half* lo = hi + (size_t)128 * HW;
+        for (int i = 0; i < HW; ++i)
+            for (int j = 0; j < HW; ++j) {
+                const float w = (float)W[(size_t)i * HW + j];
+                const __half whi = __float2half_rn(w);
+                const size_t off = tc_img_index(j, i);                    // B[n = out][k = in]
+                hi[off] = whi;
+                lo[off] = __float2half_rn((w - __half2float(whi)) * NEMPC_TC_LO_SCALE);
+            }
+    }
+    std::vector<float> cb((size_t)d * HW + (size_t)HW * xp + (size_t)nhid * HW + xp, 0.f);
+    float* W0 = cb.data(); float* Wout = W0 + (size_t)d * HW; float* b = Wout + (size_t)HW * xp; float* bout = b + (size_t)nhid * HW;
+    for (int c = 0; c < d; ++c) for (int j = 0; j < HW; ++j) W0[c * HW + j] = (float)h->W[0][(size_t)c * HW + j];
+    for (int j = 0; j < HW; ++j) for (int p = 0; p < x; ++p) Wout[j * xp + p] = (float)h->W[nhid][(size_t)j * x + p];
+    for (int l = 0; l < nhid; ++l) for (int j = 0; j < HW; ++j) b[l * HW + j] = (float)h->bvec[l][j];
+    for (int p = 0; p < x; ++p) bout[p] = (float)h->bvec[nhid][p];
+    if (!h->d_tcimg) {
+        CU(h, cudaMalloc(&h->d_tcimg, img.size() * sizeof(__half)));
+        CU(h, cudaMalloc((void**)&h->d_tccb, cb.size() * sizeof(float)));
+    }
+    CU(h, cudaMemcpy(h->d_tcimg, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_tccb, cb.data(), cb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return NEMPC_OK;
+}
+
 extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const double* b) {
     if (!h || !W || !b || layer < 0 || layer >= h->L) { SET_ERR(h, "nempc_set_weights: bad argument"); return NEMPC_EINVAL; }
     const int fin = h->dims[layer], fout = h->dims[layer + 1];
@@ -417,6 +471,7 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
             case 2: fill_fast<2, 1, 16, 16, 1>(h); break;
         }
     }
+    if (all && h->tc_id >= 0) { rc = upload_tc(h); if (rc) return rc; }
     return NEMPC_OK;
 }
 
@@ -536,6 +591,42 @@ template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<T
     return NEMPC_EINVAL;
 }
 
+template <int X, int U, int NHID, int MODE, typename TIO>
+static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
+    typedef TcCfg<X, U, NHID, MODE> C;
+    auto kern = nempc_tc_kernel<C, TIO>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
+    const long long ntiles = (ar.nsteps + C::SPT - 1) / C::SPT;
+    const unsigned grid = (unsigned)std::max(1LL, std::min(ntiles, (long long)h->sm_count));
+    kern<<<grid, NEMPC_TC_THREADS, C::TOTAL, s>>>((const __half*)h->d_tcimg, h->d_tccb, st, h->lay, ar);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+template <int X, int U, int NHID, typename TIO>
+static int launch_tc_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    switch (mode) {
+        case 0: return launch_tc_mode<X, U, NHID, 0, TIO>(h, ar, s);
+        case 1: return launch_tc_mode<X, U, NHID, 1, TIO>(h, ar, s);
+        default: return launch_tc_mode<X, U, NHID, 2, TIO>(h, ar, s);
+    }
+}
+template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    switch (h->tc_id) {
+        case 0: return launch_tc_shape<4, 1, 3, TIO>(h, ar, mode, s);
+        case 1: return launch_tc_shape<4, 1, 2, TIO>(h, ar, mode, s);
+        case 2: return launch_tc_shape<2, 1, 3, TIO>(h, ar, mode, s);
+        case 3: return launch_tc_shape<2, 1, 2, TIO>(h, ar, mode, s);
+        case 4: return launch_tc_shape<3, 1, 3, TIO>(h, ar, mode, s);
+        case 5: return launch_tc_shape<3, 1, 2, TIO>(h, ar, mode, s);
+        case 6: return launch_tc_shape<4, 2, 3, TIO>(h, ar, mode, s);
+        case 7: return launch_tc_shape<4, 2, 2, TIO>(h, ar, mode, s);
+    }
+    SET_ERR(h, "internal: bad tc_id");
+    return NEMPC_EINVAL;
+}
+
 template <typename TIO>
 static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda, const void* obj_factor,
                   double sigma, void* resid, void* jac, void* hes, void* obj, void* grad, cudaStream_t s) {
@@ -548,7 +639,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         const int mode = hes ? 2 : (jac ? 1 : 0);
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
-        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s);
+        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s) : (h->use_tc ? launch_tc<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s));
         if (rc) return rc;
     }
     if (obj || grad) {

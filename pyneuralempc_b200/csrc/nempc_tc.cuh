@@ -1,0 +1,472 @@
+// Tensor-core kernel for wide tanh networks (hidden width 128: the cart-pole class of BASELINE config C3,
+// 5 -> 128 -> 128 -> 128 -> 4): the per-step chain of nempc_generic.cuh with the hidden-to-hidden layers on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory).
+//
+// Formulation: FORWARD second order.  Per horizon step and RK4 stage the network is evaluated on a stack of
+// RPS = 1 + d + d(d+1)/2 rows
+//      P        the activations                 h_l
+//      T_c      first-order tangents            V_l[., c]    = s'(a_l) * da_l/dz_c
+//      S_(c,c2) second-order tangents           Q_l[., c,c2] = s''(a_l) * da_l/dz_c * da_l/dz_c2 + s'(a_l) * d2a_l/dz_c dz_c2
+// Every row goes through the SAME weights, so a hidden-to-hidden layer is one GEMM [128 rows x 128] x [128 x 128] for
+// SPT = 128 / RPS steps at once, and the linear output layer turns the three row kinds into k = f(z_s), the local
+// Jacobian J_s and the per-output local Hessians M_p.  No adjoint sweep and no per-layer state survives a layer: that
+// is what lets both hidden-to-hidden weight matrices stay resident in shared memory next to the operand tile.
+// (The adjoint form needs d*sum_h or x*sum_h floats per step across layers -- 15 KB per step for C3 -- which is why
+// nempc_generic.cuh holds only ~15 steps per SM.)  The stage algebra (dk = J R, h_s = R^T M R + a_s J h_{s-1},
+// R_{s+1} = I + a_{s+1} E dk) and the sparse scatter are those of nempc_generic.cuh (reference integrator/rk4.py:113-285).
+//
+// Arithmetic: the reference network is float32 (model/tensorflow.py:85-91); plain TF32/F16 tensor-core inputs are
+// ~1e-3 accurate, far from the 1e-5 parity bound.  Operands are therefore split in two f16 terms, x = hi + lo/2^11
+// (tcx::split_f16), and a layer is three MMAs per K step into two f32 accumulators in tensor memory:
+//      D_main += A_hi W_hi          D_corr += A_lo W_hi + A_hi W_lo          D = D_main + D_corr / 2^11
+// which carries ~22 mantissa bits (measured 4e-7 relative, tests/tools/tc_gemm_probe.cu) at 1.5x the cost of one TF32
+// pass and HALF the shared-memory footprint of a 3xTF32 scheme -- the footprint is what decides residency here.
+//
+// One CTA per SM (persistent), 256 threads: thread (m = tid & 127, hf = tid >> 7) owns row m of the tile and the 64
+// neurons [64 hf, 64 hf + 64).  Row order is kind-major (m = kind * SPT + step).  Per layer:
+//   thread 0 issues 8 K-steps x 3 tcgen05.mma (M = 128, N = 128, K = 16) and commits to an mbarrier;
+//   pass 1: P rows add the bias and park a_l in a side buffer, T rows park their raw tangents (needed by the S rows);
+//   tanh  : the SPT x 128 activations are spread over all 256 threads (MUFU tanh, as in nempc_fast.cuh);
+//   pass 2: every row forms its post-activation quantity from tensor memory + the side buffers, splits it and writes
+//           its 16-byte K chunks of the next operand tile (canonical K-major no-swizzle layout, conflict-free stores);
+//           after the LAST hidden layer the rows are contracted with W_out in registers instead (exact f32).
+// The first layer (K = d) and the output layer (N = x) are too thin for the tensor core and stay on FFMA.
+#pragma once
+#include "nempc_fast.cuh"
+#include "nempc_generic.cuh"
+#include "nempc_tc_ptx.cuh"
+
+#define NEMPC_TC_HW 128
+#define NEMPC_TC_THREADS 256
+#define NEMPC_TC_SMEM_MAX 232448
+
+template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
+    static constexpr int X = X_, U = U_, NHID = NHID_, MODE = MODE_;
+    static constexpr int D = X + U, NTRI = D * (D + 1) / 2, HW = NEMPC_TC_HW, NMM = NHID - 1;
+    static constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
+    static constexpr int RPS = 1 + (JAC ? D : 0) + (HES ? NTRI : 0);      // rows per step
+    static constexpr int SPT = (128 / RPS) < 32 ? (128 / RPS) : 32;       // steps per tile
+    static constexpr int ROWS = SPT * RPS;
+    static constexpr int XP = (X + 3) / 4 * 4;
+    static constexpr int SROW = HW + 4;                                   // padded side-buffer row (bank spread)
+    // per-step state that lives across the RK4 stages (floats)
+    static constexpr int P_Z = 0, P_KPREV = P_Z + D, P_KACC = P_KPREV + X, P_R = P_KACC + X, P_DKACC = P_R + D * D,
+                         P_HPREV = P_DKACC + X * D, P_HACC = P_HPREV + (HES ? X * D * D : 0),
+                         P_TOTAL = P_HACC + (HES ? X * D * D : 0);
+    // per-step temporaries of one stage (floats); they alias the operand tile, which is dead at that point
+    static constexpr int T_KCUR = 0, T_J = XP, T_DK = T_J + X * D, T_M = T_DK + X * D, T_TMP = T_M + X * D * D,
+                         T_TOTAL = T_TMP + X * D * D;
+    // shared-memory map (bytes)
+    static constexpr int IMG = 128 * HW * 2;                              // one f16 operand image: 32 KB
+    static constexpr int OFF_W = 0;                                       // NMM x (hi image, lo image)
+    static constexpr int OFF_A = NMM * 2 * IMG;                           // operand tile: hi image, lo image
+    static constexpr int OFF_C = OFF_A + 2 * IMG;                         // f32 constants
+    static constexpr int C_W0 = 0, C_WOUT = D * HW, C_B = C_WOUT + HW * XP, C_BOUT = C_B + NHID * HW, C_FLOATS = C_BOUT + XP;
+    static constexpr int OFF_SH = OFF_C + C_FLOATS * 4;                   // a_l / h_l     [SPT][SROW]
+    static constexpr int OFF_ST = OFF_SH + SPT * SROW * 4;                // raw tangents  [D][SPT][SROW]   (Hessian only)
+    static constexpr int OFF_P = OFF_ST + (HES ? D * SPT * SROW * 4 : 0);
+    static constexpr int TOTAL = OFF_P + SPT * P_TOTAL * 4;
+    static constexpr int A_PART = 0;                                      // [128][XP] partial output sums of the upper half
+    static constexpr int A_TMP = 128 * XP * 4;
+    static_assert(TOTAL <= NEMPC_TC_SMEM_MAX, "tensor-core kernel: shared-memory map exceeds 227 KB");
+    static_assert(A_TMP + SPT * T_TOTAL * 4 <= 2 * IMG, "stage temporaries do not fit into the operand tile");
+    static_assert(NHID >= 2 && NHID <= 3, "two or three hidden layers");
+    static_assert(X <= 16 && RPS <= 128, "row stack too tall");
+};
+
+// host: element (n, k) of a K-major no-swizzle operand image with 128 rows: 16-byte chunk (n, k/8) at (k/8)*2048 + n*16
+inline size_t tc_img_index(int n, int k) { return (size_t)(k / 8) * (128 * 8) + (size_t)n * 8 + (k % 8); }
+
+#if defined(__CUDACC__)
+template <class C, typename TIO>
+__global__ void __launch_bounds__(NEMPC_TC_THREADS, 1)
+nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk, const StageTable<float> st,
+                const NlpLayout L, const EvalArgs<TIO> ar) {
+    using namespace tcx;
+    constexpr int X = C::X, U = C::U, D = C::D, HW = C::HW, NHID = C::NHID, NMM = C::NMM, SPT = C::SPT, XP = C::XP,
+                  SROW = C::SROW, DD = D * D;
+    constexpr bool JAC = C::JAC, HES = C::HES;
+    typedef typename WideOf<float, TIO>::type TW;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ uint64_t mbar_store[2];
+    __shared__ uint32_t tmem_holder;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m = tid & 127, hf = tid >> 7;
+    const int kind = m / SPT, sl = m - kind * SPT;
+    const bool valid = m < C::ROWS;
+    // row coefficients of the unified post-activation formula  out = alpha h + s1 (beta v) + s2 (gamma tc tc2)
+    float alpha = 0.f, beta = 0.f, gamma = 0.f;
+    int cT = 0, c1 = 0, c2 = 0;                       // tangent column of a T row; column pair of an S row
+    if (valid) {
+        if (kind == 0) alpha = 1.f;
+        else if (kind <= D) { beta = 1.f; cT = kind - 1; }
+        else {
+            beta = 1.f; gamma = 1.f;
+            int e = kind - 1 - D;
+            while (e > c1) { e -= c1 + 1; ++c1; }     // e-th entry of the lower triangle -> (c1, c2)
+            c2 = e;
+        }
+    }
+    const bool is_T = valid && kind >= 1 && kind <= D;
+    const bool is_S = valid && kind > D;
+
+    float* cb = reinterpret_cast<float*>(tc_smem + C::OFF_C);
+    const float* W0 = cb + C::C_W0;                   // [D][HW]
+    const float* Wout = cb + C::C_WOUT;               // [HW][XP]
+    const float* bias = cb + C::C_B;                  // [NHID][HW]
+    const float* bout = cb + C::C_BOUT;
+    float* sideH = reinterpret_cast<float*>(tc_smem + C::OFF_SH);
+    float* sideT = reinterpret_cast<float*>(tc_smem + C::OFF_ST);
+    float* pers = reinterpret_cast<float*>(tc_smem + C::OFF_P);
+    unsigned char* Ahi = tc_smem + C::OFF_A;
+    unsigned char* Alo = Ahi + C::IMG;
+    float* part = reinterpret_cast<float*>(Ahi + C::A_PART);
+    float* temps = reinterpret_cast<float*>(Ahi + C::A_TMP);
+
+    const uint32_t mbar_w = smem_u32(&mbar_store[0]), mbar_mma = smem_u32(&mbar_store[1]);
+    if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(mbar_mma, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), 256);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_holder;
+    const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's lane quadrant
+    // weights: resident for the life of the CTA, brought in by the TMA unit as plain 1-D bulk copies
+    if (tid == 0) {
+        mbar_expect_tx(mbar_w, NMM * 2 * C::IMG);
+        for (int i = 0; i < NMM * 2; ++i)
+            bulk_g2s(smem_u32(tc_smem + C::OFF_W + i * C::IMG), wimg + (size_t)i * (C::IMG / 2), C::IMG, mbar_w);
+    }
+    for (int i = tid; i < C::C_FLOATS; i += NEMPC_TC_THREADS) cb[i] = cblk[i];
+    mbar_wait(mbar_w, 0);
+    __syncthreads();
+
+    const bool unity = (ar.flags & NEMPC_UNITY) != 0;
+    const uint32_t idesc = make_idesc_f16(128, HW);
+    uint32_t parity = 0;
+    const long long ntiles = (ar.nsteps + SPT - 1) / SPT;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long step0 = tile * SPT;
+        // ---- inputs and per-step state ------------------------------------------------------------------------------
+        for (int idx = tid; idx < SPT * C::P_TOTAL; idx += NEMPC_TC_THREADS) {
+            const int s_ = idx / C::P_TOTAL, o = idx - s_ * C::P_TOTAL;
+            float v = 0.f;
+            const long long step = step0 + s_;
+            if (o < D) {
+                if (step < ar.nsteps) {
+                    const long long b = step / L.H;
+                    const int t = (int)(step - b * L.H);
+                    const TIO* zb = ar.z + b * (long long)L.n;
+                    if (o < X) v = (float)((t == 0) ? ar.x0[b * X + o] : zb[(t - 1) * X + o]);
+                    else v = (float)zb[L.H * X + t * U + (o - X)];
+                }
+            } else if (o >= C::P_R && o < C::P_R + DD) {
+                const int r = o - C::P_R;
+                v = (r / D == r % D) ? 1.f : 0.f;
+            }
+            pers[idx] = v;
+        }
+        __syncthreads();
+
+        for (int s = 0; s < st.S; ++s) {
+            const float a_s = st.a[s], c_s = st.c[s];
+            // ---- first layer (K = d, FFMA): activations of all SPT steps spread over the CTA ------------------------------
+            for (int e = tid; e < SPT * HW; e += NEMPC_TC_THREADS) {
+                const int s_ = e / HW, j = e - s_ * HW;
+                const float* ps = pers + s_ * C::P_TOTAL;
+                float a = bias[j];
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float zc = (c < X) ? fmaf(a_s, ps[C::P_KPREV + (c < X ? c : 0)], ps[C::P_Z + c]) : ps[C::P_Z + c];
+                    a = fmaf(W0[c * HW + j], zc, a);
+                }
+                sideH[s_ * SROW + j] = fast_tanh(a);
+            }
+            __syncthreads();
+
+            float oacc[X];
+#pragma unroll
+            for (int p = 0; p < X; ++p) oacc[p] = 0.f;
+
+#pragma unroll 1
+            for (int l = 0; l < NHID; ++l) {
+                // ---- pass 2 of layer l: post-activation rows -> next operand tile (or the output contraction) ---------------
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int col = 64 * hf + 16 * q4;
+                    float v[16];
+                    if (l > 0) {                                   // warp-collective tensor-memory loads: every lane takes part
+                        float vc[16];
+                        tmem_ld16(tm_row + col, v);
+                        tmem_ld16(tm_row + 128 + col, vc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]);
+                    }
+                    float out[16];
+                    if (valid) {
+                        const float* hrow = sideH + sl * SROW + col;
+                        const float* t1 = (l == 0) ? W0 + c1 * HW + col : sideT + (c1 * SPT + sl) * SROW + col;
+                        const float* t2 = (l == 0) ? W0 + c2 * HW + col : sideT + (c2 * SPT + sl) * SROW + col;
+                        const float* w0t = W0 + cT * HW + col;
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, w4 = a4;
+                            if (HES && is_S) { a4 = *reinterpret_cast<const float4*>(t1 + 4 * i4); b4 = *reinterpret_cast<const float4*>(t2 + 4 * i4); }
+                            if (l == 0 && is_T) w4 = *reinterpret_cast<const float4*>(w0t + 4 * i4);
+                            const float hh[4] = {h4.x, h4.y, h4.z, h4.w}, ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w},
+                                        ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float h = hh[i];
+                                const float s1 = fmaf(-h, h, 1.f);
+                                const float s2 = -2.f * h * s1;
+                                const float vv = (l == 0) ? ww[i] : v[4 * i4 + i];      // first layer: da_0/dz_c = W0[c], second order 0
+                                out[4 * i4 + i] = fmaf(alpha, h, fmaf(s1, beta * ((l == 0 && !is_T) ? 0.f : vv), s2 * gamma * ta[i] * tb[i]));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) out[i] = 0.f;
+                    }
+                    if (l < NHID - 1) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            __half hi[8], lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) split_f16(out[8 * g + i], hi[i], lo[i]);
+                            const int kc = col / 8 + g;
+                            *reinterpret_cast<uint4*>(Ahi + kc * (128 * 16) + m * 16) = *reinterpret_cast<const uint4*>(hi);
+                            *reinterpret_cast<uint4*>(Alo + kc * (128 * 16) + m * 16) = *reinterpret_cast<const uint4*>(lo);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float* wo = Wout + (col + i) * XP;
+#pragma unroll
+                            for (int p = 0; p < X; ++p) oacc[p] = fmaf(out[i], wo[p], oacc[p]);
+                        }
+                    }
+                }
+                if (l == NHID - 1) break;
+
+                // ---- hidden-to-hidden layer l -> l+1 on the tensor core -------------------------------------------------------
+                fence_async_smem();
+                fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after_sync();
+                    const uint32_t whi = smem_u32(tc_smem + C::OFF_W + l * 2 * C::IMG), wlo = whi + C::IMG;
+                    const uint32_t ahi = smem_u32(Ahi), alo = smem_u32(Alo);
+#pragma unroll 1
+                    for (int ks = 0; ks < HW / 16; ++ks) {
+                        const uint32_t off = ks * 2 * 2048;
+                        const uint64_t a1 = make_desc_kmajor(ahi + off, 2048, 128), a2 = make_desc_kmajor(alo + off, 2048, 128);
+                        const uint64_t w1 = make_desc_kmajor(whi + off, 2048, 128), w2 = make_desc_kmajor(wlo + off, 2048, 128);
+                        mma_f16_ss(tmem, a1, w1, idesc, ks > 0);
+                        mma_f16_ss(tmem + 128, a2, w1, idesc, ks > 0);
+                        mma_f16_ss(tmem + 128, a1, w2, idesc, 1);
+                    }
+                    mma_commit(mbar_mma);
+                }
+                mbar_wait(mbar_mma, parity);
+                parity ^= 1;
+                fence_after_sync();
+
+                // ---- pass 1 of layer l+1: P rows park a_{l+1} (+ bias), T rows park their raw tangents ---------------------------
+                {
+                    const int need_rows = SPT * (1 + (HES ? D : 0));      // kind-major: P rows first, then T rows
+                    if ((warp & 3) * 32 < need_rows) {
+                        const float* bl = bias + (l + 1) * HW;
+#pragma unroll 1
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int col = 64 * hf + 16 * q4;
+                            float v[16], vc[16];
+                            tmem_ld16(tm_row + col, v);
+                            tmem_ld16(tm_row + 128 + col, vc);
+                            tmem_ld_wait();
+                            if (valid && kind == 0) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) sideH[sl * SROW + col + i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]) + bl[col + i];
+                            } else if (HES && is_T) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) sideT[(cT * SPT + sl) * SROW + col + i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < SPT * HW; e += NEMPC_TC_THREADS) {
+                    const int s_ = e / HW, j = e - s_ * HW;
+                    sideH[s_ * SROW + j] = fast_tanh(sideH[s_ * SROW + j]);
+                }
+                __syncthreads();
+            }
+
+            // ---- linear output layer: join the two neuron halves; k, J, M_p of this stage -------------------------------------
+            __syncthreads();                                       // every thread is done with tensor memory and the side buffers
+            if (hf == 1 && valid) {
+#pragma unroll
+                for (int p = 0; p < X; ++p) part[m * XP + p] = oacc[p];
+            }
+            __syncthreads();
+            if (hf == 0 && valid) {
+                float* tp = temps + sl * C::T_TOTAL;
+#pragma unroll
+                for (int p = 0; p < X; ++p) {
+                    const float tot = oacc[p] + part[m * XP + p];
+                    if (kind == 0) tp[C::T_KCUR + p] = tot + bout[p];
+                    else if (kind <= D) tp[C::T_J + p * D + cT] = tot;
+                    else { tp[C::T_M + p * DD + c1 * D + c2] = tot; tp[C::T_M + p * DD + c2 * D + c1] = tot; }
+                }
+            }
+            __syncthreads();
+
+            // ---- stage algebra (as nempc_generic.cuh), flattened over the SPT steps of the tile ---------------------------------
+            if (JAC) {
+                for (int idx = tid; idx < SPT * X * D; idx += NEMPC_TC_THREADS) {
+                    const int s_ = idx / (X * D), r = idx - s_ * (X * D), p = r / D, c = r - p * D;
+                    const float* tp = temps + s_ * C::T_TOTAL;
+                    const float* R = pers + s_ * C::P_TOTAL + C::P_R;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc = fmaf(tp[C::T_J + p * D + k], R[k * D + c], acc);
+                    temps[s_ * C::T_TOTAL + C::T_DK + r] = acc;
+                }
+                if (HES) {
+                    for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                        const int s_ = idx / (X * DD), r = idx - s_ * (X * DD), p = r / DD, k = (r - p * DD) / D, c = r % D;
+                        const float* tp = temps + s_ * C::T_TOTAL;
+                        const float* R = pers + s_ * C::P_TOTAL + C::P_R;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int l2 = 0; l2 < D; ++l2) acc = fmaf(tp[C::T_M + p * DD + k * D + l2], R[l2 * D + c], acc);
+                        temps[s_ * C::T_TOTAL + C::T_TMP + r] = acc;
+                    }
+                }
+                __syncthreads();
+                if (HES) {
+                    for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                        const int s_ = idx / (X * DD), r = idx - s_ * (X * DD), p = r / DD, a = (r - p * DD) / D, c = r % D;
+                        float* tp = temps + s_ * C::T_TOTAL;
+                        const float* ps = pers + s_ * C::P_TOTAL;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) acc = fmaf(ps[C::P_R + k * D + a], tp[C::T_TMP + p * DD + k * D + c], acc);
+                        if (s > 0) {
+#pragma unroll
+                            for (int k = 0; k < X; ++k) acc = fmaf(a_s * tp[C::T_J + p * D + k], ps[C::P_HPREV + k * DD + a * D + c], acc);
+                        }
+                        tp[C::T_M + r] = acc;                      // M_p was consumed before the barrier; it now holds h_s[p]
+                    }
+                }
+                for (int idx = tid; idx < SPT * X * D; idx += NEMPC_TC_THREADS) {
+                    const int s_ = idx / (X * D), r = idx - s_ * (X * D);
+                    float* dkacc = pers + s_ * C::P_TOTAL + C::P_DKACC + r;
+                    *dkacc = fmaf(c_s, temps[s_ * C::T_TOTAL + C::T_DK + r], *dkacc);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {
+                const int s_ = idx / X, p = idx - s_ * X;
+                float* ps = pers + s_ * C::P_TOTAL;
+                const float kc = temps[s_ * C::T_TOTAL + C::T_KCUR + p];
+                ps[C::P_KACC + p] = fmaf(c_s, kc, ps[C::P_KACC + p]);
+                ps[C::P_KPREV + p] = kc;
+            }
+            if (HES) {
+                for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                    const int s_ = idx / (X * DD), r = idx - s_ * (X * DD);
+                    float* ps = pers + s_ * C::P_TOTAL;
+                    const float hv = temps[s_ * C::T_TOTAL + C::T_M + r];
+                    ps[C::P_HACC + r] = fmaf(c_s, hv, ps[C::P_HACC + r]);
+                    ps[C::P_HPREV + r] = hv;
+                }
+            }
+            if (JAC && s + 1 < st.S) {
+                const float an = st.a[s + 1];
+                for (int idx = tid; idx < SPT * DD; idx += NEMPC_TC_THREADS) {
+                    const int s_ = idx / DD, r = idx - s_ * DD, k = r / D, c = r - k * D;
+                    pers[s_ * C::P_TOTAL + C::P_R + r] = (k == c ? 1.f : 0.f) + (k < X ? an * temps[s_ * C::T_TOTAL + C::T_DK + k * D + c] : 0.f);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- outputs (same slots as nempc_generic.cuh) ----------------------------------------------------------------------
+        if (ar.resid) {
+            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {
+                const int s_ = idx / X, p = idx - s_ * X;
+                const long long step = step0 + s_;
+                if (step >= ar.nsteps) continue;
+                const long long b = step / L.H;
+                const int t = (int)(step - b * L.H);
+                const TIO* zb = ar.z + b * (long long)L.n;
+                const TW xt = (TW)zb[t * X + p];
+                const TW xp = unity ? (TW)0 : (TW)((t == 0) ? ar.x0[b * X + p] : zb[(t - 1) * X + p]);
+                ar.resid[b * L.m + t * X + p] = (TIO)(xp + (TW)pers[s_ * C::P_TOTAL + C::P_KACC + p] - xt);
+            }
+        }
+        if (JAC && ar.jac) {
+            for (int idx = tid; idx < SPT * X * (D + 1); idx += NEMPC_TC_THREADS) {
+                const int s_ = idx / (X * (D + 1)), r = idx - s_ * (X * (D + 1)), p = r / (D + 1), c = r - p * (D + 1);
+                const long long step = step0 + s_;
+                if (step >= ar.nsteps) continue;
+                const long long b = step / L.H;
+                const int t = (int)(step - b * L.H);
+                TIO* jv = ar.jac + b * L.nnz_jac;
+                if (c == D) { jv[jac_slot_minus1(L, t, p)] = (TIO)-1; continue; }
+                const TW v = (TW)pers[s_ * C::P_TOTAL + C::P_DKACC + p * D + c] + ((!unity && c == p) ? (TW)1 : (TW)0);
+                if (c < X) { if (t > 0) jv[jac_slot_A(L, t, p, c)] = (TIO)v; }
+                else jv[jac_slot_B(L, t, p, c - X)] = (TIO)v;
+            }
+        }
+        if (HES && ar.hes) {
+            for (int idx = tid; idx < SPT * DD; idx += NEMPC_TC_THREADS) {
+                const int s_ = idx / DD, r = idx - s_ * DD, a = r / D, c = r - a * D;
+                const long long step = step0 + s_;
+                if (step >= ar.nsteps || c > a) continue;
+                const long long b = step / L.H;
+                const int t = (int)(step - b * L.H);
+                if (t == 0 && c < X) continue;                          // x0 is data, not a variable (discret.py:70-78)
+                TIO* hv = ar.hes + b * L.nnz_hes;
+                const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
+                const float* ha = pers + s_ * C::P_TOTAL + C::P_HACC;
+                float acc = 0.f;
+#pragma unroll
+                for (int p = 0; p < X; ++p) acc = fmaf((float)ar.lam[b * L.m + t * X + p], ha[p * DD + a * D + c], acc);
+                TW v = (TW)acc;
+                int slot;
+                if (a < X) {
+                    slot = hes_slot_xx(L, t, a, c);
+                    if (a == c && ar.quad) v += sig * (TW)2 * (TW)ar.quad[(t - 1) * X + a];
+                } else if (c < X) {
+                    slot = hes_slot_ux(L, t, a - X, c);
+                } else {
+                    slot = hes_slot_uu(L, t, a - X, c - X);
+                    if (a == c && ar.quad) v += sig * (TW)2 * (TW)ar.quad[L.H * X + t * U + (a - X)];
+                }
+                hv[slot] = (TIO)v;
+            }
+            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {   // objective-only diagonal of x_H
+                const int s_ = idx / X, p = idx - s_ * X;
+                const long long step = step0 + s_;
+                if (step >= ar.nsteps) continue;
+                const long long b = step / L.H;
+                const int t = (int)(step - b * L.H);
+                if (t != L.H - 1 || L.hes_last_slot[p] < 0) continue;
+                const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
+                ar.hes[b * L.nnz_hes + L.hes_last_slot[p]] = (TIO)(sig * (TW)2 * (TW)ar.quad[(L.H - 1) * X + p]);
+            }
+        }
+        __syncthreads();                                           // per-step state is rewritten by the next tile
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+#endif  // __CUDACC__

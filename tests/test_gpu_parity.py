@@ -98,6 +98,41 @@ def test_fast_kernel_vs_oracle(kind, h, lv_weights):
     ev.close()
 
 
+TC_CASES = [("rk4", [5, 128, 128, 128, 4], 4, 1, 13, 7), ("discrete", [5, 128, 128, 4], 4, 1, 9, 30),
+            ("unity", [3, 128, 128, 128, 2], 2, 1, 25, 11), ("rk4", [3, 128, 128, 2], 2, 1, 50, 5),
+            ("rk4", [4, 128, 128, 128, 3], 3, 1, 6, 9), ("discrete", [6, 128, 128, 4], 4, 2, 3, 17),
+            ("rk4", [6, 128, 128, 128, 4], 4, 2, 4, 3)]
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,B", TC_CASES)
+def test_tensor_core_kernel_vs_oracle(kind, dims, xd, ud, H, B):
+    """tcgen05 kernel (split-f16 operands, forward second-order rows) against the float64 oracle: several tiles per
+    launch with a ragged last tile; the reduced request sets run the residual-only / Jacobian-only row stacks."""
+    import torch
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=len(dims) + H)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "tc", obj)
+    assert "tcgen05" in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < TOL32, (kg, _relerr(got[kg], ref[kr]))
+    t = lambda a: torch.as_tensor(a).cuda()
+    o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+    o0 = ev.eval(t(Z), t(X0), want=("resid",))
+    torch.cuda.synchronize()
+    assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL32
+    assert _relerr(o1["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    assert _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    ev.close()
+    # "auto" picks the tensor-core kernel for this class, and float32 I/O agrees too
+    ev32 = _evaluator(mlp, kind, H, "float32", "auto", obj, io="float32")
+    assert "tcgen05" in ev32.kernel_name
+    got32 = _run(ev32, Z, X0, lam, sig)
+    for kr, kg in KEYS[:3]:
+        assert _relerr(got32[kg], ref[kr]) < TOL32, (kg, _relerr(got32[kg], ref[kr]))
+    ev32.close()
+
+
 @pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
 @pytest.mark.parametrize("H", (6, 25))
 def test_against_reference_goldens(golden_dir, lv_weights, kind, H):
