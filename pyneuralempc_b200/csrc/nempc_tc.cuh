@@ -95,14 +95,10 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     const int m = tid & 127, hf = tid >> 7;
     const int kind = m / SPT, sl = m - kind * SPT;
     const bool valid = m < C::ROWS;
-    // row coefficients of the unified post-activation formula  out = alpha h + s1 (beta v) + s2 (gamma tc tc2)
-    float alpha = 0.f, beta = 0.f, gamma = 0.f;
     int cT = 0, c1 = 0, c2 = 0;                       // tangent column of a T row; column pair of an S row
-    if (valid) {
-        if (kind == 0) alpha = 1.f;
-        else if (kind <= D) { beta = 1.f; cT = kind - 1; }
+    if (valid && kind >= 1) {
+        if (kind <= D) cT = kind - 1;
         else {
-            beta = 1.f; gamma = 1.f;
             int e = kind - 1 - D;
             while (e > c1) { e -= c1 + 1; ++c1; }     // e-th entry of the lower triangle -> (c1, c2)
             c2 = e;
@@ -186,72 +182,106 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
             __syncthreads();
 
-            float oacc[X];
+            constexpr int XH = (X + 1) / 2;
+            f2 oacc2[XH];                                          // output-layer partial sums, packed over output pairs
 #pragma unroll
-            for (int p = 0; p < X; ++p) oacc[p] = 0.f;
+            for (int q = 0; q < XH; ++q) oacc2[q] = pk(0.f, 0.f);
 
-#pragma unroll 1
-            for (int l = 0; l < NHID; ++l) {
+#pragma unroll
+            for (int l = 0; l < NHID; ++l) {                       // fully unrolled: FIRST / LAST are compile-time below
+                const bool FIRST = (l == 0), LAST = (l == NHID - 1);
                 // ---- pass 2 of layer l: post-activation rows -> next operand tile (or the output contraction) ---------------
-#pragma unroll 1
+                // Packed f32x2 arithmetic (FFMA2); the row class (P / T / S) is a per-thread branch that only diverges in the
+                // two warps that straddle a class boundary (row order is kind-major).
+#pragma unroll 2
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int col = 64 * hf + 16 * q4;
-                    float v[16];
-                    if (l > 0) {                                   // warp-collective tensor-memory loads: every lane takes part
-                        float vc[16];
+                    f2 v2[8];
+                    if (!FIRST) {                                  // warp-collective tensor-memory loads: every lane takes part
+                        float v[16], vc[16];
                         tmem_ld16(tm_row + col, v);
                         tmem_ld16(tm_row + 128 + col, vc);
                         tmem_ld_wait();
+                        const f2 inv = pk(NEMPC_TC_LO_INV, NEMPC_TC_LO_INV);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]);
+                        for (int i = 0; i < 8; ++i) v2[i] = fma2(pk(vc[2 * i], vc[2 * i + 1]), inv, pk(v[2 * i], v[2 * i + 1]));
                     }
-                    float out[16];
-                    if (valid) {
+                    f2 out2[8];
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) out2[i] = pk(0.f, 0.f);
+                    } else {
                         const float* hrow = sideH + sl * SROW + col;
-                        const float* t1 = (l == 0) ? W0 + c1 * HW + col : sideT + (c1 * SPT + sl) * SROW + col;
-                        const float* t2 = (l == 0) ? W0 + c2 * HW + col : sideT + (c2 * SPT + sl) * SROW + col;
-                        const float* w0t = W0 + cT * HW + col;
+                        if (kind == 0) {                           // P: the activations themselves
 #pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4) {
-                            const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
-                            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, w4 = a4;
-                            if (HES && is_S) { a4 = *reinterpret_cast<const float4*>(t1 + 4 * i4); b4 = *reinterpret_cast<const float4*>(t2 + 4 * i4); }
-                            if (l == 0 && is_T) w4 = *reinterpret_cast<const float4*>(w0t + 4 * i4);
-                            const float hh[4] = {h4.x, h4.y, h4.z, h4.w}, ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w},
-                                        ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                                out2[2 * i4] = pk(h4.x, h4.y); out2[2 * i4 + 1] = pk(h4.z, h4.w);
+                            }
+                        } else if (!is_S) {                        // T_c: s'(a) * da/dz_c   (first layer: da_0/dz_c = W0[c])
+                            const float* w0t = W0 + cT * HW + col;
+                            const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float h = hh[i];
-                                const float s1 = fmaf(-h, h, 1.f);
-                                const float s2 = -2.f * h * s1;
-                                const float vv = (l == 0) ? ww[i] : v[4 * i4 + i];      // first layer: da_0/dz_c = W0[c], second order 0
-                                out[4 * i4 + i] = fmaf(alpha, h, fmaf(s1, beta * ((l == 0 && !is_T) ? 0.f : vv), s2 * gamma * ta[i] * tb[i]));
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                                f2 va, vb;
+                                if (FIRST) { const float4 w4 = *reinterpret_cast<const float4*>(w0t + 4 * i4); va = pk(w4.x, w4.y); vb = pk(w4.z, w4.w); }
+                                else { va = v2[2 * i4]; vb = v2[2 * i4 + 1]; }
+                                const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
+                                out2[2 * i4] = mul2(fma2(mul2(ha, m1), ha, one), va);
+                                out2[2 * i4 + 1] = mul2(fma2(mul2(hb, m1), hb, one), vb);
+                            }
+                        } else {                                   // S_(c1,c2): s''(a) T_c1 T_c2 + s'(a) d2a   (first layer: d2a_0 = 0)
+                            const float* t1 = FIRST ? W0 + c1 * HW + col : sideT + (c1 * SPT + sl) * SROW + col;
+                            const float* t2 = FIRST ? W0 + c2 * HW + col : sideT + (c2 * SPT + sl) * SROW + col;
+                            const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f), m2 = pk(-2.f, -2.f);
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                                const float4 a4 = *reinterpret_cast<const float4*>(t1 + 4 * i4);
+                                const float4 b4 = *reinterpret_cast<const float4*>(t2 + 4 * i4);
+                                const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
+                                const f2 s1a = fma2(mul2(ha, m1), ha, one), s1b = fma2(mul2(hb, m1), hb, one);
+                                const f2 qa = mul2(mul2(ha, s1a), mul2(pk(a4.x, a4.y), pk(b4.x, b4.y)));      // h s' T_c1 T_c2
+                                const f2 qb = mul2(mul2(hb, s1b), mul2(pk(a4.z, a4.w), pk(b4.z, b4.w)));
+                                if (FIRST) { out2[2 * i4] = mul2(qa, m2); out2[2 * i4 + 1] = mul2(qb, m2); }
+                                else { out2[2 * i4] = fma2(qa, m2, mul2(s1a, v2[2 * i4])); out2[2 * i4 + 1] = fma2(qb, m2, mul2(s1b, v2[2 * i4 + 1])); }
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) out[i] = 0.f;
                     }
-                    if (l < NHID - 1) {
+                    if (!LAST) {
+                        const f2 sc = pk(NEMPC_TC_LO_SCALE, NEMPC_TC_LO_SCALE), nsc = pk(-NEMPC_TC_LO_SCALE, -NEMPC_TC_LO_SCALE);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
-                            __half hi[8], lo[8];
+                            uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) split_f16(out[8 * g + i], hi[i], lo[i]);
+                            for (int i = 0; i < 4; ++i) {          // x = hi + lo / 2^11, two neurons per instruction
+                                const f2 x = out2[4 * g + i];
+                                const __half2 h2 = __floats2half2_rn(f2lo(x), f2hi(x));
+                                const float2 hf2 = __half22float2(h2);
+                                const f2 r = fma2(x, sc, mul2(pk(hf2.x, hf2.y), nsc));            // (x - hi) * 2^11, exact
+                                const __half2 l2 = __floats2half2_rn(f2lo(r), f2hi(r));
+                                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
                             const int kc = col / 8 + g;
-                            *reinterpret_cast<uint4*>(Ahi + kc * (128 * 16) + m * 16) = *reinterpret_cast<const uint4*>(hi);
-                            *reinterpret_cast<uint4*>(Alo + kc * (128 * 16) + m * 16) = *reinterpret_cast<const uint4*>(lo);
+                            *reinterpret_cast<uint4*>(Ahi + kc * (128 * 16) + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(Alo + kc * (128 * 16) + m * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
+                            const float o = (i & 1) ? f2hi(out2[i / 2]) : f2lo(out2[i / 2]);
                             const float* wo = Wout + (col + i) * XP;
 #pragma unroll
-                            for (int p = 0; p < X; ++p) oacc[p] = fmaf(out[i], wo[p], oacc[p]);
+                            for (int q = 0; q < XH; ++q) {
+                                const float2 w2 = *reinterpret_cast<const float2*>(wo + 2 * q);
+                                oacc2[q] = fma2(pk(o, o), pk(w2.x, w2.y), oacc2[q]);
+                            }
                         }
                     }
                 }
-                if (l == NHID - 1) break;
+                if (LAST) break;
 
                 // ---- hidden-to-hidden layer l -> l+1 on the tensor core -------------------------------------------------------
                 fence_async_smem();
@@ -290,10 +320,18 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                             tmem_ld_wait();
                             if (valid && kind == 0) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) sideH[sl * SROW + col + i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]) + bl[col + i];
+                                for (int i4 = 0; i4 < 4; ++i4) {
+                                    const float4 b4 = *reinterpret_cast<const float4*>(bl + col + 4 * i4);
+                                    *reinterpret_cast<float4*>(sideH + sl * SROW + col + 4 * i4) =
+                                        make_float4(fmaf(vc[4 * i4], NEMPC_TC_LO_INV, v[4 * i4]) + b4.x, fmaf(vc[4 * i4 + 1], NEMPC_TC_LO_INV, v[4 * i4 + 1]) + b4.y,
+                                                    fmaf(vc[4 * i4 + 2], NEMPC_TC_LO_INV, v[4 * i4 + 2]) + b4.z, fmaf(vc[4 * i4 + 3], NEMPC_TC_LO_INV, v[4 * i4 + 3]) + b4.w);
+                                }
                             } else if (HES && is_T) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) sideT[(cT * SPT + sl) * SROW + col + i] = fmaf(vc[i], NEMPC_TC_LO_INV, v[i]);
+                                for (int i4 = 0; i4 < 4; ++i4)
+                                    *reinterpret_cast<float4*>(sideT + (cT * SPT + sl) * SROW + col + 4 * i4) =
+                                        make_float4(fmaf(vc[4 * i4], NEMPC_TC_LO_INV, v[4 * i4]), fmaf(vc[4 * i4 + 1], NEMPC_TC_LO_INV, v[4 * i4 + 1]),
+                                                    fmaf(vc[4 * i4 + 2], NEMPC_TC_LO_INV, v[4 * i4 + 2]), fmaf(vc[4 * i4 + 3], NEMPC_TC_LO_INV, v[4 * i4 + 3]));
                             }
                         }
                     }
@@ -307,6 +345,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
 
             // ---- linear output layer: join the two neuron halves; k, J, M_p of this stage -------------------------------------
+            float oacc[X];
+#pragma unroll
+            for (int p = 0; p < X; ++p) oacc[p] = (p & 1) ? f2hi(oacc2[p / 2]) : f2lo(oacc2[p / 2]);
             __syncthreads();                                       // every thread is done with tensor memory and the side buffers
             if (hf == 1 && valid) {
 #pragma unroll
