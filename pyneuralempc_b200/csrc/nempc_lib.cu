@@ -866,6 +866,17 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     return NEMPC_OK;
 }
 
+#ifdef NEMPC_TC_PROFILE
+// development builds only: cycles per phase of nempc_tc_kernel summed over all CTAs (thread 0's clock), then reset
+extern "C" int nempc_debug_tc_profile(unsigned long long* out16) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return NEMPC_ECUDA;
+    if (cudaMemcpyFromSymbol(out16, nempc_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return NEMPC_ECUDA;
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(nempc_tc_prof, z, sizeof z);
+    return NEMPC_OK;
+}
+#endif
+
 // ---- introspection ------------------------------------------------------------------------------------------------
 extern "C" int64_t nempc_launch_count(const nempc_handle* h) { return h ? h->launches : 0; }
 extern "C" const char* nempc_kernel_name(const nempc_handle* h) { return h ? h->kname.c_str() : ""; }

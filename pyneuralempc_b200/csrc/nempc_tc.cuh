@@ -17,16 +17,18 @@
 //
 // Arithmetic: the reference network is float32 (model/tensorflow.py:85-91); plain TF32/F16 tensor-core inputs are
 // ~1e-3 accurate, far from the 1e-5 parity bound.  Operands are therefore split in two f16 terms, x = hi + lo/2^11
-// (tcx::split_f16), and a layer is three MMAs per K step into two f32 accumulators in tensor memory:
-//      D_main += A_hi W_hi          D_corr += A_lo W_hi + A_hi W_lo          D = D_main + D_corr / 2^11
+// (tcx::split_f16), and a layer is three MMAs per K step into ONE f32 accumulator in tensor memory:
+//      D  = A_lo W_hi + A_hi W_lo            (both products carry the factor 2^11)
+//      D  = A_hi W_hi + D * 2^-11            (first main MMA, tcgen05.mma scale-input-d = 11), then D += A_hi W_hi for the other K steps
+// (a single accumulator matters: tensor memory is read at only ~52 B/clk/SM, tests/tools/tc_tmem_probe.cu),
 // which carries ~22 mantissa bits (measured 4e-7 relative, tests/tools/tc_gemm_probe.cu) at 1.5x the cost of one TF32
 // pass and HALF the shared-memory footprint of a 3xTF32 scheme -- the footprint is what decides residency here.
 //
-// One CTA per SM (persistent), 256 threads: thread (m = tid & 127, hf = tid >> 7) owns row m of the tile and the 64
-// neurons [64 hf, 64 hf + 64).  Row order is kind-major (m = kind * SPT + step).  Per layer:
+// One CTA per SM (persistent), NEMPC_TC_THREADS threads: thread (m = tid & 127, cq = tid >> 7) owns row m of the tile and the
+// neurons [CPT cq, CPT cq + CPT).  Row order is kind-major (m = kind * SPT + step).  Per layer:
 //   thread 0 issues 8 K-steps x 3 tcgen05.mma (M = 128, N = 128, K = 16) and commits to an mbarrier;
 //   pass 1: P rows add the bias and park a_l in a side buffer, T rows park their raw tangents (needed by the S rows);
-//   tanh  : the SPT x 128 activations are spread over all 256 threads (MUFU tanh, as in nempc_fast.cuh);
+//   tanh  : the SPT x 128 activations are spread over all threads of the CTA (MUFU tanh, as in nempc_fast.cuh);
 //   pass 2: every row forms its post-activation quantity from tensor memory + the side buffers, splits it and writes
 //           its 16-byte K chunks of the next operand tile (canonical K-major no-swizzle layout, conflict-free stores);
 //           after the LAST hidden layer the rows are contracted with W_out in registers instead (exact f32).
@@ -36,9 +38,16 @@
 #include "nempc_generic.cuh"
 #include "nempc_tc_ptx.cuh"
 
+#include <type_traits>
+
 #define NEMPC_TC_HW 128
-#define NEMPC_TC_THREADS 256
+#ifndef NEMPC_TC_THREADS
+#define NEMPC_TC_THREADS 512            // 16 warps: 4 per scheduler hide the LDS / LDTM / MUFU latencies of the epilogue (256 was latency bound)
+#endif
 #define NEMPC_TC_SMEM_MAX 232448
+#ifndef NEMPC_TC_P2_UNROLL
+#define NEMPC_TC_P2_UNROLL 2          // unroll factor of the 16-neuron chunk loop of pass 2 (2: both tensor-memory loads in flight; +3% on C3)
+#endif
 
 template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
     static constexpr int X = X_, U = U_, NHID = NHID_, MODE = MODE_;
@@ -65,9 +74,13 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
     static constexpr int OFF_SH = OFF_C + C_FLOATS * 4;                   // a_l / h_l     [SPT][SROW]
     static constexpr int OFF_ST = OFF_SH + SPT * SROW * 4;                // raw tangents  [D][SPT][SROW]   (Hessian only)
     static constexpr int OFF_P = OFF_ST + (HES ? D * SPT * SROW * 4 : 0);
-    static constexpr int TOTAL = OFF_P + SPT * P_TOTAL * 4;
-    static constexpr int A_PART = 0;                                      // [128][XP] partial output sums of the upper half
-    static constexpr int A_TMP = 128 * XP * 4;
+    static constexpr int OFF_I = OFF_P + SPT * P_TOTAL * 4;               // (problem, time index) of each step of the tile
+    static constexpr int TOTAL = OFF_I + SPT * 8;
+    static constexpr int NQ = NEMPC_TC_THREADS / 128;                     // threads per row: each owns CPT consecutive neurons
+    static constexpr int CPT = HW / NQ;
+    static constexpr int A_PART = 0;                                      // [NQ-1][128][XP] partial output sums of the upper column groups
+    static constexpr int A_TMP = (NQ - 1) * 128 * XP * 4;
+    static_assert(NEMPC_TC_THREADS % 128 == 0 && CPT % 16 == 0, "128 rows x NQ column groups of a multiple of 16 neurons");
     static_assert(TOTAL <= NEMPC_TC_SMEM_MAX, "tensor-core kernel: shared-memory map exceeds 227 KB");
     static_assert(A_TMP + SPT * T_TOTAL * 4 <= 2 * IMG, "stage temporaries do not fit into the operand tile");
     static_assert(NHID >= 2 && NHID <= 3, "two or three hidden layers");
@@ -78,6 +91,18 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
 inline size_t tc_img_index(int n, int k) { return (size_t)(k / 8) * (128 * 8) + (size_t)n * 8 + (k % 8); }
 
 #if defined(__CUDACC__)
+// -DNEMPC_TC_PROFILE: thread 0 of every CTA accumulates the cycles between phase boundaries (development builds only)
+#ifdef NEMPC_TC_PROFILE
+__device__ unsigned long long nempc_tc_prof[16];
+#define TC_PROF_DECL long long prof_t0 = clock64(); unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TC_PROF(i) do { const long long t_ = clock64(); prof_acc[i] += (unsigned long long)(t_ - prof_t0); prof_t0 = t_; } while (0)
+#define TC_PROF_FLUSH do { if (tid == 0) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&nempc_tc_prof[i_], prof_acc[i_]); } while (0)
+#else
+#define TC_PROF_DECL
+#define TC_PROF(i) do {} while (0)
+#define TC_PROF_FLUSH do {} while (0)
+#endif
+
 template <class C, typename TIO>
 __global__ void __launch_bounds__(NEMPC_TC_THREADS, 1)
 nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk, const StageTable<float> st,
@@ -92,7 +117,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int m = tid & 127, hf = tid >> 7;
+    const int m = tid & 127, cq = tid >> 7;         // row, column group
     const int kind = m / SPT, sl = m - kind * SPT;
     const bool valid = m < C::ROWS;
     int cT = 0, c1 = 0, c2 = 0;                       // tangent column of a T row; column pair of an S row
@@ -104,6 +129,10 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             c2 = e;
         }
     }
+    // pass 2 reads tensor memory only for rows that did not park their values in pass 1: S rows (Hessian mode) or T rows
+    // (Jacobian mode); the load is warp-collective, so the test is per lane quadrant
+    const int first_tmem_row = HES ? SPT * (1 + D) : SPT;
+    const bool quad_reads_tmem = JAC && ((warp & 3) * 32 + 31 >= first_tmem_row) && ((warp & 3) * 32 < C::ROWS);
     const bool is_T = valid && kind >= 1 && kind <= D;
     const bool is_S = valid && kind > D;
 
@@ -115,6 +144,8 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     float* sideH = reinterpret_cast<float*>(tc_smem + C::OFF_SH);
     float* sideT = reinterpret_cast<float*>(tc_smem + C::OFF_ST);
     float* pers = reinterpret_cast<float*>(tc_smem + C::OFF_P);
+    int* step_b = reinterpret_cast<int*>(tc_smem + C::OFF_I);       // problem index of step s_ of the tile, -1 past the end
+    int* step_t = step_b + SPT;
     unsigned char* Ahi = tc_smem + C::OFF_A;
     unsigned char* Alo = Ahi + C::IMG;
     float* part = reinterpret_cast<float*>(Ahi + C::A_PART);
@@ -122,7 +153,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
 
     const uint32_t mbar_w = smem_u32(&mbar_store[0]), mbar_mma = smem_u32(&mbar_store[1]);
     if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(mbar_mma, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), 256);
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), 128);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -143,17 +174,25 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     uint32_t parity = 0;
     const long long ntiles = (ar.nsteps + SPT - 1) / SPT;
 
+    TC_PROF_DECL
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long step0 = tile * SPT;
+        TC_PROF(11);
         // ---- inputs and per-step state ------------------------------------------------------------------------------
+        if (tid < SPT) {
+            const long long step = step0 + tid;
+            const long long b = step / L.H;
+            step_b[tid] = step < ar.nsteps ? (int)b : -1;
+            step_t[tid] = (int)(step - b * L.H);
+        }
+        __syncthreads();
         for (int idx = tid; idx < SPT * C::P_TOTAL; idx += NEMPC_TC_THREADS) {
             const int s_ = idx / C::P_TOTAL, o = idx - s_ * C::P_TOTAL;
             float v = 0.f;
-            const long long step = step0 + s_;
             if (o < D) {
-                if (step < ar.nsteps) {
-                    const long long b = step / L.H;
-                    const int t = (int)(step - b * L.H);
+                const long long b = step_b[s_];
+                if (b >= 0) {
+                    const int t = step_t[s_];
                     const TIO* zb = ar.z + b * (long long)L.n;
                     if (o < X) v = (float)((t == 0) ? ar.x0[b * X + o] : zb[(t - 1) * X + o]);
                     else v = (float)zb[L.H * X + t * U + (o - X)];
@@ -165,6 +204,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             pers[idx] = v;
         }
         __syncthreads();
+        TC_PROF(0);
 
         for (int s = 0; s < st.S; ++s) {
             const float a_s = st.a[s], c_s = st.c[s];
@@ -180,31 +220,40 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 }
                 sideH[s_ * SROW + j] = fast_tanh(a);
             }
+            if (HES) {      // da_0/dz_c = W0[c]: park it like the raw tangents of any other layer, so pass 2 has ONE code path
+                for (int e = tid; e < D * SPT * (HW / 4); e += NEMPC_TC_THREADS) {
+                    const int c = e / (SPT * (HW / 4)), r = e - c * (SPT * (HW / 4)), s_ = r / (HW / 4), j4 = r - s_ * (HW / 4);
+                    *reinterpret_cast<float4*>(sideT + (c * SPT + s_) * SROW + 4 * j4) = *reinterpret_cast<const float4*>(W0 + c * HW + 4 * j4);
+                }
+            }
             __syncthreads();
+            TC_PROF(1);
 
             constexpr int XH = (X + 1) / 2;
             f2 oacc2[XH];                                          // output-layer partial sums, packed over output pairs
 #pragma unroll
             for (int q = 0; q < XH; ++q) oacc2[q] = pk(0.f, 0.f);
 
-#pragma unroll
-            for (int l = 0; l < NHID; ++l) {                       // fully unrolled: FIRST / LAST are compile-time below
-                const bool FIRST = (l == 0), LAST = (l == NHID - 1);
-                // ---- pass 2 of layer l: post-activation rows -> next operand tile (or the output contraction) ---------------
-                // Packed f32x2 arithmetic (FFMA2); the row class (P / T / S) is a per-thread branch that only diverges in the
-                // two warps that straddle a class boundary (row order is kind-major).
-#pragma unroll 2
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int col = 64 * hf + 16 * q4;
+            // ---- pass 2 of a layer: post-activation rows -> next operand tile (or, LAST, the output contraction) ---------------
+            // Packed f32x2 arithmetic (FFMA2); the row class (P / T / S) is a per-thread branch that only diverges in the two
+            // warps that straddle a class boundary (row order is kind-major).  One instance serves every layer but the last
+            // (the kernel is kept small on purpose: the lone MMA-issuing thread pays every instruction-cache miss in full).
+            auto pass2 = [&](auto last_tag, const bool first) {
+                constexpr bool LAST = decltype(last_tag)::value;
+                constexpr int P2U = NEMPC_TC_P2_UNROLL;
+#pragma unroll P2U
+                for (int q4 = 0; q4 < C::CPT / 16; ++q4) {
+                    const int col = C::CPT * cq + 16 * q4;
                     f2 v2[8];
-                    if (!FIRST) {                                  // warp-collective tensor-memory loads: every lane takes part
-                        float v[16], vc[16];
+                    if (!first && quad_reads_tmem) {               // warp-collective tensor-memory load: every lane of the warp takes part
+                        float v[16];
                         tmem_ld16(tm_row + col, v);
-                        tmem_ld16(tm_row + 128 + col, vc);
                         tmem_ld_wait();
-                        const f2 inv = pk(NEMPC_TC_LO_INV, NEMPC_TC_LO_INV);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v2[i] = fma2(pk(vc[2 * i], vc[2 * i + 1]), inv, pk(v[2 * i], v[2 * i + 1]));
+                        for (int i = 0; i < 8; ++i) v2[i] = pk(v[2 * i], v[2 * i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v2[i] = pk(0.f, 0.f);    // first layer: d2a_0 = 0
                     }
                     f2 out2[8];
                     if (!valid) {
@@ -218,22 +267,25 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                                 const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
                                 out2[2 * i4] = pk(h4.x, h4.y); out2[2 * i4 + 1] = pk(h4.z, h4.w);
                             }
-                        } else if (!is_S) {                        // T_c: s'(a) * da/dz_c   (first layer: da_0/dz_c = W0[c])
-                            const float* w0t = W0 + cT * HW + col;
+                        } else if (!is_S) {                        // T_c: s'(a) * da/dz_c
+                            // raw tangent: parked in sideT (Hessian mode); else W0[c] for the first layer, tensor memory otherwise
+                            const float* traw = HES ? sideT + (cT * SPT + sl) * SROW + col : W0 + cT * HW + col;
                             const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f);
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
                                 const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
-                                f2 va, vb;
-                                if (FIRST) { const float4 w4 = *reinterpret_cast<const float4*>(w0t + 4 * i4); va = pk(w4.x, w4.y); vb = pk(w4.z, w4.w); }
-                                else { va = v2[2 * i4]; vb = v2[2 * i4 + 1]; }
+                                f2 va = v2[2 * i4], vb = v2[2 * i4 + 1];
+                                if (HES || first) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(traw + 4 * i4);
+                                    va = pk(w4.x, w4.y); vb = pk(w4.z, w4.w);
+                                }
                                 const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
                                 out2[2 * i4] = mul2(fma2(mul2(ha, m1), ha, one), va);
                                 out2[2 * i4 + 1] = mul2(fma2(mul2(hb, m1), hb, one), vb);
                             }
-                        } else {                                   // S_(c1,c2): s''(a) T_c1 T_c2 + s'(a) d2a   (first layer: d2a_0 = 0)
-                            const float* t1 = FIRST ? W0 + c1 * HW + col : sideT + (c1 * SPT + sl) * SROW + col;
-                            const float* t2 = FIRST ? W0 + c2 * HW + col : sideT + (c2 * SPT + sl) * SROW + col;
+                        } else {                                   // S_(c1,c2): s''(a) T_c1 T_c2 + s'(a) d2a
+                            const float* t1 = sideT + (c1 * SPT + sl) * SROW + col;
+                            const float* t2 = sideT + (c2 * SPT + sl) * SROW + col;
                             const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f), m2 = pk(-2.f, -2.f);
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
@@ -244,8 +296,8 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                                 const f2 s1a = fma2(mul2(ha, m1), ha, one), s1b = fma2(mul2(hb, m1), hb, one);
                                 const f2 qa = mul2(mul2(ha, s1a), mul2(pk(a4.x, a4.y), pk(b4.x, b4.y)));      // h s' T_c1 T_c2
                                 const f2 qb = mul2(mul2(hb, s1b), mul2(pk(a4.z, a4.w), pk(b4.z, b4.w)));
-                                if (FIRST) { out2[2 * i4] = mul2(qa, m2); out2[2 * i4 + 1] = mul2(qb, m2); }
-                                else { out2[2 * i4] = fma2(qa, m2, mul2(s1a, v2[2 * i4])); out2[2 * i4 + 1] = fma2(qb, m2, mul2(s1b, v2[2 * i4 + 1])); }
+                                out2[2 * i4] = fma2(qa, m2, mul2(s1a, v2[2 * i4]));
+                                out2[2 * i4 + 1] = fma2(qb, m2, mul2(s1b, v2[2 * i4 + 1]));
                             }
                         }
                     }
@@ -281,30 +333,59 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         }
                     }
                 }
-                if (LAST) break;
+            };
+
+#pragma unroll 1
+            for (int l = 0; l < NHID - 1; ++l) {
+                pass2(std::false_type{}, l == 0);
+                TC_PROF(2);
 
                 // ---- hidden-to-hidden layer l -> l+1 on the tensor core -------------------------------------------------------
                 fence_async_smem();
                 fence_before_sync();
                 __syncthreads();
-                if (tid == 0) {
+                TC_PROF(3);
+                if (warp == 0) {
+                  if (tid == 0) {
                     fence_after_sync();
-                    const uint32_t whi = smem_u32(tc_smem + C::OFF_W + l * 2 * C::IMG), wlo = whi + C::IMG;
-                    const uint32_t ahi = smem_u32(Ahi), alo = smem_u32(Alo);
-#pragma unroll 1
-                    for (int ks = 0; ks < HW / 16; ++ks) {
-                        const uint32_t off = ks * 2 * 2048;
-                        const uint64_t a1 = make_desc_kmajor(ahi + off, 2048, 128), a2 = make_desc_kmajor(alo + off, 2048, 128);
-                        const uint64_t w1 = make_desc_kmajor(whi + off, 2048, 128), w2 = make_desc_kmajor(wlo + off, 2048, 128);
-                        mma_f16_ss(tmem, a1, w1, idesc, ks > 0);
-                        mma_f16_ss(tmem + 128, a2, w1, idesc, ks > 0);
-                        mma_f16_ss(tmem + 128, a1, w2, idesc, 1);
-                    }
+                    // The weight-image offset must be a COMPILE-TIME constant: with a runtime layer index ptxas cannot prove the
+                    // descriptors warp-uniform inside this single-thread branch and wraps every MMA in an ELECT / R2UR loop
+                    // (~110 clk per MMA instead of the tensor core's 64).  Hence one unrolled instance per layer.
+                    auto issue = [&](auto layer_tag) {
+                        constexpr int LI = decltype(layer_tag)::value;
+                        const uint32_t whi = smem_u32(tc_smem) + C::OFF_W + LI * 2 * C::IMG, wlo = whi + C::IMG;
+                        const uint32_t ahi = smem_u32(tc_smem) + C::OFF_A, alo = ahi + C::IMG;
+                        // correction terms first (both carry the factor 2^11), then the first main MMA folds them in with
+                        // scale-input-d: D = A_hi W_hi + D * 2^-11 -- ONE f32 accumulator, half the tensor-memory read volume.
+                        // Fully unrolled, descriptors advanced in their low word only (uniform-register arithmetic).
+                        const uint32_t dhi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+                        const uint32_t dlo = (2048u >> 4) << 16;                             // LBO = 2048 B
+                        const uint32_t la1 = dlo | (ahi >> 4), la2 = dlo | (alo >> 4), lw1 = dlo | (whi >> 4), lw2 = dlo | (wlo >> 4);
+#define NEMPC_TC_DESC(lo, ks) ((((uint64_t)dhi) << 32) | (uint64_t)((lo) + (ks) * 256u))
+                        TC_PROF(12);
+#pragma unroll
+                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la2, ks), NEMPC_TC_DESC(lw1, ks), idesc, ks != 0);
+                        TC_PROF(13);
+#pragma unroll
+                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la1, ks), NEMPC_TC_DESC(lw2, ks), idesc, 1);
+                        TC_PROF(14);
+                        mma_f16_ss_scaled_d<11>(tmem, NEMPC_TC_DESC(la1, 0), NEMPC_TC_DESC(lw1, 0), idesc);
+#pragma unroll
+                        for (int ks = 1; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la1, ks), NEMPC_TC_DESC(lw1, ks), idesc, 1);
+#undef NEMPC_TC_DESC
+                    };
+                    if (l == 0) issue(std::integral_constant<int, 0>{});
+                    else issue(std::integral_constant<int, (NMM > 1 ? 1 : 0)>{});
                     mma_commit(mbar_mma);
+                    TC_PROF(4);
+                    mbar_wait(mbar_mma, parity);                   // ONE polling thread; everybody else blocks on the hardware barrier below
+                  }
+                  __syncwarp();
                 }
-                mbar_wait(mbar_mma, parity);
                 parity ^= 1;
+                __syncthreads();                                   // everybody else blocks on the hardware barrier
                 fence_after_sync();
+                TC_PROF(5);
 
                 // ---- pass 1 of layer l+1: P rows park a_{l+1} (+ bias), T rows park their raw tangents ---------------------------
                 {
@@ -312,53 +393,56 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     if ((warp & 3) * 32 < need_rows) {
                         const float* bl = bias + (l + 1) * HW;
 #pragma unroll 1
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int col = 64 * hf + 16 * q4;
-                            float v[16], vc[16];
+                        for (int q4 = 0; q4 < C::CPT / 16; ++q4) {
+                            const int col = C::CPT * cq + 16 * q4;
+                            float v[16];
                             tmem_ld16(tm_row + col, v);
-                            tmem_ld16(tm_row + 128 + col, vc);
                             tmem_ld_wait();
                             if (valid && kind == 0) {
 #pragma unroll
                                 for (int i4 = 0; i4 < 4; ++i4) {
                                     const float4 b4 = *reinterpret_cast<const float4*>(bl + col + 4 * i4);
                                     *reinterpret_cast<float4*>(sideH + sl * SROW + col + 4 * i4) =
-                                        make_float4(fmaf(vc[4 * i4], NEMPC_TC_LO_INV, v[4 * i4]) + b4.x, fmaf(vc[4 * i4 + 1], NEMPC_TC_LO_INV, v[4 * i4 + 1]) + b4.y,
-                                                    fmaf(vc[4 * i4 + 2], NEMPC_TC_LO_INV, v[4 * i4 + 2]) + b4.z, fmaf(vc[4 * i4 + 3], NEMPC_TC_LO_INV, v[4 * i4 + 3]) + b4.w);
+                                        make_float4(v[4 * i4] + b4.x, v[4 * i4 + 1] + b4.y, v[4 * i4 + 2] + b4.z, v[4 * i4 + 3] + b4.w);
                                 }
                             } else if (HES && is_T) {
 #pragma unroll
                                 for (int i4 = 0; i4 < 4; ++i4)
                                     *reinterpret_cast<float4*>(sideT + (cT * SPT + sl) * SROW + col + 4 * i4) =
-                                        make_float4(fmaf(vc[4 * i4], NEMPC_TC_LO_INV, v[4 * i4]), fmaf(vc[4 * i4 + 1], NEMPC_TC_LO_INV, v[4 * i4 + 1]),
-                                                    fmaf(vc[4 * i4 + 2], NEMPC_TC_LO_INV, v[4 * i4 + 2]), fmaf(vc[4 * i4 + 3], NEMPC_TC_LO_INV, v[4 * i4 + 3]));
+                                        make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
                             }
                         }
                     }
                 }
                 __syncthreads();
+                TC_PROF(6);
                 for (int e = tid; e < SPT * HW; e += NEMPC_TC_THREADS) {
                     const int s_ = e / HW, j = e - s_ * HW;
                     sideH[s_ * SROW + j] = fast_tanh(sideH[s_ * SROW + j]);
                 }
                 __syncthreads();
+                TC_PROF(7);
             }
+            pass2(std::true_type{}, false);                        // last hidden layer: rows contracted with W_out in registers
+            TC_PROF(2);
 
             // ---- linear output layer: join the two neuron halves; k, J, M_p of this stage -------------------------------------
             float oacc[X];
 #pragma unroll
             for (int p = 0; p < X; ++p) oacc[p] = (p & 1) ? f2hi(oacc2[p / 2]) : f2lo(oacc2[p / 2]);
             __syncthreads();                                       // every thread is done with tensor memory and the side buffers
-            if (hf == 1 && valid) {
+            if (cq > 0 && valid) {
 #pragma unroll
-                for (int p = 0; p < X; ++p) part[m * XP + p] = oacc[p];
+                for (int p = 0; p < X; ++p) part[((cq - 1) * 128 + m) * XP + p] = oacc[p];
             }
             __syncthreads();
-            if (hf == 0 && valid) {
+            if (cq == 0 && valid) {
                 float* tp = temps + sl * C::T_TOTAL;
 #pragma unroll
                 for (int p = 0; p < X; ++p) {
-                    const float tot = oacc[p] + part[m * XP + p];
+                    float tot = oacc[p];
+#pragma unroll
+                    for (int g = 0; g + 1 < C::NQ; ++g) tot += part[(g * 128 + m) * XP + p];
                     if (kind == 0) tp[C::T_KCUR + p] = tot + bout[p];
                     else if (kind <= D) tp[C::T_J + p * D + cT] = tot;
                     else { tp[C::T_M + p * DD + c1 * D + c2] = tot; tp[C::T_M + p * DD + c2 * D + c1] = tot; }
@@ -366,6 +450,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
             __syncthreads();
 
+            TC_PROF(8);
             // ---- stage algebra (as nempc_generic.cuh), flattened over the SPT steps of the tile ---------------------------------
             if (JAC) {
                 for (int idx = tid; idx < SPT * X * D; idx += NEMPC_TC_THREADS) {
@@ -437,14 +522,14 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             __syncthreads();
         }
 
+        TC_PROF(9);
         // ---- outputs (same slots as nempc_generic.cuh) ----------------------------------------------------------------------
         if (ar.resid) {
             for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {
                 const int s_ = idx / X, p = idx - s_ * X;
-                const long long step = step0 + s_;
-                if (step >= ar.nsteps) continue;
-                const long long b = step / L.H;
-                const int t = (int)(step - b * L.H);
+                const long long b = step_b[s_];
+                if (b < 0) continue;
+                const int t = step_t[s_];
                 const TIO* zb = ar.z + b * (long long)L.n;
                 const TW xt = (TW)zb[t * X + p];
                 const TW xp = unity ? (TW)0 : (TW)((t == 0) ? ar.x0[b * X + p] : zb[(t - 1) * X + p]);
@@ -454,10 +539,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
         if (JAC && ar.jac) {
             for (int idx = tid; idx < SPT * X * (D + 1); idx += NEMPC_TC_THREADS) {
                 const int s_ = idx / (X * (D + 1)), r = idx - s_ * (X * (D + 1)), p = r / (D + 1), c = r - p * (D + 1);
-                const long long step = step0 + s_;
-                if (step >= ar.nsteps) continue;
-                const long long b = step / L.H;
-                const int t = (int)(step - b * L.H);
+                const long long b = step_b[s_];
+                if (b < 0) continue;
+                const int t = step_t[s_];
                 TIO* jv = ar.jac + b * L.nnz_jac;
                 if (c == D) { jv[jac_slot_minus1(L, t, p)] = (TIO)-1; continue; }
                 const TW v = (TW)pers[s_ * C::P_TOTAL + C::P_DKACC + p * D + c] + ((!unity && c == p) ? (TW)1 : (TW)0);
@@ -468,10 +552,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
         if (HES && ar.hes) {
             for (int idx = tid; idx < SPT * DD; idx += NEMPC_TC_THREADS) {
                 const int s_ = idx / DD, r = idx - s_ * DD, a = r / D, c = r - a * D;
-                const long long step = step0 + s_;
-                if (step >= ar.nsteps || c > a) continue;
-                const long long b = step / L.H;
-                const int t = (int)(step - b * L.H);
+                const long long b = step_b[s_];
+                if (b < 0 || c > a) continue;
+                const int t = step_t[s_];
                 if (t == 0 && c < X) continue;                          // x0 is data, not a variable (discret.py:70-78)
                 TIO* hv = ar.hes + b * L.nnz_hes;
                 const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
@@ -494,20 +577,21 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
             for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {   // objective-only diagonal of x_H
                 const int s_ = idx / X, p = idx - s_ * X;
-                const long long step = step0 + s_;
-                if (step >= ar.nsteps) continue;
-                const long long b = step / L.H;
-                const int t = (int)(step - b * L.H);
+                const long long b = step_b[s_];
+                if (b < 0) continue;
+                const int t = step_t[s_];
                 if (t != L.H - 1 || L.hes_last_slot[p] < 0) continue;
                 const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
                 ar.hes[b * L.nnz_hes + L.hes_last_slot[p]] = (TIO)(sig * (TW)2 * (TW)ar.quad[(L.H - 1) * X + p]);
             }
         }
         __syncthreads();                                           // per-step state is rewritten by the next tile
+        TC_PROF(10);
     }
+    TC_PROF_FLUSH;
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 #endif  // __CUDACC__

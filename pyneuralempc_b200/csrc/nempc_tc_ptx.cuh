@@ -35,6 +35,18 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
         : "memory");
 }
 
+// D = A B + D * 2^-SCALE  (scale-input-d, kind::f16 / kind::tf32 only; SCALE is an immediate in [0, 15])
+template <int SCALE>
+__device__ __forceinline__ void mma_f16_ss_scaled_d(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(SCALE)
+        : "memory");
+}
+
 // all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");

@@ -45,6 +45,16 @@ def main():
     steps = B * wl["H"]
     print(f"{args.workload} {wl['integ']} B={B} H={wl['H']} want={args.want} kernel={ev.kernel_name}\n"
           f"  {ms:.3f} ms/eval  {steps / ms * 1e3:.4g} horizon-steps/s  {ev.flops_per_step * steps / ms / 1e9:.2f} TFLOP/s algorithmic", flush=True)
+    if hasattr(ev.lib, "nempc_debug_tc_profile"):      # -DNEMPC_TC_PROFILE build (NEMPC_LIB_PATH): cycles per phase, thread 0 of each CTA
+        import ctypes
+        buf = (ctypes.c_ulonglong * 16)()
+        ev.lib.nempc_debug_tc_profile(buf)
+        names = ["init", "l0 tanh", "pass2", "sync->mma", "mma issue", "mma wait", "pass1", "tanh", "out combine", "algebra", "outputs", "loop"]
+        tot = sum(buf[:16]) or 1
+        print("  phase cycles (share): " + ", ".join(f"{n} {buf[i] / tot:.1%}" for i, n in enumerate(names)), flush=True)
+        ntl = (steps + 5) // 6 * (args.reps + 2)
+        print(f"  cycles per tile (thread 0, C3 SPT=6): {tot / ntl:.0f}")
+        print("  mma issue detail (cycles per batch): setup %.0f, corr-1 x8 %.0f, corr-2 x8 %.0f, main x8 + commit %.0f" % tuple(buf[i] / (ntl * 8) for i in (12, 13, 14, 4)))
     ev.close()
 
 
