@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -127,13 +128,80 @@ __global__ void nempc_ipm_init_kernel(const NlpLayout L, const SolverWs w, const
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) ipm_init_problem(L, w, b, o, has_init != 0);
 }
-template <int XM, int UM>
+template <int XM, int UM, int XC, int UC>
 __global__ void nempc_ipm_kkt_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    ipm_kkt_problem<XM, UM>(L, w, b, o);
+    ipm_kkt_problem<XM, UM, XC, UC>(L, w, b, o);
     if (w.status[b] == NEMPC_ST_RUNNING) { atomicAdd(&counts[0], 1); if (!w.accepted[b]) atomicAdd(&counts[1], 1); }
 }
+// Staged variant: ONE WARP PER PROBLEM.  The Riccati sweeps are a long chain of dependent float64 operations per problem;
+// with one thread per problem reading its rows straight from global memory (row stride n doubles between threads, nothing
+// coalesces) and doing ~2000 divisions and ~100 logarithms inside that chain, the kernel took 1.08 ms for 4096 problems
+// (profiles/r1k).  Here the warp copies the problem's rows (iterate, duals, gradient, residual, Jacobian / Hessian values)
+// into shared memory with coalesced loads and runs ipm_kkt_warp: per-variable work on 32 lanes, the Riccati recursion on
+// lane 0, bit-identical results.  Bounds are staged once per CTA.
+template <int XM, int UM, int XC, int UC>
+__global__ void __launch_bounds__(512)
+nempc_ipm_kkt_staged_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
+    extern __shared__ __align__(16) double kkt_sm[];
+    const int n = L.n, m = L.m, nj = (int)L.nnz_jac, nh = (int)L.nnz_hes, nK = L.H * L.u * L.x, nk = L.H * L.u;
+    const int per = 8 * n + 3 * m + nj + nh + nK + nk;
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* slb = kkt_sm; double* sub = kkt_sm + n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { slb[i] = w.lb[i]; sub[i] = w.ub[i]; }
+    const long long b = (long long)blockIdx.x * wpb + warp;
+    double* p = kkt_sm + 2 * n + (size_t)warp * per;
+    double* sz = p; p += n; double* szL = p; p += n; double* szU = p; p += n; double* sgr = p; p += n;
+    double* slam = p; p += m; double* sres = p; p += m; double* sjac = p; p += nj; double* shes = p; p += nh;
+    double* sdz = p; p += n; double* slamn = p; p += m; double* sK = p; p += nK; double* skf = p; p += nk;
+    double* s1 = p; p += n; double* s2 = p; p += n; double* s3 = p;
+    const bool live = b < B && w.status[b < B ? b : 0] == NEMPC_ST_RUNNING;
+    if (live) {
+        for (int i = lane; i < n; i += 32) { sz[i] = w.z[b * n + i]; szL[i] = w.zL[b * n + i]; szU[i] = w.zU[b * n + i]; sgr[i] = w.grad[b * n + i]; }
+        for (int i = lane; i < m; i += 32) { slam[i] = w.lam[b * m + i]; sres[i] = w.resid[b * m + i]; }
+        for (int i = lane; i < nj; i += 32) sjac[i] = w.jac[b * L.nnz_jac + i];
+        for (int i = lane; i < nh; i += 32) shes[i] = w.hes[b * L.nnz_hes + i];
+    } else if (b < B && lane == 0) w.accepted[b] = 1;
+    __syncthreads();
+    if (!live) return;
+    SolverWs w2 = w;
+    w2.lb = slb; w2.ub = sub;
+    KktRows r;
+    r.z = sz; r.lam = slam; r.zL = szL; r.zU = szU; r.gr = sgr; r.c = sres; r.jv = sjac; r.hv = shes;
+    r.dz = sdz; r.lamn = slamn; r.Kb = sK; r.kfb = skf;
+    r.dzL = w.dzL + b * n; r.dzU = w.dzU + b * n; r.zt = w.zt + b * n;
+    r.s1 = s1; r.s2 = s2; r.s3 = s3;
+    ipm_kkt_warp<XM, UM, XC, UC>(L, w2, b, o, r, lane);
+    __syncwarp();
+    if (lane == 0 && w.status[b] == NEMPC_ST_RUNNING) { atomicAdd(&counts[0], 1); if (!w.accepted[b]) atomicAdd(&counts[1], 1); }
+    for (int i = lane; i < n; i += 32) w.dz[b * n + i] = sdz[i];
+    for (int i = lane; i < m; i += 32) w.lamn[b * m + i] = slamn[i];
+    for (int i = lane; i < nK; i += 32) w.K[b * (long long)nK + i] = sK[i];
+    for (int i = lane; i < nk; i += 32) w.kf[b * (long long)nk + i] = skf[i];
+}
+
+// iterate update, one thread per (problem, variable): same arithmetic as ipm_update_problem, coalesced
+__global__ void nempc_ipm_update_flat_kernel(const NlpLayout L, const SolverWs w, long long B) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = L.n, m = L.m;
+    if (idx >= B * n) return;
+    const long long b = idx / n;
+    const int i = (int)(idx - b * n);
+    if (w.status[b] != NEMPC_ST_RUNNING) return;
+    const double a = w.alpha[b], aD = w.alphaD[b], mu = w.mu[b];
+    const double ks = 1e10;
+    const double zi = w.z[idx] + a * w.dz[idx];
+    w.z[idx] = zi;
+    if (nempc_finite(w.lb[i])) { const double d = zi - w.lb[i]; w.zL[idx] = fmin(fmax(w.zL[idx] + aD * w.dzL[idx], mu / (ks * d)), ks * mu / d); }
+    if (nempc_finite(w.ub[i])) { const double d = w.ub[i] - zi; w.zU[idx] = fmin(fmax(w.zU[idx] + aD * w.dzU[idx], mu / (ks * d)), ks * mu / d); }
+    if (i < m) { const long long j = b * m + i; w.lam[j] += a * (w.lamn[j] - w.lam[j]); }
+}
+__global__ void nempc_ipm_count_iter_kernel(const SolverWs w, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && w.status[b] == NEMPC_ST_RUNNING) w.iters[b] += 1;
+}
+
 __global__ void nempc_ipm_linesearch_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -832,7 +900,33 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     w.status = ip; w.iters = ip + B; w.accepted = ip + 2 * B;
     const int threads = 128;
     const unsigned grid = (unsigned)((B + threads - 1) / threads);
-    const bool small = L.x <= 4 && L.u <= 2;
+    // KKT kernel instance: exact (x_dim, u_dim) instantiations for the common small systems, run-time dimensions otherwise;
+    // staged = one warp per problem with the problem's rows copied to shared memory first (used whenever a problem fits;
+    // NEMPC_KKT_STAGED=0 forces the thread-per-problem kernel)
+    typedef void (*kkt_fn)(const NlpLayout, const SolverWs, const SolverOpts, long long, int*);
+    kkt_fn kkt_plain, kkt_staged;
+#define NEMPC_KKT_PICK(XM_, UM_, XC_, UC_) do { kkt_plain = nempc_ipm_kkt_kernel<XM_, UM_, XC_, UC_>; kkt_staged = nempc_ipm_kkt_staged_kernel<XM_, UM_, XC_, UC_>; } while (0)
+    if (L.x == 2 && L.u == 1) NEMPC_KKT_PICK(2, 1, 2, 1);
+    else if (L.x == 3 && L.u == 1) NEMPC_KKT_PICK(3, 1, 3, 1);
+    else if (L.x == 4 && L.u == 1) NEMPC_KKT_PICK(4, 1, 4, 1);
+    else if (L.x == 4 && L.u == 2) NEMPC_KKT_PICK(4, 2, 4, 2);
+    else if (L.x <= 4 && L.u <= 2) NEMPC_KKT_PICK(4, 2, 0, 0);
+    else NEMPC_KKT_PICK(NEMPC_SOLVER_XM, NEMPC_SOLVER_UM, 0, 0);
+#undef NEMPC_KKT_PICK
+    // warps (= problems) per CTA: the count that packs the most problems per SM into shared memory (bounds are per CTA)
+    const size_t per_bytes = (8 * n + 3 * m + nj + nh + Hux + Hu) * sizeof(double), bnd_bytes = 2 * n * sizeof(double);
+    // at most 192 KB of the SM for staging: the Riccati body keeps its small matrices in local memory and needs the L1 that is left
+    const size_t smem_sm = 192 * 1024, smem_cta_max = std::min<size_t>(smem_sm - 1024, (size_t)std::max(0, h->max_smem_optin - 1024));
+    int staged_wpb = 0; size_t staged_smem = 0; long long best = 0;
+    for (int wpb = 1; wpb <= 16; ++wpb) {
+        const size_t need = bnd_bytes + wpb * per_bytes;
+        if (need > smem_cta_max) break;
+        const long long ctas = std::min<long long>(32, (long long)(smem_sm / (need + 1024))), per_sm = std::min<long long>(ctas * wpb, 64);
+        if (per_sm > best) { best = per_sm; staged_wpb = wpb; staged_smem = need; }
+    }
+    const char* force = getenv("NEMPC_KKT_STAGED");
+    if (force && force[0] == '0') staged_smem = 0;
+    if (staged_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kkt_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
     nempc_ipm_init_kernel<<<grid, threads, 0, s>>>(L, w, o, B, use_init);
     CU(h, cudaGetLastError()); h->launches++;
     int it = 0;
@@ -840,8 +934,8 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
         rc = nempc_eval(h, B, w.z, x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)s);
         if (rc) return rc;
         CU(h, cudaMemsetAsync(h->sv_counts, 0, 2 * sizeof(int), s));
-        if (small) nempc_ipm_kkt_kernel<4, 2><<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
-        else nempc_ipm_kkt_kernel<NEMPC_SOLVER_XM, NEMPC_SOLVER_UM><<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+        if (staged_smem) kkt_staged<<<(unsigned)((B + staged_wpb - 1) / staged_wpb), 32 * staged_wpb, staged_smem, s>>>(L, w, o, B, h->sv_counts);
+        else kkt_plain<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
         CU(h, cudaGetLastError()); h->launches++;
         CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
@@ -855,8 +949,12 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
             CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             CU(h, cudaStreamSynchronize(s));
         }
-        nempc_ipm_update_kernel<<<grid, threads, 0, s>>>(L, w, o, B);
-        CU(h, cudaGetLastError()); h->launches++;
+        {
+            const long long tot = (long long)B * L.n;
+            nempc_ipm_update_flat_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(L, w, B);
+            nempc_ipm_count_iter_kernel<<<grid, threads, 0, s>>>(w, B);
+        }
+        CU(h, cudaGetLastError()); h->launches += 2;
     }
     nempc_ipm_finish_kernel<<<grid, threads, 0, s>>>(w, B, status, iterations, kkt_error);
     CU(h, cudaGetLastError()); h->launches++;

@@ -114,20 +114,16 @@ NEMPC_HD double ipm_chol_solve(int u, const double* F, double* R, int nr, const 
     return delta;
 }
 
-// One interior-point iteration up to (and including) the first line-search trial point.
+// ---- Newton step of the barrier problem: Riccati sweeps over the block-tridiagonal KKT system ----------------------------
+// sig(i) = Sigma_i (bound-dual curvature), gb(i) = gradient of the barrier objective; functors so that the one-thread body
+// evaluates them on the fly while the warp-cooperative kernel reads arrays it filled in parallel (same values either way).
 // XM / UM: compile-time capacity of the per-thread matrices (x_dim <= XM, u_dim <= UM).
-template <int XM, int UM>
-NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b, const SolverOpts& o) {
-    if (w.status[b] != NEMPC_ST_RUNNING) { w.accepted[b] = 1; return; }
-    const int H = L.H, x = L.x, u = L.u, n = L.n, m = L.m, nx = H * x;
-    const double* z = w.z + b * n; const double* lam = w.lam + b * m;
-    const double* zL = w.zL + b * n; const double* zU = w.zU + b * n;
-    const double* gr = w.grad + b * n; const double* c = w.resid + b * m;
-    const double* jv = w.jac + b * L.nnz_jac; const double* hv = w.hes + b * L.nnz_hes;
-    double* dz = w.dz + b * n; double* lamn = w.lamn + b * m; double* dzL = w.dzL + b * n; double* dzU = w.dzU + b * n;
-    double* Kb = w.K + b * (long long)H * u * x; double* kfb = w.kf + b * (long long)H * u;
-    double mu = w.mu[b];
-
+// XC / UC: exact x_dim / u_dim when known at compile time (0 = run time): every inner loop unrolls and the small matrices
+// live in registers instead of local memory.
+template <int XM, int UM, int XC, int UC, class SigF, class GbF>
+NEMPC_HD void ipm_kkt_riccati(const NlpLayout& L, const SolverOpts& o, const double* c, const double* jv, const double* hv,
+                              double* dz, double* lamn, double* Kb, double* kfb, SigF sig, GbF gb) {
+    const int H = L.H, x = XC ? XC : L.x, u = UC ? UC : L.u, nx = H * x;
 #define A_(k, p, q) ((k) > 0 ? jv[jac_slot_A(L, (k), (p), (q))] : 0.0)
 #define B_(k, p, q) (jv[jac_slot_B(L, (k), (p), (q))])
 #define WXX_(k, p, q) (hv[hes_slot_xx(L, (k), (p) >= (q) ? (p) : (q), (p) >= (q) ? (q) : (p))])
@@ -135,50 +131,6 @@ NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b
 #define WUU_(k, q, r) (hv[hes_slot_uu(L, (k), (q) >= (r) ? (q) : (r), (q) >= (r) ? (r) : (q))])
 #define XI_(node, p) (((node) - 1) * x + (p))          /* variable index of (X_node)_p, node = 1..H */
 #define UI_(k, q) (nx + (k) * u + (q))
-
-    // ---- optimality error (max-norm of dual infeasibility, constraint violation, complementarity) -------------------
-    double e_d = 0.0, e_c = 0.0, e_comp = 0.0, e_compmu = 0.0;
-    for (int i = 0; i < m; ++i) e_c = fmax(e_c, fabs(c[i]));
-    for (int k = 0; k < H; ++k) {
-        for (int p = 0; p < x; ++p) {                      // X_{k+1}
-            const int i = XI_(k + 1, p);
-            double r = gr[i] - lam[k * x + p] - zL[i] + zU[i];
-            if (k + 1 < H) for (int q = 0; q < x; ++q) r += A_(k + 1, q, p) * lam[(k + 1) * x + q];
-            e_d = fmax(e_d, fabs(r));
-        }
-        for (int q = 0; q < u; ++q) {                      // U_k
-            const int i = UI_(k, q);
-            double r = gr[i] - zL[i] + zU[i];
-            for (int p = 0; p < x; ++p) r += B_(k, p, q) * lam[k * x + p];
-            e_d = fmax(e_d, fabs(r));
-        }
-    }
-    for (int i = 0; i < n; ++i) {
-        if (nempc_finite(w.lb[i])) { const double v = (z[i] - w.lb[i]) * zL[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
-        if (nempc_finite(w.ub[i])) { const double v = (w.ub[i] - z[i]) * zU[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
-    }
-    const double err = fmax(e_d, fmax(e_c, e_comp));
-    w.err[b] = err;
-    if (err <= o.tol) { w.status[b] = NEMPC_ST_CONVERGED; w.accepted[b] = 1; return; }
-    if (fmax(e_d, fmax(e_c, e_compmu)) <= o.kappa_eps * mu) {
-        mu = fmax(o.mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
-        w.mu[b] = mu;
-    }
-
-    // barrier gradient g_i and Sigma_i on the fly
-    auto sig = [&](int i) {
-        double s = 0.0;
-        if (nempc_finite(w.lb[i])) s += zL[i] / (z[i] - w.lb[i]);
-        if (nempc_finite(w.ub[i])) s += zU[i] / (w.ub[i] - z[i]);
-        return s;
-    };
-    auto gb = [&](int i) {
-        double g = gr[i];
-        if (nempc_finite(w.lb[i])) g -= mu / (z[i] - w.lb[i]);
-        if (nempc_finite(w.ub[i])) g += mu / (w.ub[i] - z[i]);
-        return g;
-    };
-
     // ---- backward Riccati sweep ------------------------------------------------------------------------------------------
     double P[XM * XM], pv[XM], h[XM];
     double PA[XM * XM], PB[XM * UM];
@@ -267,26 +219,103 @@ NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b
             lamn[k * x + p] = r;
         }
     }
+#undef WXX_
+#undef WUX_
+#undef WUU_
+}
+
+// dual-infeasibility residual of variable block (k, j): j < x -> (X_{k+1})_j, else (U_k)_{j-x}
+NEMPC_HD double ipm_dual_residual(const NlpLayout& L, int x, int u, const double* gr, const double* lam, const double* zL,
+                                  const double* zU, const double* jv, int k, int j) {
+    const int H = L.H, nx = H * x;
+    if (j < x) {
+        const int p = j, i = XI_(k + 1, p);
+        double r = gr[i] - lam[k * x + p] - zL[i] + zU[i];
+        if (k + 1 < H) for (int q = 0; q < x; ++q) r += A_(k + 1, q, p) * lam[(k + 1) * x + q];
+        return r;
+    }
+    const int q = j - x, i = UI_(k, q);
+    double r = gr[i] - zL[i] + zU[i];
+    for (int p = 0; p < x; ++p) r += B_(k, p, q) * lam[k * x + p];
+    return r;
+}
+#undef A_
+#undef B_
+#undef XI_
+#undef UI_
+
+NEMPC_HD double ipm_sigma(const SolverWs& w, const double* z, const double* zL, const double* zU, int i) {
+    double s = 0.0;
+    if (nempc_finite(w.lb[i])) s += zL[i] / (z[i] - w.lb[i]);
+    if (nempc_finite(w.ub[i])) s += zU[i] / (w.ub[i] - z[i]);
+    return s;
+}
+NEMPC_HD double ipm_gbar(const SolverWs& w, const double* z, const double* gr, double mu, int i) {
+    double g = gr[i];
+    if (nempc_finite(w.lb[i])) g -= mu / (z[i] - w.lb[i]);
+    if (nempc_finite(w.ub[i])) g += mu / (w.ub[i] - z[i]);
+    return g;
+}
+// bound-dual steps of variable i and its fraction-to-the-boundary limits (aP, aD are running minima)
+NEMPC_HD void ipm_bound_step(const SolverWs& w, const double* z, const double* zL, const double* zU, const double* dz, double mu,
+                             double tau, int i, double& dl, double& du, double& aP, double& aD) {
+    dl = 0.0; du = 0.0;
+    if (nempc_finite(w.lb[i])) {
+        const double d = z[i] - w.lb[i];
+        dl = mu / d - zL[i] - zL[i] / d * dz[i];
+        if (dz[i] < 0.0) aP = fmin(aP, -tau * d / dz[i]);
+        if (dl < 0.0) aD = fmin(aD, -tau * zL[i] / dl);
+    }
+    if (nempc_finite(w.ub[i])) {
+        const double d = w.ub[i] - z[i];
+        du = mu / d - zU[i] + zU[i] / d * dz[i];
+        if (dz[i] > 0.0) aP = fmin(aP, tau * d / dz[i]);
+        if (du < 0.0) aD = fmin(aD, -tau * zU[i] / du);
+    }
+}
+
+// One interior-point iteration up to (and including) the first line-search trial point: ONE THREAD per problem.
+template <int XM, int UM, int XC = 0, int UC = 0>
+NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b, const SolverOpts& o) {
+    if (w.status[b] != NEMPC_ST_RUNNING) { w.accepted[b] = 1; return; }
+    const int H = L.H, x = XC ? XC : L.x, u = UC ? UC : L.u, n = L.n, m = L.m;
+    const double* z = w.z + b * n; const double* lam = w.lam + b * m;
+    const double* zL = w.zL + b * n; const double* zU = w.zU + b * n;
+    const double* gr = w.grad + b * n; const double* c = w.resid + b * m;
+    const double* jv = w.jac + b * L.nnz_jac; const double* hv = w.hes + b * L.nnz_hes;
+    double* dz = w.dz + b * n; double* lamn = w.lamn + b * m; double* dzL = w.dzL + b * n; double* dzU = w.dzU + b * n;
+    double* Kb = w.K + b * (long long)H * u * x; double* kfb = w.kf + b * (long long)H * u;
+    double mu = w.mu[b];
+
+    // ---- optimality error (max-norm of dual infeasibility, constraint violation, complementarity) -------------------
+    double e_d = 0.0, e_c = 0.0, e_comp = 0.0, e_compmu = 0.0;
+    for (int i = 0; i < m; ++i) e_c = fmax(e_c, fabs(c[i]));
+    for (int k = 0; k < H; ++k)
+        for (int j = 0; j < x + u; ++j) e_d = fmax(e_d, fabs(ipm_dual_residual(L, x, u, gr, lam, zL, zU, jv, k, j)));
+    for (int i = 0; i < n; ++i) {
+        if (nempc_finite(w.lb[i])) { const double v = (z[i] - w.lb[i]) * zL[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
+        if (nempc_finite(w.ub[i])) { const double v = (w.ub[i] - z[i]) * zU[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
+    }
+    const double err = fmax(e_d, fmax(e_c, e_comp));
+    w.err[b] = err;
+    if (err <= o.tol) { w.status[b] = NEMPC_ST_CONVERGED; w.accepted[b] = 1; return; }
+    if (fmax(e_d, fmax(e_c, e_compmu)) <= o.kappa_eps * mu) {
+        mu = fmax(o.mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+        w.mu[b] = mu;
+    }
+
+    ipm_kkt_riccati<XM, UM, XC, UC>(L, o, c, jv, hv, dz, lamn, Kb, kfb,
+                                    [&](int i) { return ipm_sigma(w, z, zL, zU, i); }, [&](int i) { return ipm_gbar(w, z, gr, mu, i); });
+
     // ---- bound-dual steps, fraction to the boundary, merit ------------------------------------------------------------------
     const double tau = fmax(o.tau_min, 1.0 - mu);
     double aP = 1.0, aD = 1.0, lmax = 0.0, gdz = 0.0, c1 = 0.0;
     bool finite = true;
     for (int i = 0; i < n; ++i) {
-        double dl = 0.0, du = 0.0;
-        if (nempc_finite(w.lb[i])) {
-            const double d = z[i] - w.lb[i];
-            dl = mu / d - zL[i] - zL[i] / d * dz[i];
-            if (dz[i] < 0.0) aP = fmin(aP, -tau * d / dz[i]);
-            if (dl < 0.0) aD = fmin(aD, -tau * zL[i] / dl);
-        }
-        if (nempc_finite(w.ub[i])) {
-            const double d = w.ub[i] - z[i];
-            du = mu / d - zU[i] + zU[i] / d * dz[i];
-            if (dz[i] > 0.0) aP = fmin(aP, tau * d / dz[i]);
-            if (du < 0.0) aD = fmin(aD, -tau * zU[i] / du);
-        }
+        double dl, du;
+        ipm_bound_step(w, z, zL, zU, dz, mu, tau, i, dl, du, aP, aD);
         dzL[i] = dl; dzU[i] = du;
-        gdz += gb(i) * dz[i];
+        gdz += ipm_gbar(w, z, gr, mu, i) * dz[i];
         finite = finite && nempc_finite(dz[i]) && nempc_finite(dl) && nempc_finite(du);
     }
     for (int i = 0; i < m; ++i) { lmax = fmax(lmax, fabs(lamn[i])); c1 += fabs(c[i]); finite = finite && nempc_finite(lamn[i]); }
@@ -298,14 +327,88 @@ NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b
     w.alpha[b] = aP; w.alphaD[b] = aD; w.accepted[b] = 0;
     double* zt = w.zt + b * n;
     for (int i = 0; i < n; ++i) zt[i] = z[i] + aP * dz[i];
-#undef A_
-#undef B_
-#undef WXX_
-#undef WUX_
-#undef WUU_
-#undef XI_
-#undef UI_
 }
+
+#if defined(__CUDACC__)
+// The same iteration by ONE WARP per problem on a shared-memory copy of the problem's rows (nempc_ipm_kkt_staged_kernel).
+// Everything that is independent per variable -- the residual norms, Sigma and the barrier gradient (two divisions each),
+// the bound-dual steps (six divisions), the barrier logarithms -- is spread over the 32 lanes; maxima and minima are exact
+// under any order, and the three running SUMS (g^T dz, |c|_1, the barrier) are added by lane 0 in the sequential order from
+// terms computed in parallel, so every value equals the one-thread body bit for bit.  Lane 0 alone runs the Riccati sweeps.
+// s1, s2, s3: three scratch arrays of n doubles in shared memory.  All pointers are the problem's own rows (no b offset).
+struct KktRows {
+    const double *z, *lam, *zL, *zU, *gr, *c, *jv, *hv;       // shared-memory copies
+    double *dz, *lamn, *Kb, *kfb;                             // shared memory, copied out by the caller
+    double *dzL, *dzU, *zt;                                   // global rows (write only, coalesced)
+    double *s1, *s2, *s3;
+};
+__device__ __forceinline__ double warp_max_f64(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ double warp_min_f64(double v) { for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+
+template <int XM, int UM, int XC, int UC>
+__device__ void ipm_kkt_warp(const NlpLayout& L, const SolverWs& w, long long b, const SolverOpts& o, const KktRows& r, int lane) {
+    const int H = L.H, x = XC ? XC : L.x, u = UC ? UC : L.u, n = L.n, m = L.m, d = x + u;
+    double mu = w.mu[b];
+    // ---- optimality error ---------------------------------------------------------------------------------------------------
+    double e_d = 0.0, e_c = 0.0, e_comp = 0.0, e_compmu = 0.0;
+    for (int i = lane; i < m; i += 32) e_c = fmax(e_c, fabs(r.c[i]));
+    for (int e = lane; e < H * d; e += 32) e_d = fmax(e_d, fabs(ipm_dual_residual(L, x, u, r.gr, r.lam, r.zL, r.zU, r.jv, e / d, e % d)));
+    for (int i = lane; i < n; i += 32) {
+        if (nempc_finite(w.lb[i])) { const double v = (r.z[i] - w.lb[i]) * r.zL[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
+        if (nempc_finite(w.ub[i])) { const double v = (w.ub[i] - r.z[i]) * r.zU[i]; e_comp = fmax(e_comp, fabs(v)); e_compmu = fmax(e_compmu, fabs(v - mu)); }
+    }
+    e_d = warp_max_f64(e_d); e_c = warp_max_f64(e_c); e_comp = warp_max_f64(e_comp); e_compmu = warp_max_f64(e_compmu);
+    const double err = fmax(e_d, fmax(e_c, e_comp));
+    if (lane == 0) w.err[b] = err;
+    if (err <= o.tol) { if (lane == 0) { w.status[b] = NEMPC_ST_CONVERGED; w.accepted[b] = 1; } return; }
+    if (fmax(e_d, fmax(e_c, e_compmu)) <= o.kappa_eps * mu) {
+        mu = fmax(o.mu_min, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+        if (lane == 0) w.mu[b] = mu;
+    }
+    // ---- Sigma and barrier gradient of every variable, in parallel -------------------------------------------------------------
+    for (int i = lane; i < n; i += 32) { r.s1[i] = ipm_sigma(w, r.z, r.zL, r.zU, i); r.s2[i] = ipm_gbar(w, r.z, r.gr, mu, i); }
+    __syncwarp();
+    if (lane == 0) {
+        const double* sg = r.s1; const double* gbv = r.s2;
+        ipm_kkt_riccati<XM, UM, XC, UC>(L, o, r.c, r.jv, r.hv, r.dz, r.lamn, r.Kb, r.kfb, [sg](int i) { return sg[i]; }, [gbv](int i) { return gbv[i]; });
+    }
+    __syncwarp();
+    // ---- bound-dual steps, fraction to the boundary, merit ------------------------------------------------------------------------
+    const double tau = fmax(o.tau_min, 1.0 - mu);
+    double aP = 1.0, aD = 1.0, lmax = 0.0;
+    bool finite = true;
+    for (int i = lane; i < n; i += 32) {
+        double dl, du;
+        ipm_bound_step(w, r.z, r.zL, r.zU, r.dz, mu, tau, i, dl, du, aP, aD);
+        r.dzL[i] = dl; r.dzU[i] = du;
+        const double dzi = r.dz[i], zi = r.z[i];
+        r.s3[i] = r.s2[i] * dzi;                                             // gb(i) * dz[i]
+        finite = finite && nempc_finite(dzi) && nempc_finite(dl) && nempc_finite(du);
+        // barrier terms at z (ipm_barrier adds the lower-bound term, then the upper-bound term, variable by variable)
+        double tl = 0.0, tu = 0.0;
+        if (nempc_finite(w.lb[i])) { const double dd = zi - w.lb[i]; tl = log(dd > 1e-300 ? dd : 1e-300); }
+        if (nempc_finite(w.ub[i])) { const double dd = w.ub[i] - zi; tu = log(dd > 1e-300 ? dd : 1e-300); }
+        r.s1[i] = tl; r.s2[i] = tu;
+    }
+    for (int i = lane; i < m; i += 32) { lmax = fmax(lmax, fabs(r.lamn[i])); finite = finite && nempc_finite(r.lamn[i]); }
+    aP = warp_min_f64(aP); aD = warp_min_f64(aD); lmax = warp_max_f64(lmax);
+    finite = __all_sync(0xffffffffu, finite);
+    if (!finite) { if (lane == 0) { w.status[b] = NEMPC_ST_FAILED; w.accepted[b] = 1; } return; }
+    __syncwarp();
+    if (lane == 0) {
+        double gdz = 0.0, c1 = 0.0, bar = 0.0;
+        for (int i = 0; i < n; ++i) gdz += r.s3[i];
+        for (int i = 0; i < m; ++i) c1 += fabs(r.c[i]);
+        for (int i = 0; i < n; ++i) { if (nempc_finite(w.lb[i])) bar += r.s1[i]; if (nempc_finite(w.ub[i])) bar += r.s2[i]; }
+        const double nu = fmax(w.nu[b], lmax + 1.0);
+        w.nu[b] = nu;
+        w.phi0[b] = w.obj[b] - mu * bar + nu * c1;
+        w.dphi[b] = gdz - nu * c1;
+        w.alpha[b] = aP; w.alphaD[b] = aD; w.accepted[b] = 0;
+    }
+    for (int i = lane; i < n; i += 32) r.zt[i] = r.z[i] + aP * r.dz[i];
+}
+#endif
 
 // after residt / objt were evaluated at the trial point: Armijo test on the l1 merit; halve the step otherwise
 NEMPC_HD void ipm_linesearch_problem(const NlpLayout& L, const SolverWs& w, long long b, const SolverOpts& o) {
