@@ -201,6 +201,32 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def side_workload(name, B, device, reps=5):
+    """device-resident Jacobian+Hessian evaluation of another BASELINE config on a reduced batch (reported beside the headline,
+    not a bench line of its own): which kernel `auto` picks for it and what it reaches."""
+    import torch
+    from pyneuralempc_b200 import NlpEvaluator
+    wl = WORKLOADS[name]
+    mlp, obj, Z, X0, lam = make_problem(wl, B, seed=99)
+    ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"], compute_dtype="float32", io_dtype="float64", device=device)
+    ev.set_objective(obj.lin, obj.quad, obj.ref)
+    z, x0, lm = (torch.as_tensor(a, device=ev.tdevice) for a in (Z, X0, lam))
+    out = ev.alloc_outputs(B, ("resid", "jac", "hes"))
+    for _ in range(2):
+        ev.eval(z, x0, lm, 1.0, want=("resid", "jac", "hes"), out=out)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(reps):
+        ev.eval(z, x0, lm, 1.0, want=("resid", "jac", "hes"), out=out)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    steps = B * wl["H"]
+    res = {"workload": name + ": " + wl["desc"], "batch": B, "kernel": ev.kernel_name, "ms_per_eval": ms, "value": steps / (ms * 1e-3), "unit": UNIT,
+           "algorithmic_tflops": ev.flops_per_step * steps / (ms * 1e-3) / 1e12}
+    ev.close()
+    return res
+
+
 def gpu_run(args):
     import torch
     import torch.distributed as dist
@@ -327,6 +353,12 @@ def gpu_run(args):
                   "ipm_iterations_mean": float(so["iterations"].double().mean().item()), "outer_iterations": so["outer_iterations"],
                   "tol": sopt["tol"], "solver": "nempc_solve: primal-dual interior point, Riccati KKT sweep on the block-banded values, x0 device-resident",
                   "bounds": "u in [-1, 0.2] (run.py:72-74), states free"}
+    side = None
+    if rank == 0 and args.workload == "C2" and not args.no_side_workloads:
+        try:
+            side = {"C3": side_workload("C3", 2048, local)}
+        except Exception as exc:                      # a side measurement must never cost the headline line
+            side = {"C3": {"error": repr(exc)[:200]}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,6 +381,7 @@ def gpu_run(args):
             traffic = json.load(open(tr_path)).get(args.workload)
         except (OSError, ValueError):
             traffic = None
+    tensor_kernel = "tcgen05" in ev.kernel_name
     roofline = {"bound": "fp32-fma" if args.dtype == "float32" else "fp64-fma",
                 "note": "compute bound on the CUDA-core FMA pipe (arithmetic intensity %.0f flop/B); neither HBM nor tensor cores bound this kernel" % (flops / alg_bytes),
                 "kernel": ev.kernel_name, "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
@@ -357,6 +390,21 @@ def gpu_run(args):
                 "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "hbm_frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "traffic": traffic}
+    if tensor_kernel:
+        # tensor-core kernel: the denominator is the measured dense 16-bit tensor peak; `achieved` stays ALGORITHMIC flop (SURVEY 8d
+        # formula), the executed MMA flop (forward second-order rows x 3 split products) is reported beside it
+        tpeak = peaks.get("bf16_tflops", 1590.0)
+        d_in = wl["x"] + wl["u"]
+        rows = 1 + d_in + d_in * (d_in + 1) // 2
+        stages = 4 if wl["integ"] == "rk4" else 1
+        nmm = len(wl["dims"]) - 3
+        executed = 3 * 2.0 * 128 * 128 * rows * nmm * stages * steps_per_eval
+        roofline.update({"bound": "tensor", "peak": tpeak, "frac": achieved / tpeak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (f16 runs at the same rate)" if peaks else "fallback 1590 TFLOP/s",
+                         "executed_mma_tflops": executed / (k_ms * 1e-3) / 1e12,
+                         "note": "tcgen05 kind::f16, operands split in two f16 terms (3 MMAs per K step, f32-grade accuracy); forward second-order "
+                                 "rows make the executed MMA flop %.1fx the algorithmic count; the epilogue (tensor-memory reads at ~52 B/clk/SM, "
+                                 "f16 splitting) bounds the kernel, see DESIGN.md 5.4" % (executed / flops)})
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--workload", args.workload,
@@ -378,7 +426,7 @@ def gpu_run(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te.item()) / args.steps * 1e3, "api": "NlpEvaluator.eval_pinned -> nempc_eval_host (pinned host buffers, chunk-pipelined H2D|kernels|D2H)",
                     "numpy_callback_ms_per_step": cb_ms},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mpc_solves": solves}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mpc_solves": solves, "other_workloads": side}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -409,7 +457,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the workload's)")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"], help="arithmetic type of the network/chain rule")
     ap.add_argument("--io-dtype", default="float64", choices=["float32", "float64"], help="element type of z/lambda/values (reference: float64)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast", "tc"])
+    ap.add_argument("--no-side-workloads", action="store_true", help="skip the short C3 (tensor-core kernel) measurement reported beside the headline")
     ap.add_argument("--sets", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=128, help="problems per CPU-baseline step")
     ap.add_argument("--cpu-budget", type=float, default=90.0, help="--impl reference: target wall seconds of the timed loop (sets the sample size)")

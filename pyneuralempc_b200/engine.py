@@ -68,6 +68,16 @@ class NlpEvaluator:
         self._refresh_dims()
         self._pinned = {}
 
+    def set_weights(self, layer, W, b):
+        """replace the kernel / bias of one dense layer (same shapes), e.g. after the dynamics model was re-trained online;
+        the reference would rebuild its KerasTFModel (model/tensorflow.py:9-29)."""
+        W = np.ascontiguousarray(W, np.float64); b = np.ascontiguousarray(b, np.float64)
+        if W.shape != self.weights[layer][0].shape or b.shape != self.weights[layer][1].shape:
+            raise ValueError(f"layer {layer}: expected shapes {self.weights[layer][0].shape} {self.weights[layer][1].shape}")
+        self._check(self.lib.nempc_set_weights(self._h, layer, W.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)),
+                    "nempc_set_weights")
+        self.weights[layer] = (W, b)
+
     # ---- lifetime / errors ------------------------------------------------------------------------------
     def _check(self, rc, what):
         _lib.check(rc, self._h, what)

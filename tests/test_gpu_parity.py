@@ -247,3 +247,37 @@ def test_full_size_c2_properties():
     # constant structural entries
     assert (a["jac"][:, fast.jac_rows == fast.jac_cols] == -1.0).all()
     fast.close(); gen.close()
+
+
+def test_eval_host_graph_replay_tracks_inputs_weights_and_objective(lv_weights):
+    """nempc_eval_host replays its chunk pipeline as a CUDA graph from the third call with unchanged buffers: every replay
+    must read the CURRENT contents of the pinned inputs, and new weights / a new objective must invalidate the graph
+    (kernel parameters are captured by value)."""
+    H, B = 20, 700                                     # >= 512 problems: the multi-chunk pipeline
+    mlp = MLP(lv_weights, 2, 1)
+    rng = np.random.default_rng(5)
+    obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 0.5], [0.3], x_ref=rng.uniform(-1, 1, (H, 2)))
+    ev = _evaluator(mlp, "rk4", H, "float32", "auto", obj)
+    buf = ev.pinned_buffers(B)
+    launches = []
+    for it in range(5):
+        Z, X0, lam = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2)), rng.standard_normal((B, H * 2))
+        buf["z"][...] = Z; buf["x0"][...] = X0; buf["lam"][...] = lam
+        l0 = ev.launch_count
+        out = ev.eval_pinned(B, 0.7)
+        launches.append(ev.launch_count - l0)
+        ref = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Z, X0, lam, 0.7)
+        for kr, kg in KEYS:
+            assert _relerr(out[kg], ref[kr]) < TOL32, (it, kg)
+    assert len(set(launches)) == 1 and launches[0] > 0          # replays account for the same kernels as direct submission
+    # new weights and a new objective: same buffers, different answers
+    mlp2 = MLP.glorot([3, 30, 30, 2], 2, 1, seed=77)
+    for l, (W, b) in enumerate(mlp2.weights):
+        ev.set_weights(l, W, b)
+    obj2 = SeparableQuadraticObjective.tracking(H, 2, 1, [2.0, 0.1], [0.9], x_ref=rng.uniform(-1, 1, (H, 2)))
+    ev.set_objective(obj2.lin, obj2.quad, obj2.ref)
+    out = ev.eval_pinned(B, 0.7)
+    ref = BlockEvaluator(mlp2, "rk4", H, DT=0.1, objective=obj2).evaluate(Z, X0, lam, 0.7)
+    for kr, kg in KEYS:
+        assert _relerr(out[kg], ref[kr]) < TOL32, ("after update", kg)
+    ev.close()
