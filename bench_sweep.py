@@ -50,7 +50,7 @@ def main():
                         ms = a.elapsed_time(b) / reps
                         tf = gflop / ms
                         rows.append(dict(dtype=dtype, integrator=integ, width=width, depth=depth, x=xd, u=ud, H=H, B=B, steps=B * H,
-                                         kernel="fast" if "fast" in ev.kernel_name else "generic", ms=round(ms, 4),
+                                         kernel="fast" if "fast" in ev.kernel_name else ("tc" if "tcgen05" in ev.kernel_name else "generic"), ms=round(ms, 4),
                                          steps_per_s=round(B * H / ms * 1e3), tflops=round(tf, 3), frac_of_fma_peak=round(tf / peak[dtype], 4)))
                         print(rows[-1], flush=True)
                         ev.close()
