@@ -281,3 +281,46 @@ def test_eval_host_graph_replay_tracks_inputs_weights_and_objective(lv_weights):
     for kr, kg in KEYS:
         assert _relerr(out[kg], ref[kr]) < TOL32, ("after update", kg)
     ev.close()
+
+
+def test_c3_full_size_properties_tensor_core():
+    """BASELINE config C3 at full size (cart-pole MLP 5-128-128-128-4, RK4, H=100, B=16384 -> 1 638 400 horizon steps,
+    tensor-core kernel): size-independent properties plus oracle / generic-kernel agreement on a sample of problems.
+    float32 I/O keeps the value arrays of two evaluations (2 x 6.2 GB in float64) small."""
+    import torch
+    H, B = 100, 16384
+    rng = np.random.default_rng(3)
+    mlp = MLP.glorot([5, 128, 128, 128, 4], 4, 1, seed=0)
+    obj = SeparableQuadraticObjective.tracking(H, 4, 1, [1.0, 2.0, 0.5, 1.5], [0.1])
+    tc = _evaluator(mlp, "rk4", H, "float32", "auto", obj, io="float32")
+    assert "tcgen05" in tc.kernel_name
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32).cuda()
+    Z, X0 = t(rng.uniform(-1, 1, (B, H * 5))), t(rng.uniform(-1, 1, (B, 4)))
+    l1, l2 = t(rng.standard_normal((B, H * 4))), t(rng.standard_normal((B, H * 4)))
+    a = {k: v.clone() for k, v in tc.eval(Z, X0, l1, 1.0).items()}
+    # (1) Hessian is linear in lambda and in the objective factor: hes(l1 + l2, 1) = hes(l1, 1) + hes(l2, 0)
+    b = tc.eval(Z, X0, l2, 0.0, want=("hes",))["hes"].clone()
+    c = tc.eval(Z, X0, l1 + l2, 1.0, want=("hes",))["hes"]
+    scale = float(a["hes"].abs().max())
+    assert float((c - (a["hes"] + b)).abs().max()) < 2e-5 * scale            # f32 I/O rounds each stored value
+    del b, c
+    # (2) batch-permutation equivariance (bit-exact: a problem's values do not depend on its position in the batch)
+    perm = torch.as_tensor(rng.permutation(B)).cuda()
+    p = tc.eval(Z[perm], X0[perm], l1[perm], 1.0)
+    for k in ("resid", "jac", "hes"):
+        assert torch.equal(p[k], a[k][perm]), k
+    # (3) constant structural entries and finiteness everywhere
+    jr, jc = torch.as_tensor(tc.jac_rows).cuda(), torch.as_tensor(tc.jac_cols).cuda()
+    assert bool((a["jac"][:, jr == jc] == -1.0).all())
+    assert all(bool(torch.isfinite(a[k]).all()) for k in ("resid", "jac", "hes", "obj", "grad"))
+    # (4) a sample of problems against the float64 oracle and against the FFMA generic kernel
+    idx = rng.choice(B, 6, replace=False)
+    Zs, X0s, ls = (v[torch.as_tensor(idx).cuda()].double().cpu().numpy() for v in (Z, X0, l1))
+    ref = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Zs, X0s, ls, 1.0)
+    for kr, kg in KEYS:
+        assert _relerr(a[kg][torch.as_tensor(idx).cuda()].double().cpu().numpy(), ref[kr]) < TOL32, kg
+    gen = _evaluator(mlp, "rk4", H, "float32", "generic", obj)
+    g = _run(gen, Zs, X0s, ls, np.ones(len(idx)))
+    for kr, kg in KEYS[:3]:
+        assert _relerr(g[kg], ref[kr]) < TOL32, kg
+    tc.close(); gen.close()
