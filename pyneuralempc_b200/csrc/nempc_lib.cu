@@ -681,7 +681,7 @@ static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
     const long long ntiles = (ar.nsteps + C::SPT - 1) / C::SPT;
-    const unsigned grid = (unsigned)std::max(1LL, std::min(ntiles, (long long)h->sm_count));
+    const unsigned grid = (unsigned)std::max(1LL, std::min((ntiles + C::NG - 1) / C::NG, (long long)h->sm_count));     // NG tiles in flight per CTA
     kern<<<grid, NEMPC_TC_THREADS, C::TOTAL, s>>>((const __half*)h->d_tcimg, h->d_tccb, st, h->lay, ar);
     CU(h, cudaGetLastError());
     h->launches++;

@@ -59,30 +59,36 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
     static constexpr int XP = (X + 3) / 4 * 4;
     static constexpr int SROW = HW + 4;                                   // padded side-buffer row (bank spread)
     // per-step state that lives across the RK4 stages (floats)
-    static constexpr int P_Z = 0, P_KPREV = P_Z + D, P_KACC = P_KPREV + X, P_R = P_KACC + X, P_DKACC = P_R + D * D,
-                         P_HPREV = P_DKACC + X * D, P_HACC = P_HPREV + (HES ? X * D * D : 0),
+    static constexpr int P_Z = 0, P_KPREV = P_Z + D, P_KACC = P_KPREV + X, P_R = P_KACC + X, P_DKACC = P_R + (JAC ? D * D : 0),
+                         P_HPREV = P_DKACC + (JAC ? X * D : 0), P_HACC = P_HPREV + (HES ? X * D * D : 0),
                          P_TOTAL = P_HACC + (HES ? X * D * D : 0);
-    // per-step temporaries of one stage (floats); they alias the operand tile, which is dead at that point
-    static constexpr int T_KCUR = 0, T_J = XP, T_DK = T_J + X * D, T_M = T_DK + X * D, T_TMP = T_M + X * D * D,
-                         T_TOTAL = T_TMP + X * D * D;
-    // shared-memory map (bytes)
-    static constexpr int IMG = 128 * HW * 2;                              // one f16 operand image: 32 KB
-    static constexpr int OFF_W = 0;                                       // NMM x (hi image, lo image)
-    static constexpr int OFF_A = NMM * 2 * IMG;                           // operand tile: hi image, lo image
-    static constexpr int OFF_C = OFF_A + 2 * IMG;                         // f32 constants
-    static constexpr int C_W0 = 0, C_WOUT = D * HW, C_B = C_WOUT + HW * XP, C_BOUT = C_B + NHID * HW, C_FLOATS = C_BOUT + XP;
-    static constexpr int OFF_SH = OFF_C + C_FLOATS * 4;                   // a_l / h_l     [SPT][SROW]
-    static constexpr int OFF_ST = OFF_SH + SPT * SROW * 4;                // raw tangents  [D][SPT][SROW]   (Hessian only)
-    static constexpr int OFF_P = OFF_ST + (HES ? D * SPT * SROW * 4 : 0);
-    static constexpr int OFF_I = OFF_P + SPT * P_TOTAL * 4;               // (problem, time index) of each step of the tile
-    static constexpr int TOTAL = OFF_I + SPT * 8;
-    static constexpr int NQ = NEMPC_TC_THREADS / 128;                     // threads per row: each owns CPT consecutive neurons
+    // per-step temporaries of one stage (floats)
+    static constexpr int T_KCUR = 0, T_J = XP, T_DK = T_J + (JAC ? X * D : 0), T_M = T_DK + (JAC ? X * D : 0),
+                         T_TMP = T_M + (HES ? X * D * D : 0), T_TOTAL = T_TMP + (HES ? X * D * D : 0);
+    // two independent row tiles per CTA ("groups" of GT threads): while one group waits for its MMA batch the other runs its
+    // epilogue -- the overlap a second CTA per SM would give, without a second copy of the weights
+    static constexpr int NG = 2, GT = NEMPC_TC_THREADS / NG;
+    static constexpr int NQ = GT / 128;                                   // threads per row: each owns CPT consecutive neurons
     static constexpr int CPT = HW / NQ;
-    static constexpr int A_PART = 0;                                      // [NQ-1][128][XP] partial output sums of the upper column groups
-    static constexpr int A_TMP = (NQ - 1) * 128 * XP * 4;
-    static_assert(NEMPC_TC_THREADS % 128 == 0 && CPT % 16 == 0, "128 rows x NQ column groups of a multiple of 16 neurons");
+    // tensor memory, per group: D (f32 accumulator) | A_hi | A_lo (f16 operand tile, two K elements per 32-bit column)
+    static constexpr int TM_GROUP = 256, TM_D = 0, TM_AHI = HW, TM_ALO = HW + HW / 2, TM_COLS = NG * TM_GROUP;
+    // shared-memory map (bytes)
+    static constexpr int IMG = 128 * HW * 2;                              // one f16 weight image: 32 KB
+    static constexpr int OFF_W = 0;                                       // NMM x (hi image, lo image)
+    static constexpr int OFF_C = NMM * 2 * IMG;                           // f32 constants
+    static constexpr int C_W0 = 0, C_WOUT = D * HW, C_B = C_WOUT + HW * XP, C_BOUT = C_B + NHID * HW, C_FLOATS = C_BOUT + XP;
+    static constexpr int OFF_G = OFF_C + C_FLOATS * 4;                    // group blocks
+    static constexpr int G_SH = 0;                                        // a_l / h_l     [SPT][SROW]
+    static constexpr int G_ST = G_SH + SPT * SROW * 4;                    // raw tangents  [D][SPT][SROW]   (Hessian only)
+    static constexpr int G_P = G_ST + (HES ? D * SPT * SROW * 4 : 0);     // per-step state across the stages
+    static constexpr int G_I = G_P + SPT * P_TOTAL * 4;                   // (problem, time index) of each step of the tile
+    static constexpr int G_PART = G_I + SPT * 8;                          // [NQ-1][128][XP] partial output sums of the upper column groups
+    static constexpr int G_TMP = G_PART + (NQ - 1) * 128 * XP * 4;        // stage temporaries
+    static constexpr int G_BYTES = (G_TMP + SPT * T_TOTAL * 4 + 15) / 16 * 16;
+    static constexpr int TOTAL = OFF_G + NG * G_BYTES;
+    static_assert(NEMPC_TC_THREADS % (128 * NG) == 0 && CPT % 16 == 0, "128 rows x NQ column groups of a multiple of 16 neurons per group");
     static_assert(TOTAL <= NEMPC_TC_SMEM_MAX, "tensor-core kernel: shared-memory map exceeds 227 KB");
-    static_assert(A_TMP + SPT * T_TOTAL * 4 <= 2 * IMG, "stage temporaries do not fit into the operand tile");
+    static_assert(TM_COLS <= 512 && TM_ALO + HW / 2 <= TM_GROUP, "tensor memory: 512 columns");
     static_assert(NHID >= 2 && NHID <= 3, "two or three hidden layers");
     static_assert(X <= 16 && RPS <= 128, "row stack too tall");
 };
@@ -113,11 +119,13 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     constexpr bool JAC = C::JAC, HES = C::HES;
     typedef typename WideOf<float, TIO>::type TW;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    __shared__ uint64_t mbar_store[2];
+    __shared__ uint64_t mbar_store[3];
     __shared__ uint32_t tmem_holder;
 
+    constexpr int GT = C::GT;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int m = tid & 127, cq = tid >> 7;         // row, column group
+    const int grp = tid / GT, gtid = tid - grp * GT;   // tile group of this thread, index inside the group
+    const int m = gtid & 127, cq = gtid >> 7;          // row, column group
     const int kind = m / SPT, sl = m - kind * SPT;
     const bool valid = m < C::ROWS;
     int cT = 0, c1 = 0, c2 = 0;                       // tangent column of a T row; column pair of an S row
@@ -141,24 +149,25 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     const float* Wout = cb + C::C_WOUT;               // [HW][XP]
     const float* bias = cb + C::C_B;                  // [NHID][HW]
     const float* bout = cb + C::C_BOUT;
-    float* sideH = reinterpret_cast<float*>(tc_smem + C::OFF_SH);
-    float* sideT = reinterpret_cast<float*>(tc_smem + C::OFF_ST);
-    float* pers = reinterpret_cast<float*>(tc_smem + C::OFF_P);
-    int* step_b = reinterpret_cast<int*>(tc_smem + C::OFF_I);       // problem index of step s_ of the tile, -1 past the end
+    unsigned char* gblk = tc_smem + C::OFF_G + grp * C::G_BYTES;     // this group's block
+    float* sideH = reinterpret_cast<float*>(gblk + C::G_SH);
+    float* sideT = reinterpret_cast<float*>(gblk + C::G_ST);
+    float* pers = reinterpret_cast<float*>(gblk + C::G_P);
+    int* step_b = reinterpret_cast<int*>(gblk + C::G_I);             // problem index of step s_ of the tile, -1 past the end
     int* step_t = step_b + SPT;
-    unsigned char* Ahi = tc_smem + C::OFF_A;
-    unsigned char* Alo = Ahi + C::IMG;
-    float* part = reinterpret_cast<float*>(Ahi + C::A_PART);
-    float* temps = reinterpret_cast<float*>(Ahi + C::A_TMP);
+    float* part = reinterpret_cast<float*>(gblk + C::G_PART);
+    float* temps = reinterpret_cast<float*>(gblk + C::G_TMP);
+    // the threads of one group meet on their own named barrier; the two groups never wait for each other inside the tile loop
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); };
 
-    const uint32_t mbar_w = smem_u32(&mbar_store[0]), mbar_mma = smem_u32(&mbar_store[1]);
-    if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(mbar_mma, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), 128);
+    const uint32_t mbar_w = smem_u32(&mbar_store[0]), mbar_mma = smem_u32(&mbar_store[1 + grp]);
+    if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(smem_u32(&mbar_store[1]), 1); mbar_init(smem_u32(&mbar_store[2]), 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), C::TM_COLS);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = tmem_holder;
-    const uint32_t tm_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's lane quadrant
+    const uint32_t tm_row = tmem + grp * C::TM_GROUP + ((uint32_t)((warp & 3) * 32) << 16);     // this group's columns, this warp's lane quadrant
     // weights: resident for the life of the CTA, brought in by the TMA unit as plain 1-D bulk copies
     if (tid == 0) {
         mbar_expect_tx(mbar_w, NMM * 2 * C::IMG);
@@ -175,18 +184,18 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     const long long ntiles = (ar.nsteps + SPT - 1) / SPT;
 
     TC_PROF_DECL
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * C::NG + grp; tile < ntiles; tile += (long long)gridDim.x * C::NG) {
         const long long step0 = tile * SPT;
         TC_PROF(11);
         // ---- inputs and per-step state ------------------------------------------------------------------------------
-        if (tid < SPT) {
-            const long long step = step0 + tid;
+        if (gtid < SPT) {
+            const long long step = step0 + gtid;
             const long long b = step / L.H;
-            step_b[tid] = step < ar.nsteps ? (int)b : -1;
-            step_t[tid] = (int)(step - b * L.H);
+            step_b[gtid] = step < ar.nsteps ? (int)b : -1;
+            step_t[gtid] = (int)(step - b * L.H);
         }
-        __syncthreads();
-        for (int idx = tid; idx < SPT * C::P_TOTAL; idx += NEMPC_TC_THREADS) {
+        gsync();
+        for (int idx = gtid; idx < SPT * C::P_TOTAL; idx += GT) {
             const int s_ = idx / C::P_TOTAL, o = idx - s_ * C::P_TOTAL;
             float v = 0.f;
             if (o < D) {
@@ -197,19 +206,19 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     if (o < X) v = (float)((t == 0) ? ar.x0[b * X + o] : zb[(t - 1) * X + o]);
                     else v = (float)zb[L.H * X + t * U + (o - X)];
                 }
-            } else if (o >= C::P_R && o < C::P_R + DD) {
+            } else if (JAC && o >= C::P_R && o < C::P_R + DD) {
                 const int r = o - C::P_R;
                 v = (r / D == r % D) ? 1.f : 0.f;
             }
             pers[idx] = v;
         }
-        __syncthreads();
+        gsync();
         TC_PROF(0);
 
         for (int s = 0; s < st.S; ++s) {
             const float a_s = st.a[s], c_s = st.c[s];
             // ---- first layer (K = d, FFMA): activations of all SPT steps spread over the CTA ------------------------------
-            for (int e = tid; e < SPT * HW; e += NEMPC_TC_THREADS) {
+            for (int e = gtid; e < SPT * HW; e += GT) {
                 const int s_ = e / HW, j = e - s_ * HW;
                 const float* ps = pers + s_ * C::P_TOTAL;
                 float a = bias[j];
@@ -221,12 +230,12 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 sideH[s_ * SROW + j] = fast_tanh(a);
             }
             if (HES) {      // da_0/dz_c = W0[c]: park it like the raw tangents of any other layer, so pass 2 has ONE code path
-                for (int e = tid; e < D * SPT * (HW / 4); e += NEMPC_TC_THREADS) {
+                for (int e = gtid; e < D * SPT * (HW / 4); e += GT) {
                     const int c = e / (SPT * (HW / 4)), r = e - c * (SPT * (HW / 4)), s_ = r / (HW / 4), j4 = r - s_ * (HW / 4);
                     *reinterpret_cast<float4*>(sideT + (c * SPT + s_) * SROW + 4 * j4) = *reinterpret_cast<const float4*>(W0 + c * HW + 4 * j4);
                 }
             }
-            __syncthreads();
+            gsync();
             TC_PROF(1);
 
             constexpr int XH = (X + 1) / 2;
@@ -302,24 +311,22 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         }
                     }
                     if (!LAST) {
+                        // x = hi + lo / 2^11, two neurons per instruction; the operand tile lives in TENSOR MEMORY (two f16 K elements
+                        // per 32-bit column, lane = row): 8 words = 16 neurons per tcgen05.st, hi and lo image
                         const f2 sc = pk(NEMPC_TC_LO_SCALE, NEMPC_TC_LO_SCALE), nsc = pk(-NEMPC_TC_LO_SCALE, -NEMPC_TC_LO_SCALE);
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint32_t hi[4], lo[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {          // x = hi + lo / 2^11, two neurons per instruction
-                                const f2 x = out2[4 * g + i];
-                                const __half2 h2 = __floats2half2_rn(f2lo(x), f2hi(x));
-                                const float2 hf2 = __half22float2(h2);
-                                const f2 r = fma2(x, sc, mul2(pk(hf2.x, hf2.y), nsc));            // (x - hi) * 2^11, exact
-                                const __half2 l2 = __floats2half2_rn(f2lo(r), f2hi(r));
-                                hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                                lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
-                            }
-                            const int kc = col / 8 + g;
-                            *reinterpret_cast<uint4*>(Ahi + kc * (128 * 16) + m * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(Alo + kc * (128 * 16) + m * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        for (int i = 0; i < 8; ++i) {
+                            const f2 x = out2[i];
+                            const __half2 h2 = __floats2half2_rn(f2lo(x), f2hi(x));
+                            const float2 hf2 = __half22float2(h2);
+                            const f2 r = fma2(x, sc, mul2(pk(hf2.x, hf2.y), nsc));            // (x - hi) * 2^11, exact
+                            const __half2 l2 = __floats2half2_rn(f2lo(r), f2hi(r));
+                            hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
+                        tmem_st8(tm_row + C::TM_AHI + col / 2, hi);           // warp-collective: invalid rows store zeros
+                        tmem_st8(tm_row + C::TM_ALO + col / 2, lo);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -341,49 +348,49 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 TC_PROF(2);
 
                 // ---- hidden-to-hidden layer l -> l+1 on the tensor core -------------------------------------------------------
-                fence_async_smem();
+                tmem_st_wait();                                    // this thread's operand-tile stores have landed in tensor memory
                 fence_before_sync();
-                __syncthreads();
+                gsync();
                 TC_PROF(3);
-                if (warp == 0) {
-                  if (tid == 0) {
+                if (gtid < 32) {                                   // first warp of the group
+                  if (gtid == 0) {
                     fence_after_sync();
-                    // The weight-image offset must be a COMPILE-TIME constant: with a runtime layer index ptxas cannot prove the
-                    // descriptors warp-uniform inside this single-thread branch and wraps every MMA in an ELECT / R2UR loop
-                    // (~110 clk per MMA instead of the tensor core's 64).  Hence one unrolled instance per layer.
-                    auto issue = [&](auto layer_tag) {
-                        constexpr int LI = decltype(layer_tag)::value;
+                    // Layer and group offsets must be COMPILE-TIME constants: with run-time indices ptxas cannot prove the operands
+                    // warp-uniform inside this single-thread branch and wraps every MMA in an ELECT / R2UR loop (~110 clk per MMA
+                    // instead of the tensor core's 64).  Hence one unrolled instance per (layer, group).
+                    auto issue = [&](auto layer_tag, auto group_tag) {
+                        constexpr int LI = decltype(layer_tag)::value, GI = decltype(group_tag)::value;
                         const uint32_t whi = smem_u32(tc_smem) + C::OFF_W + LI * 2 * C::IMG, wlo = whi + C::IMG;
-                        const uint32_t ahi = smem_u32(tc_smem) + C::OFF_A, alo = ahi + C::IMG;
+                        const uint32_t td = tmem + GI * C::TM_GROUP + C::TM_D, ta1 = tmem + GI * C::TM_GROUP + C::TM_AHI, ta2 = tmem + GI * C::TM_GROUP + C::TM_ALO;
                         // correction terms first (both carry the factor 2^11), then the first main MMA folds them in with
                         // scale-input-d: D = A_hi W_hi + D * 2^-11 -- ONE f32 accumulator, half the tensor-memory read volume.
-                        // Fully unrolled, descriptors advanced in their low word only (uniform-register arithmetic).
+                        // A operand from tensor memory (8 columns = 16 K elements per MMA), B descriptors advanced in their low word.
                         const uint32_t dhi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
                         const uint32_t dlo = (2048u >> 4) << 16;                             // LBO = 2048 B
-                        const uint32_t la1 = dlo | (ahi >> 4), la2 = dlo | (alo >> 4), lw1 = dlo | (whi >> 4), lw2 = dlo | (wlo >> 4);
+                        const uint32_t lw1 = dlo | (whi >> 4), lw2 = dlo | (wlo >> 4);
 #define NEMPC_TC_DESC(lo, ks) ((((uint64_t)dhi) << 32) | (uint64_t)((lo) + (ks) * 256u))
-                        TC_PROF(12);
 #pragma unroll
-                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la2, ks), NEMPC_TC_DESC(lw1, ks), idesc, ks != 0);
-                        TC_PROF(13);
+                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ts(td, ta2 + ks * 8, NEMPC_TC_DESC(lw1, ks), idesc, ks != 0);
 #pragma unroll
-                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la1, ks), NEMPC_TC_DESC(lw2, ks), idesc, 1);
-                        TC_PROF(14);
-                        mma_f16_ss_scaled_d<11>(tmem, NEMPC_TC_DESC(la1, 0), NEMPC_TC_DESC(lw1, 0), idesc);
+                        for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ts(td, ta1 + ks * 8, NEMPC_TC_DESC(lw2, ks), idesc, 1);
+                        mma_f16_ts_scaled_d<11>(td, ta1, NEMPC_TC_DESC(lw1, 0), idesc);
 #pragma unroll
-                        for (int ks = 1; ks < HW / 16; ++ks) mma_f16_ss(tmem, NEMPC_TC_DESC(la1, ks), NEMPC_TC_DESC(lw1, ks), idesc, 1);
+                        for (int ks = 1; ks < HW / 16; ++ks) mma_f16_ts(td, ta1 + ks * 8, NEMPC_TC_DESC(lw1, ks), idesc, 1);
 #undef NEMPC_TC_DESC
                     };
-                    if (l == 0) issue(std::integral_constant<int, 0>{});
-                    else issue(std::integral_constant<int, (NMM > 1 ? 1 : 0)>{});
+                    typedef std::integral_constant<int, 0> I0;
+                    typedef std::integral_constant<int, (NMM > 1 ? 1 : 0)> I1;
+                    typedef std::integral_constant<int, 1> G1;
+                    if (grp == 0) { if (l == 0) issue(I0{}, I0{}); else issue(I1{}, I0{}); }
+                    else          { if (l == 0) issue(I0{}, G1{}); else issue(I1{}, G1{}); }
                     mma_commit(mbar_mma);
                     TC_PROF(4);
-                    mbar_wait(mbar_mma, parity);                   // ONE polling thread; everybody else blocks on the hardware barrier below
+                    mbar_wait(mbar_mma, parity);                   // ONE polling thread; the rest of the group blocks on its barrier below
                   }
                   __syncwarp();
                 }
                 parity ^= 1;
-                __syncthreads();                                   // everybody else blocks on the hardware barrier
+                gsync();                                   // everybody else blocks on the hardware barrier
                 fence_after_sync();
                 TC_PROF(5);
 
@@ -414,13 +421,13 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         }
                     }
                 }
-                __syncthreads();
+                gsync();
                 TC_PROF(6);
-                for (int e = tid; e < SPT * HW; e += NEMPC_TC_THREADS) {
+                for (int e = gtid; e < SPT * HW; e += GT) {
                     const int s_ = e / HW, j = e - s_ * HW;
                     sideH[s_ * SROW + j] = fast_tanh(sideH[s_ * SROW + j]);
                 }
-                __syncthreads();
+                gsync();
                 TC_PROF(7);
             }
             pass2(std::true_type{}, false);                        // last hidden layer: rows contracted with W_out in registers
@@ -430,12 +437,12 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             float oacc[X];
 #pragma unroll
             for (int p = 0; p < X; ++p) oacc[p] = (p & 1) ? f2hi(oacc2[p / 2]) : f2lo(oacc2[p / 2]);
-            __syncthreads();                                       // every thread is done with tensor memory and the side buffers
+            gsync();                                       // every thread is done with tensor memory and the side buffers
             if (cq > 0 && valid) {
 #pragma unroll
                 for (int p = 0; p < X; ++p) part[((cq - 1) * 128 + m) * XP + p] = oacc[p];
             }
-            __syncthreads();
+            gsync();
             if (cq == 0 && valid) {
                 float* tp = temps + sl * C::T_TOTAL;
 #pragma unroll
@@ -448,12 +455,12 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     else { tp[C::T_M + p * DD + c1 * D + c2] = tot; tp[C::T_M + p * DD + c2 * D + c1] = tot; }
                 }
             }
-            __syncthreads();
+            gsync();
 
             TC_PROF(8);
             // ---- stage algebra (as nempc_generic.cuh), flattened over the SPT steps of the tile ---------------------------------
             if (JAC) {
-                for (int idx = tid; idx < SPT * X * D; idx += NEMPC_TC_THREADS) {
+                for (int idx = gtid; idx < SPT * X * D; idx += GT) {
                     const int s_ = idx / (X * D), r = idx - s_ * (X * D), p = r / D, c = r - p * D;
                     const float* tp = temps + s_ * C::T_TOTAL;
                     const float* R = pers + s_ * C::P_TOTAL + C::P_R;
@@ -463,7 +470,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     temps[s_ * C::T_TOTAL + C::T_DK + r] = acc;
                 }
                 if (HES) {
-                    for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                    for (int idx = gtid; idx < SPT * X * DD; idx += GT) {
                         const int s_ = idx / (X * DD), r = idx - s_ * (X * DD), p = r / DD, k = (r - p * DD) / D, c = r % D;
                         const float* tp = temps + s_ * C::T_TOTAL;
                         const float* R = pers + s_ * C::P_TOTAL + C::P_R;
@@ -473,9 +480,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         temps[s_ * C::T_TOTAL + C::T_TMP + r] = acc;
                     }
                 }
-                __syncthreads();
+                gsync();
                 if (HES) {
-                    for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                    for (int idx = gtid; idx < SPT * X * DD; idx += GT) {
                         const int s_ = idx / (X * DD), r = idx - s_ * (X * DD), p = r / DD, a = (r - p * DD) / D, c = r % D;
                         float* tp = temps + s_ * C::T_TOTAL;
                         const float* ps = pers + s_ * C::P_TOTAL;
@@ -489,14 +496,14 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         tp[C::T_M + r] = acc;                      // M_p was consumed before the barrier; it now holds h_s[p]
                     }
                 }
-                for (int idx = tid; idx < SPT * X * D; idx += NEMPC_TC_THREADS) {
+                for (int idx = gtid; idx < SPT * X * D; idx += GT) {
                     const int s_ = idx / (X * D), r = idx - s_ * (X * D);
                     float* dkacc = pers + s_ * C::P_TOTAL + C::P_DKACC + r;
                     *dkacc = fmaf(c_s, temps[s_ * C::T_TOTAL + C::T_DK + r], *dkacc);
                 }
             }
-            __syncthreads();
-            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {
+            gsync();
+            for (int idx = gtid; idx < SPT * X; idx += GT) {
                 const int s_ = idx / X, p = idx - s_ * X;
                 float* ps = pers + s_ * C::P_TOTAL;
                 const float kc = temps[s_ * C::T_TOTAL + C::T_KCUR + p];
@@ -504,7 +511,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 ps[C::P_KPREV + p] = kc;
             }
             if (HES) {
-                for (int idx = tid; idx < SPT * X * DD; idx += NEMPC_TC_THREADS) {
+                for (int idx = gtid; idx < SPT * X * DD; idx += GT) {
                     const int s_ = idx / (X * DD), r = idx - s_ * (X * DD);
                     float* ps = pers + s_ * C::P_TOTAL;
                     const float hv = temps[s_ * C::T_TOTAL + C::T_M + r];
@@ -514,18 +521,18 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
             if (JAC && s + 1 < st.S) {
                 const float an = st.a[s + 1];
-                for (int idx = tid; idx < SPT * DD; idx += NEMPC_TC_THREADS) {
+                for (int idx = gtid; idx < SPT * DD; idx += GT) {
                     const int s_ = idx / DD, r = idx - s_ * DD, k = r / D, c = r - k * D;
                     pers[s_ * C::P_TOTAL + C::P_R + r] = (k == c ? 1.f : 0.f) + (k < X ? an * temps[s_ * C::T_TOTAL + C::T_DK + k * D + c] : 0.f);
                 }
             }
-            __syncthreads();
+            gsync();
         }
 
         TC_PROF(9);
         // ---- outputs (same slots as nempc_generic.cuh) ----------------------------------------------------------------------
         if (ar.resid) {
-            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {
+            for (int idx = gtid; idx < SPT * X; idx += GT) {
                 const int s_ = idx / X, p = idx - s_ * X;
                 const long long b = step_b[s_];
                 if (b < 0) continue;
@@ -537,7 +544,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
         }
         if (JAC && ar.jac) {
-            for (int idx = tid; idx < SPT * X * (D + 1); idx += NEMPC_TC_THREADS) {
+            for (int idx = gtid; idx < SPT * X * (D + 1); idx += GT) {
                 const int s_ = idx / (X * (D + 1)), r = idx - s_ * (X * (D + 1)), p = r / (D + 1), c = r - p * (D + 1);
                 const long long b = step_b[s_];
                 if (b < 0) continue;
@@ -550,7 +557,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
             }
         }
         if (HES && ar.hes) {
-            for (int idx = tid; idx < SPT * DD; idx += NEMPC_TC_THREADS) {
+            for (int idx = gtid; idx < SPT * DD; idx += GT) {
                 const int s_ = idx / DD, r = idx - s_ * DD, a = r / D, c = r - a * D;
                 const long long b = step_b[s_];
                 if (b < 0 || c > a) continue;
@@ -575,7 +582,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 }
                 hv[slot] = (TIO)v;
             }
-            for (int idx = tid; idx < SPT * X; idx += NEMPC_TC_THREADS) {   // objective-only diagonal of x_H
+            for (int idx = gtid; idx < SPT * X; idx += GT) {   // objective-only diagonal of x_H
                 const int s_ = idx / X, p = idx - s_ * X;
                 const long long b = step_b[s_];
                 if (b < 0) continue;
@@ -585,13 +592,13 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 ar.hes[b * L.nnz_hes + L.hes_last_slot[p]] = (TIO)(sig * (TW)2 * (TW)ar.quad[(L.H - 1) * X + p]);
             }
         }
-        __syncthreads();                                           // per-step state is rewritten by the next tile
+        gsync();                                           // per-step state is rewritten by the next tile
         TC_PROF(10);
     }
     TC_PROF_FLUSH;
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, C::TM_COLS);
 }
 #endif  // __CUDACC__
