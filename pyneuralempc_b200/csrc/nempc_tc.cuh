@@ -10,7 +10,7 @@
 // Every row goes through the SAME weights, so a hidden-to-hidden layer is one GEMM [128 rows x 128] x [128 x 128] for
 // SPT = 128 / RPS steps at once, and the linear output layer turns the three row kinds into k = f(z_s), the local
 // Jacobian J_s and the per-output local Hessians M_p.  No adjoint sweep and no per-layer state survives a layer: that
-// is what lets both hidden-to-hidden weight matrices stay resident in shared memory next to the operand tile.
+// is what lets both hidden-to-hidden weight matrices stay resident in shared memory for the life of the CTA.
 // (The adjoint form needs d*sum_h or x*sum_h floats per step across layers -- 15 KB per step for C3 -- which is why
 // nempc_generic.cuh holds only ~15 steps per SM.)  The stage algebra (dk = J R, h_s = R^T M R + a_s J h_{s-1},
 // R_{s+1} = I + a_{s+1} E dk) and the sparse scatter are those of nempc_generic.cuh (reference integrator/rk4.py:113-285).
@@ -24,14 +24,17 @@
 // which carries ~22 mantissa bits (measured 4e-7 relative, tests/tools/tc_gemm_probe.cu) at 1.5x the cost of one TF32
 // pass and HALF the shared-memory footprint of a 3xTF32 scheme -- the footprint is what decides residency here.
 //
-// One CTA per SM (persistent), NEMPC_TC_THREADS threads: thread (m = tid & 127, cq = tid >> 7) owns row m of the tile and the
-// neurons [CPT cq, CPT cq + CPT).  Row order is kind-major (m = kind * SPT + step).  Per layer:
-//   thread 0 issues 8 K-steps x 3 tcgen05.mma (M = 128, N = 128, K = 16) and commits to an mbarrier;
+// One persistent CTA per SM, NEMPC_TC_THREADS = 512 threads = TWO GROUPS of 256 threads, each working on its own row tile with its
+// own named barrier, mbarrier and 256 tensor-memory columns: while one group waits for its MMA batch the other runs its epilogue
+// (the overlap a second CTA per SM would give, without a second copy of the weights).  Thread (m = gtid & 127, cq = gtid >> 7) of a
+// group owns row m of the tile and the neurons [CPT cq, CPT cq + CPT).  Row order is kind-major (m = kind * SPT + step).
+// The operand tile lives in TENSOR MEMORY (tcgen05.st, two f16 K elements per 32-bit column, lane = row; TS-mode MMA), which is
+// what makes room for the second tile.  Per layer:
+//   the group's first thread issues 8 K-steps x 3 tcgen05.mma (M = 128, N = 128, K = 16) and commits to the group's mbarrier;
 //   pass 1: P rows add the bias and park a_l in a side buffer, T rows park their raw tangents (needed by the S rows);
-//   tanh  : the SPT x 128 activations are spread over all threads of the CTA (MUFU tanh, as in nempc_fast.cuh);
-//   pass 2: every row forms its post-activation quantity from tensor memory + the side buffers, splits it and writes
-//           its 16-byte K chunks of the next operand tile (canonical K-major no-swizzle layout, conflict-free stores);
-//           after the LAST hidden layer the rows are contracted with W_out in registers instead (exact f32).
+//   tanh  : the SPT x 128 activations are spread over all threads of the group (MUFU tanh, as in nempc_fast.cuh);
+//   pass 2: every row forms its post-activation quantity from tensor memory + the side buffers, splits it and stores its part of the
+//           next operand tile; after the LAST hidden layer the rows are contracted with W_out in registers instead (exact f32).
 // The first layer (K = d) and the output layer (N = x) are too thin for the tensor core and stay on FFMA.
 #pragma once
 #include "nempc_fast.cuh"
@@ -42,7 +45,7 @@
 
 #define NEMPC_TC_HW 128
 #ifndef NEMPC_TC_THREADS
-#define NEMPC_TC_THREADS 512            // 16 warps: 4 per scheduler hide the LDS / LDTM / MUFU latencies of the epilogue (256 was latency bound)
+#define NEMPC_TC_THREADS 512            // two tile groups of 256 threads
 #endif
 #define NEMPC_TC_SMEM_MAX 232448
 #ifndef NEMPC_TC_P2_UNROLL
