@@ -115,3 +115,25 @@ def test_optimizer_and_controllers(lv_weights):
     np.testing.assert_allclose(xp[0, 0].cpu().numpy(), X[0])
     with pytest.raises(ValueError):
         model.evaluator().solve(X, np.zeros(3), np.zeros(3))   # no objective / wrong bounds
+
+
+def test_solver_on_the_tensor_core_kernel():
+    """nempc_solve with the tcgen05 evaluation kernel (cart-pole-class network 5-128-128-4, RK4): every problem converges, the
+    solutions are feasible and agree with the float64 generic-kernel solve to the solver tolerance."""
+    from pyneuralempc_b200 import NlpEvaluator
+    H, B = 12, 40
+    mlp, obj, lb, ub, X0 = _setup("rk4", [5, 128, 128, 4], 4, 1, H, 0.05, 5.0, None, B=B)
+    tc = NlpEvaluator(mlp.weights, 4, 1, H, "rk4", DT=0.05, compute_dtype="float32", io_dtype="float64", kernel="tc")
+    tc.set_objective(obj.lin, obj.quad, obj.ref)
+    assert "tcgen05" in tc.kernel_name
+    o32 = tc.solve(X0, lb, ub, tol=1e-5)
+    o64 = _ev(mlp, "rk4", H, 0.05, obj, "float64").solve(X0, lb, ub, tol=1e-8)
+    assert (o32["status"].cpu().numpy() == 0).all() and (o64["status"].cpu().numpy() == 0).all()
+    z32, z64 = o32["z"].cpu().numpy(), o64["z"].cpu().numpy()
+    oe = BlockEvaluator(mlp, "rk4", H, DT=0.05, objective=obj)
+    r32 = oe.evaluate(z32, X0, None, 1.0, need_jac=False, need_hes=False)
+    r64 = oe.evaluate(z64, X0, None, 1.0, need_jac=False, need_hes=False)
+    assert np.abs(r32["resid"]).max() < 1e-5
+    assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-4 * max(1.0, np.abs(r64["obj"]).max())
+    assert np.abs(z32 - z64).max() < 1e-2
+    assert (z32 >= lb - 1e-9).all() and (z32 <= ub + 1e-9).all()
