@@ -227,6 +227,30 @@ def side_workload(name, B, device, reps=5):
     return res
 
 
+def callback_latency(device, n=1000):
+    """BASELINE config C1 (Lotka-Volterra MLP, H=25, ONE problem): wall time of one solver callback through the host-buffer C-ABI
+    call -- all five outputs -- with the shipped RK4 integrator (examples/lotka_volterra/run.py:77) and the discrete one."""
+    from pyneuralempc_b200 import NlpEvaluator
+    res = {}
+    for integ in ("rk4", "discrete"):
+        wl = dict(WORKLOADS["C1"]); wl["integ"] = integ; wl["DT"] = 0.1
+        mlp, obj, Z, X0, lam = make_problem({k: v for k, v in wl.items() if k != "desc"}, 1, seed=7)
+        ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], integ, DT=0.1, device=device)
+        ev.set_objective(obj.lin, obj.quad, obj.ref)
+        buf = ev.pinned_buffers(1)
+        buf["z"][...] = Z; buf["x0"][...] = X0; buf["lam"][...] = lam
+        for _ in range(20):
+            ev.eval_pinned(1, 1.0)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            ev.eval_pinned(1, 1.0)
+        res[integ] = (time.perf_counter() - t0) / n * 1e6
+        ev.close()
+    return {"workload": "C1: " + WORKLOADS["C1"]["desc"], "us_per_callback_rk4": res["rk4"], "us_per_callback_discrete": res["discrete"],
+            "outputs": "residual + Jacobian + Hessian values + objective + gradient",
+            "api": "NlpEvaluator.eval_pinned -> nempc_eval_host: zero-copy on mapped pinned buffers, warp-per-step kernel (nempc_small_kernel)"}
+
+
 def gpu_run(args):
     import torch
     import torch.distributed as dist
@@ -356,7 +380,7 @@ def gpu_run(args):
     side = None
     if rank == 0 and args.workload == "C2" and not args.no_side_workloads:
         try:
-            side = {"C3": side_workload("C3", 2048, local)}
+            side = {"C3": side_workload("C3", 2048, local), "C1_callback": callback_latency(local)}
         except Exception as exc:                      # a side measurement must never cost the headline line
             side = {"C3": {"error": repr(exc)[:200]}}
     if rank != 0:

@@ -15,6 +15,7 @@
 #include "nempc_fast.cuh"
 #include "nempc_generic.cuh"
 #include "nempc_layout.h"
+#include "nempc_small.cuh"
 #include "nempc_solver.cuh"
 #include "nempc_tc.cuh"
 
@@ -452,8 +453,9 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     else h->smem_bytes = per_slot * slots;
     h->slots = slots;
 
-    char nm[160];
-    if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank)", D.x_dim, D.u_dim, D.widths[0], D.widths[1]);
+    char nm[224];
+    if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
+                              D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
     else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, NEMPC_TC_HW);
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
     h->kname = nm;
@@ -664,7 +666,36 @@ static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode,
     return NEMPC_OK;
 }
 
+// small batches of the same networks: one WARP per horizon step (nempc_small.cuh) -- latency instead of throughput
+#ifndef NEMPC_SMALL_MAX_STEPS
+#define NEMPC_SMALL_MAX_STEPS 6144      // measured crossover with the thread-per-step kernel: 52 vs 63 us at 6400 steps, 91 vs 64 us at 12800
+#endif
+template <int X, int U, int H1, int H2, typename TIO>
+static int launch_small_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
+    const int threads = 128;                                            // 4 warps = 4 steps per CTA
+    const unsigned grid = (unsigned)((ar.nsteps * 32 + threads - 1) / threads);
+    const float *W1 = (const float*)h->dW[0], *b1 = (const float*)h->db[0], *W2 = (const float*)h->dW[1], *b2 = (const float*)h->db[1],
+                *W3 = (const float*)h->dW[2], *b3 = (const float*)h->db[2];
+    switch (mode) {
+        case 0: nempc_small_kernel<X, U, H1, H2, 0, TIO><<<grid, threads, 0, s>>>(W1, b1, W2, b2, W3, b3, st, h->lay, ar); break;
+        case 1: nempc_small_kernel<X, U, H1, H2, 1, TIO><<<grid, threads, 0, s>>>(W1, b1, W2, b2, W3, b3, st, h->lay, ar); break;
+        default: nempc_small_kernel<X, U, H1, H2, 2, TIO><<<grid, threads, 0, s>>>(W1, b1, W2, b2, W3, b3, st, h->lay, ar); break;
+    }
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+
 template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    static const long long small_max = getenv("NEMPC_SMALL_MAX_STEPS") ? atoll(getenv("NEMPC_SMALL_MAX_STEPS")) : NEMPC_SMALL_MAX_STEPS;
+    if (ar.nsteps <= small_max && h->desc.kernel == NEMPC_KERNEL_AUTO) {
+        switch (h->fast_id) {
+            case 0: return launch_small_shape<2, 1, 30, 30, TIO>(h, ar, mode, s);
+            case 1: return launch_small_shape<2, 1, 32, 32, TIO>(h, ar, mode, s);
+            case 2: return launch_small_shape<2, 1, 16, 16, TIO>(h, ar, mode, s);
+        }
+    }
     switch (h->fast_id) {
         case 0: return launch_fast_shape<2, 1, 30, 30, NEMPC_FAST_NCHUNK30, TIO>(h, ar, mode, s);
         case 1: return launch_fast_shape<2, 1, 32, 32, 2, TIO>(h, ar, mode, s);

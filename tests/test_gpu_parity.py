@@ -324,3 +324,34 @@ def test_c3_full_size_properties_tensor_core():
     for kr, kg in KEYS[:3]:
         assert _relerr(g[kg], ref[kr]) < TOL32, kg
     tc.close(); gen.close()
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+@pytest.mark.parametrize("h", (30, 32, 16))
+def test_small_batch_warp_kernel_vs_oracle(kind, h, lv_weights):
+    """below 4096 horizon steps `auto` runs the warp-per-step kernel (nempc_small.cuh): oracle parity for all request sets, and
+    agreement with the thread-per-step kernel (different summation order, so float32 rounding, not bit equality)."""
+    import torch
+    H, B = 25, 3                         # BASELINE config C1 shape; 75 steps = 75 warps, ragged last CTA
+    mlp = MLP(lv_weights, 2, 1) if h == 30 else MLP.glorot([3, h, h, 2], 2, 1, seed=h)
+    rng = np.random.default_rng(h + 1)
+    obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 0.5], [0.3], x_ref=rng.uniform(-1, 1, (H, 2)))
+    Z, X0 = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2))
+    lam, sig = rng.standard_normal((B, H * 2)), rng.uniform(0.5, 1.5, B)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "auto", obj)
+    assert "nempc_small_kernel" in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < TOL32, (kg, _relerr(got[kg], ref[kr]))
+    t = lambda a: torch.as_tensor(a).cuda()
+    o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+    o0 = ev.eval(t(Z), t(X0), want=("resid",))
+    torch.cuda.synchronize()
+    assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL32
+    assert _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    fast = _evaluator(mlp, kind, H, "float32", "fast", obj)
+    gf = _run(fast, Z, X0, lam, sig)
+    for k in ("resid", "jac", "hes"):
+        assert _relerr(got[k], gf[k]) < 2e-6, k
+    ev.close(); fast.close()
