@@ -36,5 +36,34 @@ def main():
         ev.close()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--solve" not in sys.argv:
     main()
+
+
+def single_problem_solve():
+    """one NMPC solve of ONE problem (the reference's NMPC.next situation) with the on-device interior-point solver"""
+    import torch
+    from bench import WORKLOADS, make_problem, solver_bounds
+    from pyneuralempc_b200 import NlpEvaluator
+    for integ in ("discrete", "rk4"):
+        wl = dict(WORKLOADS["C1"]); wl["integ"] = integ; wl["DT"] = 0.1
+        mlp, obj, Z, X0, lam = make_problem({k: v for k, v in wl.items() if k != "desc"}, 1)
+        ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], integ, DT=0.1)
+        ev.set_objective(obj.lin, obj.quad, obj.ref)
+        lb, ub = solver_bounds(wl)
+        x0 = torch.as_tensor(X0).cuda()
+        for _ in range(3):
+            so = ev.solve(x0, lb, ub, tol=1e-4, max_iter=40)
+        torch.cuda.synchronize()
+        n = 50
+        t0 = time.perf_counter()
+        for _ in range(n):
+            so = ev.solve(x0, lb, ub, tol=1e-4, max_iter=40)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / n * 1e3
+        print(f"C1 {integ:8s} single-problem NMPC solve (nempc_solve, tol 1e-4): {ms:.2f} ms, {int(so['iterations'][0])} IPM iterations, status {int(so['status'][0])}", flush=True)
+        ev.close()
+
+
+if __name__ == "__main__" and "--solve" in sys.argv:
+    single_problem_solve()
