@@ -448,7 +448,7 @@ def gpu_run(args):
                        "l2": f"{nsets} rotating input/output sets, {set_bytes * nsets / 1e6:.0f} MB total > 126 MB L2",
                        "eval": "residual + sparse Jacobian + lambda-contracted sparse Lagrangian Hessian + objective value/gradient"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(te.item()) / args.steps * 1e3, "api": "NlpEvaluator.eval_pinned -> nempc_eval_host (pinned host buffers, chunk-pipelined H2D|kernels|D2H)",
+                    "ms_per_step": float(te.item()) / args.steps * 1e3, "api": "NlpEvaluator.eval_pinned -> nempc_eval_host (pinned host buffers, chunk-pipelined H2D|kernels|D2H, replayed as a CUDA graph)",
                     "numpy_callback_ms_per_step": cb_ms},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "mpc_solves": solves, "other_workloads": side}
     print(json.dumps(line))

@@ -104,8 +104,12 @@ int nempc_eval(nempc_handle* h, int64_t B, const void* z, const void* x0, const 
                const void* obj_factor, double obj_factor_scalar,
                void* resid, void* jac_vals, void* hes_vals, void* obj, void* grad, void* stream);
 
-/* Same call with HOST buffers (the cyipopt callback situation): copies inputs to the handle's device staging,
- * evaluates, copies the requested outputs back and synchronises.  Pinned host memory makes the copies async DMA. */
+/* Same call with HOST buffers (the cyipopt callback situation); synchronises before it returns.
+ *   - page-locked (mapped) buffers and a small call (<= 256 KB moved): ZERO-COPY, the kernels read / write the host buffers directly;
+ *   - otherwise the batch is cut in chunks that pipeline H2D | kernels | D2H on three streams through device staging owned by the
+ *     handle; with page-locked buffers the pipeline of an unchanged argument set is captured once and replayed as a CUDA graph
+ *     (nempc_set_weights / nempc_set_objective invalidate it);
+ *   - pageable buffers work too (the copies are then synchronous in the driver). */
 int nempc_eval_host(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda,
                     const void* obj_factor, double obj_factor_scalar,
                     void* resid, void* jac_vals, void* hes_vals, void* obj, void* grad);
