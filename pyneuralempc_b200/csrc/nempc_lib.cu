@@ -203,6 +203,42 @@ __global__ void nempc_ipm_count_iter_kernel(const SolverWs w, long long B) {
     if (b < B && w.status[b] == NEMPC_ST_RUNNING) w.iters[b] += 1;
 }
 
+// line search, ONE WARP PER PROBLEM: |c|_1 and the barrier terms (a logarithm per bounded variable) are computed on 32 lanes into
+// shared memory and added by lane 0 in the order of ipm_linesearch_problem / ipm_barrier, so the Armijo test sees the same bits.
+__global__ void __launch_bounds__(256)
+nempc_ipm_linesearch_warp_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
+    extern __shared__ __align__(16) double ls_sm[];
+    const int n = L.n, m = L.m, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * wpb + warp;
+    if (b >= B || w.status[b] != NEMPC_ST_RUNNING || w.accepted[b]) return;          // whole warps leave together
+    double* tl = ls_sm + (size_t)warp * (2 * n + m); double* tu = tl + n; double* tc = tu + n;
+    const double* zt = w.zt + b * n; const double* ct = w.residt + b * m;
+    for (int i = lane; i < m; i += 32) tc[i] = fabs(ct[i]);
+    for (int i = lane; i < n; i += 32) {
+        double a = 0.0, c = 0.0;
+        if (nempc_finite(w.lb[i])) { const double d = zt[i] - w.lb[i]; a = log(d > 1e-300 ? d : 1e-300); }
+        if (nempc_finite(w.ub[i])) { const double d = w.ub[i] - zt[i]; c = log(d > 1e-300 ? d : 1e-300); }
+        tl[i] = a; tu[i] = c;
+    }
+    __syncwarp();
+    int accept = 0;
+    double an = 0.0;
+    if (lane == 0) {
+        double c1 = 0.0, bar = 0.0;
+        for (int i = 0; i < m; ++i) c1 += tc[i];
+        for (int i = 0; i < n; ++i) { if (nempc_finite(w.lb[i])) bar += tl[i]; if (nempc_finite(w.ub[i])) bar += tu[i]; }
+        const double phi = w.objt[b] - w.mu[b] * bar + w.nu[b] * c1;
+        const double a = w.alpha[b];
+        if (nempc_finite(phi) && phi <= w.phi0[b] + o.eta * a * fmin(w.dphi[b], 0.0)) { w.accepted[b] = 1; accept = 1; }
+        else { an = 0.5 * a; w.alpha[b] = an; atomicAdd(&counts[1], 1); }
+    }
+    accept = __shfl_sync(0xffffffffu, accept, 0);
+    if (accept) return;
+    an = __shfl_sync(0xffffffffu, an, 0);
+    const double* z = w.z + b * n; const double* dz = w.dz + b * n; double* ztw = w.zt + b * n;
+    for (int i = lane; i < n; i += 32) ztw[i] = z[i] + an * dz[i];
+}
+
 __global__ void nempc_ipm_linesearch_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -1073,6 +1109,7 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
         const long long ctas = std::min<long long>(32, (long long)(smem_sm / (need + 1024))), per_sm = std::min<long long>(ctas * wpb, 64);
         if (per_sm > best) { best = per_sm; staged_wpb = wpb; staged_smem = need; }
     }
+    const size_t ls_smem = (size_t)8 * (2 * n + m) * sizeof(double);           // line-search kernel: 8 warps (problems) per CTA
     const char* force = getenv("NEMPC_KKT_STAGED");
     if (force && force[0] == '0') staged_smem = 0;
     if (staged_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kkt_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
@@ -1093,7 +1130,8 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
             rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
             if (rc) return rc;
             CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
-            nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+            if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, s>>>(L, w, o, B, h->sv_counts);
+            else nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
             CU(h, cudaGetLastError()); h->launches++;
             CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             CU(h, cudaStreamSynchronize(s));
