@@ -1123,19 +1123,23 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
         if (staged_smem) kkt_staged<<<(unsigned)((B + staged_wpb - 1) / staged_wpb), 32 * staged_wpb, staged_smem, s>>>(L, w, o, B, h->sv_counts);
         else kkt_plain<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
         CU(h, cudaGetLastError()); h->launches++;
-        CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CU(h, cudaStreamSynchronize(s));
-        if (h->sv_counts_host[0] == 0) break;                      // every problem converged or failed
-        for (int t = 0; t < o.max_backtrack && h->sv_counts_host[1] > 0; ++t) {
-            rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
-            if (rc) return rc;
-            CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
-            if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, s>>>(L, w, o, B, h->sv_counts);
-            else nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
-            CU(h, cudaGetLastError()); h->launches++;
+        // After a KKT step every running problem needs at least one line-search trial, so the first trial is issued WITHOUT waiting
+        // for the counters (one host synchronisation per iteration instead of two); further trials only when some problem backtracks.
+        // When nothing is running any more the trial is a wasted residual evaluation, once per solve.
+        int trial = 0;
+        do {
+            if (o.max_backtrack > 0) {
+                rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
+                if (rc) return rc;
+                CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
+                if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, s>>>(L, w, o, B, h->sv_counts);
+                else nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
+                CU(h, cudaGetLastError()); h->launches++;
+            }
             CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
             CU(h, cudaStreamSynchronize(s));
-        }
+        } while (++trial < o.max_backtrack && h->sv_counts_host[0] > 0 && h->sv_counts_host[1] > 0);
+        if (h->sv_counts_host[0] == 0) break;                      // every problem converged or failed
         {
             const long long tot = (long long)B * L.n;
             nempc_ipm_update_flat_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(L, w, B);
