@@ -355,3 +355,22 @@ def test_small_batch_warp_kernel_vs_oracle(kind, h, lv_weights):
     for k in ("resid", "jac", "hes"):
         assert _relerr(got[k], gf[k]) < 2e-6, k
     ev.close(); fast.close()
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,B", [("rk4", [5, 128, 128, 128, 4], 4, 1, 1, 1), ("discrete", [3, 128, 128, 2], 2, 1, 1, 3),
+                                                  ("unity", [6, 128, 128, 128, 4], 4, 2, 2, 1), ("rk4", [4, 128, 128, 3], 3, 1, 5, 2)])
+def test_tensor_core_kernel_edge_sizes(kind, dims, xd, ud, H, B):
+    """fewer horizon steps than one row tile holds (the second tile group of the CTA stays idle), H = 1 (no A block, no x-x Hessian
+    block), and an empty batch."""
+    import torch
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=H + B)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "tc", obj)
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert got[kg].shape == ref[kr].shape
+        assert _relerr(got[kg], ref[kr]) < TOL32, (kg, _relerr(got[kg], ref[kr]))
+    empty = ev.eval(torch.zeros((0, ev.n), dtype=torch.float64).cuda(), torch.zeros((0, xd), dtype=torch.float64).cuda(),
+                    torch.zeros((0, ev.m), dtype=torch.float64).cuda(), 1.0)
+    assert all(v.shape[0] == 0 for v in empty.values())
+    ev.close()
