@@ -62,6 +62,28 @@ class CudaMLPModel(Model):
 
     # ---- constructors -------------------------------------------------------------------------------------
     @classmethod
+    # ---- constructors from common containers (importers.py) -------------------------------------------------------------
+    @classmethod
+    def from_torch(cls, seq, x_dim, u_dim, **kw):
+        """``torch.nn.Sequential`` of Linear / Tanh|Sigmoid|Softplus modules (linear last layer)."""
+        from . import importers
+        weights, act = importers.from_torch_sequential(seq)
+        return cls(weights, x_dim, u_dim, activation=act, **kw)
+
+    @classmethod
+    def from_keras(cls, keras_model, x_dim, u_dim, **kw):
+        """a live Keras ``Sequential`` of Dense layers -- the object the reference hands to KerasTFModel (model/tensorflow.py:9)."""
+        from . import importers
+        weights, act = importers.from_keras_model(keras_model)
+        return cls(weights, x_dim, u_dim, activation=act, **kw)
+
+    @classmethod
+    def from_safetensors(cls, path, x_dim, u_dim, activation="tanh", prefix="", **kw):
+        """a safetensors checkpoint of an ``nn.Sequential`` (``<k>.weight`` [out, in], ``<k>.bias``)."""
+        from . import importers
+        weights, act = importers.from_state_dict(importers.read_safetensors(path), activation, prefix)
+        return cls(weights, x_dim, u_dim, activation=act, **kw)
+
     def from_npz(cls, path, x_dim, u_dim, **kw):
         """weights stored as W0,b0,W1,b1,... (tests/golden/lv_mlp_weights.npz has this layout)."""
         d = np.load(path)
