@@ -61,15 +61,7 @@ class CudaMLPModel(Model):
         self._ev = None
 
     # ---- constructors -------------------------------------------------------------------------------------
-    @classmethod
     # ---- constructors from common containers (importers.py) -------------------------------------------------------------
-    @classmethod
-    def from_torch(cls, seq, x_dim, u_dim, **kw):
-        """``torch.nn.Sequential`` of Linear / Tanh|Sigmoid|Softplus modules (linear last layer)."""
-        from . import importers
-        weights, act = importers.from_torch_sequential(seq)
-        return cls(weights, x_dim, u_dim, activation=act, **kw)
-
     @classmethod
     def from_keras(cls, keras_model, x_dim, u_dim, **kw):
         """a live Keras ``Sequential`` of Dense layers -- the object the reference hands to KerasTFModel (model/tensorflow.py:9)."""
@@ -84,6 +76,7 @@ class CudaMLPModel(Model):
         weights, act = importers.from_state_dict(importers.read_safetensors(path), activation, prefix)
         return cls(weights, x_dim, u_dim, activation=act, **kw)
 
+    @classmethod
     def from_npz(cls, path, x_dim, u_dim, **kw):
         """weights stored as W0,b0,W1,b1,... (tests/golden/lv_mlp_weights.npz has this layout)."""
         d = np.load(path)
