@@ -83,7 +83,9 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
     static constexpr int OFF_G = OFF_C + C_FLOATS * 4;                    // group blocks
     static constexpr int G_SH = 0;                                        // a_l / h_l     [SPT][SROW]
     static constexpr int G_ST = G_SH + SPT * SROW * 4;                    // raw tangents  [D][SPT][SROW]   (Hessian only)
-    static constexpr int G_P = G_ST + (HES ? D * SPT * SROW * 4 : 0);     // per-step state across the stages
+    static constexpr int G_S1 = G_ST + (HES ? D * SPT * SROW * 4 : 0);    // s'(a_l)  and  s''(a_l)  [SPT][SROW] each (Hessian only): computed
+    static constexpr int G_S2 = G_S1 + (HES ? SPT * SROW * 4 : 0);        // once per (step, neuron) by the tanh pass, not once per row
+    static constexpr int G_P = G_S2 + (HES ? SPT * SROW * 4 : 0);         // per-step state across the stages
     static constexpr int G_I = G_P + SPT * P_TOTAL * 4;                   // (problem, time index) of each step of the tile
     static constexpr int G_PART = G_I + SPT * 8;                          // [NQ-1][128][XP] partial output sums of the upper column groups
     static constexpr int G_TMP = G_PART + (NQ - 1) * 128 * XP * 4;        // stage temporaries
@@ -129,8 +131,8 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = tid / GT, gtid = tid - grp * GT;   // tile group of this thread, index inside the group
     const int m = gtid & 127, cq = gtid >> 7;          // row, column group
-    const int kind = m / SPT, sl = m - kind * SPT;
     const bool valid = m < C::ROWS;
+    const int kind = valid ? m / SPT : 0, sl = valid ? m - (m / SPT) * SPT : 0;     // spare rows of the tile act as a second copy of P row 0 (finite, unused)
     int cT = 0, c1 = 0, c2 = 0;                       // tangent column of a T row; column pair of an S row
     if (valid && kind >= 1) {
         if (kind <= D) cT = kind - 1;
@@ -155,6 +157,8 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     unsigned char* gblk = tc_smem + C::OFF_G + grp * C::G_BYTES;     // this group's block
     float* sideH = reinterpret_cast<float*>(gblk + C::G_SH);
     float* sideT = reinterpret_cast<float*>(gblk + C::G_ST);
+    float* sideS1 = reinterpret_cast<float*>(gblk + C::G_S1);
+    float* sideS2 = reinterpret_cast<float*>(gblk + C::G_S2);
     float* pers = reinterpret_cast<float*>(gblk + C::G_P);
     int* step_b = reinterpret_cast<int*>(gblk + C::G_I);             // problem index of step s_ of the tile, -1 past the end
     int* step_t = step_b + SPT;
@@ -230,7 +234,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     const float zc = (c < X) ? fmaf(a_s, ps[C::P_KPREV + (c < X ? c : 0)], ps[C::P_Z + c]) : ps[C::P_Z + c];
                     a = fmaf(W0[c * HW + j], zc, a);
                 }
-                sideH[s_ * SROW + j] = fast_tanh(a);
+                const float h = fast_tanh(a);
+                sideH[s_ * SROW + j] = h;
+                if (HES) { const float s1 = fmaf(-h, h, 1.f); sideS1[s_ * SROW + j] = s1; sideS2[s_ * SROW + j] = -2.f * h * s1; }
             }
             if (HES) {      // da_0/dz_c = W0[c]: park it like the raw tangents of any other layer, so pass 2 has ONE code path
                 for (int e = gtid; e < D * SPT * (HW / 4); e += GT) {
@@ -268,10 +274,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         for (int i = 0; i < 8; ++i) v2[i] = pk(0.f, 0.f);    // first layer: d2a_0 = 0
                     }
                     f2 out2[8];
-                    if (!valid) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) out2[i] = pk(0.f, 0.f);
-                    } else {
+                    {
                         const float* hrow = sideH + sl * SROW + col;
                         if (kind == 0) {                           // P: the activations themselves
 #pragma unroll
@@ -282,34 +285,39 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         } else if (!is_S) {                        // T_c: s'(a) * da/dz_c
                             // raw tangent: parked in sideT (Hessian mode); else W0[c] for the first layer, tensor memory otherwise
                             const float* traw = HES ? sideT + (cT * SPT + sl) * SROW + col : W0 + cT * HW + col;
+                            const float* s1row = sideS1 + sl * SROW + col;
                             const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f);
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
-                                const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
                                 f2 va = v2[2 * i4], vb = v2[2 * i4 + 1];
                                 if (HES || first) {
                                     const float4 w4 = *reinterpret_cast<const float4*>(traw + 4 * i4);
                                     va = pk(w4.x, w4.y); vb = pk(w4.z, w4.w);
                                 }
-                                const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
-                                out2[2 * i4] = mul2(fma2(mul2(ha, m1), ha, one), va);
-                                out2[2 * i4 + 1] = mul2(fma2(mul2(hb, m1), hb, one), vb);
+                                if (HES) {
+                                    const float4 s4 = *reinterpret_cast<const float4*>(s1row + 4 * i4);
+                                    out2[2 * i4] = mul2(pk(s4.x, s4.y), va);
+                                    out2[2 * i4 + 1] = mul2(pk(s4.z, s4.w), vb);
+                                } else {
+                                    const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                                    const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
+                                    out2[2 * i4] = mul2(fma2(mul2(ha, m1), ha, one), va);
+                                    out2[2 * i4 + 1] = mul2(fma2(mul2(hb, m1), hb, one), vb);
+                                }
                             }
                         } else {                                   // S_(c1,c2): s''(a) T_c1 T_c2 + s'(a) d2a
                             const float* t1 = sideT + (c1 * SPT + sl) * SROW + col;
                             const float* t2 = sideT + (c2 * SPT + sl) * SROW + col;
-                            const f2 m1 = pk(-1.f, -1.f), one = pk(1.f, 1.f), m2 = pk(-2.f, -2.f);
+                            const float* s1row = sideS1 + sl * SROW + col;
+                            const float* s2row = sideS2 + sl * SROW + col;
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
-                                const float4 h4 = *reinterpret_cast<const float4*>(hrow + 4 * i4);
+                                const float4 s4 = *reinterpret_cast<const float4*>(s1row + 4 * i4);
+                                const float4 r4 = *reinterpret_cast<const float4*>(s2row + 4 * i4);
                                 const float4 a4 = *reinterpret_cast<const float4*>(t1 + 4 * i4);
                                 const float4 b4 = *reinterpret_cast<const float4*>(t2 + 4 * i4);
-                                const f2 ha = pk(h4.x, h4.y), hb = pk(h4.z, h4.w);
-                                const f2 s1a = fma2(mul2(ha, m1), ha, one), s1b = fma2(mul2(hb, m1), hb, one);
-                                const f2 qa = mul2(mul2(ha, s1a), mul2(pk(a4.x, a4.y), pk(b4.x, b4.y)));      // h s' T_c1 T_c2
-                                const f2 qb = mul2(mul2(hb, s1b), mul2(pk(a4.z, a4.w), pk(b4.z, b4.w)));
-                                out2[2 * i4] = fma2(qa, m2, mul2(s1a, v2[2 * i4]));
-                                out2[2 * i4 + 1] = fma2(qb, m2, mul2(s1b, v2[2 * i4 + 1]));
+                                out2[2 * i4] = fma2(mul2(pk(a4.x, a4.y), pk(b4.x, b4.y)), pk(r4.x, r4.y), mul2(pk(s4.x, s4.y), v2[2 * i4]));
+                                out2[2 * i4 + 1] = fma2(mul2(pk(a4.z, a4.w), pk(b4.z, b4.w)), pk(r4.z, r4.w), mul2(pk(s4.z, s4.w), v2[2 * i4 + 1]));
                             }
                         }
                     }
@@ -428,7 +436,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 TC_PROF(6);
                 for (int e = gtid; e < SPT * HW; e += GT) {
                     const int s_ = e / HW, j = e - s_ * HW;
-                    sideH[s_ * SROW + j] = fast_tanh(sideH[s_ * SROW + j]);
+                    const float h = fast_tanh(sideH[s_ * SROW + j]);
+                    sideH[s_ * SROW + j] = h;
+                    if (HES) { const float s1 = fmaf(-h, h, 1.f); sideS1[s_ * SROW + j] = s1; sideS2[s_ * SROW + j] = -2.f * h * s1; }
                 }
                 gsync();
                 TC_PROF(7);
