@@ -52,8 +52,8 @@ def main():
         names = ["init", "l0 tanh", "pass2", "sync->mma", "mma issue", "mma wait", "pass1", "tanh", "out combine", "algebra", "outputs", "loop"]
         tot = sum(buf[:16]) or 1
         print("  phase cycles (share): " + ", ".join(f"{n} {buf[i] / tot:.1%}" for i, n in enumerate(names)), flush=True)
-        ntl = (steps + 5) // 6 * (args.reps + 2)
-        print(f"  cycles per tile (thread 0, C3 SPT=6): {tot / ntl:.0f}")
+        ntl = (steps + 5) // 6 * (args.reps + 2) / 2          # thread 0 belongs to tile group 0: half of the tiles
+        print(f"  cycles per tile of one group (C3 SPT=6; two groups in flight per SM): {tot / ntl:.0f}")
         print("  mma issue detail (cycles per batch): setup %.0f, corr-1 x8 %.0f, corr-2 x8 %.0f, main x8 + commit %.0f" % tuple(buf[i] / (ntl * 8) for i in (12, 13, 14, 4)))
     ev.close()
 
