@@ -245,10 +245,6 @@ __global__ void nempc_ipm_linesearch_kernel(const NlpLayout L, const SolverWs w,
     ipm_linesearch_problem(L, w, b, o);
     if (w.status[b] == NEMPC_ST_RUNNING && !w.accepted[b]) atomicAdd(&counts[1], 1);
 }
-__global__ void nempc_ipm_update_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) ipm_update_problem(L, w, b, o);
-}
 __global__ void nempc_ipm_finish_kernel(const SolverWs w, long long B, int* status, int* iters, double* err) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
