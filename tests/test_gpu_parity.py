@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI, libnempc.so) with the CPU oracle and the golden files recorded
 from the unmodified reference.  Tolerances: network arithmetic float32 -> 1e-5 relative to the largest magnitude of
 the compared array; float64 -> 1e-10 (BASELINE.json north_star).  Sparsity indices are compared bit-exactly."""
+import ctypes
 import os
 
 import numpy as np
@@ -373,4 +374,32 @@ def test_tensor_core_kernel_edge_sizes(kind, dims, xd, ud, H, B):
     empty = ev.eval(torch.zeros((0, ev.n), dtype=torch.float64).cuda(), torch.zeros((0, xd), dtype=torch.float64).cuda(),
                     torch.zeros((0, ev.m), dtype=torch.float64).cuda(), 1.0)
     assert all(v.shape[0] == 0 for v in empty.values())
+    ev.close()
+
+
+@pytest.mark.parametrize("kernel,dims,xd,ud", [("tc", [5, 128, 128, 4], 4, 1), ("fast", [3, 30, 30, 2], 2, 1), ("auto", [3, 30, 30, 2], 2, 1),
+                                                ("generic", [5, 12, 9, 4], 4, 1)])
+def test_evaluation_without_an_objective(kernel, dims, xd, ud):
+    """no nempc_set_objective: residual / Jacobian / Hessian still evaluate (the Hessian pattern has no objective-only diagonal of
+    x_H, obj / grad are refused) -- the reference's IpoptProblem with a zero cost (optimizer/ipopt.py:55-62)."""
+    import torch
+    from pyneuralempc_b200._lib import NempcError
+    H, B = 7, 9
+    mlp, _, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=11)
+    oe = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=None)
+    ref = oe.evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, "rk4", H, "float32", kernel, None)
+    np.testing.assert_array_equal(ev.hes_rows, oe.hes_rows)
+    np.testing.assert_array_equal(ev.hes_cols, oe.hes_cols)
+    t = lambda a: torch.as_tensor(a).cuda()
+    got = ev.eval(t(Z), t(X0), t(lam), t(sig), want=("resid", "jac", "hes"))
+    torch.cuda.synchronize()
+    for kr, kg in KEYS[:3]:
+        assert _relerr(got[kg].cpu().numpy(), ref[kr]) < TOL32, kg
+    assert "obj" not in ev.eval(t(Z), t(X0), t(lam), t(sig), want=("resid", "obj", "grad"))     # the Python layer drops them ...
+    buf = (ctypes.c_double * B)()
+    rc = ev.lib.nempc_eval(ev._h, B, ctypes.c_void_p(t(Z).data_ptr()), ctypes.c_void_p(t(X0).data_ptr()), None, None, 1.0,
+                           None, None, None, ctypes.c_void_p(t(np.zeros(B)).data_ptr()), None, None)
+    assert rc == -4                                                                              # ... and the C ABI answers NEMPC_ESTATE
+    del buf, NempcError
     ev.close()
