@@ -138,6 +138,12 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
     const bool want_hes = (flags & NEMPC_WANT_HES) != 0;
     const bool want_jac = want_hes || (flags & NEMPC_WANT_JAC) != 0;
     const bool unity = (flags & NEMPC_UNITY) != 0;
+    // Single-stage integrators (discrete / unity) have no stage recursion, so the Lagrangian Hessian block is sum_p lambda_p M_p and
+    // the multipliers can be contracted into the adjoint SEED: one adjoint column and one curvature matrix per step instead of x_dim
+    // of each (12x less Hessian work for the quadrotor network of BASELINE config C4).  RK4 needs the per-output form (h_s recursion),
+    // and so do the block / model entry points, which return per-output Hessians.
+    const bool contract = want_hes && st.S == 1 && !model_mode && !(flags & NEMPC_MODE_BLOCKS);
+    const int xh = contract ? 1 : x;
     const long long b = model_mode ? 0 : step / L.H;
     const int t = model_mode ? 0 : (int)(step - b * L.H);
     const TIO* zb = model_mode ? ar.z + step * d : ar.z + b * (long long)L.n;
@@ -157,10 +163,11 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
         else v = zb[L.H * x + t * L.u + (c - x)];
         z[c] = (T)v;
     }
+    if (contract) for (int p = lt; p < x; p += tps) (ws + sl.lam)[p] = (T)ar.lam[b * L.m + t * x + p];
     for (int i = lt; i < x; i += tps) { kprev[i] = (T)0; kacc[i] = (T)0; }
     for (int i = lt; i < x * d; i += tps) dkacc[i] = (T)0;
     for (int i = lt; i < dd; i += tps) R[i] = (i / d == i % d) ? (T)1 : (T)0;
-    if (want_hes) for (int i = lt; i < x * dd; i += tps) { Hacc[i] = (T)0; Hprev[i] = (T)0; }
+    if (want_hes) for (int i = lt; i < xh * dd; i += tps) { Hacc[i] = (T)0; Hprev[i] = (T)0; }
     slot_barrier(bar_id, tps);
 
     const int nh = net.L - 1;   // hidden layers
@@ -237,8 +244,17 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                 }
             }
             if (want_hes) {
-                for (int idx = lt; idx < hin * x; idx += tps) Gb[0][idx] = Wo[idx];
-                for (int idx = lt; idx < x * dd; idx += tps) M[idx] = (T)0;
+                if (contract) {
+                    const T* lamv = ws + sl.lam;
+                    for (int j = lt; j < hin; j += tps) {
+                        T g = (T)0;
+                        for (int p = 0; p < x; ++p) g += lamv[p] * Wo[j * x + p];
+                        Gb[0][j] = g;
+                    }
+                } else {
+                    for (int idx = lt; idx < hin * x; idx += tps) Gb[0][idx] = Wo[idx];
+                }
+                for (int idx = lt; idx < xh * dd; idx += tps) M[idx] = (T)0;
             }
         }
         slot_barrier(bar_id, tps);
@@ -250,21 +266,21 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                 const int hl = net.dims[l + 1];
                 T* G = Gb[cur]; T* Gn = Gb[cur ^ 1];
                 const T* hv = act + net.hoff[l];
-                for (int idx = lt; idx < hl * x; idx += tps) {
-                    T s1, s2; act_derivs<T>(net.act, hv[idx / x], s1, s2);
+                for (int idx = lt; idx < hl * xh; idx += tps) {
+                    T s1, s2; act_derivs<T>(net.act, hv[idx / xh], s1, s2);
                     const T g = G[idx];
                     coef[idx] = s2 * g;
                     G[idx] = s1 * g;
                 }
                 slot_barrier(bar_id, tps);
                 const T* Tt = Tl + (long long)net.hoff[l] * d;
-                for (int e = lt; e < x * ntri; e += tps) {
+                for (int e = lt; e < xh * ntri; e += tps) {
                     const int p = e / ntri;
                     int r = e - p * ntri, c = 0;
                     while (r > c) { r -= c + 1; ++c; }       // r-th entry of the lower triangle -> (c, r)
                     const int c2 = r;
                     T acc = (T)0;
-                    for (int j = 0; j < hl; ++j) acc += coef[j * x + p] * Tt[j * d + c] * Tt[j * d + c2];
+                    for (int j = 0; j < hl; ++j) acc += coef[j * xh + p] * Tt[j * d + c] * Tt[j * d + c2];
                     M[p * dd + c * d + c2] += acc;
                     if (c != c2) M[p * dd + c2 * d + c] += acc;
                 }
@@ -278,10 +294,10 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                         for (int j = 0; j < hl; ++j) {
                             const T w = WT[j * hp + i];
 #pragma unroll
-                            for (int p = 0; p < DMAX; ++p) if (p < x) ap[p] += w * G[j * x + p];
+                            for (int p = 0; p < DMAX; ++p) if (p < xh) ap[p] += w * G[j * xh + p];
                         }
 #pragma unroll
-                        for (int p = 0; p < DMAX; ++p) if (p < x) Gn[i * x + p] = ap[p];
+                        for (int p = 0; p < DMAX; ++p) if (p < xh) Gn[i * xh + p] = ap[p];
                     }
                 }
                 slot_barrier(bar_id, tps);
@@ -297,7 +313,7 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                 dk[idx] = acc;
             }
             if (want_hes) {
-                for (int idx = lt; idx < x * dd; idx += tps) {      // tmp[p] = M[p] R
+                for (int idx = lt; idx < xh * dd; idx += tps) {     // tmp[p] = M[p] R
                     const int p = idx / dd, k = (idx % dd) / d, c = idx % d;
                     T acc = (T)0;
                     for (int l2 = 0; l2 < d; ++l2) acc += M[p * dd + k * d + l2] * R[l2 * d + c];
@@ -306,7 +322,7 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
             }
             slot_barrier(bar_id, tps);
             if (want_hes) {
-                for (int idx = lt; idx < x * dd; idx += tps) {      // h_s[p] = R^T tmp[p] + a_s sum_k J[p,k] h_{s-1}[k]
+                for (int idx = lt; idx < xh * dd; idx += tps) {     // h_s[p] = R^T tmp[p] + a_s sum_k J[p,k] h_{s-1}[k]
                     const int p = idx / dd, a = (idx % dd) / d, c = idx % d;
                     T acc = (T)0;
                     for (int k = 0; k < d; ++k) acc += R[k * d + a] * tmp[p * dd + k * d + c];
@@ -319,7 +335,7 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
         for (int idx = lt; idx < x; idx += tps) { kacc[idx] += c_s * kcur[idx]; kprev[idx] = kcur[idx]; }
         slot_barrier(bar_id, tps);
         if (want_hes)
-            for (int idx = lt; idx < x * dd; idx += tps) { Hacc[idx] += c_s * M[idx]; Hprev[idx] = M[idx]; }
+            for (int idx = lt; idx < xh * dd; idx += tps) { Hacc[idx] += c_s * M[idx]; Hprev[idx] = M[idx]; }
         if (want_jac && s + 1 < st.S) {
             const T an = st.a[s + 1];
             for (int idx = lt; idx < dd; idx += tps) {
@@ -360,14 +376,15 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
         TIO* hv = ar.hes + b * L.nnz_hes;
         const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
         T* lam = ws + sl.lam;
-        for (int p = lt; p < x; p += tps) lam[p] = (T)ar.lam[b * L.m + t * x + p];
+        if (!contract) for (int p = lt; p < x; p += tps) lam[p] = (T)ar.lam[b * L.m + t * x + p];
         slot_barrier(bar_id, tps);
         for (int idx = lt; idx < dd; idx += tps) {
             const int a = idx / d, c = idx % d;
             if (c > a) continue;
             if (t == 0 && c < x) continue;                      // x0 is data, not a variable (discret.py:70-78)
             T acc = (T)0;
-            for (int p = 0; p < x; ++p) acc += lam[p] * Hacc[p * dd + a * d + c];
+            if (contract) acc = Hacc[a * d + c];                // the multipliers went into the adjoint seed
+            else for (int p = 0; p < x; ++p) acc += lam[p] * Hacc[p * dd + a * d + c];
             TW v = (TW)acc;
             int slot;
             if (a < x) {
