@@ -132,6 +132,9 @@ template <typename T, typename TIO, int DMAX>
 NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const NlpLayout& L, const SlotLayout& sl,
                            const EvalArgs<TIO>& ar, long long step, T* ws, int lt, int tps, int bar_id) {
     typedef typename WideOf<T, TIO>::type TW;
+    // weight loads in flight per thread in the layer loops: wide-input networks (the C4 class, 256-wide layers whose weights live in
+    // L2) are bound by the latency of those loads (ncu r1u: long_scoreboard 60 %), small ones prefer the shorter schedule
+    constexpr int WU = DMAX >= 16 ? 16 : 4;
     const int x = L.x, d = L.d, dd = d * d;
     const int flags = ar.flags;
     const bool model_mode = (flags & NEMPC_MODE_MODEL) != 0;
@@ -205,13 +208,15 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
 #pragma unroll
                 for (int c = 0; c < DMAX; ++c) at[c] = (T)0;
                 if (want_jac) {
-                    for (int i = 0; i < hin; ++i) {
+#pragma unroll WU
+                    for (int i = 0; i < hin; ++i) {                       // unrolled: WU independent weight loads (L2 latency) in flight
                         const T w = W[i * hout + j];
                         acc += w * hprev[i];
 #pragma unroll
                         for (int c = 0; c < DMAX; ++c) if (c < d) at[c] += w * Vin[i * d + c];
                     }
                 } else {
+#pragma unroll 8
                     for (int i = 0; i < hin; ++i) acc += W[i * hout + j] * hprev[i];
                 }
                 const T h = act_value<T>(net.act, acc);
@@ -291,6 +296,7 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                         T ap[DMAX];
 #pragma unroll
                         for (int p = 0; p < DMAX; ++p) ap[p] = (T)0;
+#pragma unroll WU
                         for (int j = 0; j < hl; ++j) {
                             const T w = WT[j * hp + i];
 #pragma unroll
