@@ -292,18 +292,27 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                 if (l > 0) {
                     const int hp = net.dims[l];
                     const T* WT = net.WT[l];
-                    for (int i = lt; i < hp; i += tps) {
-                        T ap[DMAX];
-#pragma unroll
-                        for (int p = 0; p < DMAX; ++p) ap[p] = (T)0;
+                    if (xh == 1) {                             // contracted adjoint: one column, no predicated DMAX-wide loop
+                        for (int i = lt; i < hp; i += tps) {
+                            T a0 = (T)0;
 #pragma unroll WU
-                        for (int j = 0; j < hl; ++j) {
-                            const T w = WT[j * hp + i];
-#pragma unroll
-                            for (int p = 0; p < DMAX; ++p) if (p < xh) ap[p] += w * G[j * xh + p];
+                            for (int j = 0; j < hl; ++j) a0 += WT[j * hp + i] * G[j];
+                            Gn[i] = a0;
                         }
+                    } else {
+                        for (int i = lt; i < hp; i += tps) {
+                            T ap[DMAX];
 #pragma unroll
-                        for (int p = 0; p < DMAX; ++p) if (p < xh) Gn[i * xh + p] = ap[p];
+                            for (int p = 0; p < DMAX; ++p) ap[p] = (T)0;
+#pragma unroll WU
+                            for (int j = 0; j < hl; ++j) {
+                                const T w = WT[j * hp + i];
+#pragma unroll
+                                for (int p = 0; p < DMAX; ++p) if (p < xh) ap[p] += w * G[j * xh + p];
+                            }
+#pragma unroll
+                            for (int p = 0; p < DMAX; ++p) if (p < xh) Gn[i * xh + p] = ap[p];
+                        }
                     }
                 }
                 slot_barrier(bar_id, tps);
