@@ -100,6 +100,20 @@ template <typename TIO> struct EvalArgs {
 template <typename A, typename B> struct WideOf { typedef double type; };
 template <> struct WideOf<float, float> { typedef float type; };
 
+// ---- four consecutive workspace values with one 16-byte (float) / two 16-byte (double) shared-memory loads ---------------------
+// p must be 16-byte aligned: true for rows of the tangent buffers whenever d is a multiple of 4 (offsets are multiples of 4 elements)
+template <typename T> NEMPC_HD void ld4(const T* p, T* v) { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3]; }
+#if defined(__CUDA_ARCH__)
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float* v) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <> __device__ __forceinline__ void ld4<double>(const double* p, double* v) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+#endif
+
 // ---- slot barrier ------------------------------------------------------------------------------------
 NEMPC_HD void slot_barrier(int bar_id, int tps) {
 #if defined(__CUDA_ARCH__)
@@ -207,9 +221,23 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                 T at[DMAX];
 #pragma unroll
                 for (int c = 0; c < DMAX; ++c) at[c] = (T)0;
-                if (want_jac) {
+                if (want_jac && (d & 3) == 0) {                           // tangent rows read as 16-byte vectors
 #pragma unroll WU
                     for (int i = 0; i < hin; ++i) {                       // unrolled: WU independent weight loads (L2 latency) in flight
+                        const T w = W[i * hout + j];
+                        acc += w * hprev[i];
+#pragma unroll
+                        for (int q = 0; q < DMAX / 4; ++q)
+                            if (4 * q < d) {
+                                T v4[4];
+                                ld4<T>(Vin + i * d + 4 * q, v4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) at[4 * q + k] += w * v4[k];
+                            }
+                    }
+                } else if (want_jac) {
+#pragma unroll WU
+                    for (int i = 0; i < hin; ++i) {
                         const T w = W[i * hout + j];
                         acc += w * hprev[i];
 #pragma unroll
