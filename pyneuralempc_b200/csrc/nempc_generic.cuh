@@ -332,11 +332,26 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
                             T ap[DMAX];
 #pragma unroll
                             for (int p = 0; p < DMAX; ++p) ap[p] = (T)0;
+                            if ((xh & 3) == 0) {                   // adjoint rows read as 16-byte vectors
 #pragma unroll WU
-                            for (int j = 0; j < hl; ++j) {
-                                const T w = WT[j * hp + i];
+                                for (int j = 0; j < hl; ++j) {
+                                    const T w = WT[j * hp + i];
 #pragma unroll
-                                for (int p = 0; p < DMAX; ++p) if (p < xh) ap[p] += w * G[j * xh + p];
+                                    for (int q = 0; q < DMAX / 4; ++q)
+                                        if (4 * q < xh) {
+                                            T g4[4];
+                                            ld4<T>(G + j * xh + 4 * q, g4);
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) ap[4 * q + k] += w * g4[k];
+                                        }
+                                }
+                            } else {
+#pragma unroll WU
+                                for (int j = 0; j < hl; ++j) {
+                                    const T w = WT[j * hp + i];
+#pragma unroll
+                                    for (int p = 0; p < DMAX; ++p) if (p < xh) ap[p] += w * G[j * xh + p];
+                                }
                             }
 #pragma unroll
                             for (int p = 0; p < DMAX; ++p) if (p < xh) Gn[i * xh + p] = ap[p];
