@@ -403,3 +403,21 @@ def test_evaluation_without_an_objective(kernel, dims, xd, ud):
     assert rc == -4                                                                              # ... and the C ABI answers NEMPC_ESTATE
     del buf, NempcError
     ev.close()
+
+
+def test_tensor_core_kernel_is_deterministic():
+    """two row tiles share a CTA through named barriers, mbarriers and tensor memory: repeated evaluations of the same batch
+    must be bit-identical (a race between the tile groups would show up here long before it shows up in a tolerance)."""
+    import torch
+    H, B = 50, 300
+    mlp, obj, Z, X0, lam, sig = _problem([5, 128, 128, 128, 4], 4, 1, H, B, seed=9)
+    ev = _evaluator(mlp, "rk4", H, "float32", "tc", obj)
+    t = lambda a: torch.as_tensor(a).cuda()
+    z, x0, lm, sg = t(Z), t(X0), t(lam), t(sig)
+    ref = {k: v.clone() for k, v in ev.eval(z, x0, lm, sg).items()}
+    for _ in range(12):
+        out = ev.eval(z, x0, lm, sg)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    ev.close()
