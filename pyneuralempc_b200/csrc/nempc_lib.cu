@@ -226,7 +226,7 @@ nempc_ipm_linesearch_warp_kernel(const NlpLayout L, const SolverWs w, const Solv
     if (lane == 0) {
         double c1 = 0.0, bar = 0.0;
         for (int i = 0; i < m; ++i) c1 += tc[i];
-        for (int i = 0; i < n; ++i) { if (nempc_finite(w.lb[i])) bar += tl[i]; if (nempc_finite(w.ub[i])) bar += tu[i]; }
+        for (int i = 0; i < n; ++i) { bar += tl[i]; bar += tu[i]; }          // terms of infinite bounds are +0.0: adding them changes no bit
         const double phi = w.objt[b] - w.mu[b] * bar + w.nu[b] * c1;
         const double a = w.alpha[b];
         if (nempc_finite(phi) && phi <= w.phi0[b] + o.eta * a * fmin(w.dphi[b], 0.0)) { w.accepted[b] = 1; accept = 1; }

@@ -399,7 +399,7 @@ __device__ void ipm_kkt_warp(const NlpLayout& L, const SolverWs& w, long long b,
         double gdz = 0.0, c1 = 0.0, bar = 0.0;
         for (int i = 0; i < n; ++i) gdz += r.s3[i];
         for (int i = 0; i < m; ++i) c1 += fabs(r.c[i]);
-        for (int i = 0; i < n; ++i) { if (nempc_finite(w.lb[i])) bar += r.s1[i]; if (nempc_finite(w.ub[i])) bar += r.s2[i]; }
+        for (int i = 0; i < n; ++i) { bar += r.s1[i]; bar += r.s2[i]; }      // terms of infinite bounds are +0.0: adding them changes no bit
         const double nu = fmax(w.nu[b], lmax + 1.0);
         w.nu[b] = nu;
         w.phi0[b] = w.obj[b] - mu * bar + nu * c1;
