@@ -356,6 +356,17 @@ def test_small_batch_warp_kernel_vs_oracle(kind, h, lv_weights):
     for k in ("resid", "jac", "hes"):
         assert _relerr(got[k], gf[k]) < 2e-6, k
     ev.close(); fast.close()
+    ev32 = _evaluator(mlp, kind, H, "float32", "auto", obj, io="float32")      # float32 I/O instantiation of the same kernel
+    g32 = _run(ev32, Z, X0, lam, sig)
+    for kr, kg in KEYS[:3]:
+        assert _relerr(g32[kg], ref[kr]) < TOL32, kg
+    # and through the host-buffer call: zero-copy on the mapped pinned buffers (a single solver callback)
+    buf = ev32.pinned_buffers(B, per_problem_factor=True)
+    buf["z"][...] = Z; buf["x0"][...] = X0; buf["lam"][...] = lam; buf["sig"][...] = sig
+    out = ev32.eval_pinned(B, per_problem_factor=True)
+    for kr, kg in KEYS:
+        assert _relerr(out[kg], ref[kr]) < TOL32, kg
+    ev32.close()
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", [("rk4", [5, 128, 128, 128, 4], 4, 1, 1, 1), ("discrete", [3, 128, 128, 2], 2, 1, 1, 3),
