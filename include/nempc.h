@@ -34,6 +34,7 @@ extern "C" {
 
 #define NEMPC_MAX_LAYERS 8   /* dense layers including the linear output layer */
 #define NEMPC_MAX_D 16       /* x_dim + u_dim */
+#define NEMPC_MAX_EXO 64     /* tvp_dim + p_dim */
 
 enum { NEMPC_OK = 0, NEMPC_EINVAL = -1, NEMPC_ECUDA = -2, NEMPC_ENOMEM = -3, NEMPC_ESTATE = -4, NEMPC_EUNSUPPORTED = -5 };
 enum { NEMPC_F32 = 0, NEMPC_F64 = 1 };
@@ -56,6 +57,9 @@ typedef struct nempc_desc {
     int32_t io_dtype;                    /* element type of every I/O buffer (reference: f64, ipopt.py) */
     int32_t device;                      /* CUDA ordinal */
     int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO: register-resident kernel for the small LV class, tensor-core kernel for 128-wide nets, else generic) */
+    int32_t tvp_dim, p_dim;              /* time-varying / constant model inputs appended to (x, u): the network input is [x, u, tvp, p]
+                                          * (model/tensorflow.py:39-47, model/base.py:4-9); 0 = none.  Layer 0 then has x+u+tvp+p input rows.
+                                          * Served by the generic kernel. */
 } nempc_desc;
 
 typedef struct nempc_handle nempc_handle;
@@ -77,6 +81,17 @@ int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const dou
  * objective/jax.py:28-57 (run.py:83-84 linear in u, test.py:59-60 squared set-point, diagonal tracking).
  * HOST pointers of length n, NULL = zeros.  Changes the Hessian pattern where quad != 0 on x_H. */
 int nempc_set_objective(nempc_handle* h, const double* lin, const double* quad, const double* ref);
+
+/* Exogenous model inputs of the following nempc_eval* / nempc_solve calls: what NMPC.next hands down as `tvp` (H, tvp_dim) and `p`
+ * (p_dim,) (controller.py:65-113 -> ProblemFactory.set_tvp / set_p -> Model.forward(x, u, p=, tvp=), model/tensorflow.py:39-47).
+ * They are inputs of the network but not decision variables: the Jacobian / Hessian keep their (x, u) shape, exactly the column
+ * slicing of model/tensorflow.py:65-66, 97-98.  The reference's `p` branch is mis-shaped (tensorflow.py:44-45, its own TODO); the
+ * intended meaning -- the same p row appended to every sample of a problem -- is implemented.
+ *   tvp: tvp_rows x tvp_dim doubles; tvp_rows == H shares one table between all problems of a batch, otherwise row b*H + t belongs
+ *        to step t of problem b (nempc_model_eval: row i belongs to sample i).
+ *   p:   p_rows x p_dim doubles; p_rows == 1 shares one row between all problems, otherwise row b belongs to problem b.
+ * HOST or DEVICE pointers (copied into buffers owned by the handle; synchronises the device).  NULL for a kind the model lacks. */
+int nempc_set_exogenous(nempc_handle* h, int64_t tvp_rows, const double* tvp, int64_t p_rows, const double* p);
 
 /* ---- sparsity (host only, no device needed) ----------------------------------------------------------- */
 /* replaces Integrator.hessianstructure / JAXObjectifFunc.hessianstructure / IpoptProblem.hessianstructure

@@ -148,6 +148,69 @@ class MLP:
         return out
 
 
+class ExoMLP:
+    """Network over the gathered input ``[x, u, tvp, p]`` (``model/tensorflow.py:39-47``), bound to the exogenous rows of the
+    samples it is evaluated at.  Derivatives are taken w.r.t. the whole input and the tvp / p columns dropped, as the reference
+    does (``model/tensorflow.py:65-66, 97-98``).  The reference's ``p`` branch is mis-shaped (``:44-45``, its own TODO); the
+    intended meaning -- the same ``p`` row appended to every sample -- is what is restated.
+
+    Duck-types the part of :class:`MLP` that ``blocks_np`` / ``dense_ref`` use (``x_dim, u_dim, d, dtype, forward_z, blocks,
+    forward, dense_jacobian, dense_hessian``)."""
+
+    def __init__(self, weights, x_dim, u_dim, tvp_dim=0, p_dim=0, activation="tanh", dtype=np.float64, ext=None):
+        self.tvp_dim, self.p_dim = int(tvp_dim), int(p_dim)
+        self.full = MLP(weights, x_dim, u_dim + self.tvp_dim + self.p_dim, activation, dtype)
+        self.x_dim, self.u_dim = int(x_dim), int(u_dim)
+        self.d = self.x_dim + self.u_dim
+        self.dtype, self.activation, self.weights = self.full.dtype, activation, self.full.weights
+        self.ext = ext
+
+    def astype(self, dtype):
+        return ExoMLP(self.weights, self.x_dim, self.u_dim, self.tvp_dim, self.p_dim, self.activation, dtype, self.ext)
+
+    def bind(self, tvp=None, p=None, B=1, H=None):
+        """``tvp``: (H, tvp_dim) shared by the B problems or (B, H, tvp_dim); ``p``: (p_dim,) or (B, p_dim); ``H`` is needed when there
+        is no tvp to read it from.  Rows are laid
+        out like the steps ``blocks_np.BlockEvaluator`` stacks: problem-major, step-minor."""
+        cols = []
+        if self.tvp_dim:
+            tvp = np.asarray(tvp, np.float64)
+            if tvp.ndim == 2:
+                tvp = np.broadcast_to(tvp, (B,) + tvp.shape)
+            H = tvp.shape[1]
+            cols.append(tvp.reshape(-1, self.tvp_dim))
+        if self.p_dim:
+            p = np.asarray(p, np.float64)
+            if p.ndim == 1:
+                p = np.broadcast_to(p, (B, self.p_dim))
+            reps = H if H is not None else 1
+            cols.append(np.repeat(p, reps, axis=0))
+        ext = np.concatenate(cols, axis=1) if cols else None
+        return ExoMLP(self.weights, self.x_dim, self.u_dim, self.tvp_dim, self.p_dim, self.activation, self.dtype, ext)
+
+    def _gather(self, z):
+        z = np.asarray(z, self.dtype)
+        if self.ext is None:
+            assert self.tvp_dim + self.p_dim == 0, "bind() the exogenous rows first"
+            return z
+        assert self.ext.shape[0] == z.shape[0], "one exogenous row per sample"
+        return np.concatenate([z, self.ext.astype(self.dtype)], axis=1)
+
+    def forward_z(self, z):
+        return self.full.forward_z(self._gather(z))
+
+    def blocks(self, z, need_hessian=True):
+        f, J, Hs = self.full.blocks(self._gather(z), need_hessian=need_hessian)
+        d = self.d
+        return f, J[:, :, :d], (None if Hs is None else Hs[:, :, :d, :d])
+
+    def forward(self, x, u, p=None, tvp=None):
+        return self.forward_z(np.concatenate([x, u], axis=1))
+
+    dense_jacobian = MLP.dense_jacobian
+    dense_hessian = MLP.dense_hessian
+
+
 class DenseModelView:
     """Duck-typed ``Model`` (``model/base.py:3-18`` as actually called: ``discret.py:27,48,64``,
     ``rk4.py:69-72,86,97``) serving the dense layouts from an :class:`MLP`.  ``net_dtype``

@@ -15,7 +15,7 @@ ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2}
 KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
 
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",
-           "nempc_set_objective", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
+           "nempc_set_objective", "nempc_set_exogenous", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
            "nempc_eval", "nempc_eval_host", "nempc_eval_blocks", "nempc_model_eval", "nempc_launch_count",
            "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve")
 
@@ -25,7 +25,7 @@ class NempcDesc(ctypes.Structure):
                 ("n_layers", ctypes.c_int32), ("widths", ctypes.c_int32 * MAX_LAYERS),
                 ("activation", ctypes.c_int32), ("integrator", ctypes.c_int32), ("dt", ctypes.c_double),
                 ("compute_dtype", ctypes.c_int32), ("io_dtype", ctypes.c_int32), ("device", ctypes.c_int32),
-                ("kernel", ctypes.c_int32)]
+                ("kernel", ctypes.c_int32), ("tvp_dim", ctypes.c_int32), ("p_dim", ctypes.c_int32)]
 
 
 class SolverOpts(ctypes.Structure):
@@ -58,6 +58,7 @@ def load():
     lib.nempc_destroy.argtypes = [vp]
     lib.nempc_set_weights.argtypes = [vp, i32, vp, vp]
     lib.nempc_set_objective.argtypes = [vp, vp, vp, vp]
+    lib.nempc_set_exogenous.argtypes = [vp, i64, vp, i64, vp]
     lib.nempc_structure_counts.argtypes = [i32, i32, i32, vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.nempc_structure_fill.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp]
     lib.nempc_dims.argtypes = [vp] + [ctypes.POINTER(i64)] * 4

@@ -103,9 +103,14 @@ class BatchedNMPC:
         nx = xd * H
         return torch.cat([Z[:, xd:nx], Z[:, nx - xd:nx], Z[:, nx + ud:], Z[:, nx + ud * (H - 1):nx + ud * H]], dim=1)
 
-    def next(self, X0):
+    def next(self, X0, p=None, tvp=None):
+        """``p``: (p_dim,) shared or (B, p_dim); ``tvp``: (H, tvp_dim) shared or (B, H, tvp_dim) -- when the model declares them."""
         X0 = np.asarray(X0, np.float64) if not hasattr(X0, "device") else X0
         assert X0.ndim == 2 and X0.shape[1] == self.ev.x_dim, "X0 must be (B, x_dim)"
+        if self.ev.tvp_dim or self.ev.p_dim:
+            self.ev.set_exogenous(tvp, p)
+        else:
+            assert p is None and tvp is None, "the model declares no p / tvp input"
         z0 = None
         if self.warm_start and self._prev is not None and self._prev.shape[0] == X0.shape[0]:
             z0 = self._shifted(self._prev)

@@ -36,6 +36,7 @@ template <typename T> struct NetView {
     int hoff[NEMPC_MAXL];         // neuron offset of hidden layer l inside the concatenated hidden vector
     int sum_h, hmax;
     int act;
+    int tvp_dim, p_dim;           // exogenous inputs appended to (x, u) (model/tensorflow.py:39-47); W[0] then has d + tvp_dim + p_dim rows
     const T* W[NEMPC_MAXL];       // [in][out]   (Keras kernel layout)
     const T* WT[NEMPC_MAXL];      // [out][in]   (for the adjoint sweep: coalesced over `in`)
     const T* b[NEMPC_MAXL];
@@ -63,10 +64,10 @@ template <typename T> inline StageTable<T> make_stage_table(bool rk4, double dt)
 }
 
 struct SlotLayout {
-    int z, zs, lam, kprev, kcur, kacc, R, J, dk, dkacc, M, tmp, Hprev, Hacc, act, Tl, V0, V1, G0, G1, coef, total;
+    int z, zs, lam, kprev, kcur, kacc, R, J, dk, dkacc, M, tmp, Hprev, Hacc, act, Tl, V0, V1, G0, G1, coef, ext, total;
 };
 
-inline SlotLayout make_slot_layout(int x, int d, int sum_h, int hmax) {
+inline SlotLayout make_slot_layout(int x, int d, int sum_h, int hmax, int n_ext = 0) {
     SlotLayout s;
     int o = 0;
     auto take = [&](int cnt) { int r = o; o += (cnt + 3) & ~3; return r; };
@@ -76,6 +77,7 @@ inline SlotLayout make_slot_layout(int x, int d, int sum_h, int hmax) {
     s.act = take(sum_h); s.Tl = take(sum_h * d);
     s.V0 = take(hmax * d); s.V1 = take(hmax * d);
     s.G0 = take(hmax * x); s.G1 = take(hmax * x); s.coef = take(hmax * x);
+    s.ext = take(n_ext);
     s.total = o;
     return s;
 }
@@ -95,6 +97,10 @@ template <typename TIO> struct EvalArgs {
     TIO* Hblk;           // blocks / model: (N, x, d, d)
     long long nsteps;    // B*H  (MODEL mode: N)
     int flags;
+    // exogenous model inputs (always double; not differentiated): tvp row of step (b, t) at tvp + b * tvp_bstride + t * tvp_dim
+    // (MODEL mode: sample i at tvp + i * tvp_dim), p row of problem b at p + b * p_bstride; a stride of 0 shares one set between problems
+    const double* tvp; const double* p;
+    long long tvp_bstride, p_bstride;
 };
 
 template <typename A, typename B> struct WideOf { typedef double type; };
@@ -181,6 +187,11 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
         z[c] = (T)v;
     }
     if (contract) for (int p = lt; p < x; p += tps) (ws + sl.lam)[p] = (T)ar.lam[b * L.m + t * x + p];
+    const int n_ext = net.tvp_dim + net.p_dim;
+    T* ext = ws + sl.ext;
+    for (int e = lt; e < n_ext; e += tps)
+        ext[e] = (T)(e < net.tvp_dim ? ar.tvp[(model_mode ? step * net.tvp_dim : b * ar.tvp_bstride + (long long)t * net.tvp_dim) + e]
+                                     : ar.p[b * ar.p_bstride + (e - net.tvp_dim)]);
     for (int i = lt; i < x; i += tps) { kprev[i] = (T)0; kacc[i] = (T)0; }
     for (int i = lt; i < x * d; i += tps) dkacc[i] = (T)0;
     for (int i = lt; i < dd; i += tps) R[i] = (i / d == i % d) ? (T)1 : (T)0;
@@ -201,6 +212,7 @@ NEMPC_HD void generic_step(const NetView<T>& net, const StageTable<T>& st, const
             for (int j = lt; j < h0; j += tps) {
                 T a = bb[j];
                 for (int c = 0; c < d; ++c) a += W[c * h0 + j] * zs[c];
+                for (int e = 0; e < n_ext; ++e) a += W[(d + e) * h0 + j] * ext[e];     // tvp / p rows of the first layer: a bias shift
                 const T h = act_value<T>(net.act, a);
                 act[j] = h;
                 if (want_jac) {

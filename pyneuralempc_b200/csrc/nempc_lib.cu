@@ -284,6 +284,9 @@ struct nempc_handle {
     // staging for eval_host
     void* st_buf[10] = {}; size_t st_cap[10] = {};
     long long launches = 0;
+    // exogenous model inputs (nempc_set_exogenous): device copies, rows held, and the problem offset of the chunk being issued
+    int n_ext = 0; double *d_tvp = nullptr, *d_p = nullptr; size_t tvp_cap = 0, p_cap = 0;
+    long long tvp_rows = 0, p_rows = 0, exo_base = 0;
     // nempc_eval_host replay: the chunk pipeline of the last argument set, captured as a CUDA graph (one submission per call)
     struct HostKey { int64_t B; const void* in[4]; void* out[5]; double sigma; bool operator==(const HostKey& o) const { return memcmp(this, &o, sizeof(HostKey)) == 0; } };
     HostKey hk{}; int hk_seen = 0; cudaGraphExec_t hk_exec = nullptr; long long hk_launches = 0; bool hk_disabled = false;
@@ -313,7 +316,7 @@ static const FastShape kFastShapes[] = {{2, 1, 30, 30}, {2, 1, 32, 32}, {2, 1, 1
 static const int kNumFastShapes = sizeof(kFastShapes) / sizeof(kFastShapes[0]);
 
 static int fast_shape_id(const nempc_desc& d) {
-    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.n_layers != 3) return -1;
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.n_layers != 3 || d.tvp_dim + d.p_dim > 0) return -1;
     for (int i = 0; i < kNumFastShapes; ++i)
         if (d.x_dim == kFastShapes[i].x && d.u_dim == kFastShapes[i].u && d.widths[0] == kFastShapes[i].h1 &&
             d.widths[1] == kFastShapes[i].h2)
@@ -327,7 +330,7 @@ static const TcShape kTcShapes[] = {{4, 1, 3}, {4, 1, 2}, {2, 1, 3}, {2, 1, 2}, 
 static const int kNumTcShapes = sizeof(kTcShapes) / sizeof(kTcShapes[0]);
 
 static int tc_shape_id(const nempc_desc& d) {
-    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH) return -1;
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
     for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_TC_HW) return -1;
     for (int i = 0; i < kNumTcShapes; ++i)
         if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid) return i;
@@ -411,6 +414,7 @@ extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, 
 static void free_device(nempc_handle* h) {
     for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
     cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws); cudaFree(h->d_tcimg); cudaFree(h->d_tccb);
+    cudaFree(h->d_tvp); cudaFree(h->d_p);
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->hk_exec) cudaGraphExecDestroy(h->hk_exec);
@@ -436,9 +440,15 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     if ((D.compute_dtype != NEMPC_F32 && D.compute_dtype != NEMPC_F64) || (D.io_dtype != NEMPC_F32 && D.io_dtype != NEMPC_F64) ||
         (D.compute_dtype == NEMPC_F64 && D.io_dtype == NEMPC_F32)) { SET_ERR((nempc_handle*)nullptr, "unsupported dtype combination"); return NEMPC_EINVAL; }
 
+    if (D.tvp_dim < 0 || D.p_dim < 0 || D.tvp_dim + D.p_dim > NEMPC_MAX_EXO) { SET_ERR((nempc_handle*)nullptr, "tvp_dim + p_dim must be in [0,%d]", NEMPC_MAX_EXO); return NEMPC_EINVAL; }
+    if (D.tvp_dim + D.p_dim > 0 && (D.kernel == NEMPC_KERNEL_FAST || D.kernel == NEMPC_KERNEL_TC)) {
+        SET_ERR((nempc_handle*)nullptr, "tvp / p model inputs are served by the generic kernel only (kernel must be AUTO or GENERIC)");
+        return NEMPC_EUNSUPPORTED;
+    }
+
     nempc_handle* h = new nempc_handle();
-    h->desc = D; h->d = D.x_dim + D.u_dim; h->L = D.n_layers;
-    h->dims.push_back(h->d);
+    h->desc = D; h->d = D.x_dim + D.u_dim; h->L = D.n_layers; h->n_ext = D.tvp_dim + D.p_dim;
+    h->dims.push_back(h->d + h->n_ext);         // fan-in of the first layer: [x, u, tvp, p] (model/tensorflow.py:39-47)
     for (int l = 0; l < D.n_layers; ++l) h->dims.push_back(D.widths[l]);
     h->W.resize(h->L); h->bvec.resize(h->L); h->wset.assign(h->L, false);
     nlp_layout_init(h->lay, D.horizon, D.x_dim, D.u_dim, nullptr);
@@ -473,7 +483,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
     int sum_h = 0, hmax = 0;
     for (int l = 0; l + 1 < h->L; ++l) { sum_h += D.widths[l]; hmax = std::max(hmax, D.widths[l]); }
-    h->sl = make_slot_layout(D.x_dim, h->d, sum_h, hmax);
+    h->sl = make_slot_layout(D.x_dim, h->d, sum_h, hmax, h->n_ext);
     h->dmax = h->d <= 4 ? 4 : (h->d <= 8 ? 8 : 16);
     h->tps = std::min(256, std::max(32, (hmax + 31) / 32 * 32));
     const size_t per_slot = (size_t)h->sl.total * dsize(D.compute_dtype);
@@ -613,6 +623,31 @@ extern "C" int nempc_set_objective(nempc_handle* h, const double* lin, const dou
     return NEMPC_OK;
 }
 
+extern "C" int nempc_set_exogenous(nempc_handle* h, int64_t tvp_rows, const double* tvp, int64_t p_rows, const double* p) {
+    if (!h) return NEMPC_EINVAL;
+    const int td = h->desc.tvp_dim, pd = h->desc.p_dim;
+    if ((td > 0 && (!tvp || tvp_rows < 1)) || (pd > 0 && (!p || p_rows < 1)) || (td == 0 && tvp) || (pd == 0 && p)) {
+        SET_ERR(h, "nempc_set_exogenous: arguments do not match tvp_dim=%d p_dim=%d", td, pd);
+        return NEMPC_EINVAL;
+    }
+    drop_host_graph(h);
+    CU(h, cudaSetDevice(h->desc.device));
+    CU(h, cudaDeviceSynchronize());                       // earlier launches may still read the old rows
+    if (td > 0) {
+        const size_t bytes = (size_t)tvp_rows * td * sizeof(double);
+        if (bytes > h->tvp_cap) { cudaFree(h->d_tvp); h->d_tvp = nullptr; h->tvp_cap = 0; CU(h, cudaMalloc(&h->d_tvp, bytes)); h->tvp_cap = bytes; }
+        CU(h, cudaMemcpy(h->d_tvp, tvp, bytes, cudaMemcpyDefault));
+        h->tvp_rows = tvp_rows;
+    }
+    if (pd > 0) {
+        const size_t bytes = (size_t)p_rows * pd * sizeof(double);
+        if (bytes > h->p_cap) { cudaFree(h->d_p); h->d_p = nullptr; h->p_cap = 0; CU(h, cudaMalloc(&h->d_p, bytes)); h->p_cap = bytes; }
+        CU(h, cudaMemcpy(h->d_p, p, bytes, cudaMemcpyDefault));
+        h->p_rows = p_rows;
+    }
+    return NEMPC_OK;
+}
+
 // ---- launches ------------------------------------------------------------------------------------------------
 static int ready(nempc_handle* h) {
     if (!h) return NEMPC_EINVAL;
@@ -623,13 +658,41 @@ static int ready(nempc_handle* h) {
 
 template <typename T> static NetView<T> make_net(const nempc_handle* h) {
     NetView<T> n{};
-    n.L = h->L; n.act = h->desc.activation;
+    n.L = h->L; n.act = h->desc.activation; n.tvp_dim = h->desc.tvp_dim; n.p_dim = h->desc.p_dim;
     int off = 0, hm = 0;
     for (int l = 0; l <= h->L; ++l) n.dims[l] = h->dims[l];
     for (int l = 0; l + 1 < h->L; ++l) { n.hoff[l] = off; off += h->dims[l + 1]; hm = std::max(hm, h->dims[l + 1]); }
     n.sum_h = off; n.hmax = hm;
     for (int l = 0; l < h->L; ++l) { n.W[l] = (const T*)h->dW[l]; n.WT[l] = (const T*)h->dWT[l]; n.b[l] = (const T*)h->db[l]; }
     return n;
+}
+
+// attach the handle's exogenous rows to a launch: problems [exo_base, exo_base + B) of the set given to nempc_set_exogenous
+template <typename TIO>
+static int bind_exogenous(nempc_handle* h, EvalArgs<TIO>& ax, bool model_mode) {
+    const int td = h->desc.tvp_dim, pd = h->desc.p_dim, H = h->desc.horizon;
+    if ((td > 0 && !h->d_tvp) || (pd > 0 && !h->d_p)) { SET_ERR(h, "the model has tvp / p inputs: call nempc_set_exogenous first"); return NEMPC_ESTATE; }
+    const long long units = model_mode ? ax.nsteps : ax.nsteps / H;          // samples (model) or problems (NLP)
+    ax.tvp = h->d_tvp; ax.p = h->d_p; ax.tvp_bstride = 0; ax.p_bstride = 0;
+    if (td > 0) {
+        const long long per = model_mode ? 1 : H;                             // tvp rows per unit
+        if (!model_mode && h->tvp_rows == H) ax.tvp_bstride = 0;              // one (H, tvp_dim) table shared by every problem
+        else {
+            if (h->tvp_rows < (h->exo_base + units) * per) { SET_ERR(h, "nempc_set_exogenous holds %lld tvp rows, this call needs %lld", h->tvp_rows, (h->exo_base + units) * per); return NEMPC_EINVAL; }
+            ax.tvp_bstride = (long long)H * td;
+            ax.tvp = h->d_tvp + h->exo_base * per * td;
+        }
+    }
+    if (pd > 0) {
+        if (h->p_rows == 1) ax.p_bstride = 0;
+        else if (model_mode) { SET_ERR(h, "nempc_model_eval takes one p row"); return NEMPC_EINVAL; }
+        else {
+            if (h->p_rows < h->exo_base + units) { SET_ERR(h, "nempc_set_exogenous holds %lld p rows, this call needs %lld", h->p_rows, h->exo_base + units); return NEMPC_EINVAL; }
+            ax.p_bstride = pd;
+            ax.p = h->d_p + h->exo_base * pd;
+        }
+    }
+    return NEMPC_OK;
 }
 
 template <typename T, typename TIO, int DMAX>
@@ -655,7 +718,12 @@ static int launch_generic_t(nempc_handle* h, const EvalArgs<TIO>& ar, bool model
     }
     NetView<T> net = make_net<T>(h);
     StageTable<T> st = make_stage_table<T>(h->desc.integrator == NEMPC_INTEG_RK4 && !model_mode, h->desc.dt);
-    kern<<<(unsigned)grid, threads, h->smem_bytes, s>>>(net, st, h->lay, h->sl, ar, h->tps, gws);
+    EvalArgs<TIO> ax = ar;
+    if (h->n_ext > 0) {
+        int rc = bind_exogenous(h, ax, model_mode);
+        if (rc) return rc;
+    }
+    kern<<<(unsigned)grid, threads, h->smem_bytes, s>>>(net, st, h->lay, h->sl, ax, h->tps, gws);
     CU(h, cudaGetLastError());
     h->launches++;
     return NEMPC_OK;
@@ -849,7 +917,9 @@ static int eval_host_issue(nempc_handle* h, int64_t B, const void* const in[4], 
             if (sz[i]) CU(h, cudaMemcpyAsync(din[i], (const char*)in[i] + c0 * in_w[i], nb * in_w[i], cudaMemcpyHostToDevice, s));
         }
         for (int i = 0; i < 5; ++i) dout[i] = sz[4 + i] ? (char*)h->st_buf[4 + i] + c0 * out_w[i] : nullptr;
+        h->exo_base = c0;
         int rc = nempc_eval(h, nb, din[0], din[1], din[2], din[3], sigma, dout[0], dout[1], dout[2], dout[3], dout[4], (void*)s);
+        h->exo_base = 0;
         if (rc) return rc;
         for (int i = 0; i < 5; ++i)
             if (sz[4 + i]) CU(h, cudaMemcpyAsync((char*)outp[i] + c0 * out_w[i], dout[i], nb * out_w[i], cudaMemcpyDeviceToHost, s));
@@ -1172,7 +1242,7 @@ extern "C" double nempc_flops_per_step(const nempc_handle* h) {
     double sumW = 0, sumh = 0;
     for (int l = 0; l < h->L; ++l) sumW += (double)h->dims[l] * h->dims[l + 1];
     for (int l = 0; l + 1 < h->L; ++l) sumh += h->dims[l + 1];
-    const double stage = 2 * sumW + 2 * d * (sumW - d * h->dims[1]) + 2 * sumW + d * (d + 1) * sumh;
+    const double stage = 2 * sumW + 2 * d * (sumW - (double)h->dims[0] * h->dims[1]) + 2 * sumW + d * (d + 1) * sumh;
     const int S = h->desc.integrator == NEMPC_INTEG_RK4 ? 4 : 1;
     return S * stage + (S == 4 ? 6 * x * d * d + 6 * x * x : 0.0);
 }

@@ -24,12 +24,13 @@ def _vp(t):
 
 class NlpEvaluator:
     def __init__(self, weights, x_dim, u_dim, H, integrator="discrete", DT=None, activation="tanh",
-                 compute_dtype="float32", io_dtype="float64", device=0, kernel="auto"):
+                 compute_dtype="float32", io_dtype="float64", device=0, kernel="auto", tvp_dim=0, p_dim=0):
         import torch
         self._torch = torch
         self.lib = _lib.load()
         self.x_dim, self.u_dim, self.H = int(x_dim), int(u_dim), int(H)
         self.d = self.x_dim + self.u_dim
+        self.tvp_dim, self.p_dim = int(tvp_dim or 0), int(p_dim or 0)
         self.integrator, self.DT, self.activation = integrator, DT, activation
         self.compute_dtype, self.io_dtype = str(compute_dtype), str(io_dtype)
         self.device = int(device)
@@ -42,7 +43,8 @@ class NlpEvaluator:
             raise ValueError("too many layers")
         desc = _lib.NempcDesc()
         desc.x_dim, desc.u_dim, desc.horizon, desc.n_layers = self.x_dim, self.u_dim, self.H, len(weights)
-        fan_in = self.d
+        desc.tvp_dim, desc.p_dim = self.tvp_dim, self.p_dim
+        fan_in = self.d + self.tvp_dim + self.p_dim            # the network sees [x, u, tvp, p] (model/tensorflow.py:39-47)
         for l, (W, b) in enumerate(weights):
             if W.ndim != 2 or W.shape[0] != fan_in or b.shape != (W.shape[1],):
                 raise ValueError(f"layer {l}: expected kernel ({fan_in}, out) and bias (out,), got {W.shape} {b.shape}")
@@ -77,6 +79,30 @@ class NlpEvaluator:
         self._check(self.lib.nempc_set_weights(self._h, layer, W.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)),
                     "nempc_set_weights")
         self.weights[layer] = (W, b)
+
+    def set_exogenous(self, tvp=None, p=None):
+        """time-varying / constant model inputs of the following evaluations and solves (``NMPC.next(x0, p=, tvp=)``,
+        controller.py:65-113).  ``tvp``: (H, tvp_dim) shared by every problem of a batch, or (B, H, tvp_dim) [model_eval: (N, tvp_dim)];
+        ``p``: (p_dim,) shared, or (B, p_dim).  numpy arrays or CUDA tensors (float64)."""
+        def prep(a, dim, what):
+            if dim == 0:
+                if a is not None:
+                    raise ValueError(f"the model has no {what} input")
+                return None, 0, None
+            if a is None:
+                raise ValueError(f"the model has a {what} input of width {dim}")
+            if self._torch.is_tensor(a):
+                a = a.to(self._torch.float64).contiguous()
+                if a.shape[-1] != dim:
+                    raise ValueError(f"{what} must have last dim {dim}")
+                return a, a.numel() // dim, ctypes.c_void_p(a.data_ptr())
+            a = np.ascontiguousarray(a, np.float64)
+            if a.shape[-1] != dim:
+                raise ValueError(f"{what} must have last dim {dim}")
+            return a, a.size // dim, a.ctypes.data_as(ctypes.c_void_p)
+        ta, tr, tp = prep(tvp, self.tvp_dim, "tvp")
+        pa, pr, pp = prep(p, self.p_dim, "p")
+        self._check(self.lib.nempc_set_exogenous(self._h, tr, tp, pr, pp), "nempc_set_exogenous")
 
     # ---- lifetime / errors ------------------------------------------------------------------------------
     def _check(self, rc, what):

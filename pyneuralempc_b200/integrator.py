@@ -67,7 +67,25 @@ class _CudaIntegrator(Integrator):
         self._cache, self._cache_size = [], max(1, int(cache_size))
         self.evaluator = NlpEvaluator(model.weights, model.x_dim, model.u_dim, H, self.KIND, DT=DT,
                                       activation=model.activation, compute_dtype=model.dtype, io_dtype="float64",
-                                      device=model.device, kernel=model.kernel)
+                                      device=model.device, kernel=model.kernel,
+                                      tvp_dim=model.tvp_dim or 0, p_dim=model.p_dim or 0)
+        self._exo_key = None
+
+    def _set_exogenous(self, p, tvp):
+        """hand the model's tvp (H, tvp_dim) / p (p_dim,) rows to the evaluator when they changed (they are fixed during one solve:
+        controller.py:65-113 sets them once per NMPC.next)."""
+        m = self.model
+        if not (m.tvp_dim or m.p_dim):
+            assert p is None and tvp is None, "the model declares no p / tvp input"
+            return
+        assert (tvp is None) == (not m.tvp_dim) and (p is None) == (not m.p_dim), "p / tvp must match the model's p_dim / tvp_dim"
+        tvp = None if tvp is None else np.asarray(tvp, np.float64).reshape(self.H, m.tvp_dim)
+        p = None if p is None else np.asarray(p, np.float64).reshape(m.p_dim)
+        key = (b"" if tvp is None else tvp.tobytes()) + b"|" + (b"" if p is None else p.tobytes())
+        if key != self._exo_key:
+            self.evaluator.set_exogenous(tvp, p)
+            self._exo_key = key
+            self._cache = []
 
     # ---- helpers --------------------------------------------------------------------------------------------
     def _pack(self, x, u, x0):
@@ -94,17 +112,20 @@ class _CudaIntegrator(Integrator):
     # ---- reference interface ------------------------------------------------------------------------------------
     def forward(self, x, u, x0, p=None, tvp=None):
         assert len(np.shape(x0)) == 1, "x0 shape must have dim 1"                            # discret.py:17
+        self._set_exogenous(p, tvp)
         return self._first_order(x, u, x0, ("resid",))["resid"][0].copy()
 
     def jacobian(self, x, u, x0, p=None, tvp=None):
         ev = self.evaluator
+        self._set_exogenous(p, tvp)
         vals = self._first_order(x, u, x0, ("jac",))["jac"][0]
         J = np.zeros((ev.m, ev.n))
         J[ev.jac_rows, ev.jac_cols] = vals
         return J
 
-    def hessian_blocks(self, x, u, x0):
+    def hessian_blocks(self, x, u, x0, p=None, tvp=None):
         """per-step, per-output second derivatives (H, x_dim, d, d) -- what rk4.py:266 calls ``model_H``."""
+        self._set_exogenous(p, tvp)
         z, x0v = self._pack(x, u, x0)
         _, _, Hb = self.evaluator.eval_blocks(z[None], x0v[None])
         return Hb[0].cpu().numpy()
@@ -112,7 +133,7 @@ class _CudaIntegrator(Integrator):
     def hessian(self, x, u, x0, p=None, tvp=None):
         H, xd, ud = self.H, self.model.x_dim, self.model.u_dim
         n = H * (xd + ud)
-        blk = self.hessian_blocks(x, u, x0)
+        blk = self.hessian_blocks(x, u, x0, p, tvp)
         out = np.zeros((H, xd, n, n))
         off = xd * H
         for t in range(H):                                   # same scatter as rk4.py:270-283 / discret.py:70-78

@@ -48,12 +48,11 @@ class CudaMLPModel(Model):
                  device=0, kernel="auto", standardScaler=None):
         if standardScaler is not None:
             raise NotImplementedError("This feature isn't supported yet !")        # tensorflow.py:11-12
-        if p_dim or tvp_dim:
-            raise NotImplementedError("p / tvp inputs are not supported on the CUDA path yet")
+        p_dim, tvp_dim = int(p_dim or 0), int(tvp_dim or 0)
         weights = [(np.asarray(W, np.float64), np.asarray(b, np.float64)) for W, b in weights]
         if weights[-1][0].shape[1] != x_dim:                                       # tensorflow.py:20-21
             raise ValueError("Your model do not provide a suitable output dim ! \n It must get the same dim as the state dim.")
-        if weights[0][0].shape[0] != x_dim + u_dim:                                # tensorflow.py:23-24
+        if weights[0][0].shape[0] != x_dim + u_dim + p_dim + tvp_dim:              # tensorflow.py:23-24
             raise ValueError("Your model do not provide a suitable input dim ! \n It must get the same dim as the sum of all input vars (x, u, p, tvp).")
         super().__init__(x_dim, u_dim, p_dim, tvp_dim)
         self.weights = weights
@@ -110,12 +109,19 @@ class CudaMLPModel(Model):
     def evaluator(self):
         if self._ev is None:
             self._ev = NlpEvaluator(self.weights, self.x_dim, self.u_dim, 1, "unity", activation=self.activation,
-                                    compute_dtype=self.dtype, io_dtype="float64", device=self.device, kernel=self.kernel)
+                                    compute_dtype=self.dtype, io_dtype="float64", device=self.device, kernel=self.kernel,
+                                    tvp_dim=self.tvp_dim, p_dim=self.p_dim)
         return self._ev
 
     def _gather_input(self, x, u, p=None, tvp=None):          # tensorflow.py:39-47
-        if p is not None or tvp is not None:
-            raise NotImplementedError("p / tvp inputs are not supported on the CUDA path yet")
+        """(x, u) rows go to the kernel as the differentiated input; tvp / p are handed over as exogenous rows (the network input is
+        [x, u, tvp, p], its tvp / p derivative columns are never formed -- the slicing of tensorflow.py:65-66, 97-98)."""
+        if (tvp is None) != (self.tvp_dim == 0) or (p is None) != (self.p_dim == 0):
+            raise ValueError("p / tvp must be given exactly when the model declares p_dim / tvp_dim")
+        if self.tvp_dim or self.p_dim:
+            tvp = None if tvp is None else np.asarray(tvp, np.float64).reshape(np.asarray(x).shape[0], self.tvp_dim)
+            p = None if p is None else np.asarray(p, np.float64).reshape(self.p_dim)
+            self.evaluator().set_exogenous(tvp, p)
         return np.concatenate([np.asarray(x, np.float64), np.asarray(u, np.float64)], axis=1)
 
     def blocks(self, x, u, p=None, tvp=None, want_jac=True, want_hes=True):

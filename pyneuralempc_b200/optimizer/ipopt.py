@@ -22,10 +22,9 @@ class CudaIpoptProblem(ProblemInterface):
     def __init__(self, x0, objective_func, constraints, integrator, p=None, tvp=None, use_hessian=True,
                  init_x=None, init_u=None, sparse_jacobian=True):
         super().__init__(use_hessian)
-        if p is not None or tvp is not None:
-            raise NotImplementedError("p / tvp are not supported on the CUDA path yet")
         if not hasattr(integrator, "evaluator"):
             raise ValueError("CudaIpoptProblem needs a CUDA integrator (pyneuralempc_b200.integrator)")
+        integrator._set_exogenous(p, tvp)          # model inputs that stay fixed during this solve (controller.py:65-113)
         self.x0 = np.asarray(x0, np.float64)
         self.objective_func = objective_func
         self.constraints_list = list(constraints)

@@ -12,6 +12,8 @@ What is recorded (all float64 unless noted):
   ref_discrete_d5_H5.npz  x_dim=4,u_dim=1 network through Discret/Unity (RK4 of the reference
                           crashes unless x_dim+u_dim == 3 -- recorded as ``rk4_d5_error``)
   ref_rk4_f32_H6.npz      RK4 with the network evaluated in float32 (TensorFlow numerics mimic)
+  ref_exo_H6.npz          tvp / p inputs: network over [x, u, tvp, p] (2+1+2+1 -> 8 -> 8 -> 2) through the reference's Discret /
+                          Unity / RK4 integrators called with ``p=, tvp=`` (integrator/rk4.py:69-72, discret.py:27,48,64)
 The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
 reference's ``Model`` (TensorFlow is not installed), so these files pin the integrator / IPOPT
 glue of the oracle, not TensorFlow's autodiff.
@@ -25,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 
 from oracle import shim  # noqa: E402
-from oracle.mlp_np import MLP, read_lv_fixture_h5  # noqa: E402
+from oracle.mlp_np import MLP, ExoMLP, read_lv_fixture_h5  # noqa: E402
 from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
 
 DT_RK4 = 0.1  # examples/lotka_volterra/run.py:77
@@ -93,6 +95,41 @@ def record(ref, mlp, kind, H, seed, objective_kind, full_dense):
     return out
 
 
+def record_exo(ref, H=6, seed=500):
+    """the reference integrators with time-varying (tvp) and constant (p) model inputs; the model adapter gathers
+    [x, u, tvp, p] and drops the tvp / p derivative columns like KerasTFModel (model/tensorflow.py:39-47, 65-66, 97-98)."""
+    rng = np.random.default_rng(seed)
+    xd, ud, td, pd = 2, 1, 2, 1
+    full = MLP.glorot([xd + ud + td + pd, 8, 8, xd], xd, ud + td + pd, seed=11)
+    exo = ExoMLP(full.weights, xd, ud, td, pd)
+
+    class ExoBackedModel(ref.model.base.Model):
+        def __init__(self):
+            super().__init__(xd, ud, pd, td)
+
+        def forward(self, x, u, p=None, tvp=None):
+            return exo.bind(tvp, p).forward(x, u)
+
+        def jacobian(self, x, u, p=None, tvp=None):
+            return exo.bind(tvp, p).dense_jacobian(x, u)
+
+        def hessian(self, x, u, p=None, tvp=None):
+            return exo.bind(tvp, p).dense_hessian(x, u)
+
+    states, u, x0 = rng.uniform(-1, 1, (H, xd)), rng.uniform(-1, 1, (H, ud)), rng.uniform(-1, 1, xd)
+    tvp, p = rng.uniform(-1, 1, (H, td)), rng.uniform(-1, 1, pd)
+    out = dict(H=H, x_dim=xd, u_dim=ud, tvp_dim=td, p_dim=pd, DT=DT_RK4, states=states, u=u, x0=x0, tvp=tvp, p=p,
+               lam=rng.standard_normal(H * xd))
+    out.update({f"net_W{i}": W for i, (W, _) in enumerate(full.weights)})
+    out.update({f"net_b{i}": b for i, (_, b) in enumerate(full.weights)})
+    for kind in ("discrete", "unity", "rk4"):
+        integ = make_integrator(ref, kind, ExoBackedModel(), H)
+        out[f"{kind}_forward"] = integ.forward(states, u, x0, p=p, tvp=tvp)
+        out[f"{kind}_jacobian"] = integ.jacobian(states, u, x0, p=p, tvp=tvp)
+        out[f"{kind}_hessian"] = integ.hessian(states, u, x0, p=p, tvp=tvp)
+    return out
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -132,6 +169,7 @@ def main():
     out.update(rk4_x=xs, rk4_u=us, rk4_x0=x0, rk4_forward=integ.forward(xs, us, x0),
                rk4_jacobian=integ.jacobian(xs, us, x0))
     np.savez_compressed(os.path.join(HERE, "ref_discrete_d5_H5.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "ref_exo_H6.npz"), **record_exo(ref))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -44,9 +44,13 @@ void build_net(HostNet<T>& hn, int d, int n_layers, const int* widths, int act, 
     v.sum_h = off; v.hmax = hm;
 }
 
+// exogenous model inputs of the NEXT hostsim_run call (generic kernel only); cleared by that call
+struct Exo { int tvp_dim = 0, p_dim = 0; const double* tvp = nullptr; const double* p = nullptr; long long tvp_bstride = 0, p_bstride = 0; };
+Exo g_exo;
+
 template <typename T, int DMAX>
 void run_generic(const HostNet<T>& hn, const StageTable<T>& st, const NlpLayout& L, const EvalArgs<double>& ar) {
-    SlotLayout sl = make_slot_layout(L.x, L.d, hn.view.sum_h, hn.view.hmax);
+    SlotLayout sl = make_slot_layout(L.x, L.d, hn.view.sum_h, hn.view.hmax, hn.view.tvp_dim + hn.view.p_dim);
     std::vector<T> ws(sl.total);
     for (long long s = 0; s < ar.nsteps; ++s) generic_step<T, double, DMAX>(hn.view, st, L, sl, ar, s, ws.data(), 0, 1, 0);
 }
@@ -78,6 +82,10 @@ void run_fast(const double* wflat, const StageTable<float>& st, const NlpLayout&
 
 }  // namespace
 
+extern "C" void hostsim_set_exo(int tvp_dim, int p_dim, const double* tvp, long long tvp_bstride, const double* p, long long p_bstride) {
+    g_exo.tvp_dim = tvp_dim; g_exo.p_dim = p_dim; g_exo.tvp = tvp; g_exo.p = p; g_exo.tvp_bstride = tvp_bstride; g_exo.p_bstride = p_bstride;
+}
+
 // kernel: 0 generic, 1 fast.  what: 0 eval (resid/jac/hes), 1 blocks (pred/AB/Hblk), 2 model (zin -> f/jac/hes).
 // Returns 0, or -1 when the combination is unsupported.  All arrays are double (io_dtype f64).
 extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths, int act, int integ, double dt,
@@ -101,7 +109,12 @@ extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths,
         ar.flags = (model ? NEMPC_MODE_MODEL : NEMPC_MODE_BLOCKS) | (out1 || out2 ? NEMPC_WANT_JAC : 0) | (out2 ? NEMPC_WANT_HES : 0) | unity;
     }
     const bool rk4 = integ == 2 && !model;
+    const Exo exo = g_exo;
+    g_exo = Exo();
+    ar.tvp = exo.tvp; ar.p = exo.p; ar.tvp_bstride = exo.tvp_bstride; ar.p_bstride = exo.p_bstride;
+    const int n_ext = exo.tvp_dim + exo.p_dim;
     if (kernel == 1) {
+        if (n_ext) return -1;
         if (what != 0 || compute_f64 || act != 0 || n_layers != 3 || x != 2 || u != 1) return -1;
         StageTable<float> st = make_stage_table<float>(rk4, dt);
         const int mode = out2 ? 2 : (out1 ? 1 : 0);
@@ -112,10 +125,12 @@ extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths,
         return 0;
     }
     if (compute_f64) {
-        HostNet<double> hn; build_net(hn, d, n_layers, widths, act, wflat);
+        HostNet<double> hn; build_net(hn, d + n_ext, n_layers, widths, act, wflat);
+        hn.view.tvp_dim = exo.tvp_dim; hn.view.p_dim = exo.p_dim;
         run_generic_d<double>(hn, make_stage_table<double>(rk4, dt), L, ar);
     } else {
-        HostNet<float> hn; build_net(hn, d, n_layers, widths, act, wflat);
+        HostNet<float> hn; build_net(hn, d + n_ext, n_layers, widths, act, wflat);
+        hn.view.tvp_dim = exo.tvp_dim; hn.view.p_dim = exo.p_dim;
         run_generic_d<float>(hn, make_stage_table<float>(rk4, dt), L, ar);
     }
     return 0;

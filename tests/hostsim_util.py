@@ -40,7 +40,7 @@ def _p(a):
 
 
 def run(mlp, kind, H, DT, Z, X0, lam=None, sigma=1.0, quad=None, compute_f64=True, kernel="generic",
-        what="eval", want_jac=True, want_hes=True):
+        what="eval", want_jac=True, want_hes=True, tvp=None, p=None):
     """what='eval' -> dict(resid, jac_vals, hes_vals); 'blocks' -> (pred, AB, Hblk); 'model' -> (f, J, Hs) with
     Z holding the stacked network inputs (N, d)."""
     from oracle import structure as S
@@ -73,6 +73,13 @@ def run(mlp, kind, H, DT, Z, X0, lam=None, sigma=1.0, quad=None, compute_f64=Tru
         o0 = np.full((N, xd), np.nan)
         o1 = np.full((N, xd, d), np.nan) if (want_jac or want_hes) else None
         o2 = np.full((N, xd, d, d), np.nan) if want_hes else None
+    if tvp is not None or p is not None:                      # ExoMLP: rows in C-ABI layout (include/nempc.h nempc_set_exogenous)
+        tvp = None if tvp is None else np.ascontiguousarray(tvp, np.float64)
+        p = None if p is None else np.ascontiguousarray(p, np.float64)
+        td, pd = (0 if tvp is None else tvp.shape[-1]), (0 if p is None else p.shape[-1])
+        tvp_b = 0 if (tvp is None or tvp.ndim == 2 and what != "model") else H * td
+        p_b = 0 if (p is None or p.ndim == 1) else pd
+        lib().hostsim_set_exo(td, pd, _p(tvp), ctypes.c_longlong(tvp_b), _p(p), ctypes.c_longlong(p_b))
     rc = lib().hostsim_run(xd, ud, int(H), len(widths), _p(widths), ACT[mlp.activation], INTEG.get(kind, 0),
                            ctypes.c_double(0.0 if DT is None else DT), int(compute_f64), 1 if kernel == "fast" else 0, w,
                            _p(wflat), _p(quad), ctypes.c_longlong(B), _p(Z), _p(X0), _p(lam), _p(sig_arr),

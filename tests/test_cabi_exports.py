@@ -36,8 +36,9 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_desc_struct_matches_header():
     from pyneuralempc_b200._lib import NempcDesc
-    # 4 int32 + 8 int32 widths + 2 int32 + (pad) double + 4 int32
-    assert ctypes.sizeof(NempcDesc) == 4 * 4 + 8 * 4 + 2 * 4 + 8 + 4 * 4
+    # 4 int32 + 8 int32 widths + 2 int32 + (pad) double + 6 int32
+    assert ctypes.sizeof(NempcDesc) == 4 * 4 + 8 * 4 + 2 * 4 + 8 + 6 * 4
+    assert NempcDesc.tvp_dim.offset == NempcDesc.kernel.offset + 4 and NempcDesc.p_dim.offset == NempcDesc.kernel.offset + 8
     assert NempcDesc.dt.offset % 8 == 0
 
 

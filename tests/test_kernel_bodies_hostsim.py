@@ -86,3 +86,32 @@ def test_blocks_and_model_modes():
     np.testing.assert_allclose(f2, f, atol=1e-13)
     np.testing.assert_allclose(J2, J, atol=1e-12)
     np.testing.assert_allclose(Hs2, Hs, atol=1e-11)
+
+
+EXO_CASES = [("discrete", 2, 1, 2, 1, 5), ("rk4", 2, 1, 2, 0, 4), ("unity", 3, 2, 0, 2, 3), ("rk4", 4, 1, 1, 1, 3)]
+
+
+def _exo_problem(kind, xd, ud, td, pd, H, seed, B=3, shared=False):
+    from oracle.mlp_np import ExoMLP
+    rng = np.random.default_rng(seed)
+    full = MLP.glorot([xd + ud + td + pd, 10, 7, xd], xd, ud + td + pd, seed=seed + 1)
+    exo = ExoMLP(full.weights, xd, ud, td, pd)
+    tvp = None if td == 0 else rng.uniform(-1, 1, (H, td) if shared else (B, H, td))
+    p = None if pd == 0 else rng.uniform(-1, 1, (pd,) if shared else (B, pd))
+    n, m = H * (xd + ud), H * xd
+    return exo, tvp, p, rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, xd)), rng.standard_normal((B, m))
+
+
+@pytest.mark.parametrize("kind,xd,ud,td,pd,H", EXO_CASES)
+@pytest.mark.parametrize("shared", (False, True))
+def test_generic_body_with_tvp_and_p(kind, xd, ud, td, pd, H, shared):
+    """exogenous (tvp / p) network inputs: a per-step shift of the first layer's pre-activation, not a decision variable"""
+    exo, tvp, p, Z, X0, lam = _exo_problem(kind, xd, ud, td, pd, H, 21, shared=shared)
+    ref = BlockEvaluator(exo.bind(tvp, p, B=Z.shape[0], H=H), kind, H, DT=0.1).evaluate(Z, X0, lam)
+    got = hs.run(exo, kind, H, 0.1, Z, X0, lam, compute_f64=True, tvp=tvp, p=p)
+    np.testing.assert_allclose(got["resid"], ref["resid"], atol=1e-13)
+    np.testing.assert_allclose(got["jac_vals"], ref["jac_vals"], atol=1e-12)
+    np.testing.assert_allclose(got["hes_vals"], ref["hes_vals"], atol=1e-11)
+    got32 = hs.run(exo, kind, H, 0.1, Z, X0, lam, compute_f64=False, tvp=tvp, p=p)
+    for k in ("resid", "jac_vals", "hes_vals"):
+        assert np.abs(got32[k] - ref[k]).max() < 1e-5 * max(1.0, np.abs(ref[k]).max()), k

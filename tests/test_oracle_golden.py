@@ -121,3 +121,29 @@ def test_d5_network_discrete_unity_and_rk4_first_order(golden_dir):
     integ = DenseIntegrator(DenseModelView(mlp), H, "rk4", DT=float(g["DT"]))
     np.testing.assert_allclose(integ.forward(g["rk4_x"], g["rk4_u"], g["rk4_x0"]), g["rk4_forward"], atol=1e-14)
     np.testing.assert_allclose(integ.jacobian(g["rk4_x"], g["rk4_u"], g["rk4_x0"]), g["rk4_jacobian"], atol=1e-13)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_block_oracle_with_tvp_and_p_equals_reference(golden_dir, kind):
+    """time-varying (tvp) and constant (p) model inputs through the reference's own integrators (called with ``p=, tvp=``)
+    against the per-step oracle bound to the same exogenous rows."""
+    from oracle.mlp_np import ExoMLP
+    g = _load(golden_dir, "ref_exo_H6.npz")
+    H, xd, ud = int(g["H"]), int(g["x_dim"]), int(g["u_dim"])
+    weights = [(g[f"net_W{i}"], g[f"net_b{i}"]) for i in range(3)]
+    exo = ExoMLP(weights, xd, ud, int(g["tvp_dim"]), int(g["p_dim"])).bind(g["tvp"], g["p"], B=1)
+    ev = BlockEvaluator(exo, kind, H, DT=float(g["DT"]))
+    z = np.concatenate([g["states"].ravel(), g["u"].ravel()])[None, :]
+    lam = g["lam"]
+    out = ev.evaluate(z, g["x0"][None, :], lam=lam[None, :])
+    np.testing.assert_allclose(out["resid"][0], g[f"{kind}_forward"], rtol=0, atol=1e-14)
+    dense_j = g[f"{kind}_jacobian"]
+    np.testing.assert_allclose(out["jac_vals"][0], dense_j[ev.jac_rows, ev.jac_cols], rtol=0, atol=1e-13)
+    mask = np.zeros_like(dense_j, bool)
+    mask[ev.jac_rows, ev.jac_cols] = True
+    assert np.all(dense_j[~mask] == 0.0)
+    dense_h = np.einsum("i,iab->ab", lam, g[f"{kind}_hessian"])
+    np.testing.assert_allclose(out["hes_vals"][0], dense_h[ev.hes_rows, ev.hes_cols], rtol=0, atol=1e-12)
+    hm = np.zeros_like(dense_h, bool)
+    hm[ev.hes_rows, ev.hes_cols] = True
+    assert np.all(np.tril(dense_h)[~hm] == 0.0)
