@@ -36,6 +36,9 @@ class CudaIpm(Optimizer):
         return dict(max_iter=int(self.max_iteration), tol=float(self.tolerance), **self.solver_options)
 
     def solve(self, problem, domain_constraint):
+        if problem.constraints_list:
+            raise NotImplementedError("the on-device solver handles the integrator constraints and the DomainConstraint box only; "
+                                      "use optimizer.TrustConstr / Slsqp / Ipopt with extra constraints")
         H = problem.integrator.H
         lb, ub = domain_constraint.get_lower_bounds(H), domain_constraint.get_upper_bounds(H)
         warm = (self.init_with_last_result and self.prev_result is not None) or problem.get_init_variables()[0] is not None

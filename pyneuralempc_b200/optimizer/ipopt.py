@@ -41,8 +41,8 @@ class CudaIpoptProblem(ProblemInterface):
             self.ev.set_objective(objective_func.lin, objective_func.quad, objective_func.ref)
         elif use_hessian:
             raise NotImplementedError("the Lagrangian-Hessian path needs a CudaSeparableObjective")
-        if self.constraints_list and (use_hessian or sparse_jacobian):
-            raise NotImplementedError("extra constraints are only supported Hessian-free with sparse_jacobian=False")
+        # extra (user, host-side) constraints: rows appended after the integrator's, ipopt.py:49-50, 93-94; their Jacobian rows are dense
+        self._extra_dims = [int(np.size(c.get_lower_bounds(self.H))) for c in self.constraints_list]
         self._key, self._point = None, None
 
     # ---- one launch per iterate -----------------------------------------------------------------------------
@@ -80,12 +80,21 @@ class CudaIpoptProblem(ProblemInterface):
         return np.concatenate([res] + [c.forward(s, u, p=p, tvp=tvp) for c in self.constraints_list])
 
     def jacobianstructure(self):
-        return self.ev.jac_rows.astype(np.int64), self.ev.jac_cols.astype(np.int64)
+        rows, cols = self.ev.jac_rows.astype(np.int64), self.ev.jac_cols.astype(np.int64)
+        extra = sum(self._extra_dims)
+        if extra:                                                 # user constraints may touch any variable: dense rows
+            rows = np.concatenate([rows, np.repeat(np.arange(self.ev.m, self.ev.m + extra), self.ev.n)])
+            cols = np.concatenate([cols, np.tile(np.arange(self.ev.n), extra)])
+        return rows, cols
 
     def jacobian(self, x):
         vals = self._at(x)["jac"]
         if self.sparse_jacobian:
-            return vals
+            if not self.constraints_list:
+                return vals
+            s, u, tvp, p = self._split(np.asarray(x))
+            return np.concatenate([vals] + [np.asarray(c.jacobian(s, u, p=p, tvp=tvp), np.float64).reshape(-1)
+                                            for c in self.constraints_list])
         J = np.zeros((self.ev.m, self.ev.n))                      # dense (m, n) like ipopt.py:88-96
         J[self.ev.jac_rows, self.ev.jac_cols] = vals
         if self.constraints_list:
@@ -100,7 +109,20 @@ class CudaIpoptProblem(ProblemInterface):
         x = np.ascontiguousarray(x, np.float64)
         out = self.ev.eval_host(x, self.x0, lam=np.asarray(lagrange, np.float64)[: self.ev.m], obj_factor=float(obj_factor),
                                 want=("hes",))
-        return out["hes"][0].copy()
+        vals = out["hes"][0].copy()
+        if self.constraints_list:
+            # ipopt.py:75-80: sum_i lagrange_i * ctr.hessian[i], gathered on the objective + integrator pattern (ipopt.py:55-62, 84-86:
+            # entries of a constraint Hessian outside that pattern are dropped by the reference as well).  A constraint without a
+            # ``hessian`` method counts as linear; the reference raises AttributeError there (constraints.py:36-96 defines none).
+            s, u, tvp, p = self._split(x)
+            lam = np.asarray(lagrange, np.float64)
+            off = self.ev.m
+            for c, dim in zip(self.constraints_list, self._extra_dims):
+                if hasattr(c, "hessian"):
+                    Hc = np.asarray(c.hessian(s, u, p=p, tvp=tvp), np.float64).reshape(dim, self.ev.n, self.ev.n)
+                    vals += np.einsum("i,ik->k", lam[off:off + dim], Hc[:, self.ev.hes_rows, self.ev.hes_cols])
+                off += dim
+        return vals
 
     def get_init_value(self):
         return self.x0

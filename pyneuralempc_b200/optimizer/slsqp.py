@@ -144,7 +144,9 @@ class TrustConstr(Optimizer):
     def solve(self, problem, domain_constraint):
         x_init = initial_guess(problem, self)
         H = problem.integrator.H
-        n, m = problem.ev.n, problem.ev.m
+        n = problem.ev.n
+        cl, cu = problem.get_constraint_lower_bounds(), problem.get_constraint_upper_bounds()
+        m = len(cl)                         # integrator rows + the rows of the extra constraints
         jr, jc = problem.jacobianstructure()
         hr, hc = problem.hessianstructure()
         off = hr != hc
@@ -162,7 +164,7 @@ class TrustConstr(Optimizer):
             return coo_matrix((np.concatenate([vals, vals[off]]), (np.concatenate([hr, hc[off]]), np.concatenate([hc, hr[off]]))),
                               shape=(n, n)).tocsr()
 
-        con = NonlinearConstraint(problem.constraints, 0.0, 0.0, jac=jac, hess=lag_hess)
+        con = NonlinearConstraint(problem.constraints, cl, cu, jac=jac, hess=lag_hess)
         res = minimize(problem.objective, x_init, method="trust-constr", jac=problem.gradient, hess=obj_hess, constraints=[con],
                        bounds=Bounds(domain_constraint.get_lower_bounds(H), domain_constraint.get_upper_bounds(H)),
                        options={"maxiter": self.max_iteration, "gtol": self.gtol, "xtol": self.xtol, "verbose": self.verbose})

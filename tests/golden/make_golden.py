@@ -12,6 +12,7 @@ What is recorded (all float64 unless noted):
   ref_discrete_d5_H5.npz  x_dim=4,u_dim=1 network through Discret/Unity (RK4 of the reference
                           crashes unless x_dim+u_dim == 3 -- recorded as ``rk4_d5_error``)
   ref_rk4_f32_H6.npz      RK4 with the network evaluated in float32 (TensorFlow numerics mimic)
+  ref_constraints_H6.npz  IpoptProblem callbacks with one extra InequalityConstraint that has a Hessian (ipopt.py:49-50, 75-80, 93-94)
   ref_exo_H6.npz          tvp / p inputs: network over [x, u, tvp, p] (2+1+2+1 -> 8 -> 8 -> 2) through the reference's Discret /
                           Unity / RK4 integrators called with ``p=, tvp=`` (integrator/rk4.py:69-72, discret.py:27,48,64)
 The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
@@ -130,6 +131,52 @@ def record_exo(ref, H=6, seed=500):
     return out
 
 
+def circle_constraint(base, H, xd, ud):
+    """c_t = x_t[0]^2 + u_t[0]^2 >= 0 rows (an InequalityConstraint with a Hessian), used by record_constraints and by the GPU test"""
+    n = H * (xd + ud)
+
+    class Circle(base):
+        def forward(self, x, u, p=None, tvp=None):
+            return x[:, 0] ** 2 + u[:, 0] ** 2
+
+        def jacobian(self, x, u, p=None, tvp=None):
+            J = np.zeros((H, n))
+            for t in range(H):
+                J[t, t * xd] = 2.0 * x[t, 0]
+                J[t, H * xd + t * ud] = 2.0 * u[t, 0]
+            return J
+
+        def hessian(self, x, u, p=None, tvp=None):
+            Hc = np.zeros((H, n, n))
+            for t in range(H):
+                Hc[t, t * xd, t * xd] = 2.0
+                Hc[t, H * xd + t * ud, H * xd + t * ud] = 2.0
+            return Hc
+
+        def get_dim(self, H_=None):
+            return H
+
+    return Circle()
+
+
+def record_constraints(ref, lv, H=6, seed=600):
+    """IpoptProblem with one extra user constraint (optimizer/ipopt.py:49-50, 75-80, 93-94)"""
+    rng = np.random.default_rng(seed)
+    xd, ud = lv.x_dim, lv.u_dim
+    n, m = H * (xd + ud), H * xd
+    sep = SeparableQuadraticObjective.tracking(H, xd, ud, rng.uniform(0.5, 2, xd), rng.uniform(0.1, 1, ud),
+                                               x_ref=rng.uniform(-1, 1, (H, xd)))
+    ctr = circle_constraint(ref.constraints.InequalityConstraint, H, xd, ud)
+    integ = make_integrator(ref, "rk4", shim.make_reference_model(lv), H)
+    z, x0, lam, sigma = rng.uniform(-1, 1, n), rng.uniform(-1, 1, xd), rng.standard_normal(m + H), 0.6
+    np.random.seed(seed)
+    pb = ref.optimizer.ipopt.IpoptProblem(x0, ref_objective(ref, sep), [ctr], integ, use_hessian=True)
+    r, c = pb.hessianstructure()
+    return dict(H=H, DT=DT_RK4, z=z, x0=x0, lam=lam, sigma=sigma, obj_lin=sep.lin, obj_quad=sep.quad, obj_ref=sep.ref,
+                constraints=pb.constraints(z), jacobian=pb.jacobian(z), hes_rows=r, hes_cols=c,
+                hessian_values=pb.hessian(z, lam, sigma), cl=pb.get_constraint_lower_bounds(), cu=pb.get_constraint_upper_bounds())
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -170,6 +217,7 @@ def main():
                rk4_jacobian=integ.jacobian(xs, us, x0))
     np.savez_compressed(os.path.join(HERE, "ref_discrete_d5_H5.npz"), **out)
     np.savez_compressed(os.path.join(HERE, "ref_exo_H6.npz"), **record_exo(ref))
+    np.savez_compressed(os.path.join(HERE, "ref_constraints_H6.npz"), **record_constraints(ref, lv))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -246,3 +246,78 @@ def test_ipopt_solve_wiring_with_stub_cyipopt(lv_weights, monkeypatch):
     # Hessian-free mode hides hessian* but keeps the sparse Jacobian structure (ipopt.py:159-160)
     xs2, _ = NMPC(integ, obj, [dom], H, 0.1, optimizer=Ipopt(), use_hessian=False).get_pb(x0).use_hessian, None
     assert xs2 is False
+
+
+def _circle(H):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                                  # module level only defines functions; the reference is not touched
+    from pyneuralempc_b200.constraints import InequalityConstraint
+    return mod.circle_constraint(InequalityConstraint, H, 2, 1)
+
+
+def test_extra_constraint_callbacks_vs_reference_golden(golden_dir, lv_weights):
+    """IpoptProblem with one user constraint (rows appended after the integrator's: ipopt.py:49-50, 93-94; its Hessian weighted by the
+    trailing multipliers: ipopt.py:75-80) -- sparse Jacobian + Hessian path against what the unmodified reference returned."""
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaSeparableObjective
+    from pyneuralempc_b200.optimizer.ipopt import CudaIpoptProblem
+    g = np.load(os.path.join(golden_dir, "ref_constraints_H6.npz"))
+    H = int(g["H"])
+    integ = I.RK4Integrator(CudaMLPModel(lv_weights, 2, 1, dtype="float64"), H, float(g["DT"]))
+    obj = CudaSeparableObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+    pb = CudaIpoptProblem(g["x0"], obj, [_circle(H)], integ, use_hessian=True)
+    z = g["z"]
+    assert _rel(pb.constraints(z), g["constraints"]) < 1e-10
+    jr, jc = pb.jacobianstructure()
+    dense = np.zeros_like(g["jacobian"])
+    dense[jr, jc] = pb.jacobian(z)
+    assert _rel(dense, g["jacobian"]) < 1e-10
+    r, c = pb.hessianstructure()
+    np.testing.assert_array_equal(r, g["hes_rows"]); np.testing.assert_array_equal(c, g["hes_cols"])
+    assert _rel(pb.hessian(z, g["lam"], float(g["sigma"])), g["hessian_values"]) < 1e-10
+    np.testing.assert_array_equal(pb.get_constraint_lower_bounds(), g["cl"])
+    np.testing.assert_array_equal(pb.get_constraint_upper_bounds(), g["cu"])
+    # dense-Jacobian mode of the same problem
+    pb2 = CudaIpoptProblem(g["x0"], obj, [_circle(H)], integ, use_hessian=False, sparse_jacobian=False)
+    assert _rel(pb2.jacobian(z), g["jacobian"]) < 1e-10
+
+
+def test_trust_constr_with_a_binding_extra_constraint(lv_weights):
+    """u_t^2 <= 0.01 as a user InequalityConstraint: the solve honours it and the on-device solver refuses the problem loudly"""
+    from pyneuralempc_b200.constraints import InequalityConstraint
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import CudaIpm, TrustConstr
+    H = 6
+    model, integ, obj, dom = _lv_setup(lv_weights, H)
+    n = 3 * H
+
+    class SmallControl(InequalityConstraint):                     # 0.01 - u_t^2 >= 0
+        def forward(self, x, u, p=None, tvp=None):
+            return 0.01 - u[:, 0] ** 2
+
+        def jacobian(self, x, u, p=None, tvp=None):
+            J = np.zeros((H, n))
+            J[np.arange(H), 2 * H + np.arange(H)] = -2.0 * u[:, 0]
+            return J
+
+        def hessian(self, x, u, p=None, tvp=None):
+            Hc = np.zeros((H, n, n))
+            Hc[np.arange(H), 2 * H + np.arange(H), 2 * H + np.arange(H)] = -2.0
+            return Hc
+
+        def get_dim(self, H_=None):
+            return H
+
+    x0 = np.array([0.66, -0.9])
+    free = NMPC(integ, obj, [dom], H, 0.1, optimizer=TrustConstr())
+    _, u_free = free.next(x0)
+    assert np.abs(u_free).max() > 0.15                            # the constraint will bind
+    opt = TrustConstr()
+    xs, us = NMPC(integ, obj, [dom, SmallControl()], H, 0.1, optimizer=opt).next(x0)
+    assert xs is not None and np.abs(us).max() <= 0.1 + 1e-6
+    assert opt.last_result.constr_violation < 1e-8
+    with pytest.raises(NotImplementedError):
+        NMPC(integ, obj, [dom, SmallControl()], H, 0.1, optimizer=CudaIpm()).next(x0)
