@@ -43,7 +43,7 @@ enum { NEMPC_INTEG_DISCRETE = 0,   /* x_{t-1} + f - x_t        integrator/discre
        NEMPC_INTEG_RK4 = 2 };      /* classical RK4, ZOH on u  integrator/rk4.py:57-83      */
 enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2 };
 enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2,
-       NEMPC_KERNEL_TC = 3 };      /* tcgen05 tensor-core kernel: f32 tanh networks whose hidden layers are all 128 wide */
+       NEMPC_KERNEL_TC = 3 };      /* tcgen05 tensor-core kernel: f32 tanh networks whose hidden layers are all 128 (or all 64) wide */
 
 typedef struct nempc_desc {
     int32_t x_dim, u_dim;                /* model/base.py:4-9 */
@@ -56,7 +56,7 @@ typedef struct nempc_desc {
     int32_t compute_dtype;               /* network + chain-rule arithmetic: NEMPC_F32 (reference: Keras f32) or F64 */
     int32_t io_dtype;                    /* element type of every I/O buffer (reference: f64, ipopt.py) */
     int32_t device;                      /* CUDA ordinal */
-    int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO: register-resident kernel for the small LV class, tensor-core kernel for 128-wide nets, else generic) */
+    int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO: register-resident kernel for the small LV class, tensor-core kernel for 128- / 64-wide nets, else generic) */
     int32_t tvp_dim, p_dim;              /* time-varying / constant model inputs appended to (x, u): the network input is [x, u, tvp, p]
                                           * (model/tensorflow.py:39-47, model/base.py:4-9); 0 = none.  Layer 0 then has x+u+tvp+p input rows.
                                           * Served by the generic kernel. */

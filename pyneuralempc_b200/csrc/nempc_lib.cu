@@ -324,16 +324,17 @@ static int fast_shape_id(const nempc_desc& d) {
     return -1;
 }
 
-// tensor-core kernel instantiations: (x, u, hidden layers), every hidden layer NEMPC_TC_HW wide
-struct TcShape { int x, u, nhid; };
-static const TcShape kTcShapes[] = {{4, 1, 3}, {4, 1, 2}, {2, 1, 3}, {2, 1, 2}, {3, 1, 3}, {3, 1, 2}, {4, 2, 3}, {4, 2, 2}};
+// tensor-core kernel instantiations: (x, u, hidden layers, width), every hidden layer `hw` wide
+struct TcShape { int x, u, nhid, hw; };
+static const TcShape kTcShapes[] = {{4, 1, 3, 128}, {4, 1, 2, 128}, {2, 1, 3, 128}, {2, 1, 2, 128}, {3, 1, 3, 128}, {3, 1, 2, 128}, {4, 2, 3, 128}, {4, 2, 2, 128},
+                                    {4, 1, 3, 64}, {4, 1, 2, 64}, {2, 1, 3, 64}, {2, 1, 2, 64}};
 static const int kNumTcShapes = sizeof(kTcShapes) / sizeof(kTcShapes[0]);
 
 static int tc_shape_id(const nempc_desc& d) {
     if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
-    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_TC_HW) return -1;
+    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
     for (int i = 0; i < kNumTcShapes; ++i)
-        if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid) return i;
+        if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid && d.widths[0] == kTcShapes[i].hw) return i;
     return -1;
 }
 
@@ -475,7 +476,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     h->use_fast = (h->fast_id >= 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST)) ? 1 : 0;
     h->tc_id = tc_shape_id(D);
     if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0) {
-        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d)", NEMPC_TC_HW);
+        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d or 64)", NEMPC_TC_HW);
         free_device(h); delete h; return NEMPC_EUNSUPPORTED;
     }
     h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
@@ -498,7 +499,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     char nm[224];
     if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
-    else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, NEMPC_TC_HW);
+    else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
     h->kname = nm;
     *out = h;
@@ -543,17 +544,17 @@ template <int X, int U, int H1, int H2, int NCHUNK> static void fill_fast(nempc_
 
 // f16 hi/lo operand images of the hidden-to-hidden layers + the f32 constant block of nempc_tc_kernel
 static int upload_tc(nempc_handle* h) {
-    const int nhid = h->L - 1, HW = NEMPC_TC_HW, x = h->desc.x_dim, d = h->d, xp = (x + 3) / 4 * 4, nmm = nhid - 1;
-    std::vector<__half> img((size_t)nmm * 2 * 128 * HW);
+    const int nhid = h->L - 1, HW = kTcShapes[h->tc_id].hw, x = h->desc.x_dim, d = h->d, xp = (x + 3) / 4 * 4, nmm = nhid - 1;
+    std::vector<__half> img((size_t)nmm * 2 * HW * HW);
     for (int l = 0; l < nmm; ++l) {
         const std::vector<double>& W = h->W[l + 1];                       // [in][out]
-        __half* hi = img.data() + (size_t)l * 2 * 128 * HW;
-        __half* lo = hi + (size_t)128 * HW;
+        __half* hi = img.data() + (size_t)l * 2 * HW * HW;
+        __half* lo = hi + (size_t)HW * HW;
         for (int i = 0; i < HW; ++i)
             for (int j = 0; j < HW; ++j) {
                 const float w = (float)W[(size_t)i * HW + j];
                 const __half whi = __float2half_rn(w);
-                const size_t off = tc_img_index(j, i);                    // B[n = out][k = in]
+                const size_t off = tc_img_index(j, i, HW);                    // B[n = out][k = in]
                 hi[off] = whi;
                 lo[off] = __float2half_rn((w - __half2float(whi)) * NEMPC_TC_LO_SCALE);
             }
@@ -805,9 +806,9 @@ template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<T
     return NEMPC_EINVAL;
 }
 
-template <int X, int U, int NHID, int MODE, typename TIO>
+template <int X, int U, int NHID, int HW, int MODE, typename TIO>
 static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    typedef TcCfg<X, U, NHID, MODE> C;
+    typedef TcCfg<X, U, NHID, MODE, HW> C;
     auto kern = nempc_tc_kernel<C, TIO>;
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
@@ -818,24 +819,28 @@ static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t
     h->launches++;
     return NEMPC_OK;
 }
-template <int X, int U, int NHID, typename TIO>
+template <int X, int U, int NHID, int HW, typename TIO>
 static int launch_tc_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
     switch (mode) {
-        case 0: return launch_tc_mode<X, U, NHID, 0, TIO>(h, ar, s);
-        case 1: return launch_tc_mode<X, U, NHID, 1, TIO>(h, ar, s);
-        default: return launch_tc_mode<X, U, NHID, 2, TIO>(h, ar, s);
+        case 0: return launch_tc_mode<X, U, NHID, HW, 0, TIO>(h, ar, s);
+        case 1: return launch_tc_mode<X, U, NHID, HW, 1, TIO>(h, ar, s);
+        default: return launch_tc_mode<X, U, NHID, HW, 2, TIO>(h, ar, s);
     }
 }
 template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    switch (h->tc_id) {
-        case 0: return launch_tc_shape<4, 1, 3, TIO>(h, ar, mode, s);
-        case 1: return launch_tc_shape<4, 1, 2, TIO>(h, ar, mode, s);
-        case 2: return launch_tc_shape<2, 1, 3, TIO>(h, ar, mode, s);
-        case 3: return launch_tc_shape<2, 1, 2, TIO>(h, ar, mode, s);
-        case 4: return launch_tc_shape<3, 1, 3, TIO>(h, ar, mode, s);
-        case 5: return launch_tc_shape<3, 1, 2, TIO>(h, ar, mode, s);
-        case 6: return launch_tc_shape<4, 2, 3, TIO>(h, ar, mode, s);
-        case 7: return launch_tc_shape<4, 2, 2, TIO>(h, ar, mode, s);
+    switch (h->tc_id) {                                    // index into kTcShapes
+        case 0: return launch_tc_shape<4, 1, 3, 128, TIO>(h, ar, mode, s);
+        case 1: return launch_tc_shape<4, 1, 2, 128, TIO>(h, ar, mode, s);
+        case 2: return launch_tc_shape<2, 1, 3, 128, TIO>(h, ar, mode, s);
+        case 3: return launch_tc_shape<2, 1, 2, 128, TIO>(h, ar, mode, s);
+        case 4: return launch_tc_shape<3, 1, 3, 128, TIO>(h, ar, mode, s);
+        case 5: return launch_tc_shape<3, 1, 2, 128, TIO>(h, ar, mode, s);
+        case 6: return launch_tc_shape<4, 2, 3, 128, TIO>(h, ar, mode, s);
+        case 7: return launch_tc_shape<4, 2, 2, 128, TIO>(h, ar, mode, s);
+        case 8: return launch_tc_shape<4, 1, 3, 64, TIO>(h, ar, mode, s);
+        case 9: return launch_tc_shape<4, 1, 2, 64, TIO>(h, ar, mode, s);
+        case 10: return launch_tc_shape<2, 1, 3, 64, TIO>(h, ar, mode, s);
+        case 11: return launch_tc_shape<2, 1, 2, 64, TIO>(h, ar, mode, s);
     }
     SET_ERR(h, "internal: bad tc_id");
     return NEMPC_EINVAL;

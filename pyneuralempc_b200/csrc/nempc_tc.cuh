@@ -24,6 +24,7 @@
 // which carries ~22 mantissa bits (measured 4e-7 relative, tests/tools/tc_gemm_probe.cu) at 1.5x the cost of one TF32
 // pass and HALF the shared-memory footprint of a 3xTF32 scheme -- the footprint is what decides residency here.
 //
+// (Hidden width 64 is the same kernel with N = 64 MMAs; its tiles need 128 tensor-memory columns, so FOUR groups of 128 threads run.)
 // One persistent CTA per SM, NEMPC_TC_THREADS = 512 threads = TWO GROUPS of 256 threads, each working on its own row tile with its
 // own named barrier, mbarrier and 256 tensor-memory columns: while one group waits for its MMA batch the other runs its epilogue
 // (the overlap a second CTA per SM would give, without a second copy of the weights).  Thread (m = gtid & 127, cq = gtid >> 7) of a
@@ -45,16 +46,19 @@
 
 #define NEMPC_TC_HW 128
 #ifndef NEMPC_TC_THREADS
-#define NEMPC_TC_THREADS 512            // two tile groups of 256 threads
+#define NEMPC_TC_THREADS 512            // two tile groups of 256 threads (width 128) or four of 128 (width 64)
+#endif
+#ifndef NEMPC_TC_NG
+#define NEMPC_TC_NG(hw) ((hw) == 64 ? 4 : 2)      // tile groups per CTA
 #endif
 #define NEMPC_TC_SMEM_MAX 232448
 #ifndef NEMPC_TC_P2_UNROLL
 #define NEMPC_TC_P2_UNROLL 2          // unroll factor of the 16-neuron chunk loop of pass 2 (2: both tensor-memory loads in flight; +3% on C3)
 #endif
 
-template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
+template <int X_, int U_, int NHID_, int MODE_, int HW_ = NEMPC_TC_HW> struct TcCfg {
     static constexpr int X = X_, U = U_, NHID = NHID_, MODE = MODE_;
-    static constexpr int D = X + U, NTRI = D * (D + 1) / 2, HW = NEMPC_TC_HW, NMM = NHID - 1;
+    static constexpr int D = X + U, NTRI = D * (D + 1) / 2, HW = HW_, NMM = NHID - 1;
     static constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
     static constexpr int RPS = 1 + (JAC ? D : 0) + (HES ? NTRI : 0);      // rows per step
     static constexpr int SPT = (128 / RPS) < 32 ? (128 / RPS) : 32;       // steps per tile
@@ -70,13 +74,14 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
                          T_TMP = T_M + (HES ? X * D * D : 0), T_TOTAL = T_TMP + (HES ? X * D * D : 0);
     // two independent row tiles per CTA ("groups" of GT threads): while one group waits for its MMA batch the other runs its
     // epilogue -- the overlap a second CTA per SM would give, without a second copy of the weights
-    static constexpr int NG = 2, GT = NEMPC_TC_THREADS / NG;
+    // (hidden width 64 needs half the tensor-memory columns per tile, so FOUR groups of 128 threads fit)
+    static constexpr int NG = NEMPC_TC_NG(HW), GT = NEMPC_TC_THREADS / NG;
     static constexpr int NQ = GT / 128;                                   // threads per row: each owns CPT consecutive neurons
     static constexpr int CPT = HW / NQ;
     // tensor memory, per group: D (f32 accumulator) | A_hi | A_lo (f16 operand tile, two K elements per 32-bit column)
-    static constexpr int TM_GROUP = 256, TM_D = 0, TM_AHI = HW, TM_ALO = HW + HW / 2, TM_COLS = NG * TM_GROUP;
+    static constexpr int TM_GROUP = 512 / NG, TM_D = 0, TM_AHI = HW, TM_ALO = HW + HW / 2, TM_COLS = NG * TM_GROUP;
     // shared-memory map (bytes)
-    static constexpr int IMG = 128 * HW * 2;                              // one f16 weight image: 32 KB
+    static constexpr int IMG = HW * HW * 2;                               // one f16 weight image [n = HW][k = HW]: 32 KB at HW = 128
     static constexpr int OFF_W = 0;                                       // NMM x (hi image, lo image)
     static constexpr int OFF_C = NMM * 2 * IMG;                           // f32 constants
     static constexpr int C_W0 = 0, C_WOUT = D * HW, C_B = C_WOUT + HW * XP, C_BOUT = C_B + NHID * HW, C_FLOATS = C_BOUT + XP;
@@ -95,11 +100,12 @@ template <int X_, int U_, int NHID_, int MODE_> struct TcCfg {
     static_assert(TOTAL <= NEMPC_TC_SMEM_MAX, "tensor-core kernel: shared-memory map exceeds 227 KB");
     static_assert(TM_COLS <= 512 && TM_ALO + HW / 2 <= TM_GROUP, "tensor memory: 512 columns");
     static_assert(NHID >= 2 && NHID <= 3, "two or three hidden layers");
+    static_assert(HW == 128 || HW == 64, "hidden width: 128 (N = 128 MMAs) or 64 (N = 64)");
     static_assert(X <= 16 && RPS <= 128, "row stack too tall");
 };
 
-// host: element (n, k) of a K-major no-swizzle operand image with 128 rows: 16-byte chunk (n, k/8) at (k/8)*2048 + n*16
-inline size_t tc_img_index(int n, int k) { return (size_t)(k / 8) * (128 * 8) + (size_t)n * 8 + (k % 8); }
+// host: element (n, k) of a K-major no-swizzle operand image with hw rows: 16-byte chunk (n, k/8) at (k/8)*(hw*16) + n*16
+inline size_t tc_img_index(int n, int k, int hw = NEMPC_TC_HW) { return (size_t)(k / 8) * ((size_t)hw * 8) + (size_t)n * 8 + (k % 8); }
 
 #if defined(__CUDACC__)
 // -DNEMPC_TC_PROFILE: thread 0 of every CTA accumulates the cycles between phase boundaries (development builds only)
@@ -124,7 +130,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     constexpr bool JAC = C::JAC, HES = C::HES;
     typedef typename WideOf<float, TIO>::type TW;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    __shared__ uint64_t mbar_store[3];
+    __shared__ uint64_t mbar_store[1 + C::NG];
     __shared__ uint32_t tmem_holder;
 
     constexpr int GT = C::GT;
@@ -168,7 +174,7 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
     auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory"); };
 
     const uint32_t mbar_w = smem_u32(&mbar_store[0]), mbar_mma = smem_u32(&mbar_store[1 + grp]);
-    if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(smem_u32(&mbar_store[1]), 1); mbar_init(smem_u32(&mbar_store[2]), 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(mbar_w, 1); for (int g = 0; g < C::NG; ++g) mbar_init(smem_u32(&mbar_store[1 + g]), 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(smem_u32(&tmem_holder), C::TM_COLS);
     fence_before_sync();
     __syncthreads();
@@ -377,9 +383,9 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                         // scale-input-d: D = A_hi W_hi + D * 2^-11 -- ONE f32 accumulator, half the tensor-memory read volume.
                         // A operand from tensor memory (8 columns = 16 K elements per MMA), B descriptors advanced in their low word.
                         const uint32_t dhi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
-                        const uint32_t dlo = (2048u >> 4) << 16;                             // LBO = 2048 B
+                        const uint32_t dlo = ((uint32_t)(HW * 16) >> 4) << 16;               // LBO = HW * 16 B: next 8-wide K chunk of the image
                         const uint32_t lw1 = dlo | (whi >> 4), lw2 = dlo | (wlo >> 4);
-#define NEMPC_TC_DESC(lo, ks) ((((uint64_t)dhi) << 32) | (uint64_t)((lo) + (ks) * 256u))
+#define NEMPC_TC_DESC(lo, ks) ((((uint64_t)dhi) << 32) | (uint64_t)((lo) + (ks) * (2u * HW)))
 #pragma unroll
                         for (int ks = 0; ks < HW / 16; ++ks) mma_f16_ts(td, ta2 + ks * 8, NEMPC_TC_DESC(lw1, ks), idesc, ks != 0);
 #pragma unroll
@@ -392,8 +398,12 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                     typedef std::integral_constant<int, 0> I0;
                     typedef std::integral_constant<int, (NMM > 1 ? 1 : 0)> I1;
                     typedef std::integral_constant<int, 1> G1;
-                    if (grp == 0) { if (l == 0) issue(I0{}, I0{}); else issue(I1{}, I0{}); }
-                    else          { if (l == 0) issue(I0{}, G1{}); else issue(I1{}, G1{}); }
+                    typedef std::integral_constant<int, (C::NG > 2 ? 2 : 0)> G2;
+                    typedef std::integral_constant<int, (C::NG > 2 ? 3 : 0)> G3;
+                    if (grp == 0)      { if (l == 0) issue(I0{}, I0{}); else issue(I1{}, I0{}); }
+                    else if (grp == 1) { if (l == 0) issue(I0{}, G1{}); else issue(I1{}, G1{}); }
+                    else if (grp == 2) { if (l == 0) issue(I0{}, G2{}); else issue(I1{}, G2{}); }
+                    else               { if (l == 0) issue(I0{}, G3{}); else issue(I1{}, G3{}); }
                     mma_commit(mbar_mma);
                     TC_PROF(4);
                     mbar_wait(mbar_mma, parity);                   // ONE polling thread; the rest of the group blocks on its barrier below

@@ -102,7 +102,10 @@ def test_fast_kernel_vs_oracle(kind, h, lv_weights):
 TC_CASES = [("rk4", [5, 128, 128, 128, 4], 4, 1, 13, 7), ("discrete", [5, 128, 128, 4], 4, 1, 9, 30),
             ("unity", [3, 128, 128, 128, 2], 2, 1, 25, 11), ("rk4", [3, 128, 128, 2], 2, 1, 50, 5),
             ("rk4", [4, 128, 128, 128, 3], 3, 1, 6, 9), ("discrete", [6, 128, 128, 4], 4, 2, 3, 17),
-            ("rk4", [6, 128, 128, 128, 4], 4, 2, 4, 3)]
+            ("rk4", [6, 128, 128, 128, 4], 4, 2, 4, 3),
+            # hidden width 64: N = 64 MMAs, four K steps
+            ("rk4", [5, 64, 64, 64, 4], 4, 1, 13, 7), ("discrete", [5, 64, 64, 4], 4, 1, 9, 30),
+            ("unity", [3, 64, 64, 64, 2], 2, 1, 25, 11), ("rk4", [3, 64, 64, 2], 2, 1, 50, 5)]
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", TC_CASES)
