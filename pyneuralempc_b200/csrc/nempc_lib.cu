@@ -327,7 +327,7 @@ static int fast_shape_id(const nempc_desc& d) {
 // tensor-core kernel instantiations: (x, u, hidden layers, width), every hidden layer `hw` wide
 struct TcShape { int x, u, nhid, hw; };
 static const TcShape kTcShapes[] = {{4, 1, 3, 128}, {4, 1, 2, 128}, {2, 1, 3, 128}, {2, 1, 2, 128}, {3, 1, 3, 128}, {3, 1, 2, 128}, {4, 2, 3, 128}, {4, 2, 2, 128},
-                                    {4, 1, 3, 64}, {4, 1, 2, 64}, {2, 1, 3, 64}, {2, 1, 2, 64}};
+                                    {4, 1, 3, 64}, {4, 1, 2, 64}, {2, 1, 3, 64}, {2, 1, 2, 64}, {2, 1, 3, 32}, {4, 1, 3, 32}};
 static const int kNumTcShapes = sizeof(kTcShapes) / sizeof(kTcShapes[0]);
 
 static int tc_shape_id(const nempc_desc& d) {
@@ -476,7 +476,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     h->use_fast = (h->fast_id >= 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST)) ? 1 : 0;
     h->tc_id = tc_shape_id(D);
     if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0) {
-        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d or 64)", NEMPC_TC_HW);
+        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d, 64 or 32)", NEMPC_TC_HW);
         free_device(h); delete h; return NEMPC_EUNSUPPORTED;
     }
     h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
@@ -841,6 +841,8 @@ template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO
         case 9: return launch_tc_shape<4, 1, 2, 64, TIO>(h, ar, mode, s);
         case 10: return launch_tc_shape<2, 1, 3, 64, TIO>(h, ar, mode, s);
         case 11: return launch_tc_shape<2, 1, 2, 64, TIO>(h, ar, mode, s);
+        case 12: return launch_tc_shape<2, 1, 3, 32, TIO>(h, ar, mode, s);
+        case 13: return launch_tc_shape<4, 1, 3, 32, TIO>(h, ar, mode, s);
     }
     SET_ERR(h, "internal: bad tc_id");
     return NEMPC_EINVAL;

@@ -24,7 +24,8 @@
 // which carries ~22 mantissa bits (measured 4e-7 relative, tests/tools/tc_gemm_probe.cu) at 1.5x the cost of one TF32
 // pass and HALF the shared-memory footprint of a 3xTF32 scheme -- the footprint is what decides residency here.
 //
-// (Hidden width 64 is the same kernel with N = 64 MMAs; its tiles need 128 tensor-memory columns, so FOUR groups of 128 threads run.)
+// (Hidden widths 64 / 32 are the same kernel with N = 64 / 32 MMAs; their tiles need <= 128 tensor-memory columns, so FOUR groups of 128
+// threads run.)
 // One persistent CTA per SM, NEMPC_TC_THREADS = 512 threads = TWO GROUPS of 256 threads, each working on its own row tile with its
 // own named barrier, mbarrier and 256 tensor-memory columns: while one group waits for its MMA batch the other runs its epilogue
 // (the overlap a second CTA per SM would give, without a second copy of the weights).  Thread (m = gtid & 127, cq = gtid >> 7) of a
@@ -49,7 +50,7 @@
 #define NEMPC_TC_THREADS 512            // two tile groups of 256 threads (width 128) or four of 128 (width 64)
 #endif
 #ifndef NEMPC_TC_NG
-#define NEMPC_TC_NG(hw) ((hw) == 64 ? 4 : 2)      // tile groups per CTA
+#define NEMPC_TC_NG(hw) ((hw) <= 64 ? 4 : 2)      // tile groups per CTA
 #endif
 #define NEMPC_TC_SMEM_MAX 232448
 #ifndef NEMPC_TC_P2_UNROLL
@@ -100,7 +101,7 @@ template <int X_, int U_, int NHID_, int MODE_, int HW_ = NEMPC_TC_HW> struct Tc
     static_assert(TOTAL <= NEMPC_TC_SMEM_MAX, "tensor-core kernel: shared-memory map exceeds 227 KB");
     static_assert(TM_COLS <= 512 && TM_ALO + HW / 2 <= TM_GROUP, "tensor memory: 512 columns");
     static_assert(NHID >= 2 && NHID <= 3, "two or three hidden layers");
-    static_assert(HW == 128 || HW == 64, "hidden width: 128 (N = 128 MMAs) or 64 (N = 64)");
+    static_assert(HW == 128 || HW == 64 || HW == 32, "hidden width: 128 (N = 128 MMAs), 64 (N = 64) or 32 (N = 32)");
     static_assert(X <= 16 && RPS <= 128, "row stack too tall");
 };
 

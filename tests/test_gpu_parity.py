@@ -105,7 +105,9 @@ TC_CASES = [("rk4", [5, 128, 128, 128, 4], 4, 1, 13, 7), ("discrete", [5, 128, 1
             ("rk4", [6, 128, 128, 128, 4], 4, 2, 4, 3),
             # hidden width 64: N = 64 MMAs, four K steps
             ("rk4", [5, 64, 64, 64, 4], 4, 1, 13, 7), ("discrete", [5, 64, 64, 4], 4, 1, 9, 30),
-            ("unity", [3, 64, 64, 64, 2], 2, 1, 25, 11), ("rk4", [3, 64, 64, 2], 2, 1, 50, 5)]
+            ("unity", [3, 64, 64, 64, 2], 2, 1, 25, 11), ("rk4", [3, 64, 64, 2], 2, 1, 50, 5),
+            # hidden width 32, three hidden layers (two-layer 32-wide LV nets belong to the register-resident kernel)
+            ("rk4", [3, 32, 32, 32, 2], 2, 1, 50, 9), ("discrete", [5, 32, 32, 32, 4], 4, 1, 7, 12)]
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", TC_CASES)

@@ -2,7 +2,7 @@ import sys, time, numpy as np, torch
 sys.path.insert(0, '.')
 from pyneuralempc_b200 import NlpEvaluator
 from oracle.mlp_np import MLP
-for hw in (64, 128):
+for hw in (32, 64, 128):
   for kern in ("generic", "tc"):
     mlp = MLP.glorot([5, hw, hw, hw, 4], 4, 1, seed=1)
     H, B = 100, 4096
