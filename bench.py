@@ -263,6 +263,10 @@ def gpu_run(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_cpus = None
+    if world > 1 and not os.environ.get("NEMPC_NO_NUMA_BIND"):
+        from pyneuralempc_b200.sharding import bind_host_to_gpu
+        numa_cpus = bind_host_to_gpu(local)        # before any pinned allocation: host staging next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
@@ -446,6 +450,7 @@ def gpu_run(args):
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "batch_per_gpu": B, "horizon": wl["H"], "io_dtype": args.io_dtype,
                        "horizon_steps_per_eval_per_gpu": steps_per_eval, "parallelism": f"independent problems sharded over {world} GPU(s), no data-path collective",
+                       "host_numa_bind": (f"rank 0 on {len(numa_cpus)} cores next to its GPU" if numa_cpus else "none"),
                        "l2": f"{nsets} rotating input/output sets, {set_bytes * nsets / 1e6:.0f} MB total > 126 MB L2",
                        "eval": "residual + sparse Jacobian + lambda-contracted sparse Lagrangian Hessian + objective value/gradient"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

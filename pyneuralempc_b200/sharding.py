@@ -19,6 +19,42 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index, sysfs="/sys/bus/pci/devices"):
+    """pin this process to the CPU cores next to GPU ``device_index`` (its PCIe root's NUMA node) BEFORE pinned host buffers are
+    allocated, so that first-touch places them in that node's memory: with one process per GPU the host <-> device copies of
+    ``nempc_eval_host`` then stay on the GPU's own socket instead of crossing the inter-socket link.  Returns the CPU set used, or None
+    when the topology is not exposed (containers without sysfs NUMA information): never fatal."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index)
+        pci = getattr(bus, "pci_bus_id", None)
+        dom = getattr(bus, "pci_domain_id", 0)
+        dev = getattr(bus, "pci_device_id", 0)
+        if pci is None:
+            return None
+        path = os.path.join(sysfs, f"{dom:04x}:{pci:02x}:{dev:02x}.0", "local_cpulist")
+        with open(path) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def max_over_ranks(value, device=None):
     """max of a python float over all ranks (device timing is reported as the slowest rank)."""
     import torch
