@@ -59,7 +59,7 @@ typedef struct nempc_desc {
     int32_t kernel;                      /* NEMPC_KERNEL_* (AUTO: register-resident kernel for the small LV class, tensor-core kernel for 128- / 64-wide nets, else generic) */
     int32_t tvp_dim, p_dim;              /* time-varying / constant model inputs appended to (x, u): the network input is [x, u, tvp, p]
                                           * (model/tensorflow.py:39-47, model/base.py:4-9); 0 = none.  Layer 0 then has x+u+tvp+p input rows.
-                                          * Served by the generic kernel. */
+                                          * Served by the generic and the tensor-core kernels. */
 } nempc_desc;
 
 typedef struct nempc_handle nempc_handle;

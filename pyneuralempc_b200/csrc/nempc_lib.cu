@@ -273,7 +273,7 @@ struct nempc_handle {
     void* dW[NEMPC_MAXL] = {}; void* dWT[NEMPC_MAXL] = {}; void* db[NEMPC_MAXL] = {};
     double *dlin = nullptr, *dquad = nullptr, *dref = nullptr;
     int use_fast = 0; int fast_id = -1;
-    int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr;   // tensor-core kernel: f16 weight images, f32 constants
+    int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr; float* d_tcwx = nullptr;   // tensor-core kernel: f16 weight images, f32 constants, first-layer rows of the exogenous inputs
     std::vector<unsigned char> fastw;            // FastWeights<...> blob
     SlotLayout sl{};
     int tps = 32, slots = 1, dmax = 4;
@@ -331,7 +331,7 @@ static const TcShape kTcShapes[] = {{4, 1, 3, 128}, {4, 1, 2, 128}, {2, 1, 3, 12
 static const int kNumTcShapes = sizeof(kTcShapes) / sizeof(kTcShapes[0]);
 
 static int tc_shape_id(const nempc_desc& d) {
-    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH) return -1;
     for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
     for (int i = 0; i < kNumTcShapes; ++i)
         if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid && d.widths[0] == kTcShapes[i].hw) return i;
@@ -415,7 +415,7 @@ extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, 
 static void free_device(nempc_handle* h) {
     for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
     cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws); cudaFree(h->d_tcimg); cudaFree(h->d_tccb);
-    cudaFree(h->d_tvp); cudaFree(h->d_p);
+    cudaFree(h->d_tvp); cudaFree(h->d_p); cudaFree(h->d_tcwx);
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->hk_exec) cudaGraphExecDestroy(h->hk_exec);
@@ -442,8 +442,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
         (D.compute_dtype == NEMPC_F64 && D.io_dtype == NEMPC_F32)) { SET_ERR((nempc_handle*)nullptr, "unsupported dtype combination"); return NEMPC_EINVAL; }
 
     if (D.tvp_dim < 0 || D.p_dim < 0 || D.tvp_dim + D.p_dim > NEMPC_MAX_EXO) { SET_ERR((nempc_handle*)nullptr, "tvp_dim + p_dim must be in [0,%d]", NEMPC_MAX_EXO); return NEMPC_EINVAL; }
-    if (D.tvp_dim + D.p_dim > 0 && (D.kernel == NEMPC_KERNEL_FAST || D.kernel == NEMPC_KERNEL_TC)) {
-        SET_ERR((nempc_handle*)nullptr, "tvp / p model inputs are served by the generic kernel only (kernel must be AUTO or GENERIC)");
+    if (D.tvp_dim + D.p_dim > 0 && D.kernel == NEMPC_KERNEL_FAST) {
+        SET_ERR((nempc_handle*)nullptr, "tvp / p model inputs are served by the generic and tensor-core kernels (kernel must be AUTO, GENERIC or TC)");
         return NEMPC_EUNSUPPORTED;
     }
 
@@ -571,6 +571,12 @@ static int upload_tc(nempc_handle* h) {
     }
     CU(h, cudaMemcpy(h->d_tcimg, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->d_tccb, cb.data(), cb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->n_ext > 0) {                                   // rows d .. d+n_ext-1 of the first kernel: the tvp / p inputs
+        std::vector<float> wx((size_t)h->n_ext * HW);
+        for (int e = 0; e < h->n_ext; ++e) for (int j = 0; j < HW; ++j) wx[(size_t)e * HW + j] = (float)h->W[0][(size_t)(d + e) * HW + j];
+        if (!h->d_tcwx) CU(h, cudaMalloc((void**)&h->d_tcwx, wx.size() * sizeof(float)));
+        CU(h, cudaMemcpy(h->d_tcwx, wx.data(), wx.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return NEMPC_OK;
 }
 
@@ -814,7 +820,12 @@ static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t
     StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
     const long long ntiles = (ar.nsteps + C::SPT - 1) / C::SPT;
     const unsigned grid = (unsigned)std::max(1LL, std::min((ntiles + C::NG - 1) / C::NG, (long long)h->sm_count));     // NG tiles in flight per CTA
-    kern<<<grid, NEMPC_TC_THREADS, C::TOTAL, s>>>((const __half*)h->d_tcimg, h->d_tccb, st, h->lay, ar);
+    EvalArgs<TIO> ax = ar;
+    if (h->n_ext > 0) {
+        int rc = bind_exogenous(h, ax, false);
+        if (rc) return rc;
+    }
+    kern<<<grid, NEMPC_TC_THREADS, C::TOTAL, s>>>((const __half*)h->d_tcimg, h->d_tccb, st, h->lay, ax, h->d_tcwx, h->desc.tvp_dim, h->desc.p_dim);
     CU(h, cudaGetLastError());
     h->launches++;
     return NEMPC_OK;

@@ -124,7 +124,7 @@ __device__ unsigned long long nempc_tc_prof[16];
 template <class C, typename TIO>
 __global__ void __launch_bounds__(NEMPC_TC_THREADS, 1)
 nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk, const StageTable<float> st,
-                const NlpLayout L, const EvalArgs<TIO> ar) {
+                const NlpLayout L, const EvalArgs<TIO> ar, const float* __restrict__ wexo, const int tvp_dim, const int p_dim) {
     using namespace tcx;
     constexpr int X = C::X, U = C::U, D = C::D, HW = C::HW, NHID = C::NHID, NMM = C::NMM, SPT = C::SPT, XP = C::XP,
                   SROW = C::SROW, DD = D * D;
@@ -240,6 +240,15 @@ nempc_tc_kernel(const __half* __restrict__ wimg, const float* __restrict__ cblk,
                 for (int c = 0; c < D; ++c) {
                     const float zc = (c < X) ? fmaf(a_s, ps[C::P_KPREV + (c < X ? c : 0)], ps[C::P_Z + c]) : ps[C::P_Z + c];
                     a = fmaf(W0[c * HW + j], zc, a);
+                }
+                if (tvp_dim + p_dim > 0) {        // exogenous inputs [tvp_t, p] (model/tensorflow.py:39-47): a shift of this pre-activation only
+                    const long long b = step_b[s_];
+                    if (b >= 0) {
+                        const double* tv = ar.tvp + b * ar.tvp_bstride + (long long)step_t[s_] * tvp_dim;
+                        for (int q = 0; q < tvp_dim; ++q) a = fmaf(__ldg(wexo + q * HW + j), (float)__ldg(tv + q), a);
+                        const double* pv = ar.p + b * ar.p_bstride;
+                        for (int q = 0; q < p_dim; ++q) a = fmaf(__ldg(wexo + (tvp_dim + q) * HW + j), (float)__ldg(pv + q), a);
+                    }
                 }
                 const float h = fast_tanh(a);
                 sideH[s_ * SROW + j] = h;

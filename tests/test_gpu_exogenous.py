@@ -33,7 +33,9 @@ def _evaluator(exo, kind, H, compute, obj=None, kernel="auto"):
 
 
 CASES = [("discrete", 2, 1, 2, 1, [30, 30], 25), ("rk4", 2, 1, 2, 0, [30, 30], 10), ("unity", 3, 2, 0, 2, [12, 9], 4),
-         ("rk4", 4, 1, 1, 1, [128, 128, 128], 5), ("discrete", 12, 4, 3, 2, [64, 64], 3)]
+         ("rk4", 4, 1, 1, 1, [128, 128, 128], 5), ("discrete", 12, 4, 3, 2, [64, 64], 3), ("discrete", 2, 1, 2, 1, [64, 64], 30),
+         ("rk4", 4, 1, 2, 0, [32, 32, 32], 9)]
+TC_SHAPES = {(4, 1, 128, 3), (2, 1, 64, 2), (4, 1, 32, 3)}        # (x, u, width, hidden layers) of the cases the tensor-core kernel serves
 
 
 @pytest.mark.parametrize("kind,xd,ud,td,pd,hidden,H", CASES)
@@ -50,7 +52,8 @@ def test_eval_with_tvp_and_p_vs_oracle(kind, xd, ud, td, pd, hidden, H, compute,
     Z, X0, lam, sig = rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, xd)), rng.standard_normal((B, m)), rng.uniform(0.5, 1.5, B)
     ref = BlockEvaluator(exo.bind(tvp, p, B=B, H=H), kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
     ev = _evaluator(exo, kind, H, compute, obj)
-    assert "generic" in ev.kernel_name
+    on_tc = compute == "float32" and (xd, ud, hidden[0], len(hidden)) in TC_SHAPES
+    assert ("tcgen05" if on_tc else "generic") in ev.kernel_name
     ev.set_exogenous(tvp, p)
     got = ev.eval_host(Z, X0, lam, sig)
     tol = TOL64 if compute == "float64" else TOL32
