@@ -375,7 +375,9 @@ def test_small_batch_warp_kernel_vs_oracle(kind, h, lv_weights):
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", [("rk4", [5, 128, 128, 128, 4], 4, 1, 1, 1), ("discrete", [3, 128, 128, 2], 2, 1, 1, 3),
-                                                  ("unity", [6, 128, 128, 128, 4], 4, 2, 2, 1), ("rk4", [4, 128, 128, 3], 3, 1, 5, 2)])
+                                                  ("unity", [6, 128, 128, 128, 4], 4, 2, 2, 1), ("rk4", [4, 128, 128, 3], 3, 1, 5, 2),
+                                                  ("rk4", [5, 64, 64, 64, 4], 4, 1, 1, 1), ("discrete", [3, 64, 64, 2], 2, 1, 1, 3),
+                                                  ("rk4", [3, 32, 32, 32, 2], 2, 1, 2, 1)])
 def test_tensor_core_kernel_edge_sizes(kind, dims, xd, ud, H, B):
     """fewer horizon steps than one row tile holds (the second tile group of the CTA stays idle), H = 1 (no A block, no x-x Hessian
     block), and an empty batch."""
@@ -421,12 +423,13 @@ def test_evaluation_without_an_objective(kernel, dims, xd, ud):
     ev.close()
 
 
-def test_tensor_core_kernel_is_deterministic():
+@pytest.mark.parametrize("hw", (128, 64, 32))
+def test_tensor_core_kernel_is_deterministic(hw):
     """two row tiles share a CTA through named barriers, mbarriers and tensor memory: repeated evaluations of the same batch
     must be bit-identical (a race between the tile groups would show up here long before it shows up in a tolerance)."""
     import torch
     H, B = 50, 300
-    mlp, obj, Z, X0, lam, sig = _problem([5, 128, 128, 128, 4], 4, 1, H, B, seed=9)
+    mlp, obj, Z, X0, lam, sig = _problem([5, hw, hw, hw, 4], 4, 1, H, B, seed=9)
     ev = _evaluator(mlp, "rk4", H, "float32", "tc", obj)
     t = lambda a: torch.as_tensor(a).cuda()
     z, x0, lm, sg = t(Z), t(X0), t(lam), t(sig)
