@@ -147,20 +147,21 @@ __global__ void __launch_bounds__(512)
 nempc_ipm_kkt_staged_kernel(const NlpLayout L, const SolverWs w, const SolverOpts o, long long B, int* counts) {
     extern __shared__ __align__(16) double kkt_sm[];
     const int n = L.n, m = L.m, nj = (int)L.nnz_jac, nh = (int)L.nnz_hes, nK = L.H * L.u * L.x, nk = L.H * L.u;
-    const int per = 8 * n + 3 * m + nj + nh + nK + nk;
+    // staged per problem: what the sequential Riccati lane reads and writes (residual, Jacobian / Hessian values, step, gains, the
+    // Sigma / barrier-gradient rows).  The iterate, its bound duals, the gradient and the multipliers are only touched by the
+    // lane-parallel phases (coalesced) and stay in global memory: less shared memory per problem = more problems in flight per SM.
+    const int per = 4 * n + 2 * m + nj + nh + nK + nk;
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* slb = kkt_sm; double* sub = kkt_sm + n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) { slb[i] = w.lb[i]; sub[i] = w.ub[i]; }
     const long long b = (long long)blockIdx.x * wpb + warp;
     double* p = kkt_sm + 2 * n + (size_t)warp * per;
-    double* sz = p; p += n; double* szL = p; p += n; double* szU = p; p += n; double* sgr = p; p += n;
-    double* slam = p; p += m; double* sres = p; p += m; double* sjac = p; p += nj; double* shes = p; p += nh;
+    double* sres = p; p += m; double* sjac = p; p += nj; double* shes = p; p += nh;
     double* sdz = p; p += n; double* slamn = p; p += m; double* sK = p; p += nK; double* skf = p; p += nk;
     double* s1 = p; p += n; double* s2 = p; p += n; double* s3 = p;
     const bool live = b < B && w.status[b < B ? b : 0] == NEMPC_ST_RUNNING;
     if (live) {
-        for (int i = lane; i < n; i += 32) { sz[i] = w.z[b * n + i]; szL[i] = w.zL[b * n + i]; szU[i] = w.zU[b * n + i]; sgr[i] = w.grad[b * n + i]; }
-        for (int i = lane; i < m; i += 32) { slam[i] = w.lam[b * m + i]; sres[i] = w.resid[b * m + i]; }
+        for (int i = lane; i < m; i += 32) sres[i] = w.resid[b * m + i];
         for (int i = lane; i < nj; i += 32) sjac[i] = w.jac[b * L.nnz_jac + i];
         for (int i = lane; i < nh; i += 32) shes[i] = w.hes[b * L.nnz_hes + i];
     } else if (b < B && lane == 0) w.accepted[b] = 1;
@@ -169,7 +170,8 @@ nempc_ipm_kkt_staged_kernel(const NlpLayout L, const SolverWs w, const SolverOpt
     SolverWs w2 = w;
     w2.lb = slb; w2.ub = sub;
     KktRows r;
-    r.z = sz; r.lam = slam; r.zL = szL; r.zU = szU; r.gr = sgr; r.c = sres; r.jv = sjac; r.hv = shes;
+    r.z = w.z + b * n; r.lam = w.lam + b * m; r.zL = w.zL + b * n; r.zU = w.zU + b * n; r.gr = w.grad + b * n;
+    r.c = sres; r.jv = sjac; r.hv = shes;
     r.dz = sdz; r.lamn = slamn; r.Kb = sK; r.kfb = skf;
     r.dzL = w.dzL + b * n; r.dzU = w.dzU + b * n; r.zt = w.zt + b * n;
     r.s1 = s1; r.s2 = s2; r.s3 = s3;
@@ -1183,7 +1185,7 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     else NEMPC_KKT_PICK(NEMPC_SOLVER_XM, NEMPC_SOLVER_UM, 0, 0);
 #undef NEMPC_KKT_PICK
     // warps (= problems) per CTA: the count that packs the most problems per SM into shared memory (bounds are per CTA)
-    const size_t per_bytes = (8 * n + 3 * m + nj + nh + Hux + Hu) * sizeof(double), bnd_bytes = 2 * n * sizeof(double);
+    const size_t per_bytes = (4 * n + 2 * m + nj + nh + Hux + Hu) * sizeof(double), bnd_bytes = 2 * n * sizeof(double);
     // at most 192 KB of the SM for staging: the Riccati body keeps its small matrices in local memory and needs the L1 that is left
     const size_t smem_sm = 192 * 1024, smem_cta_max = std::min<size_t>(smem_sm - 1024, (size_t)std::max(0, h->max_smem_optin - 1024));
     int staged_wpb = 0; size_t staged_smem = 0; long long best = 0;

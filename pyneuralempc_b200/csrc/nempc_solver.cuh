@@ -337,7 +337,8 @@ NEMPC_HD void ipm_kkt_problem(const NlpLayout& L, const SolverWs& w, long long b
 // terms computed in parallel, so every value equals the one-thread body bit for bit.  Lane 0 alone runs the Riccati sweeps.
 // s1, s2, s3: three scratch arrays of n doubles in shared memory.  All pointers are the problem's own rows (no b offset).
 struct KktRows {
-    const double *z, *lam, *zL, *zU, *gr, *c, *jv, *hv;       // shared-memory copies
+    const double *z, *lam, *zL, *zU, *gr;                     // global rows (read by the lane-parallel phases only)
+    const double *c, *jv, *hv;                                // shared-memory copies (read by the sequential Riccati lane)
     double *dz, *lamn, *Kb, *kfb;                             // shared memory, copied out by the caller
     double *dzL, *dzU, *zt;                                   // global rows (write only, coalesced)
     double *s1, *s2, *s3;
