@@ -1187,7 +1187,8 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     // warps (= problems) per CTA: the count that packs the most problems per SM into shared memory (bounds are per CTA)
     const size_t per_bytes = (4 * n + 2 * m + nj + nh + Hux + Hu) * sizeof(double), bnd_bytes = 2 * n * sizeof(double);
     // at most 192 KB of the SM for staging: the Riccati body keeps its small matrices in local memory and needs the L1 that is left
-    const size_t smem_sm = 192 * 1024, smem_cta_max = std::min<size_t>(smem_sm - 1024, (size_t)std::max(0, h->max_smem_optin - 1024));
+    static const size_t smem_kb = getenv("NEMPC_KKT_SMEM_KB") ? (size_t)std::max(16, std::min(227, atoi(getenv("NEMPC_KKT_SMEM_KB")))) : 192;
+    const size_t smem_sm = smem_kb * 1024, smem_cta_max = std::min<size_t>(smem_sm - 1024, (size_t)std::max(0, h->max_smem_optin - 1024));
     int staged_wpb = 0; size_t staged_smem = 0; long long best = 0;
     for (int wpb = 1; wpb <= 16; ++wpb) {
         const size_t need = bnd_bytes + wpb * per_bytes;
