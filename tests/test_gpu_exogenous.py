@@ -86,6 +86,34 @@ def test_chunked_host_call_offsets_the_exogenous_rows():
     ev.close()
 
 
+def test_exogenous_rows_given_as_cuda_tensors_and_batched_solver():
+    """tvp / p as device tensors (copied device-to-device), then the batched on-device solver with per-problem exogenous rows: every
+    problem's solution satisfies the oracle's constraints for ITS rows"""
+    import torch
+    H, B = 6, 5
+    rng = np.random.default_rng(8)
+    exo = _exo(2, 1, 1, 1, [16, 16], 3)
+    exo.weights[0] = (exo.weights[0][0] * 0.5, exo.weights[0][1])
+    tvp, p = rng.uniform(-1, 1, (B, H, 1)), rng.uniform(-1, 1, (B, 1))
+    Z, X0, lam = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-0.5, 0.5, (B, 2)), rng.standard_normal((B, H * 2))
+    ev = _evaluator(exo, "discrete", H, "float64")
+    ev.set_exogenous(torch.as_tensor(tvp).cuda(), torch.as_tensor(p, dtype=torch.float32).cuda())     # float32 tensor: converted
+    p32 = p.astype(np.float32).astype(np.float64)
+    ref = BlockEvaluator(exo.bind(tvp, p32, B=B, H=H), "discrete", H).evaluate(Z, X0, lam)
+    got = ev.eval_host(Z, X0, lam, want=("resid", "jac", "hes"))
+    assert _relerr(got["hes"], ref["hes_vals"]) < TOL64 and _relerr(got["resid"], ref["resid"]) < TOL64
+    n = H * 3
+    quad = np.concatenate([np.ones(H * 2), 0.1 * np.ones(H)])
+    ev.set_objective(np.zeros(n), quad, np.zeros(n))
+    lb = np.concatenate([np.full(H * 2, -5.0), np.full(H, -1.0)])
+    out = ev.solve(X0, lb, -lb, max_iter=80, tol=1e-7)
+    assert bool((out["status"] == 0).all())
+    zs = out["z"].cpu().numpy()
+    res = BlockEvaluator(exo.bind(tvp, p32, B=B, H=H), "discrete", H).evaluate(zs, X0, need_jac=False, need_hes=False)["resid"]
+    assert np.abs(res).max() < 1e-6
+    ev.close()
+
+
 def test_errors():
     from pyneuralempc_b200 import NlpEvaluator
     from pyneuralempc_b200._lib import NempcError
