@@ -18,6 +18,7 @@
 #include "nempc_small.cuh"
 #include "nempc_solver.cuh"
 #include "nempc_tc.cuh"
+#include "nempc_wide.cuh"
 
 // ======================================================================================================
 // kernels
@@ -276,6 +277,8 @@ struct nempc_handle {
     double *dlin = nullptr, *dquad = nullptr, *dref = nullptr;
     int use_fast = 0; int fast_id = -1;
     int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr; float* d_tcwx = nullptr;   // tensor-core kernel: f16 weight images, f32 constants, first-layer rows of the exogenous inputs
+    int use_wide = 0; int wide_id = -1; unsigned char* d_wblob = nullptr; float* d_wcb = nullptr; WideNet wnet{};    // width-256 tensor-core kernel: streamed operand images, biases
+    float* wide_scratch = nullptr; size_t wide_scratch_bytes = 0;
     std::vector<unsigned char> fastw;            // FastWeights<...> blob
     SlotLayout sl{};
     int tps = 32, slots = 1, dmax = 4;
@@ -337,6 +340,21 @@ static int tc_shape_id(const nempc_desc& d) {
     for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
     for (int i = 0; i < kNumTcShapes; ++i)
         if (d.x_dim == kTcShapes[i].x && d.u_dim == kTcShapes[i].u && d.n_layers - 1 == kTcShapes[i].nhid && d.widths[0] == kTcShapes[i].hw) return i;
+    return -1;
+}
+
+// width-256 tensor-core kernel (nempc_wide.cuh): (x, u) instantiations; 2..4 hidden layers, all 256 wide; discrete / unity
+struct WideShape { int x, u; };
+static const WideShape kWideShapes[] = {{12, 4}, {4, 1}, {2, 1}, {6, 2}};
+static const int kNumWideShapes = sizeof(kWideShapes) / sizeof(kWideShapes[0]);
+
+static int wide_shape_id(const nempc_desc& d) {
+    if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
+    if (d.integrator == NEMPC_INTEG_RK4) return -1;
+    if (d.n_layers - 1 < 2 || d.n_layers - 1 > NEMPC_WIDE_MAXHID) return -1;
+    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_WIDE_HW) return -1;
+    for (int i = 0; i < kNumWideShapes; ++i)
+        if (d.x_dim == kWideShapes[i].x && d.u_dim == kWideShapes[i].u) return i;
     return -1;
 }
 
@@ -417,7 +435,7 @@ extern "C" int nempc_structure(const nempc_handle* h, int32_t* jr, int32_t* jc, 
 static void free_device(nempc_handle* h) {
     for (int l = 0; l < NEMPC_MAXL; ++l) { cudaFree(h->dW[l]); cudaFree(h->dWT[l]); cudaFree(h->db[l]); }
     cudaFree(h->dlin); cudaFree(h->dquad); cudaFree(h->dref); cudaFree(h->gws); cudaFree(h->d_tcimg); cudaFree(h->d_tccb);
-    cudaFree(h->d_tvp); cudaFree(h->d_p); cudaFree(h->d_tcwx);
+    cudaFree(h->d_tvp); cudaFree(h->d_p); cudaFree(h->d_tcwx); cudaFree(h->d_wblob); cudaFree(h->d_wcb); cudaFree(h->wide_scratch);
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->hk_exec) cudaGraphExecDestroy(h->hk_exec);
@@ -477,11 +495,13 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     }
     h->use_fast = (h->fast_id >= 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST)) ? 1 : 0;
     h->tc_id = tc_shape_id(D);
-    if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0) {
+    if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0 && wide_shape_id(D) < 0) {
         SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d, 64 or 32)", NEMPC_TC_HW);
         free_device(h); delete h; return NEMPC_EUNSUPPORTED;
     }
     h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
+    h->wide_id = wide_shape_id(D);
+    h->use_wide = (h->wide_id >= 0 && !h->use_fast && !h->use_tc && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
 
     // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
     int sum_h = 0, hmax = 0;
@@ -501,6 +521,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     char nm[224];
     if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
+    else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
     else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
     h->kname = nm;
@@ -582,6 +603,53 @@ static int upload_tc(nempc_handle* h) {
     return NEMPC_OK;
 }
 
+// streamed operand images of nempc_wide_kernel: per GEMM and K step [2^11 hi | hi | lo] x [K chunk] x [n] x [8 halves]
+static int upload_wide(nempc_handle* h) {
+    const int nhid = h->L - 1, HW = NEMPC_WIDE_HW, x = h->desc.x_dim, d = h->d;
+    std::vector<__half> blob;
+    bool range_ok = true;
+    // Bm(n, k): row n of the B operand, contraction index k
+    auto add = [&](int N, int K, auto&& Bm) {
+        WideGemm gm{};
+        gm.off = (uint32_t)(blob.size() * sizeof(__half)); gm.ksteps = (uint32_t)(K / 16); gm.n = (uint32_t)N; gm.stage_bytes = (uint32_t)(96 * N);
+        const size_t base = blob.size();
+        blob.resize(base + (size_t)(K / 16) * 48 * N, __float2half_rn(0.f));
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) {
+                const float w = (float)Bm(n, k);
+                const __half whi = __float2half_rn(w);
+                const float whf = __half2float(whi);
+                if (fabsf(whf) * NEMPC_TC_LO_SCALE > 60000.f) range_ok = false;
+                blob[base + wide_img_index(N, 0, n, k)] = __float2half_rn(whf * NEMPC_TC_LO_SCALE);
+                blob[base + wide_img_index(N, 1, n, k)] = whi;
+                blob[base + wide_img_index(N, 2, n, k)] = __float2half_rn((w - whf) * NEMPC_TC_LO_SCALE);
+            }
+        return gm;
+    };
+    WideNet& wn = h->wnet;
+    wn = WideNet{};
+    wn.nhid = nhid;
+    const std::vector<double>& W0 = h->W[0];                 // [d][HW]
+    const std::vector<double>& Wo = h->W[nhid];              // [HW][x]
+    wn.in_f = add(HW, 16, [&](int n, int k) { return k < d ? W0[(size_t)k * HW + n] : 0.0; });
+    for (int l = 1; l < nhid; ++l) { const std::vector<double>& W = h->W[l]; wn.hid_f[l - 1] = add(HW, HW, [&](int n, int k) { return W[(size_t)k * HW + n]; }); }
+    wn.out_f = add(16, HW, [&](int n, int k) { return n < x ? Wo[(size_t)k * x + n] : 0.0; });
+    wn.out_b = add(HW, 16, [&](int n, int k) { return k < x ? Wo[(size_t)n * x + k] : 0.0; });
+    for (int l = 1; l < nhid; ++l) { const std::vector<double>& W = h->W[l]; wn.hid_b[l - 1] = add(HW, HW, [&](int n, int k) { return W[(size_t)n * HW + k]; }); }
+    wn.in_b = add(16, HW, [&](int n, int k) { return n < d ? W0[(size_t)n * HW + k] : 0.0; });
+    if (!range_ok) { SET_ERR(h, "nempc_wide_kernel: a weight exceeds the f16 range of the scaled operand image (|w| < 29)"); return NEMPC_EUNSUPPORTED; }
+    std::vector<float> cb((size_t)NEMPC_WIDE_MAXHID * HW + 16, 0.f);
+    for (int l = 0; l < nhid; ++l) for (int j = 0; j < HW; ++j) cb[(size_t)l * HW + j] = (float)h->bvec[l][j];
+    for (int p = 0; p < x; ++p) cb[(size_t)NEMPC_WIDE_MAXHID * HW + p] = (float)h->bvec[nhid][p];
+    CU(h, cudaDeviceSynchronize());                       // earlier launches may still stream the old images
+    cudaFree(h->d_wblob); h->d_wblob = nullptr;
+    CU(h, cudaMalloc((void**)&h->d_wblob, blob.size() * sizeof(__half)));
+    if (!h->d_wcb) CU(h, cudaMalloc((void**)&h->d_wcb, cb.size() * sizeof(float)));
+    CU(h, cudaMemcpy(h->d_wblob, blob.data(), blob.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_wcb, cb.data(), cb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return NEMPC_OK;
+}
+
 // kernel parameters (weights of the register-resident kernel, the sparse layout) are baked into a captured graph by value
 static void drop_host_graph(nempc_handle* h) {
     if (h->hk_exec) { cudaGraphExecDestroy(h->hk_exec); h->hk_exec = nullptr; }
@@ -607,6 +675,7 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
         }
     }
     if (all && h->tc_id >= 0) { rc = upload_tc(h); if (rc) return rc; }
+    if (all && h->use_wide) { rc = upload_wide(h); if (rc) return rc; }
     return NEMPC_OK;
 }
 
@@ -861,6 +930,45 @@ template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO
     return NEMPC_EINVAL;
 }
 
+template <int X, int U, int MODE, typename TIO>
+static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
+    typedef WideCfg<X, U, MODE> C;
+    auto kern = nempc_wide_kernel<C, TIO>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    StageTable<float> st = make_stage_table<float>(false, h->desc.dt);
+    const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
+    const unsigned grid = (unsigned)std::max(1LL, std::min(nsup, (long long)h->sm_count));
+    const size_t need = (size_t)h->sm_count * C::SCRATCH_FLOATS * sizeof(float);      // h_l, q_l of one super-tile per CTA (L2-resident)
+    if (need > h->wide_scratch_bytes) {
+        CU(h, cudaStreamSynchronize(s));
+        cudaFree(h->wide_scratch); h->wide_scratch = nullptr; h->wide_scratch_bytes = 0;
+        CU(h, cudaMalloc((void**)&h->wide_scratch, need));
+        h->wide_scratch_bytes = need;
+    }
+    kern<<<grid, NEMPC_WIDE_THREADS, C::TOTAL, s>>>(h->d_wblob, h->d_wcb, h->wnet, st, h->lay, ar, h->wide_scratch);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+template <int X, int U, typename TIO>
+static int launch_wide_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    switch (mode) {
+        case 0: return launch_wide_mode<X, U, 0, TIO>(h, ar, s);
+        case 1: return launch_wide_mode<X, U, 1, TIO>(h, ar, s);
+        default: return launch_wide_mode<X, U, 2, TIO>(h, ar, s);
+    }
+}
+template <typename TIO> static int launch_wide(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    switch (h->wide_id) {                                  // index into kWideShapes
+        case 0: return launch_wide_shape<12, 4, TIO>(h, ar, mode, s);
+        case 1: return launch_wide_shape<4, 1, TIO>(h, ar, mode, s);
+        case 2: return launch_wide_shape<2, 1, TIO>(h, ar, mode, s);
+        case 3: return launch_wide_shape<6, 2, TIO>(h, ar, mode, s);
+    }
+    SET_ERR(h, "internal: bad wide_id");
+    return NEMPC_EINVAL;
+}
+
 template <typename TIO>
 static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda, const void* obj_factor,
                   double sigma, void* resid, void* jac, void* hes, void* obj, void* grad, cudaStream_t s) {
@@ -873,7 +981,8 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         const int mode = hes ? 2 : (jac ? 1 : 0);
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
-        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s) : (h->use_tc ? launch_tc<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s));
+        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
+                            : (h->use_tc ? launch_tc<TIO>(h, ar, mode, s) : (h->use_wide ? launch_wide<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s)));
         if (rc) return rc;
     }
     if (obj || grad) {
