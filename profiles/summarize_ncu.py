@@ -18,6 +18,16 @@ KEYS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA-pipe instructions % of peak"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles active %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "TENSOR pipe cycles active % (any tensor sub-pipe)"),
+    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor sub-pipe HMMA cycles active %"),
+    ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor-pipe instructions % of peak"),
+    ("sm__inst_executed_pipe_tensor.sum", "tensor-pipe instructions"),
+    ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe instructions (UTCHMMA / UBLKCP issue)"),
+    ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "tensor-memory pipe (LDTM / STTM) % of peak"),
+    ("lts__t_bytes.sum", "L2 bytes (all traffic)"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed", "shared-memory pipe % of peak"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
     ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "uniform pipe %"),
@@ -40,6 +50,9 @@ def main(path):
         for key, label in KEYS:
             if key in col:
                 print(f"| {label} (`{key}`) | {r[col[key]]} | {units[col[key]]} |")
+        extra = [h for h in hdr if ("tensor" in h or "tmem" in h) and h not in dict(KEYS) and ".avg.pct_of_peak_sustained_active" in h]
+        for h in extra:
+            print(f"| `{h}` | {r[col[h]]} | {units[col[h]]} |")
         print("\nwarp stall reasons (cycles stalled per issued instruction):\n")
         st = [(h.split("issue_stalled_")[1].split("_per_issue")[0], float(r[i])) for h, i in col.items()
               if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]

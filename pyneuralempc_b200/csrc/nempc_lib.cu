@@ -611,19 +611,23 @@ static int upload_wide(nempc_handle* h) {
     // Bm(n, k): row n of the B operand, contraction index k
     auto add = [&](int N, int K, auto&& Bm) {
         WideGemm gm{};
-        gm.off = (uint32_t)(blob.size() * sizeof(__half)); gm.ksteps = (uint32_t)(K / 16); gm.n = (uint32_t)N; gm.stage_bytes = (uint32_t)(96 * N);
-        const size_t base = blob.size();
-        blob.resize(base + (size_t)(K / 16) * 48 * N, __float2half_rn(0.f));
-        for (int n = 0; n < N; ++n)
-            for (int k = 0; k < K; ++k) {
-                const float w = (float)Bm(n, k);
-                const __half whi = __float2half_rn(w);
-                const float whf = __half2float(whi);
-                if (fabsf(whf) * NEMPC_TC_LO_SCALE > 60000.f) range_ok = false;
-                blob[base + wide_img_index(N, 0, n, k)] = __float2half_rn(whf * NEMPC_TC_LO_SCALE);
-                blob[base + wide_img_index(N, 1, n, k)] = whi;
-                blob[base + wide_img_index(N, 2, n, k)] = __float2half_rn((w - whf) * NEMPC_TC_LO_SCALE);
-            }
+        gm.ksteps = (uint32_t)(K / 16); gm.n = (uint32_t)N;
+        const int Nh = N / 2;                                   // CTA r of the pair streams rows [r Nh, (r + 1) Nh)
+        for (int r = 0; r < 2; ++r) {
+            gm.off[r] = (uint32_t)(blob.size() * sizeof(__half));
+            const size_t base = blob.size();
+            blob.resize(base + (size_t)(K / 16) * 48 * Nh, __float2half_rn(0.f));
+            for (int nl = 0; nl < Nh; ++nl)
+                for (int k = 0; k < K; ++k) {
+                    const float w = (float)Bm(r * Nh + nl, k);
+                    const __half whi = __float2half_rn(w);
+                    const float whf = __half2float(whi);
+                    if (fabsf(whf) * NEMPC_TC_LO_SCALE > 60000.f) range_ok = false;
+                    blob[base + wide_img_index(Nh, K / 16, 0, nl, k)] = __float2half_rn(whf * NEMPC_TC_LO_SCALE);
+                    blob[base + wide_img_index(Nh, K / 16, 1, nl, k)] = whi;
+                    blob[base + wide_img_index(Nh, K / 16, 2, nl, k)] = __float2half_rn((w - whf) * NEMPC_TC_LO_SCALE);
+                }
+        }
         return gm;
     };
     WideNet& wn = h->wnet;
@@ -633,10 +637,10 @@ static int upload_wide(nempc_handle* h) {
     const std::vector<double>& Wo = h->W[nhid];              // [HW][x]
     wn.in_f = add(HW, 16, [&](int n, int k) { return k < d ? W0[(size_t)k * HW + n] : 0.0; });
     for (int l = 1; l < nhid; ++l) { const std::vector<double>& W = h->W[l]; wn.hid_f[l - 1] = add(HW, HW, [&](int n, int k) { return W[(size_t)k * HW + n]; }); }
-    wn.out_f = add(16, HW, [&](int n, int k) { return n < x ? Wo[(size_t)k * x + n] : 0.0; });
+    wn.out_f = add(NEMPC_WIDE_NOUT, HW, [&](int n, int k) { return n < x ? Wo[(size_t)k * x + n] : 0.0; });
     wn.out_b = add(HW, 16, [&](int n, int k) { return k < x ? Wo[(size_t)n * x + k] : 0.0; });
     for (int l = 1; l < nhid; ++l) { const std::vector<double>& W = h->W[l]; wn.hid_b[l - 1] = add(HW, HW, [&](int n, int k) { return W[(size_t)n * HW + k]; }); }
-    wn.in_b = add(16, HW, [&](int n, int k) { return n < d ? W0[(size_t)n * HW + k] : 0.0; });
+    wn.in_b = add(NEMPC_WIDE_NOUT, HW, [&](int n, int k) { return n < d ? W0[(size_t)n * HW + k] : 0.0; });
     if (!range_ok) { SET_ERR(h, "nempc_wide_kernel: a weight exceeds the f16 range of the scaled operand image (|w| < 29)"); return NEMPC_EUNSUPPORTED; }
     std::vector<float> cb((size_t)NEMPC_WIDE_MAXHID * HW + 16, 0.f);
     for (int l = 0; l < nhid; ++l) for (int j = 0; j < HW; ++j) cb[(size_t)l * HW + j] = (float)h->bvec[l][j];
@@ -937,7 +941,9 @@ static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     StageTable<float> st = make_stage_table<float>(false, h->desc.dt);
     const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
-    const unsigned grid = (unsigned)std::max(1LL, std::min(nsup, (long long)h->sm_count));
+    static const int grid_cap = getenv("NEMPC_WIDE_GRID") ? std::max(1, atoi(getenv("NEMPC_WIDE_GRID"))) : 1 << 30;      // experiments: fewer CTAs
+    const long long npair = (nsup + 1) / 2;                                  // CTA pairs (clusters of two, cta_group::2 MMAs)
+    const unsigned grid = 2u * (unsigned)std::max(1LL, std::min(npair, (long long)std::min(h->sm_count, grid_cap) / 2));
     const size_t need = (size_t)h->sm_count * C::SCRATCH_FLOATS * sizeof(float);      // h_l, q_l of one super-tile per CTA (L2-resident)
     if (need > h->wide_scratch_bytes) {
         CU(h, cudaStreamSynchronize(s));
@@ -1358,6 +1364,16 @@ extern "C" int nempc_debug_tc_profile(unsigned long long* out16) {
     if (cudaMemcpyFromSymbol(out16, nempc_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return NEMPC_ECUDA;
     unsigned long long z[16] = {};
     cudaMemcpyToSymbol(nempc_tc_prof, z, sizeof z);
+    return NEMPC_OK;
+}
+#endif
+
+#ifdef NEMPC_WIDE_PROFILE
+extern "C" int nempc_debug_wide_profile(unsigned long long* out16) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return NEMPC_ECUDA;
+    if (cudaMemcpyFromSymbol(out16, nempc_wide_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return NEMPC_ECUDA;
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(nempc_wide_prof, z, sizeof z);
     return NEMPC_OK;
 }
 #endif

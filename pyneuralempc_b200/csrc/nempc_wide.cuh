@@ -16,15 +16,23 @@
 //
 // Every product with a weight matrix -- including the thin first layer (K = 16), the output layer (N = 16) and their transposes --
 // is one "GEMM" of the same engine:  D[128 rows x N] (f32, tensor memory) = A[128 x K] (tensor memory, TS mode) * B[N x K]^T (ring).
-//   * arithmetic: x = hi + lo / 2^11 in f16 (tcx::split_f16); per K step three MMAs  A_hi (2^11 W_hi) + A_lo W_hi + A_hi W_lo  into ONE
-//     accumulator that carries the factor 2^11 (the image of 2^11 W_hi replaces the scale-input-d trick of nempc_tc.cuh, which would
-//     need a second pass over the streamed W_hi); ~22 mantissa bits.
+//   * arithmetic: x = hi + lo / 2^11 in f16 (tcx::split_f16); three products  A_hi (2^11 W_hi) + A_lo W_hi + A_hi W_lo  into ONE
+//     accumulator that carries the factor 2^11 (the image of 2^11 W_hi replaces the scale-input-d trick of nempc_tc.cuh).  The two
+//     correction products of ALL K steps are issued first, while the accumulator is small, then the main products: the tensor core
+//     rounds the f32 accumulator once per MMA, so only the 16 main MMAs round at full magnitude (instead of 48 when interleaved);
+//     ~22 mantissa bits.
 //   * tensor memory: two 256-column regions X / Y.  GEMM g reads its A operand from one and accumulates into the other; the epilogue
 //     converts the accumulator IN PLACE: the 16 f32 columns of neurons [16q, 16q+16) become 8 columns of f16 hi pairs + 8 columns of
 //     f16 lo pairs = K step q of the next GEMM's A operand.  Nothing but registers and tensor memory carries a layer to the next.
-//   * roles: 16 epilogue warps (lane = row; warp w: lane quadrant w & 3, neuron quarter w >> 2), one TMA producer thread (warp 16)
-//     that runs ahead through the ring, one MMA-issuing thread (warp 17).  mbarriers only: ring full / empty, accumulator ready
-//     (tcgen05.commit), operand ready (512 arrivals).
+//   * CTA PAIRS (cta_group::2).  One SM pulls ~26 B/clk out of L2 (the same ~6.3 KB/clk chip-wide whatever the path), i.e. 15 k clk for
+//     the 384 KB of one layer against 6.1 k clk of MMA time: a single CTA is bound by its weight stream (measured: ring waits, linear
+//     scaling with the CTA count).  So two CTAs of a cluster work on two 128-row tiles as ONE M = 256 MMA: each CTA streams only its
+//     half of the B rows (tcgen05.mma.cta_group::2 exchanges the halves between the two SMs), which halves the bytes per SM and row.
+//     The two CTAs run the same GEMM sequence on their own super-tile (a CTA without work runs it on zero rows).
+//   * roles per CTA: 16 epilogue warps (lane = row; warp w: lane quadrant w & 3, neuron quarter w >> 2), one TMA producer thread
+//     (warp 16) that runs ahead through the ring, and in warp 17 the MMA-issuing thread (leader CTA) or a thread that forwards the
+//     peer's ring-full signals to the leader.  mbarriers only: ring full (leader: own TMA + peer's forward) / empty and accumulator
+//     ready (tcgen05.commit multicast to both CTAs), operand ready (2 x 512 arrivals on the leader's barrier, the peer's arrive remotely).
 #pragma once
 #include "nempc_fast.cuh"
 #include "nempc_generic.cuh"
@@ -39,16 +47,23 @@
 #define NEMPC_WIDE_MAXHID 4
 #define NEMPC_WIDE_SUP 128                      // steps per super-tile (= rows of a phase A / B tile)
 
-// one streamed operand: `ksteps` ring stages of `stage_bytes` = 96 n bytes: [image 2^11 hi | hi | lo][K chunk 0..1][n][8 halves]
-struct WideGemm { uint32_t off, ksteps, n, stage_bytes; };
+// one streamed operand of a GEMM with n rows and `ksteps` K steps of 16, cut in two halves of nh = n / 2 rows (CTA r of the pair
+// streams rows [r nh, (r + 1) nh) from off[r]); an image of one K step = [K chunk 0..1][nh][8 halves] = 32 nh bytes:
+//   pass 1, one ring stage per TWO K steps:   [hi (ks) | lo (ks) | hi (ks + 1) | lo (ks + 1)]   128 nh bytes (64 nh for a lone K step)
+//   pass 2, one ring stage per FOUR K steps:  [2^11 hi (ks .. ks + 3)]                          128 nh bytes
+// (four MMAs per ring stage: the lone issuing thread pays ~300 clk of barrier wait + commit per stage)
+struct WideGemm { uint32_t off[2], ksteps, n; };
 struct WideNet {
     int nhid;                                   // hidden layers, 2..4, all NEMPC_WIDE_HW wide
     WideGemm in_f, hid_f[NEMPC_WIDE_MAXHID - 1], out_f, out_b, hid_b[NEMPC_WIDE_MAXHID - 1], in_b;
 };
 
-// host: half index of element (n, k) of a streamed operand with N rows
-inline size_t wide_img_index(int N, int img, int n, int k) {
-    return (size_t)(k / 16) * (48 * (size_t)N) + (size_t)img * (16 * (size_t)N) + (size_t)((k % 16) / 8) * (8 * (size_t)N) + (size_t)n * 8 + (k % 8);
+#define NEMPC_WIDE_NOUT 32                      // rows of the thin output operands (x_dim or d, zero padded): cta_group::2 needs N % 32 == 0
+// host: half index of element (n, k) of one CTA's half (N rows) of a streamed operand with K16 K steps; img 0 = 2^11 hi, 1 = hi, 2 = lo
+inline size_t wide_img_index(int N, int K16, int img, int n, int k) {
+    const size_t in_img = (size_t)((k % 16) / 8) * (8 * (size_t)N) + (size_t)n * 8 + (k % 8), ks = (size_t)(k / 16);
+    if (img == 0) return (size_t)K16 * 32 * N + ks * 16 * N + in_img;
+    return ks * 32 * N + (img == 2 ? 16 * (size_t)N : 0) + in_img;
 }
 
 template <int X_, int U_, int MODE_> struct WideCfg {
@@ -57,15 +72,22 @@ template <int X_, int U_, int MODE_> struct WideCfg {
     static constexpr int DP = D <= 4 ? 4 : (D <= 8 ? 8 : 16);          // tangent rows per step (padded to a power of two)
     static constexpr int SPT = 128 / DP;                                 // steps per phase-C tile
     static constexpr int NTILE = NEMPC_WIDE_SUP / SPT;                   // phase-C tiles per super-tile
-    static constexpr int NSTAGE = NEMPC_WIDE_NSTAGE, STAGE_BYTES = 96 * HW;
-    static constexpr int OFF_RING = 0;
+    static constexpr int STAGE_BYTES = 128 * (HW / 2);                   // four K-step images of one CTA's half of the B rows
     static constexpr int C_FLOATS = NEMPC_WIDE_MAXHID * HW + 16;        // biases, output bias
+    static constexpr int STG_WARP = HES ? 4 * 40 * 16 : 0;              // per-warp staging of a 32-row x 16-neuron chunk of T_l (4 planes of 40 granules)
+    static constexpr int SPW = 32 / DP;                                  // steps per epilogue warp in phase C
+    static constexpr int SC_WARP = JAC ? (HES ? 2 : 1) * SPW * 64 * 4 : 0;   // per-warp copy of s'(a_l) (and the curvature coefficients) of its steps and neuron quarter
+    static constexpr int PART_BYTES = HES ? 4 * SPT * DP * DP * 4 : 0;  // [4 quarters][SPT][DP][DP] partial curvature: aliases the staging area
+    static constexpr int STG_BYTES = NEMPC_WIDE_EPI_WARPS * STG_WARP > PART_BYTES ? NEMPC_WIDE_EPI_WARPS * STG_WARP : PART_BYTES;
+    static constexpr int FIXED = C_FLOATS * 4 + STG_BYTES + NEMPC_WIDE_EPI_WARPS * SC_WARP;
+    static constexpr int NSTAGE = (232448 - 1024 - FIXED) / STAGE_BYTES < 10 ? (232448 - 1024 - FIXED) / STAGE_BYTES : 10;
+    static constexpr int OFF_RING = 0;
     static constexpr int OFF_C = OFF_RING + NSTAGE * STAGE_BYTES;
-    static constexpr int STG_WARP = 4 * 40 * 16;                         // per-warp staging of a 32-row x 16-neuron chunk of T_l (4 planes of 40 granules)
     static constexpr int OFF_STG = OFF_C + C_FLOATS * 4;
-    static constexpr int OFF_PART = OFF_STG + NEMPC_WIDE_EPI_WARPS * STG_WARP;   // [4 quarters][SPT][DP][DP] partial curvature
-    static constexpr int PART_BYTES = HES ? 4 * SPT * DP * DP * 4 : 0;
-    static constexpr int TOTAL = OFF_PART + PART_BYTES;
+    static constexpr int OFF_PART = OFF_STG;
+    static constexpr int OFF_SC = OFF_STG + STG_BYTES;
+    static constexpr int TOTAL = OFF_SC + NEMPC_WIDE_EPI_WARPS * SC_WARP;
+    static_assert(NSTAGE >= 4, "wide kernel: weight ring too shallow");
     static constexpr long long SCRATCH_FLOATS = 2LL * NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;    // h_l and q_l of one super-tile
     static_assert(D <= 16 && X <= 16, "x_dim + u_dim <= 16");
     static_assert(TOTAL <= 232448, "wide kernel: shared-memory map exceeds 227 KB");
@@ -76,6 +98,45 @@ namespace widex {
 using namespace tcx;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+
+// ---- CTA pair (cluster of two, cta_group::2) ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t holder_smem, uint32_t ncols) {     // one warp of EACH CTA of the pair, same holder offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 over the pair: A rows [128 r, 128 r + 128) from CTA r's tensor memory, B rows [N/2 r, N/2 (r+1)) from CTA r's shared memory
+// (same descriptor offset in both), accumulator rows in each CTA's own tensor memory; issued by one thread of the leader CTA
+__device__ __forceinline__ void mma2_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs when all MMAs issued so far have completed
+__device__ __forceinline__ void mma2_commit(uint32_t mbar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask) : "memory");
+}
 
 // tanh with a relative error of a few 1e-7 down to 0: 1 - 2 / (e^{2|x|} + 1) cancels for small |x| (absolute error 1e-7), so a
 // degree-9 odd polynomial takes over below 0.25 (truncation 2e-9 there)
@@ -93,16 +154,41 @@ __device__ __forceinline__ float tanh_acc(float x) {
     return copysignf(ax < 0.25f ? p : big, x);
 }
 
-// 16 f32 values -> 8 words of f16 hi pairs + 8 words of f16 lo pairs (x = hi + lo / 2^11)
-__device__ __forceinline__ void split16(const float* x, uint32_t* hi, uint32_t* lo) {
+// 8 f32 pairs -> 8 words of f16 hi pairs + 8 words of f16 lo pairs (x = hi + lo / 2^11), packed arithmetic
+__device__ __forceinline__ void split16p(const f2* x, uint32_t* hi, uint32_t* lo) {
+    const f2 sc = pk(NEMPC_TC_LO_SCALE, NEMPC_TC_LO_SCALE), nsc = pk(-NEMPC_TC_LO_SCALE, -NEMPC_TC_LO_SCALE);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const __half2 h2 = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const __half2 h2 = __floats2half2_rn(f2lo(x[i]), f2hi(x[i]));
         const float2 hf = __half22float2(h2);
-        const __half2 l2 = __floats2half2_rn((x[2 * i] - hf.x) * NEMPC_TC_LO_SCALE, (x[2 * i + 1] - hf.y) * NEMPC_TC_LO_SCALE);
+        const f2 r = fma2(x[i], sc, mul2(pk(hf.x, hf.y), nsc));            // (x - hi) * 2^11, exact
+        const __half2 l2 = __floats2half2_rn(f2lo(r), f2hi(r));
         hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
         lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
+}
+__device__ __forceinline__ void split16(const float* x, uint32_t* hi, uint32_t* lo) {
+    f2 x2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x2[i] = pk(x[2 * i], x[2 * i + 1]);
+    split16p(x2, hi, lo);
+}
+
+// tensor-memory load without the wait (software pipelining: the next chunk's accumulator is in flight while this one is processed);
+// tmem_ld_pin after tcgen05.wait::ld ties every later use of the registers to the wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_pin(uint32_t* r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                      "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 
 __device__ __forceinline__ void ld16_global_cg(const float* p, float* v) {
@@ -118,34 +204,28 @@ __device__ __forceinline__ void st16_global(float* p, const float* v) {
 }
 
 // curvature of one 16-neuron chunk: acc[i][i'] += sum_j coef_j T[4 bi + i][j] T[4 bj + i'][j] for the lane's 4x4 block (bi, bj) of
-// its step; T (this lane's row, true scale) is exchanged through the warp's staging planes (granule of row r at r + r / 4: the
-// eight rows one load instruction touches fall in eight different 16-byte bank groups)
+// its step.  T = this lane's accumulator row (any common scale: `cfs` carries its inverse square) is exchanged through the warp's
+// staging planes (granule of row r at r + r / 4: the eight rows one load instruction touches fall in eight different 16-byte bank
+// groups); cfs = shared-memory rows [step of the warp][64 neurons of the warp's quarter] of the coefficients, cc0 = first neuron.
 template <int DP>
-__device__ __forceinline__ void gram_chunk(float* stg, const float* T, const float* coef, f2* acc, const int lane) {
+__device__ __forceinline__ void gram_chunk(float* stg, const uint32_t* T, const float* cfs, const int cc0, f2* acc, const int lane) {
     constexpr int NB = DP / 4, LPS = NB * NB, ACTIVE = (32 / DP) * LPS;
     {
         const int p = lane + (lane >> 2);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(stg + (g * 40 + p) * 4) = make_float4(T[4 * g], T[4 * g + 1], T[4 * g + 2], T[4 * g + 3]);
-    }
-    float cf[16];
-    const int sw = (lane / LPS) % (32 / DP);
-    if (DP == 16) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cf[i] = coef[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cf[i] = __shfl_sync(0xffffffffu, coef[i], sw * DP);     // the coefficients of the block's step live in that step's lanes
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + (g * 40 + p) * 4) = make_uint4(T[4 * g], T[4 * g + 1], T[4 * g + 2], T[4 * g + 3]);
     }
     __syncwarp();
     if (lane < ACTIVE) {
-        const int bl = lane % LPS, bi = bl / NB, bj = bl % NB;
+        const int sw = lane / LPS, bl = lane % LPS, bi = bl / NB, bj = bl % NB;
         const int ra = DP * sw + 4 * bi, rb = DP * sw + 4 * bj;
         const float* pa = stg + (ra + (ra >> 2)) * 4;
         const float* pb = stg + (rb + (rb >> 2)) * 4;
+        const float* cf = cfs + sw * 64 + cc0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const f2 c01 = pk(cf[4 * g], cf[4 * g + 1]), c23 = pk(cf[4 * g + 2], cf[4 * g + 3]);
+            const float4 c4 = *reinterpret_cast<const float4*>(cf + 4 * g);
+            const f2 c01 = pk(c4.x, c4.y), c23 = pk(c4.z, c4.w);
             f2 ua[4], ub[4], b0[4], b1[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -164,12 +244,29 @@ __device__ __forceinline__ void gram_chunk(float* stg, const float* T, const flo
 }
 }  // namespace widex
 
+// -DNEMPC_WIDE_PROFILE (development builds): cycles per phase of the three roles, summed over all CTAs
+//   0 issuer: wait operand   1 issuer: wait ring stage   2 issuer: issue + commit   3 GEMMs
+//   4 epilogue thread 0: pre   5 wait accumulator   6 epilogue body   7 between GEMMs (publish, seeds, scatter)
+//   8 producer: wait free slot   9 producer: issue
+#ifdef NEMPC_WIDE_PROFILE
+__device__ unsigned long long nempc_wide_prof[16];
+#define WPROF_DECL long long wp_t = clock64(); unsigned long long wp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define WPROF(i) do { const long long t_ = clock64(); wp_acc[i] += (unsigned long long)(t_ - wp_t); wp_t = t_; } while (0)
+#define WPROF_COUNT(i) do { wp_acc[i] += 1; } while (0)
+#define WPROF_FLUSH do { if (lane == 0 && (warp == 0 || is_prod || is_mma)) for (int i_ = 0; i_ < 16; ++i_) if (wp_acc[i_]) atomicAdd(&nempc_wide_prof[i_], wp_acc[i_]); } while (0)
+#else
+#define WPROF_DECL
+#define WPROF(i) do {} while (0)
+#define WPROF_COUNT(i) do {} while (0)
+#define WPROF_FLUSH do {} while (0)
+#endif
+
 template <class C, typename TIO>
-__global__ void __launch_bounds__(NEMPC_WIDE_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NEMPC_WIDE_THREADS, 1)     // 18 warps are allocated as 20: 96 registers per thread (112 does not launch)
 nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restrict__ cblk, const WideNet net, const StageTable<float> st,
                   const NlpLayout L, const EvalArgs<TIO> ar, float* __restrict__ scratch_all) {
     using namespace widex;
-    constexpr int X = C::X, U = C::U, D = C::D, DP = C::DP, SPT = C::SPT, HW = C::HW, NSTAGE = C::NSTAGE;
+    constexpr int X = C::X, U = C::U, D = C::D, DP = C::DP, SPT = C::SPT, SPW = C::SPW, HW = C::HW, NSTAGE = C::NSTAGE;
     constexpr bool JAC = C::JAC, HES = C::HES;
     constexpr float INV = NEMPC_TC_LO_INV;                 // accumulators carry 2^11
     typedef typename WideOf<float, TIO>::type TW;
@@ -186,28 +283,34 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     const float* bias = cb;                                 // [MAXHID][HW]
     const float* bout = cb + NEMPC_WIDE_MAXHID * HW;
     float* stg = reinterpret_cast<float*>(wide_smem + C::OFF_STG + (is_epi ? warp : 0) * C::STG_WARP);
+    float* scs = reinterpret_cast<float*>(wide_smem + C::OFF_SC + (is_epi ? warp : 0) * C::SC_WARP);   // [s' 2^-11 | coef 2^-22][SPW][64]
     float* part = reinterpret_cast<float*>(wide_smem + C::OFF_PART);
-    float* sh = scratch_all + (long long)blockIdx.x * C::SCRATCH_FLOATS;          // h_l  [128][MAXHID][HW]
-    float* sq = sh + (long long)NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;           // q_l
+    // per-CTA scratch: sa = h_l (phase A -> B), overwritten by s'(a_l) (phase B, or phase A when no Hessian is wanted); sq = s''(a_l) g_l
+    const uint32_t rank = cluster_ctarank();                // 0 = leader (issues the MMAs of the pair)
+    float* sa = scratch_all + (long long)blockIdx.x * C::SCRATCH_FLOATS;           // [128][MAXHID][HW]
+    float* sq = sa + (long long)NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;
 
     const uint32_t bar0 = smem_u32(&bars[0]);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
     const uint32_t bar_dready = bar0 + 8u * (2 * NSTAGE), bar_aready = bar_dready + 8u;
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        // leader: a ring stage is full when its own TMA bytes have landed AND the peer forwarded the same for its half
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_dready, 1);
-        mbar_init(bar_aready, NEMPC_WIDE_EPI_WARPS * 32);
+        mbar_init(bar_aready, 2 * NEMPC_WIDE_EPI_WARPS * 32);          // the epilogue threads of BOTH CTAs (used in the leader only)
         mbar_fence_init();
     }
-    if (is_mma) tmem_alloc(smem_u32(&tmem_holder), 512);
+    if (is_mma) tmem_alloc2(smem_u32(&tmem_holder), 512);
     for (int i = tid; i < C::C_FLOATS; i += NEMPC_WIDE_THREADS) cb[i] = cblk[i];
     fence_before_sync();
     __syncthreads();
+    cluster_sync_all();                                     // the peer's barriers are initialised before anything arrives on them
     fence_after_sync();
     const uint32_t tmem = tmem_holder;
     const uint32_t lane_off = (uint32_t)(32 * wq) << 16;
     const uint32_t ring = smem_u32(wide_smem + C::OFF_RING);
+    const uint32_t aready_leader = mapa_u32(bar_aready, 0);
 
     const bool unity = (ar.flags & NEMPC_UNITY) != 0;
     const int nhid = net.nhid;
@@ -217,49 +320,98 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     auto dreg = [&](uint32_t gg) { return (gg & 1u) ? 0u : 256u; };
 
     // ---- one GEMM, seen by the three roles -----------------------------------------------------------------------------------
-    // epilogue role: wait for the accumulator, run `epi(tensor-memory address of this lane quadrant's accumulator rows)`.
+    // epilogue role: `pre()` (work that does not need the accumulator: it overlaps the MMAs), wait for the accumulator, then
+    // `epi(tensor-memory address of this lane quadrant's accumulator rows)`.
     // The A operand of GEMM g must have been published (publish()) exactly once since GEMM g-1.
-    auto gemm = [&](const WideGemm& gm, auto&& epi) {
+    WPROF_DECL
+    auto gemm = [&](const WideGemm& gm, auto&& pre, auto&& epi) {
         if (is_prod) {
             if (lane == 0) {
-                for (uint32_t ks = 0; ks < gm.ksteps; ++ks, ++it) {
-                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
+                const uint32_t img = 16u * gm.n;                                               // one K-step image of this CTA's half of the rows
+                const unsigned char* src = blob + gm.off[rank];
+                for (uint32_t ks = 0; ks < gm.ksteps; ks += 2, ++it) {                         // pass 1: [hi | lo] of two K steps
+                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (ks + 1 < gm.ksteps ? 4u : 2u) * img;
                     mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
-                    mbar_expect_tx(bar_full(slot), gm.stage_bytes);
-                    bulk_g2s(ring + slot * C::STAGE_BYTES, blob + gm.off + (size_t)ks * gm.stage_bytes, gm.stage_bytes, bar_full(slot));
+                    WPROF(8);
+                    mbar_expect_tx(bar_full(slot), bytes);
+                    bulk_g2s(ring + slot * C::STAGE_BYTES, src, bytes, bar_full(slot));
+                    src += bytes;
+                    WPROF(9);
+                }
+                for (uint32_t ks = 0; ks < gm.ksteps; ks += 4, ++it) {                         // pass 2: 2^11 hi of four K steps
+                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (gm.ksteps - ks < 4u ? gm.ksteps - ks : 4u) * img;
+                    mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
+                    WPROF(8);
+                    mbar_expect_tx(bar_full(slot), bytes);
+                    bulk_g2s(ring + slot * C::STAGE_BYTES, src, bytes, bar_full(slot));
+                    src += bytes;
+                    WPROF(9);
                 }
             }
             __syncwarp();
         } else if (is_mma) {
-            if (lane == 0) {
+            if (lane == 0 && rank == 0) {
+                WPROF(2);
                 mbar_wait(bar_aready, g & 1u);
                 fence_after_sync();
+                WPROF(0); WPROF_COUNT(3);
                 const uint32_t ta = tmem + areg(g), td = tmem + dreg(g);
-                const uint32_t idesc = make_idesc_f16(128, (int)gm.n);
-                const uint32_t lbo = 16u * gm.n, img = 32u * gm.n;
-                for (uint32_t ks = 0; ks < gm.ksteps; ++ks, ++it) {
+                const uint32_t idesc = make_idesc_f16(256, (int)gm.n);
+                const uint32_t lbo = 8u * gm.n, img = 16u * gm.n;                               // per-CTA half: n / 2 rows
+                for (uint32_t ks = 0; ks < gm.ksteps; ks += 2, ++it) {                         // corrections first: the accumulator is still small
                     const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
                     mbar_wait(bar_full(slot), round & 1u);
                     fence_after_sync();
+                    WPROF(1);
                     const uint32_t sb = ring + slot * C::STAGE_BYTES;
-                    mma_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);                 // A_hi (2^11 W_hi)
-                    mma_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);           // A_lo W_hi
-                    mma_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);           // A_hi W_lo
-                    mma_commit(bar_empty(slot));
+                    mma2_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);          // A_lo W_hi
+                    mma2_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);               // A_hi W_lo
+                    if (ks + 1 < gm.ksteps) {
+                        mma2_f16_ts(td, ta + 16u * ks + 24u, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);
+                        mma2_f16_ts(td, ta + 16u * ks + 16u, make_desc_kmajor(sb + 3u * img, lbo, 128), idesc, 1);
+                    }
+                    mma2_commit(bar_empty(slot));
+                    WPROF(2);
                 }
-                mma_commit(bar_dready);
+                for (uint32_t ks = 0; ks < gm.ksteps; ks += 4, ++it) {                         // main products A_hi (2^11 W_hi)
+                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(bar_full(slot), round & 1u);
+                    fence_after_sync();
+                    WPROF(1);
+                    const uint32_t sb = ring + slot * C::STAGE_BYTES;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j)
+                        if (ks + j < gm.ksteps) mma2_f16_ts(td, ta + 16u * (ks + j), make_desc_kmajor(sb + j * img, lbo, 128), idesc, 1);
+                    mma2_commit(bar_empty(slot));
+                    WPROF(2);
+                }
+                mma2_commit(bar_dready);
+            } else if (lane == 0) {
+                // peer CTA: tell the leader when this CTA's half of a ring stage has landed
+                const uint32_t nst = (gm.ksteps + 1) / 2 + (gm.ksteps + 3) / 4;
+                for (uint32_t i = 0; i < nst; ++i, ++it) {
+                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(bar_full(slot), round & 1u);
+                    mbar_arrive_cluster(mapa_u32(bar_full(slot), 0));
+                }
             }
             __syncwarp();
         } else {
+            WPROF(7);
+            pre();
+            WPROF(4);
             mbar_wait(bar_dready, g & 1u);
             fence_after_sync();
+            WPROF(5);
             epi(tmem + dreg(g) + lane_off);
+            WPROF(6);
         }
         ++g;
     };
+    auto nopre = []() {};
     // epilogue role: this thread's part of the A operand of GEMM g (region areg(g)) is written
     auto publish = [&]() {
-        if (is_epi) { tmem_st_wait(); fence_before_sync(); mbar_arrive(bar_aready); }
+        if (is_epi) { tmem_st_wait(); fence_before_sync(); mbar_arrive_cluster(aready_leader); }
     };
     auto epi_sync = [&]() { if (is_epi) asm volatile("bar.sync 1, %0;" ::"n"(NEMPC_WIDE_EPI_WARPS * 32) : "memory"); };
     // K = 16 operand (one K step): hi pairs in columns [0, 8), lo pairs in [8, 16) of region areg(g); written by the quarter-0 warps
@@ -270,11 +422,30 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         tmem_st8(a, hi);
         tmem_st8(a + 8, lo);
     };
+    // the four 16-neuron chunks of this warp's quarter, the next chunk's accumulator in flight while `body(chunk, registers)` runs
+    auto chunks = [&](const uint32_t dbase, auto&& body) {
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(dbase + 64 * sub, va);
+        tmem_ld_wait(); tmem_ld_pin(va);
+        tmem_ld16_nowait(dbase + 64 * sub + 16, vb);
+        body(0, va);
+        tmem_ld_wait(); tmem_ld_pin(vb);
+        tmem_ld16_nowait(dbase + 64 * sub + 32, va);
+        body(1, vb);
+        tmem_ld_wait(); tmem_ld_pin(va);
+        tmem_ld16_nowait(dbase + 64 * sub + 48, vb);
+        body(2, va);
+        tmem_ld_wait(); tmem_ld_pin(vb);
+        body(3, vb);
+    };
 
+    // the pair works on super-tiles (2 i, 2 i + 1); both CTAs run the GEMM sequence of the fuller one (the leader's)
     const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
-    for (long long sup = blockIdx.x; sup < nsup; sup += gridDim.x) {
-        const long long step_base = sup * NEMPC_WIDE_SUP;
-        const int nvalid = (int)((ar.nsteps - step_base) < NEMPC_WIDE_SUP ? (ar.nsteps - step_base) : NEMPC_WIDE_SUP);
+    for (long long sup0 = 2 * (long long)(blockIdx.x >> 1); sup0 < nsup; sup0 += gridDim.x) {
+        const long long step_base = (sup0 + rank) * NEMPC_WIDE_SUP;
+        const long long left = ar.nsteps - step_base, left0 = ar.nsteps - sup0 * NEMPC_WIDE_SUP;
+        const int nvalid = (int)(left < 0 ? 0 : (left < NEMPC_WIDE_SUP ? left : NEMPC_WIDE_SUP));
+        const int nvalid_pair = (int)(left0 < NEMPC_WIDE_SUP ? left0 : NEMPC_WIDE_SUP);
 
         // ============================ phase A: primal forward, row = step ========================================================
         const long long stepA = step_base + row;
@@ -295,26 +466,29 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         }
         publish();
         for (int l = 0; l < nhid; ++l) {
-            gemm(l == 0 ? net.in_f : net.hid_f[l - 1], [&](const uint32_t dbase) {
-                const float* bl = bias + l * HW;
-#pragma unroll 1
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int col = 64 * sub + 16 * qq;
+            gemm(l == 0 ? net.in_f : net.hid_f[l - 1], nopre, [&](const uint32_t dbase) {
+                const float* bl = bias + l * HW + 64 * sub;
+                float* dst = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
+                chunks(dbase, [&](const int qq, const uint32_t* vr) {
                     float v[16];
-                    tmem_ld16(dbase + col, v);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(v[i], INV, bl[col + i]));
-                    st16_global(sh + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + col, v);
+                    for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(__uint_as_float(vr[i]), INV, bl[16 * qq + i]));
+                    if (HES) st16_global(dst + 16 * qq, v);                               // h_l: phase B needs it
+                    else if (JAC) {
+                        float s1[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) s1[i] = fmaf(-v[i], v[i], 1.f);
+                        st16_global(dst + 16 * qq, s1);                                   // s'(a_l) for phase C
+                    }
                     uint32_t hi[8], lo[8];
                     split16(v, hi, lo);
-                    tmem_st8(dbase + col, hi);
-                    tmem_st8(dbase + col + 8, lo);
-                }
+                    tmem_st8(dbase + 64 * sub + 16 * qq, hi);
+                    tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                });
             });
             publish();
         }
-        gemm(net.out_f, [&](const uint32_t dbase) {
+        gemm(net.out_f, nopre, [&](const uint32_t dbase) {
             if (sub != 0) return;
             float v[16];
             tmem_ld16(dbase, v);
@@ -344,30 +518,30 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
             }
             publish();
             for (int l = nhid - 1; l >= 0; --l) {
-                // accumulator = g_l (adjoint with respect to h_l);  q_l = -2 h_l g_l -> scratch;  next operand u_l = s'(a_l) g_l
-                gemm(l == nhid - 1 ? net.out_b : net.hid_b[l], [&](const uint32_t dbase) {
-#pragma unroll 1
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int col = 64 * sub + 16 * qq;
-                        float v[16], h[16];
-                        tmem_ld16(dbase + col, v);
-                        ld16_global_cg(sh + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + col, h);
-                        tmem_ld_wait();
-                        float qv[16];
+                // accumulator = g_l (adjoint with respect to h_l);  s'(a_l) -> sa (over h_l),  s''(a_l) g_l = -2 h_l s'(a_l) g_l -> sq;
+                // next operand u_l = s'(a_l) g_l
+                gemm(l == nhid - 1 ? net.out_b : net.hid_b[l], nopre, [&](const uint32_t dbase) {
+                    float* ph = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
+                    float* pq = sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
+                    chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                        float h[16], u[16], cf[16];
+                        ld16_global_cg(ph + 16 * qq, h);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float gl = v[i] * INV;
-                            qv[i] = -2.f * h[i] * gl;
-                            v[i] = fmaf(-h[i], h[i], 1.f) * gl;
+                            const float hv = h[i], s1 = fmaf(-hv, hv, 1.f);
+                            u[i] = s1 * (__uint_as_float(vr[i]) * INV);
+                            cf[i] = -2.f * hv * u[i];
+                            h[i] = s1;
                         }
-                        st16_global(sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + col, qv);
+                        st16_global(ph + 16 * qq, h);
+                        st16_global(pq + 16 * qq, cf);
                         if (l > 0) {
                             uint32_t hi[8], lo[8];
-                            split16(v, hi, lo);
-                            tmem_st8(dbase + col, hi);
-                            tmem_st8(dbase + col + 8, lo);
+                            split16(u, hi, lo);
+                            tmem_st8(dbase + 64 * sub + 16 * qq, hi);
+                            tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
                         }
-                    }
+                    });
                 });
                 if (l > 0) publish();
             }
@@ -376,9 +550,10 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
 
         // ============================ phase C: tangent forward (+ curvature), row = (step, tangent column) =========================
         if (JAC) {
-            const int ntile = (nvalid + SPT - 1) / SPT;
+            const int ntile = (nvalid_pair + SPT - 1) / SPT;
             for (int ti = 0; ti < ntile; ++ti) {
                 const int sidx = ti * SPT + row / DP, cc = row % DP;          // step inside the super-tile, tangent column
+                const int sidx0 = ti * SPT + (32 * wq) / DP;                  // first step of this warp
                 const bool validC = is_epi && sidx < nvalid && cc < D;
                 f2 acc[16];
 #pragma unroll
@@ -391,34 +566,45 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 }
                 publish();
                 for (int l = 0; l < nhid; ++l) {
-                    gemm(l == 0 ? net.in_f : net.hid_f[l - 1], [&](const uint32_t dbase) {
-#pragma unroll 1
-                        for (int qq = 0; qq < 4; ++qq) {
-                            const int col = 64 * sub + 16 * qq;
-                            float v[16], h[16];
-                            tmem_ld16(dbase + col, v);
-                            ld16_global_cg(sh + ((long long)sidx * NEMPC_WIDE_MAXHID + l) * HW + col, h);
-                            tmem_ld_wait();
+                    gemm(l == 0 ? net.in_f : net.hid_f[l - 1],
+                         [&]() {
+                             // while the MMAs run: this warp's s'(a_l) (x 2^-11: the accumulator's scale) and curvature coefficients (x 2^-22) of
+                             // its SPW steps and 64 neurons, global scratch -> warp-private shared memory
+                             for (int i = lane; i < SPW * 16; i += 32) {
+                                 const int sw = i >> 4, f4 = i & 15;
+                                 const long long o = ((long long)(sidx0 + sw) * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub + 4 * f4;
+                                 float4 a = __ldcg(reinterpret_cast<const float4*>(sa + o));
+                                 a.x *= INV; a.y *= INV; a.z *= INV; a.w *= INV;
+                                 *reinterpret_cast<float4*>(scs + sw * 64 + 4 * f4) = a;
+                                 if (HES) {
+                                     float4 q = __ldcg(reinterpret_cast<const float4*>(sq + o));
+                                     q.x *= INV * INV; q.y *= INV * INV; q.z *= INV * INV; q.w *= INV * INV;
+                                     *reinterpret_cast<float4*>(scs + (SPW + sw) * 64 + 4 * f4) = q;
+                                 }
+                             }
+                             __syncwarp();
+                         },
+                         [&](const uint32_t dbase) {
+                             const float* s1row = scs + (lane / DP) * 64;
+                             chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                                 if (HES) gram_chunk<DP>(stg, vr, scs + SPW * 64, 16 * qq, acc, lane);      // raw tangent T_l (x 2^11)
+                                 f2 v2[8];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) { v[i] *= INV; h[i] = fmaf(-h[i], h[i], 1.f); }          // raw tangent T_l, s'(a_l)
-                            if (HES) {
-                                float cf[16];
-                                ld16_global_cg(sq + ((long long)sidx * NEMPC_WIDE_MAXHID + l) * HW + col, cf);
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) cf[i] *= h[i];                                          // s''(a_l) g_l
-                                gram_chunk<DP>(stg, v, cf, acc, lane);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= h[i];                                               // V_l
-                            uint32_t hi[8], lo[8];
-                            split16(v, hi, lo);
-                            tmem_st8(dbase + col, hi);
-                            tmem_st8(dbase + col + 8, lo);
-                        }
-                    });
+                                 for (int i4 = 0; i4 < 4; ++i4) {
+                                     const float4 s4 = *reinterpret_cast<const float4*>(s1row + 16 * qq + 4 * i4);
+                                     v2[2 * i4] = mul2(pk(__uint_as_float(vr[4 * i4]), __uint_as_float(vr[4 * i4 + 1])), pk(s4.x, s4.y));       // V_l = s'(a_l) T_l
+                                     v2[2 * i4 + 1] = mul2(pk(__uint_as_float(vr[4 * i4 + 2]), __uint_as_float(vr[4 * i4 + 3])), pk(s4.z, s4.w));
+                                 }
+                                 uint32_t hi[8], lo[8];
+                                 split16p(v2, hi, lo);
+                                 tmem_st8(dbase + 64 * sub + 16 * qq, hi);
+                                 tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                             });
+                             __syncwarp();                                      // `scs` is rewritten for the next layer
+                         });
                     publish();
                 }
-                gemm(net.out_f, [&](const uint32_t dbase) {
+                gemm(net.out_f, nopre, [&](const uint32_t dbase) {
                     if (sub != 0) return;
                     float v[16];
                     tmem_ld16(dbase, v);
@@ -439,6 +625,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 });
                 if (HES) {
                     // ---- sum the four neuron quarters, scatter the lower triangle (same slots as nempc_generic.cuh) -----------------
+                    epi_sync();                                    // `part` aliases the staging planes: every warp is done with its curvature
                     if (is_epi) {
                         constexpr int NB = DP / 4, LPS = NB * NB, ACTIVE = (32 / DP) * LPS;
                         if (lane < ACTIVE) {
@@ -498,8 +685,10 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         epi_sync();                                                // the scratch is rewritten by the next super-tile
     }
 
+    WPROF_FLUSH;
     fence_before_sync();
     __syncthreads();
-    if (is_mma) tmem_dealloc(tmem, 512);
+    cluster_sync_all();                                     // nobody leaves (or frees tensor memory) while the peer may still use this CTA
+    if (is_mma) tmem_dealloc2(tmem, 512);
 }
 #endif  // __CUDACC__

@@ -78,6 +78,14 @@ def timing(B, H=200, integ="discrete", reps=3):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
+        if hasattr(ev.lib, "nempc_debug_wide_profile"):
+            import ctypes
+            buf = (ctypes.c_ulonglong * 16)()
+            ev.lib.nempc_debug_wide_profile(buf)
+            v = [int(x) for x in buf]
+            ng = max(1, v[3])
+            names = ["iss wait A", "iss wait ring", "iss issue", "gemms", "epi pre", "epi wait D", "epi body", "epi between", "prod wait slot", "prod issue"]
+            print("   profile (cycles per GEMM, all launches since the last read): " + ", ".join(f"{n} {x / ng:.0f}" for n, x in zip(names, v[:10]) if n != "gemms") + f"; GEMMs {ng}")
         print(f"C4-shape {integ} B={B} H={H} want={'+'.join(want):14s}: {ms:9.3f} ms  {B * H / ms * 1e3:.3e} steps/s  "
               f"{ev.flops_per_step * B * H / ms / 1e9:.1f} TFLOP/s algorithmic (Jac+Hes count)", flush=True)
     ev.close()
