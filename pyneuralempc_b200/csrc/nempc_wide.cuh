@@ -74,7 +74,7 @@ template <int X_, int U_, int MODE_> struct WideCfg {
     static constexpr int NTILE = NEMPC_WIDE_SUP / SPT;                   // phase-C tiles per super-tile
     static constexpr int STAGE_BYTES = 128 * (HW / 2);                   // four K-step images of one CTA's half of the B rows
     static constexpr int C_FLOATS = NEMPC_WIDE_MAXHID * HW + 16;        // biases, output bias
-    static constexpr int STG_WARP = HES ? 4 * 40 * 16 : 0;              // per-warp staging of a 32-row x 16-neuron chunk of T_l (4 planes of 40 granules)
+    static constexpr int STG_WARP = HES ? 4 * 32 * 16 : 0;              // per-warp staging of a 32-row x 16-neuron chunk of T_l (4 planes of 32 granules)
     static constexpr int SPW = 32 / DP;                                  // steps per epilogue warp in phase C
     static constexpr int SC_WARP = JAC ? (HES ? 2 : 1) * SPW * 64 * 4 : 0;   // per-warp copy of s'(a_l) (and the curvature coefficients) of its steps and neuron quarter
     static constexpr int PART_BYTES = HES ? 4 * SPT * DP * DP * 4 : 0;  // [4 quarters][SPT][DP][DP] partial curvature: aliases the staging area
@@ -97,6 +97,12 @@ template <int X_, int U_, int MODE_> struct WideCfg {
 namespace widex {
 using namespace tcx;
 
+// one lane of a converged warp (the branch on it keeps the surrounding values in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
 
 // ---- CTA pair (cluster of two, cta_group::2) ------------------------------------------------------------------------------------
@@ -205,22 +211,24 @@ __device__ __forceinline__ void st16_global(float* p, const float* v) {
 
 // curvature of one 16-neuron chunk: acc[i][i'] += sum_j coef_j T[4 bi + i][j] T[4 bj + i'][j] for the lane's 4x4 block (bi, bj) of
 // its step.  T = this lane's accumulator row (any common scale: `cfs` carries its inverse square) is exchanged through the warp's
-// staging planes (granule of row r at r + r / 4: the eight rows one load instruction touches fall in eight different 16-byte bank
-// groups); cfs = shared-memory rows [step of the warp][64 neurons of the warp's quarter] of the coefficients, cc0 = first neuron.
+// staging planes (32 granules of 16 bytes per plane, row r at granule r ^ 2 [r / 8 odd]: the eight consecutive rows of a store phase
+// and the rows 4 apart of a load phase fall in different 16-byte bank groups); cfs = shared-memory rows [step of the warp][64 neurons of the warp's quarter] of the coefficients, cc0 = first neuron.
 template <int DP>
 __device__ __forceinline__ void gram_chunk(float* stg, const uint32_t* T, const float* cfs, const int cc0, f2* acc, const int lane) {
     constexpr int NB = DP / 4, LPS = NB * NB, ACTIVE = (32 / DP) * LPS;
     {
-        const int p = lane + (lane >> 2);
+        const int p = lane ^ ((lane >> 2) & 2);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + (g * 40 + p) * 4) = make_uint4(T[4 * g], T[4 * g + 1], T[4 * g + 2], T[4 * g + 3]);
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + (g * 32 + p) * 4) = make_uint4(T[4 * g], T[4 * g + 1], T[4 * g + 2], T[4 * g + 3]);
     }
     __syncwarp();
     if (lane < ACTIVE) {
         const int sw = lane / LPS, bl = lane % LPS, bi = bl / NB, bj = bl % NB;
         const int ra = DP * sw + 4 * bi, rb = DP * sw + 4 * bj;
-        const float* pa = stg + (ra + (ra >> 2)) * 4;
-        const float* pb = stg + (rb + (rb >> 2)) * 4;
+        // rows ra + i, i < 4, sit at granules ra + (i ^ swz): two runs of two consecutive granules
+        const int sza = (ra >> 2) & 2, szb = (rb >> 2) & 2;
+        const float* pa[2] = {stg + (ra + sza) * 4, stg + (ra + (2 ^ sza)) * 4};
+        const float* pb[2] = {stg + (rb + szb) * 4, stg + (rb + (2 ^ szb)) * 4};
         const float* cf = cfs + sw * 64 + cc0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -229,9 +237,9 @@ __device__ __forceinline__ void gram_chunk(float* stg, const uint32_t* T, const 
             f2 ua[4], ub[4], b0[4], b1[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 a4 = *reinterpret_cast<const float4*>(pa + (g * 40 + i) * 4);
+                const float4 a4 = *reinterpret_cast<const float4*>(pa[i >> 1] + (g * 32 + (i & 1)) * 4);
                 ua[i] = mul2(pk(a4.x, a4.y), c01); ub[i] = mul2(pk(a4.z, a4.w), c23);
-                const float4 b4 = *reinterpret_cast<const float4*>(pb + (g * 40 + i) * 4);
+                const float4 b4 = *reinterpret_cast<const float4*>(pb[i >> 1] + (g * 32 + (i & 1)) * 4);
                 b0[i] = pk(b4.x, b4.y); b1[i] = pk(b4.z, b4.w);
             }
 #pragma unroll
@@ -350,7 +358,8 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
             }
             __syncwarp();
         } else if (is_mma) {
-            if (lane == 0 && rank == 0) {
+            if (rank == 0) {
+                // the whole warp runs the loop (converged: operands stay in uniform registers), one elected lane issues
                 WPROF(2);
                 mbar_wait(bar_aready, g & 1u);
                 fence_after_sync();
@@ -364,13 +373,16 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     fence_after_sync();
                     WPROF(1);
                     const uint32_t sb = ring + slot * C::STAGE_BYTES;
-                    mma2_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);          // A_lo W_hi
-                    mma2_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);               // A_hi W_lo
-                    if (ks + 1 < gm.ksteps) {
-                        mma2_f16_ts(td, ta + 16u * ks + 24u, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);
-                        mma2_f16_ts(td, ta + 16u * ks + 16u, make_desc_kmajor(sb + 3u * img, lbo, 128), idesc, 1);
+                    if (elect_one()) {
+                        mma2_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);      // A_lo W_hi
+                        mma2_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);           // A_hi W_lo
+                        if (ks + 1 < gm.ksteps) {
+                            mma2_f16_ts(td, ta + 16u * ks + 24u, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);
+                            mma2_f16_ts(td, ta + 16u * ks + 16u, make_desc_kmajor(sb + 3u * img, lbo, 128), idesc, 1);
+                        }
+                        mma2_commit(bar_empty(slot));
                     }
-                    mma2_commit(bar_empty(slot));
+                    __syncwarp();
                     WPROF(2);
                 }
                 for (uint32_t ks = 0; ks < gm.ksteps; ks += 4, ++it) {                         // main products A_hi (2^11 W_hi)
@@ -379,13 +391,17 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     fence_after_sync();
                     WPROF(1);
                     const uint32_t sb = ring + slot * C::STAGE_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j)
-                        if (ks + j < gm.ksteps) mma2_f16_ts(td, ta + 16u * (ks + j), make_desc_kmajor(sb + j * img, lbo, 128), idesc, 1);
-                    mma2_commit(bar_empty(slot));
+                        for (uint32_t j = 0; j < 4; ++j)
+                            if (ks + j < gm.ksteps) mma2_f16_ts(td, ta + 16u * (ks + j), make_desc_kmajor(sb + j * img, lbo, 128), idesc, 1);
+                        mma2_commit(bar_empty(slot));
+                    }
+                    __syncwarp();
                     WPROF(2);
                 }
-                mma2_commit(bar_dready);
+                if (elect_one()) mma2_commit(bar_dready);
+                __syncwarp();
             } else if (lane == 0) {
                 // peer CTA: tell the leader when this CTA's half of a ring stage has landed
                 const uint32_t nst = (gm.ksteps + 1) / 2 + (gm.ksteps + 3) / 4;
