@@ -9,13 +9,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+from parity_metric import elem_err  # noqa: E402
+
 from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem  # noqa: E402
 from oracle.mlp_np import MLP, DenseModelView  # noqa: E402
 from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
 
 
 def _rel(a, b):
-    return float(np.abs(np.asarray(a) - b).max()) / max(1.0, float(np.abs(b).max()))
+    return elem_err(a, b)        # elementwise: |d| <= tol |ref| + 0.1 tol max|ref| (tests/parity_metric.py)
 
 
 def test_model_dense_layouts(lv_weights):

@@ -7,6 +7,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+from parity_metric import elem_err  # noqa: E402
+
 from oracle.blocks_np import BlockEvaluator  # noqa: E402
 from oracle.mlp_np import MLP, ExoMLP  # noqa: E402
 from oracle.objectives_np import SeparableQuadraticObjective  # noqa: E402
@@ -15,7 +17,7 @@ TOL32, TOL64 = 1e-5, 1e-10
 
 
 def _relerr(got, ref):
-    return float(np.abs(np.asarray(got) - ref).max()) / max(1.0, float(np.abs(ref).max()))
+    return elem_err(got, ref)    # elementwise: |d| <= tol |ref| + 0.1 tol max|ref| (tests/parity_metric.py)
 
 
 def _exo(xd, ud, td, pd, hidden, seed):
