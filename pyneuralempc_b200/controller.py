@@ -111,6 +111,9 @@ class BatchedNMPC:
             self.ev.set_exogenous(tvp, p)
         else:
             assert p is None and tvp is None, "the model declares no p / tvp input"
+        if self.ev.bound_to is not self:               # another problem / controller used the shared evaluator since: put our cost back
+            self.ev.set_objective(self.objective_func.lin, self.objective_func.quad, self.objective_func.ref)
+            self.ev.bound_to = self
         z0 = None
         if self.warm_start and self._prev is not None and self._prev.shape[0] == X0.shape[0]:
             z0 = self._shifted(self._prev)

@@ -67,6 +67,7 @@ class NlpEvaluator:
         self.tdtype = torch.float64 if self.io_dtype == "float64" else torch.float32
         self.tdevice = torch.device("cuda", self.device)
         self._objective = None
+        self.exo_token, self.bound_to = None, None      # see set_exogenous / CudaIpoptProblem._bind
         self._refresh_dims()
         self._pinned = {}
 
@@ -103,6 +104,9 @@ class NlpEvaluator:
         ta, tr, tp = prep(tvp, self.tvp_dim, "tvp")
         pa, pr, pp = prep(p, self.p_dim, "p")
         self._check(self.lib.nempc_set_exogenous(self._h, tr, tp, pr, pp), "nempc_set_exogenous")
+        # whoever memoised "my rows are the ones on the device" (Integrator._set_exogenous, CudaIpoptProblem._bind) must look again
+        self.exo_token = object()
+        self.bound_to = None
 
     # ---- lifetime / errors ------------------------------------------------------------------------------
     def _check(self, rc, what):
@@ -138,6 +142,7 @@ class NlpEvaluator:
         p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         self._check(self.lib.nempc_set_objective(self._h, p(arrs[0]), p(arrs[1]), p(arrs[2])), "nempc_set_objective")
         self._objective = arrs
+        self.bound_to = None                  # a problem that bound its cost to this evaluator re-binds at its next evaluation
         self._refresh_dims()
 
     @property

@@ -69,7 +69,7 @@ class _CudaIntegrator(Integrator):
                                       activation=model.activation, compute_dtype=model.dtype, io_dtype="float64",
                                       device=model.device, kernel=model.kernel,
                                       tvp_dim=model.tvp_dim or 0, p_dim=model.p_dim or 0)
-        self._exo_key = None
+        self._exo_key, self._exo_token = None, None
 
     def _set_exogenous(self, p, tvp):
         """hand the model's tvp (H, tvp_dim) / p (p_dim,) rows to the evaluator when they changed (they are fixed during one solve:
@@ -82,9 +82,9 @@ class _CudaIntegrator(Integrator):
         tvp = None if tvp is None else np.asarray(tvp, np.float64).reshape(self.H, m.tvp_dim)
         p = None if p is None else np.asarray(p, np.float64).reshape(m.p_dim)
         key = (b"" if tvp is None else tvp.tobytes()) + b"|" + (b"" if p is None else p.tobytes())
-        if key != self._exo_key:
-            self.evaluator.set_exogenous(tvp, p)
-            self._exo_key = key
+        if key != self._exo_key or getattr(self.evaluator, "exo_token", None) is not self._exo_token:
+            self.evaluator.set_exogenous(tvp, p)          # also when somebody else (another problem, BatchedNMPC) replaced the rows
+            self._exo_key, self._exo_token = key, self.evaluator.exo_token
             self._cache = []
 
     # ---- helpers --------------------------------------------------------------------------------------------

@@ -24,7 +24,6 @@ class CudaIpoptProblem(ProblemInterface):
         super().__init__(use_hessian)
         if not hasattr(integrator, "evaluator"):
             raise ValueError("CudaIpoptProblem needs a CUDA integrator (pyneuralempc_b200.integrator)")
-        integrator._set_exogenous(p, tvp)          # model inputs that stay fixed during this solve (controller.py:65-113)
         self.x0 = np.asarray(x0, np.float64)
         self.objective_func = objective_func
         self.constraints_list = list(constraints)
@@ -36,11 +35,11 @@ class CudaIpoptProblem(ProblemInterface):
         self.init_x, self.init_u = init_x, init_u
         self.sparse_jacobian = sparse_jacobian
         self.ev = integrator.evaluator
+        self._key, self._point = None, None
         self._device_objective = isinstance(objective_func, CudaSeparableObjective)
-        if self._device_objective:
-            self.ev.set_objective(objective_func.lin, objective_func.quad, objective_func.ref)
-        elif use_hessian:
+        if not self._device_objective and use_hessian:
             raise NotImplementedError("the Lagrangian-Hessian path needs a CudaSeparableObjective")
+        self._bind()
         # extra (user, host-side) constraints: rows appended after the integrator's, ipopt.py:49-50, 93-94; their Jacobian rows are dense
         self._extra_dims = [int(np.size(c.get_lower_bounds(self.H))) for c in self.constraints_list]
         self._key, self._point = None, None
@@ -50,7 +49,19 @@ class CudaIpoptProblem(ProblemInterface):
         nx = self.x_dim * self.H
         return x[:nx].reshape(self.H, self.x_dim), x[nx:nx + self.u_dim * self.H].reshape(self.H, self.u_dim), self.tvp, self.p
 
+    def _bind(self):
+        """The cost and the p / tvp rows are state of the integrator's ONE shared evaluator: a problem built earlier and evaluated after
+        another problem (or a BatchedNMPC) used the evaluator puts its own back before it evaluates."""
+        if getattr(self.ev, "bound_to", None) is self:
+            return
+        self.integrator._set_exogenous(self.p, self.tvp)       # model inputs that stay fixed during this solve (controller.py:65-113)
+        if self._device_objective:
+            self.ev.set_objective(self.objective_func.lin, self.objective_func.quad, self.objective_func.ref)
+        self.ev.bound_to = self
+        self._key, self._point = None, None
+
     def _at(self, x):
+        self._bind()
         x = np.ascontiguousarray(x, np.float64)
         key = x.tobytes()
         if key != self._key:
@@ -106,6 +117,7 @@ class CudaIpoptProblem(ProblemInterface):
         return self.ev.hes_rows.astype(np.int64), self.ev.hes_cols.astype(np.int64)
 
     def hessian(self, x, lagrange, obj_factor):                   # ipopt.py:66-86
+        self._bind()
         x = np.ascontiguousarray(x, np.float64)
         out = self.ev.eval_host(x, self.x0, lam=np.asarray(lagrange, np.float64)[: self.ev.m], obj_factor=float(obj_factor),
                                 want=("hes",))

@@ -34,32 +34,39 @@ class SlsqpProblem(CudaIpoptProblem):
             self.debug_u.append(u.copy())
         return super().objective(x)
 
-    def constraints(self, x, eq=True):                          # slsqp.py:54-72 (integrator rows are the equalities)
-        if eq:
-            return super().constraints(x)
+    def _integrator_rows_dense(self, x):
+        pt = self._at(x)
+        J = np.zeros((self.ev.m, self.ev.n))
+        J[self.ev.jac_rows, self.ev.jac_cols] = pt["jac"]
+        return J
+
+    def constraints(self, x, eq=True):                          # slsqp.py:54-72
+        # eq block = integrator residual + the user's EQ_TYPE constraints ONLY; INEQ / INTER rows go to the 'ineq' block
         s, u, tvp, p = self._split(np.asarray(x))
-        rows = []
+        rows = [self._at(x)["resid"]] if eq else []
         for c in self.constraints_list:
             t = c.get_type(self.H)
-            if t == Constraint.INEQ_TYPE:
-                rows.append(c.forward(s, u, p=p, tvp=tvp))
-            elif t == Constraint.INTER_TYPE:
-                rows.append(c.forward(s, u, p=p, tvp=tvp) - c.get_lower_bounds(self.H))
-                rows.append(-c.forward(s, u, p=p, tvp=tvp) + c.get_upper_bounds(self.H))
+            if eq and t == Constraint.EQ_TYPE:
+                rows.append(np.asarray(c.forward(s, u, p=p, tvp=tvp), np.float64))
+            elif not eq and t == Constraint.INEQ_TYPE:
+                rows.append(np.asarray(c.forward(s, u, p=p, tvp=tvp), np.float64))
+            elif not eq and t == Constraint.INTER_TYPE:
+                rows.append(c.forward(s, u, p=p, tvp=tvp) - np.asarray(c.get_lower_bounds(self.H), np.float64))
+                rows.append(-c.forward(s, u, p=p, tvp=tvp) + np.asarray(c.get_upper_bounds(self.H), np.float64))
         return np.concatenate(rows, axis=0)
 
     def jacobian(self, x, eq=True):                             # slsqp.py:82-100
-        if eq:
-            return super().jacobian(x)
         s, u, tvp, p = self._split(np.asarray(x))
-        rows = []
+        rows = [self._integrator_rows_dense(x)] if eq else []
         for c in self.constraints_list:
             t = c.get_type(self.H)
-            if t == Constraint.INEQ_TYPE:
-                rows.append(c.jacobian(s, u, p=p, tvp=tvp))
-            elif t == Constraint.INTER_TYPE:
-                rows.append(c.jacobian(s, u, p=p, tvp=tvp))
-                rows.append(-c.jacobian(s, u, p=p, tvp=tvp))
+            if eq and t == Constraint.EQ_TYPE:
+                rows.append(np.asarray(c.jacobian(s, u, p=p, tvp=tvp), np.float64))
+            elif not eq and t == Constraint.INEQ_TYPE:
+                rows.append(np.asarray(c.jacobian(s, u, p=p, tvp=tvp), np.float64))
+            elif not eq and t == Constraint.INTER_TYPE:
+                rows.append(np.asarray(c.jacobian(s, u, p=p, tvp=tvp), np.float64))
+                rows.append(-np.asarray(c.jacobian(s, u, p=p, tvp=tvp), np.float64))
         return np.concatenate(rows, axis=0)
 
     def get_constraints_dict(self):                             # slsqp.py:102-110
@@ -108,14 +115,14 @@ class Slsqp(Optimizer):
             warnings.warn("Process do not converge ! ")
             if self.debug:
                 return Optimizer.FAIL
-            if np.max(problem.constraints(res.x)) > 1e-5:                        # slsqp.py:184-194
+            if np.max(problem.constraints(res.x, eq=True)) > 1e-5:               # slsqp.py:184-194 (equality rows only)
                 x0 = np.asarray(problem.get_init_value(), np.float64)
                 cold = np.concatenate([np.tile(x0, H), np.zeros(problem.integrator.model.u_dim * H)])
                 for i in range(self.nb_max_try):
                     res = self._run(problem, cold, bounds, self.tolerance * (2.0 ** i))
-                    if np.max(problem.constraints(res.x)) < 1e-5 or res.success:
+                    if np.max(problem.constraints(res.x, eq=True)) < 1e-5 or res.success:
                         break
-            if not res.success and np.max(problem.constraints(res.x)) > 1e-5:
+            if not res.success and np.max(problem.constraints(res.x, eq=True)) > 1e-5:
                 return Optimizer.FAIL
         self.prev_result = res.x
         self.last_result = res

@@ -15,6 +15,13 @@ What is recorded (all float64 unless noted):
   ref_constraints_H6.npz  IpoptProblem callbacks with one extra InequalityConstraint that has a Hessian (ipopt.py:49-50, 75-80, 93-94)
   ref_exo_H6.npz          tvp / p inputs: network over [x, u, tvp, p] (2+1+2+1 -> 8 -> 8 -> 2) through the reference's Discret /
                           Unity / RK4 integrators called with ``p=, tvp=`` (integrator/rk4.py:69-72, discret.py:27,48,64)
+  ref_rk4_w128_H6.npz     3 -> 128 -> 128 -> 2 network (float32 weights, regenerated from the recorded seed) through the reference's RK4
+                          integrator + IpoptProblem: pins the tcgen05 kernel of nempc_tc.cuh (TcCfg<2,1,2,...,128>) to the reference
+  ref_discrete_w256_H6.npz  5 -> 256 -> 256 -> 256 -> 4 network through the reference's DiscretIntegrator + IpoptProblem: pins the
+                          width-256 kernel of nempc_wide.cuh to the reference (its RK4 Hessian only runs for x_dim + u_dim == 3)
+  ref_closed_loop_c1.npz  BASELINE config C1 as named (examples/lotka_volterra/run.py:38-87): the reference's own NMPC.next with its Slsqp
+                          optimizer, H = 25, cost 1.1 * sum(u), u in [-1, 0.2], x_0 <= 1, LV fixture network, discrete and RK4 (DT 0.1)
+                          integrators: iteration count, final cost, solution
 The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
 reference's ``Model`` (TensorFlow is not installed), so these files pin the integrator / IPOPT
 glue of the oracle, not TensorFlow's autodiff.
@@ -177,6 +184,51 @@ def record_constraints(ref, lv, H=6, seed=600):
                 hessian_values=pb.hessian(z, lam, sigma), cl=pb.get_constraint_lower_bounds(), cu=pb.get_constraint_upper_bounds())
 
 
+def record_wide(ref, dims, xd, ud, kind, H, seed, net_seed):
+    """a wide network (weights NOT stored: MLP.glorot(dims, seed=net_seed, float32) regenerates them, `weights_checksum` guards it)
+    through the reference's integrator + IpoptProblem"""
+    mlp = MLP.glorot(dims, xd, ud, seed=net_seed, dtype=np.float32)
+    out = record(ref, mlp.astype(np.float64), kind, H, seed, "tracking", False)
+    out.update(dims=np.array(dims), net_seed=net_seed,
+               weights_checksum=float(sum(np.abs(np.asarray(W, np.float64)).sum() + np.abs(np.asarray(b, np.float64)).sum() for W, b in mlp.weights)))
+    return out
+
+
+def record_closed_loop_c1(ref, lv, H=25):
+    """the reference's NMPC.next + Slsqp on C1 as the shipped script names it (run.py:38-54, 72-87)"""
+    import scipy
+    from scipy.optimize import minimize as sp_minimize
+    out = dict(H=H, DT=DT_RK4, x0=np.array([0.66, -0.9]), scipy_version=scipy.__version__)
+    sep = SeparableQuadraticObjective.linear_in_u(H, 2, 1, 1.1)                        # run.py:80-87: sum(u * 1.1)
+    dom = ref.constraints.DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])
+    seen = []
+
+    def spy(*a, **kw):
+        r = sp_minimize(*a, **kw)
+        seen.append(r)
+        return r
+
+    ref.optimizer.slsqp.minimize = spy
+    try:
+        for kind in ("discrete", "rk4", "unity"):           # unity: the well-posed transcription for this next-state network
+            del seen[:]
+            integ = make_integrator(ref, kind, shim.make_reference_model(lv), H)
+            opt = ref.optimizer.slsqp.Slsqp(verbose=0)
+            mpc = ref.controller.NMPC(integ, ref_objective(ref, sep), [dom], H, DT_RK4, optimizer=opt)
+            xs, us = mpc.next(out["x0"])
+            r = seen[-1]
+            out.update({f"{kind}_nit": r.nit, f"{kind}_fun": r.fun, f"{kind}_success": bool(r.success), f"{kind}_minimize_calls": len(seen),
+                        f"{kind}_returned_none": xs is None, f"{kind}_z": np.asarray(r.x),
+                        f"{kind}_all_nit": np.array([q.nit for q in seen]), f"{kind}_all_fun": np.array([q.fun for q in seen]),
+                        f"{kind}_all_status": np.array([q.status for q in seen]),
+                        f"{kind}_eq_violation": float(np.abs(integ.forward(r.x[:2 * H].reshape(H, 2), r.x[2 * H:].reshape(H, 1), out["x0"])).max())})
+            if xs is not None:
+                out.update({f"{kind}_x": np.asarray(xs), f"{kind}_u": np.asarray(us)})
+    finally:
+        ref.optimizer.slsqp.minimize = sp_minimize
+    return out
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -218,6 +270,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_discrete_d5_H5.npz"), **out)
     np.savez_compressed(os.path.join(HERE, "ref_exo_H6.npz"), **record_exo(ref))
     np.savez_compressed(os.path.join(HERE, "ref_constraints_H6.npz"), **record_constraints(ref, lv))
+    np.savez_compressed(os.path.join(HERE, "ref_rk4_w128_H6.npz"), **record_wide(ref, [3, 128, 128, 2], 2, 1, "rk4", 6, 700, 21))
+    np.savez_compressed(os.path.join(HERE, "ref_discrete_w256_H6.npz"), **record_wide(ref, [5, 256, 256, 256, 4], 4, 1, "discrete", 6, 710, 22))
+    np.savez_compressed(os.path.join(HERE, "ref_closed_loop_c1.npz"), **record_closed_loop_c1(ref, lv))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

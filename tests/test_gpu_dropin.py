@@ -323,3 +323,152 @@ def test_trust_constr_with_a_binding_extra_constraint(lv_weights):
     assert opt.last_result.constr_violation < 1e-8
     with pytest.raises(NotImplementedError):
         NMPC(integ, obj, [dom, SmallControl()], H, 0.1, optimizer=CudaIpm()).next(x0)
+
+
+def _c1_problem(lv_weights, kind, H=25):
+    """BASELINE config C1 as the shipped script names it (examples/lotka_volterra/run.py:38-54, 72-87): LV fixture network, H = 25,
+    cost 1.1 * sum(u), u in [-1, 0.2], x_0 <= 1, start state (0.66, -0.9); discrete or RK4 (DT 0.1) integrator"""
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.constraints import DomainConstraint
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaSeparableObjective
+    model = CudaMLPModel(lv_weights, 2, 1, dtype="float64")
+    integ = {"discrete": lambda: I.DiscretIntegrator(model, H), "unity": lambda: I.UnityIntegrator(model, H),
+             "rk4": lambda: I.RK4Integrator(model, H, 0.1)}[kind]()
+    sep = SeparableQuadraticObjective.linear_in_u(H, 2, 1, 1.1)
+    obj = CudaSeparableObjective(sep.lin, sep.quad, sep.ref)
+    dom = DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])
+    return integ, obj, dom
+
+
+@pytest.mark.parametrize("kind", ("discrete", "rk4", "unity"))
+def test_closed_loop_c1_as_named_matches_the_reference_run(golden_dir, lv_weights, kind):
+    """tests/golden/ref_closed_loop_c1.npz holds what the UNMODIFIED reference's NMPC.next + Slsqp did on C1: with the discrete and the
+    RK4 integrator SLSQP stops with status 8 after 65 / 51 iterations in each of its 1 + 15 attempts and NMPC.next returns (None, None)
+    (the fixture network predicts the NEXT state: only the unity transcription is well posed, 11 iterations).  The CUDA callbacks have
+    to reproduce the run: same number of minimize calls, same iteration counts, same final cost within 1e-6, same outcome."""
+    import scipy.optimize
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import Slsqp
+    from pyneuralempc_b200.optimizer import slsqp as slsqp_mod
+    g = np.load(os.path.join(golden_dir, "ref_closed_loop_c1.npz"))
+    H = int(g["H"])
+    integ, obj, dom = _c1_problem(lv_weights, kind, H)
+    seen = []
+
+    def spy(*a, **kw):
+        r = scipy.optimize.minimize(*a, **kw)
+        seen.append(r)
+        return r
+
+    old = slsqp_mod.minimize
+    slsqp_mod.minimize = spy
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            xs, us = NMPC(integ, obj, [dom], H, 0.1, optimizer=Slsqp(verbose=0)).next(g["x0"])
+    finally:
+        slsqp_mod.minimize = old
+    assert len(seen) == int(g[f"{kind}_minimize_calls"])
+    np.testing.assert_array_equal([r.nit for r in seen], g[f"{kind}_all_nit"])
+    np.testing.assert_array_equal([r.status for r in seen], g[f"{kind}_all_status"])
+    assert np.abs(np.array([r.fun for r in seen]) - g[f"{kind}_all_fun"]).max() < 1e-6
+    assert (xs is None) == bool(g[f"{kind}_returned_none"])
+    assert np.abs(seen[-1].x - g[f"{kind}_z"]).max() < 1e-6
+    if xs is not None:
+        assert np.abs(xs - g[f"{kind}_x"]).max() < 1e-6 and np.abs(us - g[f"{kind}_u"]).max() < 1e-6
+
+
+def test_closed_loop_c1_trust_constr_and_ipm_vs_oracle_callbacks(lv_weights):
+    """C1 (unity transcription, H = 25, 1.1 * sum(u), run.py bounds): SciPy trust-constr driven by the CUDA callbacks vs the same solver on
+    the reference-literal dense callbacks -- identical iteration count, cost within 1e-6 -- and the batched on-device interior-point
+    solver on the same problem: cost within 1e-4 of it."""
+    from scipy.optimize import Bounds, NonlinearConstraint, minimize
+    from scipy.sparse import coo_matrix
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import CudaIpm, TrustConstr
+    H = 25
+    x0 = np.array([0.66, -0.9])
+    integ, obj, dom = _c1_problem(lv_weights, "unity", H)
+    o_pb = DenseIpoptProblem(x0, SeparableQuadraticObjective(obj.lin, obj.quad, obj.ref), DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "unity"))
+    n, m = 3 * H, 2 * H
+    hr, hc = o_pb.hessianstructure()
+    off = hr != hc
+    sym = lambda v: coo_matrix((np.concatenate([v, v[off]]), (np.concatenate([hr, hc[off]]), np.concatenate([hc, hr[off]]))), shape=(n, n)).tocsr()
+    x_init = np.concatenate([np.tile(x0, H), np.zeros(H)])
+    con = NonlinearConstraint(o_pb.constraints, 0.0, 0.0, jac=lambda x: coo_matrix(o_pb.jacobian(x)).tocsr(), hess=lambda x, v: sym(o_pb.hessian(x, v, 0.0)))
+    ref = minimize(o_pb.objective, x_init, method="trust-constr", jac=o_pb.gradient, hess=lambda x: sym(o_pb.hessian(x, np.zeros(m), 1.0)),
+                   constraints=[con], bounds=Bounds(dom.get_lower_bounds(H), dom.get_upper_bounds(H)), options={"maxiter": 200, "gtol": 1e-8, "xtol": 1e-10})
+    opt = TrustConstr()
+    xs, us = NMPC(integ, obj, [dom], H, 0.1, optimizer=opt).next(x0)
+    assert xs is not None and opt.last_result.nit == ref.nit
+    assert abs(opt.last_result.fun - ref.fun) < 1e-6
+    xi, ui = NMPC(integ, obj, [dom], H, 0.1, optimizer=CudaIpm(max_iteration=100, tolerance=1e-7)).next(x0)
+    assert xi is not None
+    z = np.concatenate([np.asarray(xi).ravel(), np.asarray(ui).ravel()])
+    assert np.abs(o_pb.constraints(z)).max() < 1e-6
+    assert abs(o_pb.objective(z) - ref.fun) < 1e-4
+
+
+def test_slsqp_with_a_binding_inequality_constraint(lv_weights):
+    """reference optimizer/slsqp.py:54-100: only EQ_TYPE user constraints join the equality block; an InequalityConstraint is passed once,
+    as 'ineq'.  u_t^2 <= 0.01 binds and is honoured; the integrator equalities still hold."""
+    from pyneuralempc_b200.constraints import InequalityConstraint
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.optimizer import Slsqp
+    H = 6
+    model, integ, obj, dom = _lv_setup(lv_weights, H)
+    n = 3 * H
+
+    class SmallControl(InequalityConstraint):                     # 0.01 - u_t^2 >= 0
+        def forward(self, x, u, p=None, tvp=None):
+            return 0.01 - u[:, 0] ** 2
+
+        def jacobian(self, x, u, p=None, tvp=None):
+            J = np.zeros((H, n))
+            J[np.arange(H), 2 * H + np.arange(H)] = -2.0 * u[:, 0]
+            return J
+
+        def get_dim(self, H_=None):
+            return H
+
+    x0 = np.array([0.66, -0.9])
+    _, u_free = NMPC(integ, obj, [dom], H, 0.1, optimizer=Slsqp(verbose=0)).next(x0)
+    assert np.abs(u_free).max() > 0.15
+    opt = Slsqp(verbose=0)
+    mpc = NMPC(integ, obj, [dom, SmallControl()], H, 0.1, optimizer=opt)
+    pb = mpc.get_pb(x0)
+    z = np.concatenate([np.tile(x0, H), np.full(H, 0.05)])
+    assert pb.constraints(z, eq=True).shape == (2 * H,) and pb.jacobian(z, eq=True).shape == (2 * H, n)      # integrator rows only
+    assert pb.constraints(z, eq=False).shape == (H,) and pb.jacobian(z, eq=False).shape == (H, n)
+    xs, us = mpc.next(x0)
+    assert xs is not None and opt.last_result.success
+    assert np.abs(us).max() <= 0.1 + 1e-6 and np.abs(us).max() > 0.099
+    zz = np.concatenate([xs.ravel(), us.ravel()])
+    o_pb = DenseIpoptProblem(x0, SeparableQuadraticObjective(obj.lin, obj.quad, obj.ref), DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "unity"))
+    assert np.abs(o_pb.constraints(zz)).max() < 1e-6
+
+
+def test_problems_sharing_an_integrator_keep_their_own_cost_and_inputs(lv_weights):
+    """objective and p / tvp rows are state of the integrator's one evaluator: a problem built first and evaluated after a second one was
+    created (or after a BatchedNMPC used the evaluator) must still see its own."""
+    from pyneuralempc_b200.objective import CudaQuadraticObjective
+    from pyneuralempc_b200.optimizer.ipopt import CudaIpoptProblem
+    H = 5
+    model, integ, obj_a, dom = _lv_setup(lv_weights, H)
+    obj_b = CudaQuadraticObjective(H, 2, 1, [3.0, 0.2], [0.7], x_ref=np.array([-0.3, 0.4]))
+    rng = np.random.default_rng(3)
+    x0, z = rng.uniform(-1, 1, 2), rng.uniform(-1, 1, 3 * H)
+    pa = CudaIpoptProblem(x0, obj_a, [], integ, use_hessian=True)
+    pb = CudaIpoptProblem(x0, obj_b, [], integ, use_hessian=True)           # overwrites the evaluator's cost
+    fa = SeparableQuadraticObjective(obj_a.lin, obj_a.quad, obj_a.ref)
+    fb = SeparableQuadraticObjective(obj_b.lin, obj_b.quad, obj_b.ref)
+    s, u = z[:2 * H].reshape(H, 2), z[2 * H:].reshape(H, 1)
+    assert abs(pa.objective(z) - fa.forward(s, u)) < 1e-12
+    assert abs(pb.objective(z) - fb.forward(s, u)) < 1e-12
+    assert abs(pa.objective(z) - fa.forward(s, u)) < 1e-12               # and back again (same iterate: the memo must not serve pb's value)
+    lam = rng.standard_normal(2 * H)
+    ha, hb = pa.hessian(z, lam, 1.0), pb.hessian(z, lam, 1.0)
+    assert np.abs(ha - hb).max() > 1e-3                                     # different quadratic weights on the diagonal
+    assert _rel(pa.hessian(z, lam, 1.0), ha) < 1e-15

@@ -442,3 +442,99 @@ def test_tensor_core_kernel_is_deterministic(hw):
         for k in ref:
             assert torch.equal(out[k], ref[k]), k
     ev.close()
+
+
+def _wide_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    dims = [int(v) for v in g["dims"]]
+    mlp = MLP.glorot(dims, int(g["x_dim"]), int(g["u_dim"]), seed=int(g["net_seed"]), dtype=np.float32)
+    chk = float(sum(np.abs(np.asarray(W, np.float64)).sum() + np.abs(np.asarray(b, np.float64)).sum() for W, b in mlp.weights))
+    assert chk == float(g["weights_checksum"]), "MLP.glorot no longer regenerates the weights the golden file was recorded with"
+    return g, mlp
+
+
+@pytest.mark.parametrize("name,kernel_tag", (("ref_rk4_w128_H6.npz", "nempc_tc_kernel"), ("ref_discrete_w256_H6.npz", "nempc_wide_kernel")))
+def test_tensor_core_kernels_against_reference_goldens(golden_dir, name, kernel_tag):
+    """the two tcgen05 kernels pinned DIRECTLY to the unmodified reference (not only to the oracle): IpoptProblem callbacks of
+    a 3-128-128-2 network under the reference's RK4 integrator (nempc_tc.cuh, TcCfg<2,1,2,...,128>) and of a 5-256-256-256-4 network
+    under its DiscretIntegrator (nempc_wide.cuh); tests/golden/make_golden.py record_wide()."""
+    g, mlp = _wide_golden(golden_dir, name)
+    kind, H = str(g["kind"]), int(g["H"])
+    obj = SeparableQuadraticObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+    jr, jc = np.nonzero(g["jacobian"])
+    for kernel in ("tc", "auto", "generic"):
+        ev = _evaluator(mlp, kind, H, "float32", kernel, obj)
+        assert (kernel_tag in ev.kernel_name) == (kernel != "generic"), ev.kernel_name
+        np.testing.assert_array_equal(ev.hes_rows, g["hes_rows"]); np.testing.assert_array_equal(ev.hes_cols, g["hes_cols"])
+        np.testing.assert_array_equal(ev.jac_rows, jr); np.testing.assert_array_equal(ev.jac_cols, jc)
+        got = _run(ev, g["z"][None], g["x0"][None], g["lam"][None], np.asarray([float(g["sigma"])]))
+        for k, ref in (("resid", g["constraints"]), ("jac", g["jacobian"][jr, jc]), ("hes", g["hessian_values"]), ("grad", g["gradient"])):
+            assert _relerr(got[k][0], ref) < TOL32, (kernel, k, _relerr(got[k][0], ref))
+        assert abs(got["obj"][0] - float(g["objective"])) < TOL32 * max(1.0, abs(float(g["objective"])))
+        ev.close()
+
+
+WIDE_CASES = [("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3),        # BASELINE config C4's network (quadrotor 16 -> 256 x 4 -> 12)
+              ("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 37, 9),       # several super-tiles of 128 steps, ragged tail, odd tile pairing
+              ("unity", [16, 256, 256, 12], 12, 4, 7, 2),
+              ("discrete", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("discrete", [3, 256, 256, 2], 2, 1, 6, 4),
+              ("discrete", [8, 256, 256, 256, 6], 6, 2, 6, 4), ("unity", [3, 256, 256, 256, 2], 2, 1, 300, 3)]
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,B", WIDE_CASES)
+def test_wide_kernel_vs_oracle(kind, dims, xd, ud, H, B):
+    """width-256 tcgen05 kernel (adjoint form, streamed split-f16 weights, CTA pairs) against the float64 oracle, all request sets"""
+    import torch
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=len(dims) + H)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "auto", obj)
+    assert "nempc_wide_kernel" in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < TOL32, (kg, _relerr(got[kg], ref[kr]))
+    t = lambda a: torch.as_tensor(a).cuda()
+    o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+    o0 = ev.eval(t(Z), t(X0), want=("resid",))
+    torch.cuda.synchronize()
+    assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL32
+    assert _relerr(o1["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    assert _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL32
+    # bit-determinism: the same launch twice
+    again = _run(ev, Z, X0, lam, sig)
+    for k in ("resid", "jac", "hes"):
+        np.testing.assert_array_equal(again[k], got[k])
+    ev.close()
+
+
+def test_c4_properties_wide_kernel():
+    """BASELINE config C4's network and horizon (16 -> 256 x 4 -> 12, H = 200) on a batch the oracle cannot follow: size-independent
+    properties -- linearity of the Hessian values in lambda, batch-permutation equivariance (bit-exact), the structural -1 entries, and
+    a sample of problems against the oracle."""
+    import torch
+    H, B, xd, ud = 200, 512, 12, 4
+    mlp = MLP.glorot([16, 256, 256, 256, 256, 12], xd, ud, seed=0, dtype=np.float32)
+    rng = np.random.default_rng(9)
+    n, m = H * (xd + ud), H * xd
+    Z, X0 = rng.uniform(-1, 1, (B, n)), rng.uniform(-1, 1, (B, xd))
+    l1, l2 = rng.standard_normal((B, m)), rng.standard_normal((B, m))
+    ev = _evaluator(mlp, "discrete", H, "float32", "auto")
+    assert "nempc_wide_kernel" in ev.kernel_name
+    t = lambda a: torch.as_tensor(a).cuda()
+    h = lambda lam: ev.eval(t(Z), t(X0), t(lam), 0.0, want=("resid", "jac", "hes"))
+    o1 = {k: v.clone() for k, v in h(l1).items()}
+    o2 = {k: v.clone() for k, v in h(l2).items()}
+    o3 = {k: v.clone() for k, v in h(2.0 * l1 - 0.5 * l2).items()}
+    lin = 2.0 * o1["hes"] - 0.5 * o2["hes"]
+    assert float((o3["hes"] - lin).abs().max()) < 2e-5 * float(lin.abs().max())
+    assert torch.equal(o1["jac"], o2["jac"]) and torch.equal(o1["resid"], o3["resid"])          # lambda does not touch them
+    perm = rng.permutation(B)
+    op = ev.eval(t(Z[perm]), t(X0[perm]), t(l1[perm]), 0.0, want=("resid", "jac", "hes"))
+    for k in ("resid", "jac", "hes"):
+        assert torch.equal(op[k], o1[k][torch.as_tensor(perm).cuda()]), k
+    minus1 = np.nonzero((ev.jac_cols < H * xd) & (ev.jac_cols // xd == ev.jac_rows // xd))[0]
+    assert len(minus1) == m and bool((o1["jac"][:, torch.as_tensor(minus1).cuda()] == -1.0).all())
+    pick = [0, 255, 511]
+    ref = BlockEvaluator(mlp, "discrete", H, DT=0.1).evaluate(Z[pick], X0[pick], l1[pick], 0.0)
+    for kr, kg in KEYS[:3]:
+        assert _relerr(o1[kg][pick].cpu().numpy(), ref[kr]) < TOL32, (kg, _relerr(o1[kg][pick].cpu().numpy(), ref[kr]))
+    ev.close()

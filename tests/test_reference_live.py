@@ -1,0 +1,56 @@
+"""Container-only checks against the UNMODIFIED reference under /root/reference (imported through oracle/shim.py with its absent
+third-party imports stubbed).  Skipped where the reference tree does not exist (the GPU box): there the committed goldens stand in.
+What is checked: the committed golden files are what the reference computes TODAY (bit-identical regeneration of a sample of them by
+the committed generator), and the oracle's dense restatement equals the live reference on fresh random inputs."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shim
+from oracle.dense_ref import DenseIntegrator
+from oracle.mlp_np import MLP, DenseModelView, load_lv_fixture_npz
+
+pytestmark = pytest.mark.skipif(not shim.reference_available(), reason="/root/reference is not present on this machine")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _generator():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _same(rec, path):
+    g = np.load(path)
+    assert set(g.files) == set(rec), sorted(set(g.files) ^ set(rec))
+    for k in g.files:
+        np.testing.assert_array_equal(np.asarray(rec[k]), g[k], err_msg=k)
+
+
+def test_goldens_regenerate_bit_identically_from_the_reference(golden_dir):
+    mk, ref = _generator(), shim.load_reference()
+    lv = MLP(load_lv_fixture_npz(os.path.join(golden_dir, "lv_mlp_weights.npz")), 2, 1, dtype=np.float64)
+    _same(mk.record(ref, lv, "rk4", 6, 102, "tracking", True), os.path.join(golden_dir, "ref_rk4_H6.npz"))
+    _same(mk.record(ref, lv, "discrete", 25, 200, "setpoint", False), os.path.join(golden_dir, "ref_discrete_H25.npz"))
+    _same(mk.record_wide(ref, [3, 128, 128, 2], 2, 1, "rk4", 6, 700, 21), os.path.join(golden_dir, "ref_rk4_w128_H6.npz"))
+    _same(mk.record_constraints(ref, lv), os.path.join(golden_dir, "ref_constraints_H6.npz"))
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+def test_dense_restatement_equals_the_live_reference(kind, lv_weights):
+    """oracle/dense_ref.py (the timed CPU baseline, kind "port") against the reference's own integrator on inputs no golden holds"""
+    ref = shim.load_reference()
+    mk = _generator()
+    mlp = MLP(lv_weights, 2, 1, dtype=np.float64)
+    H = 7
+    rng = np.random.default_rng(77)
+    xs, us, x0 = rng.uniform(-1, 1, (H, 2)), rng.uniform(-1, 1, (H, 1)), rng.uniform(-1, 1, 2)
+    theirs = mk.make_integrator(ref, kind, shim.make_reference_model(mlp), H)
+    ours = DenseIntegrator(DenseModelView(mlp), H, kind, DT=mk.DT_RK4)
+    np.testing.assert_allclose(ours.forward(xs, us, x0), theirs.forward(xs, us, x0), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(ours.jacobian(xs, us, x0), theirs.jacobian(xs, us, x0), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(ours.hessian(xs, us, x0), theirs.hessian(xs, us, x0), rtol=0, atol=1e-12)
