@@ -41,7 +41,7 @@ enum { NEMPC_F32 = 0, NEMPC_F64 = 1 };
 enum { NEMPC_INTEG_DISCRETE = 0,   /* x_{t-1} + f - x_t        integrator/discret.py:13-30 */
        NEMPC_INTEG_UNITY = 1,      /* f - x_t                  integrator/unity.py:15-32   */
        NEMPC_INTEG_RK4 = 2 };      /* classical RK4, ZOH on u  integrator/rk4.py:57-83      */
-enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2 };
+enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2, NEMPC_ACT_RELU = 3 };
 enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2,
        NEMPC_KERNEL_TC = 3 };      /* tcgen05 tensor-core kernel: f32 tanh networks whose hidden layers are all 128 (or all 64) wide */
 

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ACTIVATIONS = ("tanh", "sigmoid", "softplus")
+ACTIVATIONS = ("tanh", "sigmoid", "softplus", "relu")
 
 
 def _act(name, a):
@@ -39,6 +39,9 @@ def _act(name, a):
     if name == "softplus":
         s = 1.0 / (1.0 + np.exp(-a))
         return np.logaddexp(0.0, a), s, s * (1.0 - s)
+    if name == "relu":                      # piecewise linear; derivative 0 at a = 0 like tf.nn.relu's gradient
+        on = (a > 0.0).astype(a.dtype)
+        return a * on, on, np.zeros_like(a)
     raise ValueError(f"unknown activation {name!r}")
 
 

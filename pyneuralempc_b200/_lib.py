@@ -11,7 +11,7 @@ MAX_LAYERS = 8
 OK = 0
 F32, F64 = 0, 1
 INTEGRATORS = {"discrete": 0, "unity": 1, "rk4": 2}
-ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2}
+ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2, "relu": 3}
 KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
 
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",

@@ -92,6 +92,7 @@ class BatchedNMPC:
         self.optimizer = optimizer if optimizer is not None else CudaIpm()
         self.warm_start = warm_start
         self.ev = integrator.evaluator
+        objective_func.prepare(H, self.ev.x_dim, self.ev.u_dim)
         self.ev.set_objective(objective_func.lin, objective_func.quad, objective_func.ref)
         self._prev = None
         self.last_info = None

@@ -27,6 +27,7 @@
 #define NEMPC_ACT_TANH_ 0
 #define NEMPC_ACT_SIGMOID_ 1
 #define NEMPC_ACT_SOFTPLUS_ 2
+#define NEMPC_ACT_RELU_ 3
 
 enum : int { NEMPC_WANT_JAC = 1, NEMPC_WANT_HES = 2, NEMPC_MODE_MODEL = 4, NEMPC_MODE_BLOCKS = 8, NEMPC_UNITY = 16 };
 
@@ -134,16 +135,19 @@ NEMPC_HD void slot_barrier(int bar_id, int tps) {
 template <typename T> NEMPC_HD T act_value(int act, T a) {
     if (act == NEMPC_ACT_TANH_) return (T)tanh(a);
     if (act == NEMPC_ACT_SIGMOID_) return (T)1 / ((T)1 + (T)exp(-a));
+    if (act == NEMPC_ACT_RELU_) return a > (T)0 ? a : (T)0;
     return a > (T)0 ? a + (T)log1p(exp(-a)) : (T)log1p(exp(a));   // softplus
 }
 template <> NEMPC_HD float act_value<float>(int act, float a) {
     if (act == NEMPC_ACT_TANH_) return tanhf(a);
     if (act == NEMPC_ACT_SIGMOID_) return 1.0f / (1.0f + expf(-a));
+    if (act == NEMPC_ACT_RELU_) return a > 0.0f ? a : 0.0f;
     return a > 0.0f ? a + log1pf(expf(-a)) : log1pf(expf(a));
 }
 template <typename T> NEMPC_HD void act_derivs(int act, T h, T& s1, T& s2) {
     if (act == NEMPC_ACT_TANH_) { s1 = (T)1 - h * h; s2 = (T)-2 * h * s1; }
     else if (act == NEMPC_ACT_SIGMOID_) { s1 = h * ((T)1 - h); s2 = s1 * ((T)1 - (T)2 * h); }
+    else if (act == NEMPC_ACT_RELU_) { s1 = h > (T)0 ? (T)1 : (T)0; s2 = (T)0; }   // piecewise linear: the Hessian VALUES are zero, its structure is kept
     else { s1 = (T)1 - (T)exp(-h); s2 = s1 * ((T)1 - s1); }          // softplus: sigmoid(a) = 1 - exp(-softplus(a))
 }
 

@@ -456,7 +456,7 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     if (D.n_layers < 2 || D.n_layers > NEMPC_MAX_LAYERS) { SET_ERR((nempc_handle*)nullptr, "n_layers must be in [2,%d]", NEMPC_MAX_LAYERS); return NEMPC_EINVAL; }
     if (D.widths[D.n_layers - 1] != D.x_dim) { SET_ERR((nempc_handle*)nullptr, "last layer width %d != x_dim %d", D.widths[D.n_layers - 1], D.x_dim); return NEMPC_EINVAL; }
     for (int l = 0; l < D.n_layers; ++l) if (D.widths[l] < 1 || D.widths[l] > 4096) { SET_ERR((nempc_handle*)nullptr, "bad width"); return NEMPC_EINVAL; }
-    if (D.activation < 0 || D.activation > NEMPC_ACT_SOFTPLUS || D.integrator < 0 || D.integrator > NEMPC_INTEG_RK4) { SET_ERR((nempc_handle*)nullptr, "bad activation/integrator"); return NEMPC_EINVAL; }
+    if (D.activation < 0 || D.activation > NEMPC_ACT_RELU || D.integrator < 0 || D.integrator > NEMPC_INTEG_RK4) { SET_ERR((nempc_handle*)nullptr, "bad activation/integrator"); return NEMPC_EINVAL; }
     if (D.integrator == NEMPC_INTEG_RK4 && !(D.dt > 0.0)) { SET_ERR((nempc_handle*)nullptr, "RK4 needs dt > 0"); return NEMPC_EINVAL; }
     if ((D.compute_dtype != NEMPC_F32 && D.compute_dtype != NEMPC_F64) || (D.io_dtype != NEMPC_F32 && D.io_dtype != NEMPC_F64) ||
         (D.compute_dtype == NEMPC_F64 && D.io_dtype == NEMPC_F32)) { SET_ERR((nempc_handle*)nullptr, "unsupported dtype combination"); return NEMPC_EINVAL; }

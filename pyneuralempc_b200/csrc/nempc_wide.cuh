@@ -144,21 +144,8 @@ __device__ __forceinline__ void mma2_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask) : "memory");
 }
 
-// tanh with a relative error of a few 1e-7 down to 0: 1 - 2 / (e^{2|x|} + 1) cancels for small |x| (absolute error 1e-7), so a
-// degree-9 odd polynomial takes over below 0.25 (truncation 2e-9 there)
-__device__ __forceinline__ float tanh_acc(float x) {
-    const float ax = fabsf(x);
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    const float big = fmaf(-2.0f, r, 1.0f);
-    const float x2 = ax * ax;
-    float p = fmaf(x2, 0.021869488536155202f, -0.05396825396825397f);
-    p = fmaf(x2, p, 0.13333333333333333f);
-    p = fmaf(x2, p, -0.3333333333333333f);
-    p = fmaf(ax * x2, p, ax);
-    return copysignf(ax < 0.25f ? p : big, x);
-}
+// tanh with a relative error of a few 1e-7 down to 0 (nempc_fast.cuh)
+__device__ __forceinline__ float tanh_acc(float x) { return fast_tanh(x); }
 
 // 8 f32 pairs -> 8 words of f16 hi pairs + 8 words of f16 lo pairs (x = hi + lo / 2^11), packed arithmetic
 __device__ __forceinline__ void split16p(const f2* x, uint32_t* hi, uint32_t* lo) {

@@ -7,7 +7,10 @@ The reference wraps a live Keras model (``model/tensorflow.py:9-29``; ``examples
 * ``from_keras_model``        a live ``keras.Sequential`` (duck-typed: ``get_weights()`` + layer activations), no TensorFlow import here;
 * ``from_torch_sequential``   a ``torch.nn.Sequential`` of ``Linear`` / activation modules (``Linear.weight`` is ``[out, in]`` -> transposed);
 * ``from_state_dict``         a mapping name -> array with ``*.weight`` / ``*.bias`` entries (torch checkpoints, safetensors);
-* ``read_safetensors``        the safetensors container itself (8-byte header length, JSON header, raw little-endian tensors).
+* ``read_safetensors``        the safetensors container itself (8-byte header length, JSON header, raw little-endian tensors);
+* ``from_keras_h5``           a Keras ``.h5`` / ``.hdf5`` file (``model.save`` or ``save_weights``) read by ``h5lite`` -- no h5py, no TensorFlow;
+* ``from_keras_archive``      a Keras-3 ``.keras`` zip archive (``config.json`` + ``model.weights.h5``);
+* ``load_any``                dispatch on what the caller holds (object, path, or a ready weight list).
 
 Each returns ``(weights, activation)``; every hidden layer must use the same activation (tanh / sigmoid / softplus) and the last layer
 must be linear -- what ``nempc_create`` supports."""
@@ -18,7 +21,7 @@ import struct
 
 import numpy as np
 
-_ACT_NAMES = {"tanh": "tanh", "sigmoid": "sigmoid", "softplus": "softplus", "linear": None, "identity": None, None: None}
+_ACT_NAMES = {"tanh": "tanh", "sigmoid": "sigmoid", "softplus": "softplus", "relu": "relu", "linear": None, "identity": None, None: None}
 _ST_DTYPES = {"F64": "<f8", "F32": "<f4", "F16": "<f2", "I64": "<i8", "I32": "<i4", "I16": "<i2", "I8": "i1", "U8": "u1", "BOOL": "?"}
 
 
@@ -65,7 +68,7 @@ def from_torch_sequential(seq):
                 raise ValueError("Linear layers need a bias")
             weights.append((mod.weight.detach().cpu().double().numpy().T.copy(), mod.bias.detach().cpu().double().numpy().copy()))
             acts.append(None)
-        elif cls in ("Tanh", "Sigmoid", "Softplus"):
+        elif cls in ("Tanh", "Sigmoid", "Softplus", "ReLU"):
             if not weights or acts[-1] is not None:
                 raise ValueError("an activation module must follow a Linear layer")
             if cls == "Softplus" and (getattr(mod, "beta", 1) != 1):
@@ -110,3 +113,79 @@ def read_safetensors(path):
         lo, hi = meta["data_offsets"]
         out[name] = np.frombuffer(blob[lo:hi], dtype=_ST_DTYPES[meta["dtype"]]).reshape(meta["shape"]).copy()
     return out
+
+
+def from_keras_h5(path, activation=None):
+    """Keras HDF5 file (``examples/lotka_volterra/run.py:56`` loads ``nn_model.h5`` through TensorFlow; here: ``h5lite``).  The Dense
+    activations come from the embedded model config; a weights-only file needs ``activation=``."""
+    from . import h5lite
+    weights, acts = h5lite.read_keras_dense_stack(path)
+    if acts is None:
+        if activation is None:
+            raise ValueError(f"{path}: no model config in the file (save_weights?): pass activation=")
+        acts = [activation] * (len(weights) - 1) + ["linear"]
+    bad = [a for a in acts if a not in _ACT_NAMES]
+    if bad:
+        raise ValueError(f"unsupported activation(s) {bad}")
+    return _check(weights, [_ACT_NAMES[a] for a in acts])
+
+
+def from_keras_archive(path, activation=None):
+    """Keras-3 ``.keras`` archive: a zip holding ``config.json`` (layer classes and activations) and ``model.weights.h5``
+    (``layers/<name>/vars/0`` = kernel, ``vars/1`` = bias)."""
+    import zipfile
+    from . import h5lite
+    with zipfile.ZipFile(path) as zf:
+        cfg = json.loads(zf.read("config.json").decode("utf-8"))
+        f = h5lite.H5File(zf.read("model.weights.h5"))
+    dense = [l for l in cfg.get("config", {}).get("layers", []) if l.get("class_name") == "Dense"]
+    by_layer = {}
+    for p, a in f.walk():
+        parts = p.split("/")
+        if len(parts) >= 3 and parts[-2] == "vars":
+            by_layer.setdefault("/".join(parts[:-2]), {})[parts[-1]] = f.dataset(a)
+    weights, acts = [], []
+    for l in dense:
+        name = l["config"]["name"]
+        key = next((k for k in by_layer if k.split("/")[-1] == name), None)
+        if key is None or set(by_layer[key]) != {"0", "1"}:
+            raise ValueError(f"{path}: no kernel/bias pair for Dense layer {name!r}")
+        weights.append((by_layer[key]["0"].astype(np.float64), by_layer[key]["1"].astype(np.float64)))
+        a = l["config"].get("activation", "linear")
+        if a not in _ACT_NAMES:
+            raise ValueError(f"unsupported activation {a!r}")
+        acts.append(_ACT_NAMES[a])
+    if not weights:
+        raise ValueError(f"{path}: no Dense layers in config.json")
+    return _check(weights, acts)
+
+
+def load_any(model, activation=None):
+    """(weights, activation) from whatever the caller holds: a path (.h5 / .hdf5 / .keras / .npz / .safetensors), a live Keras model,
+    a ``torch.nn.Sequential``, a state dict, or a list of ``(kernel[in, out], bias[out])`` pairs."""
+    import os
+    if isinstance(model, (str, os.PathLike)):
+        path = os.fspath(model)
+        ext = os.path.splitext(path)[1].lower()
+        if ext in (".h5", ".hdf5"):
+            return from_keras_h5(path, activation)
+        if ext == ".keras":
+            return from_keras_archive(path, activation)
+        if ext == ".safetensors":
+            return from_state_dict(read_safetensors(path), activation or "tanh")
+        if ext == ".npz":
+            d = np.load(path)
+            n = len([k for k in d.files if k.startswith("W")])
+            return _check([(np.asarray(d[f"W{i}"], np.float64), np.asarray(d[f"b{i}"], np.float64)) for i in range(n)],
+                          [activation or "tanh"] * (n - 1) + [None])
+        raise ValueError(f"{path}: unknown model file type {ext!r}")
+    if isinstance(model, dict):
+        return from_state_dict(model, activation or "tanh")
+    if isinstance(model, (list, tuple)):
+        ws = [(np.asarray(W, np.float64), np.asarray(b, np.float64)) for W, b in model]
+        return _check(ws, [activation or "tanh"] * (len(ws) - 1) + [None])
+    if hasattr(model, "layers") and hasattr(model.layers[0] if len(model.layers) else None, "get_weights"):
+        return from_keras_model(model)
+    if type(model).__name__ == "Sequential" and hasattr(model, "__iter__"):
+        return from_torch_sequential(model)
+    raise ValueError(f"cannot read network weights from a {type(model).__name__}")

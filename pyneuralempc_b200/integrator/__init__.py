@@ -17,8 +17,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import NlpEvaluator
-from .model import CudaMLPModel, Model
+from ..engine import NlpEvaluator
+from ..model import CudaMLPModel, Model
 
 
 class Integrator:

@@ -15,26 +15,10 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import NlpEvaluator
+from ..engine import NlpEvaluator
 
 
-class Model:
-    """Abstract dynamics model (reference model/base.py:3-18)."""
-
-    def __init__(self, x_dim: int, u_dim: int, p_dim=None, tvp_dim=None):
-        self.x_dim = x_dim
-        self.u_dim = u_dim
-        self.p_dim = p_dim
-        self.tvp_dim = tvp_dim
-
-    def forward(self, x, u, p=None, tvp=None):
-        raise NotImplementedError("")
-
-    def jacobian(self, x, u, p=None, tvp=None):
-        raise NotImplementedError("")
-
-    def hessian(self, x, u, p=None, tvp=None):
-        raise NotImplementedError("")
+from .base import Model, adopt_reference_base  # noqa: E402,F401
 
 
 class CudaMLPModel(Model):
@@ -54,6 +38,7 @@ class CudaMLPModel(Model):
             raise ValueError("Your model do not provide a suitable output dim ! \n It must get the same dim as the state dim.")
         if weights[0][0].shape[0] != x_dim + u_dim + p_dim + tvp_dim:              # tensorflow.py:23-24
             raise ValueError("Your model do not provide a suitable input dim ! \n It must get the same dim as the sum of all input vars (x, u, p, tvp).")
+        adopt_reference_base()                  # when the reference package is loaded too: pass its isinstance(model, Model) check
         super().__init__(x_dim, u_dim, p_dim, tvp_dim)
         self.weights = weights
         self.activation, self.dtype, self.device, self.kernel = activation, dtype, device, kernel
@@ -64,14 +49,14 @@ class CudaMLPModel(Model):
     @classmethod
     def from_keras(cls, keras_model, x_dim, u_dim, **kw):
         """a live Keras ``Sequential`` of Dense layers -- the object the reference hands to KerasTFModel (model/tensorflow.py:9)."""
-        from . import importers
+        from .. import importers
         weights, act = importers.from_keras_model(keras_model)
         return cls(weights, x_dim, u_dim, activation=act, **kw)
 
     @classmethod
     def from_safetensors(cls, path, x_dim, u_dim, activation="tanh", prefix="", **kw):
         """a safetensors checkpoint of an ``nn.Sequential`` (``<k>.weight`` [out, in], ``<k>.bias``)."""
-        from . import importers
+        from .. import importers
         weights, act = importers.from_state_dict(importers.read_safetensors(path), activation, prefix)
         return cls(weights, x_dim, u_dim, activation=act, **kw)
 
@@ -87,7 +72,7 @@ class CudaMLPModel(Model):
         """``torch.nn.Sequential`` of ``Linear`` (+ Tanh/Sigmoid/Softplus) modules; Linear stores ``[out, in]``."""
         import torch
         ws, act = [], kw.pop("activation", None)
-        names = {torch.nn.Tanh: "tanh", torch.nn.Sigmoid: "sigmoid", torch.nn.Softplus: "softplus"}
+        names = {torch.nn.Tanh: "tanh", torch.nn.Sigmoid: "sigmoid", torch.nn.Softplus: "softplus", torch.nn.ReLU: "relu"}
         for mod in seq:
             if isinstance(mod, torch.nn.Linear):
                 b = mod.bias.detach().cpu().double().numpy() if mod.bias is not None else np.zeros(mod.out_features)

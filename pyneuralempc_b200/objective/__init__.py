@@ -18,7 +18,7 @@ import ctypes
 
 import numpy as np
 
-from . import _lib
+from .. import _lib
 
 
 class ObjectiveFunc:
@@ -50,7 +50,11 @@ class CudaSeparableObjective(ObjectiveFunc):
             raise ValueError("lin, quad and ref must have the same length n = H*(x_dim+u_dim)")
         self.n = self.lin.shape[0]
         self.device = device
+        self.offset = 0.0                          # constant term of the cost (objective/jax.py identifies one); not on the device
         self._dev = None
+
+    def prepare(self, H, x_dim, u_dim, p=None, tvp=None):
+        """hook for costs that are only known once the problem dimensions are (objective/jax.py); nothing to do here"""
 
     def _device_params(self):
         if self._dev is None:

@@ -37,6 +37,8 @@ class CudaIpoptProblem(ProblemInterface):
         self.ev = integrator.evaluator
         self._key, self._point = None, None
         self._device_objective = isinstance(objective_func, CudaSeparableObjective)
+        if self._device_objective:
+            objective_func.prepare(self.H, self.x_dim, self.u_dim, p, tvp)
         if not self._device_objective and use_hessian:
             raise NotImplementedError("the Lagrangian-Hessian path needs a CudaSeparableObjective")
         self._bind()
@@ -73,7 +75,7 @@ class CudaIpoptProblem(ProblemInterface):
 
     def objective(self, x):
         if self._device_objective:
-            return float(self._at(x)["obj"])
+            return float(self._at(x)["obj"]) + self.objective_func.offset
         s, u, tvp, p = self._split(np.asarray(x))
         return self.objective_func.forward(s, u, p=p, tvp=tvp)
 

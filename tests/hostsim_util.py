@@ -13,7 +13,7 @@ LIB = os.path.join(OUT_DIR, "libnempc_hostsim.so")
 _DEPS = [SRC] + [os.path.join(ROOT, "pyneuralempc_b200", "csrc", f)
                  for f in ("nempc_generic.cuh", "nempc_fast.cuh", "nempc_layout.h", "nempc_solver.cuh")]
 INTEG = {"discrete": 0, "unity": 1, "rk4": 2}
-ACT = {"tanh": 0, "sigmoid": 1, "softplus": 2}
+ACT = {"tanh": 0, "sigmoid": 1, "softplus": 2, "relu": 3}
 
 
 def build():

@@ -54,7 +54,7 @@ CASES = [("discrete", [3, 30, 30, 2], 2, 1, 25, "tanh"), ("unity", [3, 30, 30, 2
          ("rk4", [3, 30, 30, 2], 2, 1, 50, "tanh"), ("rk4", [5, 12, 9, 7, 4], 4, 1, 10, "tanh"),
          ("rk4", [6, 40, 3], 3, 3, 5, "tanh"), ("discrete", [16, 24, 12], 12, 4, 4, "tanh"),
          ("rk4", [2, 6, 1], 1, 1, 1, "tanh"), ("rk4", [3, 9, 8, 2], 2, 1, 3, "sigmoid"),
-         ("unity", [4, 6, 6, 6, 2], 2, 2, 2, "softplus"), ("rk4", [5, 128, 128, 128, 4], 4, 1, 6, "tanh"),
+         ("unity", [4, 6, 6, 6, 2], 2, 2, 2, "softplus"), ("rk4", [3, 16, 16, 2], 2, 1, 7, "relu"), ("discrete", [5, 40, 40, 4], 4, 1, 5, "relu"), ("rk4", [5, 128, 128, 128, 4], 4, 1, 6, "tanh"),
          ("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 3, "tanh"), ("rk4", [16, 64, 64, 12], 12, 4, 3, "tanh")]
 
 

@@ -69,6 +69,68 @@ def test_keras_like_object_and_errors():
     with pytest.raises(ValueError):
         importers.from_keras_model(Model([mk(3, 4, "tanh"), mk(4, 2, "tanh")]))                           # non-linear last layer
     with pytest.raises(ValueError):
-        importers.from_keras_model(Model([mk(3, 4, "relu"), mk(4, 2, "linear")]))                         # unsupported activation
+        importers.from_keras_model(Model([mk(3, 4, "gelu"), mk(4, 2, "linear")]))                         # unsupported activation
     with pytest.raises(ValueError):
-        importers.from_torch_sequential(torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.ReLU(), torch.nn.Linear(4, 2)))
+        importers.from_torch_sequential(torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.GELU(), torch.nn.Linear(4, 2)))
+    assert importers.from_keras_model(Model([mk(3, 4, "relu"), mk(4, 2, "linear")]))[1] == "relu"
+    assert importers.from_torch_sequential(torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.ReLU(), torch.nn.Linear(4, 2)))[1] == "relu"
+
+
+def test_reference_module_paths_and_names():
+    """user scripts import pyNeuralEMPC.integrator.rk4.RK4Integrator, model.tensorflow.KerasTFModel, objective.jax.JAXObjectifFunc ...
+    (examples/lotka_volterra/run.py:56-84, test.py:5): the same dotted paths exist here"""
+    import pyneuralempc_b200 as nEMPC
+    from pyneuralempc_b200.integrator import discret, rk4, unity
+    from pyneuralempc_b200.model import base as mbase, jax as mjax, tensorflow as mtf
+    from pyneuralempc_b200.objective import base as obase, jax as ojax
+    assert rk4.RK4Integrator is nEMPC.integrator.RK4Integrator and discret.DiscretIntegrator is nEMPC.integrator.DiscretIntegrator
+    assert unity.UnityIntegrator is nEMPC.integrator.UnityIntegrator
+    assert issubclass(mtf.KerasTFModel, mbase.Model) and issubclass(ojax.JAXObjectifFunc, obase.ObjectiveFunc)
+    assert nEMPC.optimizer.Slsqp and nEMPC.optimizer.Ipopt and nEMPC.constraints.DomainConstraint and nEMPC.controller.NMPC
+    with pytest.raises(NotImplementedError):
+        mjax.DiffDiscretJaxModel(lambda x, u, p=None, tvp=None: x, 2, 1)
+
+
+def test_keras_tf_model_takes_a_keras_like_object_or_a_weight_list():
+    from pyneuralempc_b200.model.tensorflow import KerasTFModel
+    rng = np.random.default_rng(0)
+    ws = [(rng.standard_normal((3, 8)), rng.standard_normal(8)), (rng.standard_normal((8, 2)), rng.standard_normal(2))]
+
+    class Act:
+        def __init__(self, n): self.__name__ = n
+
+    class Layer:
+        def __init__(self, W, b, a): self.W, self.b, self.activation, self.name = W, b, Act(a), "dense"
+        def get_weights(self): return [self.W, self.b]
+
+    class Keras:
+        layers = [Layer(*ws[0], "relu"), Layer(*ws[1], "linear")]
+
+    m = KerasTFModel(Keras(), x_dim=2, u_dim=1)
+    assert m.activation == "relu" and m.x_dim == 2 and m.u_dim == 1 and len(m.weights) == 2
+    m2 = KerasTFModel(ws, 2, 1)
+    assert m2.activation == "tanh"
+    with pytest.raises(ValueError):
+        KerasTFModel(ws, 3, 1)                                   # output width != x_dim (tensorflow.py:20-21)
+    with pytest.raises(NotImplementedError):
+        KerasTFModel(ws, 2, 1, standardScaler=object())
+    import pickle
+    assert pickle.loads(pickle.dumps(m)).model is None           # the Keras object is not pickled (tensorflow.py:31-37)
+
+
+def test_jax_objectif_func_identifies_the_shipped_costs():
+    """the two costs the reference ships (run.py:79-87, test.py:55-60) are recognised from the callable alone; a cost with cross terms is refused"""
+    from pyneuralempc_b200.objective.jax import JAXObjectifFunc
+    H, xd, ud = 5, 2, 1
+    cost_vec = np.full(H, 1.1)
+    lotka = JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum(u.reshape(-1) * cost_vec.reshape(-1)))
+    lotka.prepare(H, xd, ud)
+    assert np.allclose(lotka.lin, [0.0] * (H * xd) + [1.1] * H) and not lotka.quad.any() and lotka.offset == 0.0
+    setp = JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum((u - 2.0) ** 2).astype(np.float32))
+    setp.prepare(H, xd, ud)
+    assert np.allclose(setp.quad, [0.0] * (H * xd) + [1.0] * H) and np.allclose(setp.lin[H * xd:], -4.0) and abs(setp.offset - 4.0 * H) < 1e-5
+    assert (setp.hessianstructure() == np.diag([0.0] * (H * xd) + [1.0] * H)).all()
+    with pytest.raises(NotImplementedError):
+        JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum(np.diff(u[:, 0]) ** 2)).prepare(H, xd, ud)     # rate penalty: cross terms
+    with pytest.raises(NotImplementedError):
+        JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum(x ** 4)).prepare(H, xd, ud)

@@ -13,7 +13,7 @@ CASES = [("discrete", [3, 30, 30, 2], 2, 1, 6, "tanh"), ("unity", [3, 30, 30, 2]
          ("rk4", [3, 30, 30, 2], 2, 1, 7, "tanh"), ("rk4", [5, 12, 9, 7, 4], 4, 1, 4, "tanh"),
          ("rk4", [6, 40, 3], 3, 3, 3, "tanh"), ("discrete", [16, 20, 12], 12, 4, 2, "tanh"),
          ("rk4", [2, 6, 1], 1, 1, 1, "tanh"), ("rk4", [3, 9, 8, 2], 2, 1, 3, "sigmoid"),
-         ("unity", [4, 6, 6, 6, 2], 2, 2, 2, "softplus")]
+         ("unity", [4, 6, 6, 6, 2], 2, 2, 2, "softplus"), ("rk4", [3, 9, 8, 2], 2, 1, 3, "relu")]
 
 
 def _problem(kind, dims, xd, ud, H, act, seed=0, with_obj=True):

@@ -54,3 +54,29 @@ def test_dense_restatement_equals_the_live_reference(kind, lv_weights):
     np.testing.assert_allclose(ours.forward(xs, us, x0), theirs.forward(xs, us, x0), rtol=0, atol=1e-13)
     np.testing.assert_allclose(ours.jacobian(xs, us, x0), theirs.jacobian(xs, us, x0), rtol=0, atol=1e-13)
     np.testing.assert_allclose(ours.hessian(xs, us, x0), theirs.hessian(xs, us, x0), rtol=0, atol=1e-12)
+
+
+def test_product_h5_reader_on_the_reference_fixture(golden_dir):
+    """pyneuralempc_b200.h5lite (no h5py, no TensorFlow) on examples/lotka_volterra/nn_model.h5: the Dense stack and its activations"""
+    from pyneuralempc_b200 import importers
+    from pyneuralempc_b200.model.tensorflow import KerasTFModel
+    path = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
+    weights, act = importers.from_keras_h5(path)
+    g = np.load(os.path.join(golden_dir, "lv_mlp_weights.npz"))
+    assert act == "tanh" and len(weights) == 3
+    for i, (W, b) in enumerate(weights):
+        np.testing.assert_array_equal(W.astype(np.float32), g[f"W{i}"])
+        np.testing.assert_array_equal(b.astype(np.float32), g[f"b{i}"])
+    m = KerasTFModel(path, x_dim=2, u_dim=1)                       # what run.py:56,68 does through TensorFlow
+    assert m.activation == "tanh" and m.weights[1][0].shape == (30, 30)
+
+
+def test_cuda_model_passes_the_reference_isinstance_check(lv_weights):
+    """integrator/base.py:16-17 of the reference requires isinstance(model, pyNeuralEMPC.model.base.Model)"""
+    ref = shim.load_reference()
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.model.base import Model
+    m = CudaMLPModel(lv_weights, 2, 1)                             # no device is touched before the first evaluation
+    assert isinstance(m, ref.model.base.Model) and isinstance(m, Model)
+    integ = ref.integrator.discret.DiscretIntegrator(m, 5)
+    assert integ.model is m and integ.H == 5
