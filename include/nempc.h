@@ -65,6 +65,12 @@ typedef struct nempc_desc {
 typedef struct nempc_handle nempc_handle;
 
 const char* nempc_version(void);
+/* ABI generation of the library (NEMPC_ABI_VERSION at its build) and the sizes of the two structs it was compiled with; a binding
+ * compares them with its own after dlopen (a stale libnempc.so would otherwise misread nempc_desc / nempc_solver_opts). */
+#define NEMPC_ABI_VERSION 3
+int32_t nempc_abi_info(int32_t* desc_bytes, int32_t* solver_opts_bytes);
+/* hash of the CUDA sources the binary was built from ("unknown" for a build outside pyneuralempc_b200/build.py) */
+const char* nempc_source_hash(void);
 const char* nempc_last_error(const nempc_handle* h);
 
 /* ---- lifetime --------------------------------------------------------------------------------------- */
@@ -145,6 +151,30 @@ int nempc_model_eval(nempc_handle* h, int64_t N, const void* zin, void* f, void*
  * DEVICE arrays of io_dtype; lin / quad / ref are DEVICE arrays of n doubles.  obj or grad may be NULL. */
 int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const double* lin, const double* quad,
                          const double* ref, void* obj, void* grad, void* stream);
+
+/* ---- rolling-window (NARX) models ---------------------------------------------------------------
+ * Replaces the window logic of KerasTFModelRollingInput / DiffDiscretJaxModelRollingWindow (model/tensorflow.py:112-340,
+ * model/jax.py:93-259: rolling_input, _gather_input, the projection matrices of jacobian / hessian) together with the dense slicing
+ * the integrators apply to the model's arrays (integrator/discret.py:32-81, unity.py:34-81).  The network of step t reads the last
+ * w = rolling_window states and controls, dw = w (x + u) inputs; its per-row value / Jacobian / per-output Hessian come from
+ * nempc_model_eval on a handle created with x_dim = x, u_dim = dw - x.  All data pointers are DEVICE pointers of io_dtype, the index
+ * tables are DEVICE int32 / double arrays built once by the caller (pyneuralempc_b200/rolling.py builds them from the closed-form
+ * band structure).  No handle: both calls are stateless and asynchronous on `stream`.
+ *   gather:    zin[b, r] = z[b, gidx[r]] if gidx[r] >= 0 else aux[b, -1 - gidx[r]],  r < rows = H * dw,
+ *              aux (B, naux) = [x0 | prev_x | prev_u] (KerasTFModelRollingInput.set_prev_data, tensorflow.py:174-185)
+ *   assemble:  resid[b, r]   = f[b, r] - z[b, r] (+ the gathered x_{t-1} entry resid_base[r]; INT32_MIN = none, unity integrator)
+ *              jac_vals[b,s] = jac_add[s] (+ J[b].flat[jac_src[s]] when jac_src[s] >= 0)
+ *              hes_vals[b,s] = obj_factor_b * hes_obj[s] + sum_{e in [hes_ptr[s], hes_ptr[s+1])} sum_p lambda[b, t x + p] Hs[b, t, p].flat[ab],
+ *                              hes_src[e] = t dw^2 + ab                    (fixed summation order: deterministic)
+ * Any of resid / jac_vals / hes_vals may be NULL (skipped). */
+int nempc_rolling_gather(int32_t io_dtype, int64_t B, int32_t n, int32_t naux, int32_t rows, const int32_t* gidx,
+                         const void* z, const void* aux, void* zin, void* stream);
+int nempc_rolling_assemble(int32_t io_dtype, int64_t B, int32_t H, int32_t x, int32_t dw, int32_t n, int32_t naux,
+                           int64_t nnz_jac, int64_t nnz_hes, const int32_t* resid_base, const int32_t* jac_src,
+                           const double* jac_add, const int32_t* hes_ptr, const int32_t* hes_src, const double* hes_obj,
+                           const void* z, const void* aux, const void* f, const void* J, const void* Hs, const void* lambda,
+                           const void* obj_factor, double obj_factor_scalar, void* resid, void* jac_vals, void* hes_vals,
+                           void* stream);
 
 /* ---- batched on-device NMPC solver ----------------------------------------------------------
  * Replaces, for a batch of B independent problems, the solver call of Ipopt.solve / Slsqp.solve

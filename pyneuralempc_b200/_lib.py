@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes
 import os
 
+from . import build
 from .build import LIB_PATH
 
 MAX_LAYERS = 8
@@ -13,11 +14,13 @@ F32, F64 = 0, 1
 INTEGRATORS = {"discrete": 0, "unity": 1, "rk4": 2}
 ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2, "relu": 3}
 KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
+ABI_VERSION = 3                             # NEMPC_ABI_VERSION of include/nempc.h this binding was written against
 
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",
            "nempc_set_objective", "nempc_set_exogenous", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
            "nempc_eval", "nempc_eval_host", "nempc_eval_blocks", "nempc_model_eval", "nempc_launch_count",
-           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve")
+           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve",
+           "nempc_abi_info", "nempc_source_hash", "nempc_rolling_gather", "nempc_rolling_assemble")
 
 
 class NempcDesc(ctypes.Structure):
@@ -50,6 +53,18 @@ def load():
         raise NempcError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(pyneuralempc_b200 has no CPU fallback)")
     lib = ctypes.CDLL(LIB_PATH)
+    if not hasattr(lib, "nempc_abi_info") or not hasattr(lib, "nempc_source_hash"):
+        raise NempcError(f"{LIB_PATH} predates nempc_abi_info: rebuild it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib.nempc_source_hash.restype = ctypes.c_char_p
+    built_from = lib.nempc_source_hash().decode()
+    if not os.environ.get("NEMPC_LIB_PATH") and built_from != "unknown" and built_from != build.source_hash():
+        raise NempcError(f"{LIB_PATH} was built from other sources (hash {built_from}) than the ones in pyneuralempc_b200/csrc "
+                         f"({build.source_hash()}): rebuild it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    ds, os_ = ctypes.c_int32(), ctypes.c_int32()
+    ver = lib.nempc_abi_info(ctypes.byref(ds), ctypes.byref(os_))
+    if ver != ABI_VERSION or ds.value != ctypes.sizeof(NempcDesc) or os_.value != ctypes.sizeof(SolverOpts):
+        raise NempcError(f"{LIB_PATH}: ABI {ver} with nempc_desc {ds.value} B / nempc_solver_opts {os_.value} B, this binding expects ABI "
+                         f"{ABI_VERSION} with {ctypes.sizeof(NempcDesc)} B / {ctypes.sizeof(SolverOpts)} B: rebuild the library")
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
     lib.nempc_version.restype = ctypes.c_char_p
     lib.nempc_last_error.restype = ctypes.c_char_p
@@ -77,6 +92,9 @@ def load():
     lib.nempc_objective_eval.argtypes = [i32, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.nempc_solver_defaults.argtypes = [ctypes.POINTER(SolverOpts)]
     lib.nempc_solve.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.POINTER(SolverOpts), ctypes.POINTER(i32), vp]
+    lib.nempc_rolling_gather.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.nempc_rolling_assemble.argtypes = [i32, i64, i32, i32, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl,
+                                           vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)                  # AttributeError here = the .so does not match include/nempc.h
     _lib = lib

@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.environ.get("NEMPC_LIB_PATH") or os.path.join(CSRC, "libnempc.so")   # env override: kernel-variant experiments
 SOURCES = ["nempc_lib.cu"]
-HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_small.cuh", "nempc_tc.cuh", "nempc_wide.cuh", "nempc_tc_ptx.cuh", "nempc_solver.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
+HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_small.cuh", "nempc_tc.cuh", "nempc_wide.cuh", "nempc_rolling.cuh", "nempc_tc_ptx.cuh", "nempc_solver.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--split-compile=0",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -21,24 +21,38 @@ def find_nvcc():
     raise RuntimeError("nvcc not found: libnempc.so cannot be built (there is no CPU fallback)")
 
 
+def source_hash():
+    """sha256 over the CUDA sources and headers the library is built from; compiled into the library (nempc_source_hash) and written
+    next to it, so that staleness does not depend on file times (which a copy to another machine does not preserve)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read() + b"\0")
+    return h.hexdigest()[:32]
+
+
 def is_stale():
     if os.environ.get("NEMPC_LIB_PATH"):
         return False
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(LIB_PATH + ".srchash"):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(LIB_PATH + ".srchash") as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build_library(force=False, verbose=False):
     """compile pyneuralempc_b200/csrc/libnempc.so for sm_100a; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
+    sh = source_hash()
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+          [f'-DNEMPC_SOURCE_HASH="{sh}"', "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    with open(LIB_PATH + ".srchash", "w") as fh:
+        fh.write(sh + "\n")
     if verbose:
         print(proc.stderr)
     return LIB_PATH

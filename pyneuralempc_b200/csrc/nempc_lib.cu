@@ -19,6 +19,7 @@
 #include "nempc_solver.cuh"
 #include "nempc_tc.cuh"
 #include "nempc_wide.cuh"
+#include "nempc_rolling.cuh"
 
 // ======================================================================================================
 // kernels
@@ -358,7 +359,19 @@ static int wide_shape_id(const nempc_desc& d) {
     return -1;
 }
 
-extern "C" const char* nempc_version(void) { return "nempc 0.1 (sm_100a)"; }
+extern "C" const char* nempc_version(void) { return "nempc 0.2 (sm_100a)"; }
+#ifndef NEMPC_SOURCE_HASH
+#define NEMPC_SOURCE_HASH "unknown"
+#endif
+// sha256 (first 32 hex digits) of the sources this binary was built from (pyneuralempc_b200/build.py source_hash)
+extern "C" const char* nempc_source_hash(void) { return NEMPC_SOURCE_HASH; }
+// ABI generation (bumped whenever a signature or struct layout of include/nempc.h changes) and the struct sizes this binary was built with:
+// a binding checks them after dlopen instead of misreading a stale library
+extern "C" int32_t nempc_abi_info(int32_t* desc_bytes, int32_t* solver_opts_bytes) {
+    if (desc_bytes) *desc_bytes = (int32_t)sizeof(nempc_desc);
+    if (solver_opts_bytes) *solver_opts_bytes = (int32_t)sizeof(nempc_solver_opts);
+    return NEMPC_ABI_VERSION;
+}
 extern "C" const char* nempc_last_error(const nempc_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
 // ---- structure (host only) -----------------------------------------------------------------------------
@@ -1224,6 +1237,57 @@ extern "C" int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, cons
     else nempc_objective_kernel<float><<<grid, threads, 0, s>>>((const float*)z, lin, quad, ref, (float*)obj, (float*)grad, (int)n, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "objective kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+// ---- rolling-window (NARX) models: window gather + banded sparse assembly (nempc_rolling.cuh) -------------------------------------
+extern "C" int nempc_rolling_gather(int32_t io_dtype, int64_t B, int32_t n, int32_t naux, int32_t rows, const int32_t* gidx,
+                                    const void* z, const void* aux, void* zin, void* stream) {
+    if (B < 0 || n < 1 || naux < 1 || rows < 1 || !gidx || !z || !aux || !zin || (io_dtype != NEMPC_F32 && io_dtype != NEMPC_F64)) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_rolling_gather: bad argument");
+        return NEMPC_EINVAL;
+    }
+    if (B == 0) return NEMPC_OK;
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((B * rows + threads - 1) / threads, 148 * 16));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (io_dtype == NEMPC_F64) nempc_rolling_gather_kernel<double><<<grid, threads, 0, s>>>((const double*)z, (const double*)aux, gidx, (double*)zin, n, naux, rows, B);
+    else nempc_rolling_gather_kernel<float><<<grid, threads, 0, s>>>((const float*)z, (const float*)aux, gidx, (float*)zin, n, naux, rows, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "rolling gather kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_rolling_assemble(int32_t io_dtype, int64_t B, int32_t H, int32_t x, int32_t dw, int32_t n, int32_t naux,
+                                      int64_t nnz_jac, int64_t nnz_hes, const int32_t* resid_base, const int32_t* jac_src,
+                                      const double* jac_add, const int32_t* hes_ptr, const int32_t* hes_src, const double* hes_obj,
+                                      const void* z, const void* aux, const void* f, const void* J, const void* Hs, const void* lambda,
+                                      const void* obj_factor, double obj_factor_scalar, void* resid, void* jac_vals, void* hes_vals,
+                                      void* stream) {
+    if (B < 0 || H < 1 || x < 1 || dw < 1 || n < 1 || !z || !aux || (io_dtype != NEMPC_F32 && io_dtype != NEMPC_F64)) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_rolling_assemble: bad argument");
+        return NEMPC_EINVAL;
+    }
+    if ((resid && (!f || !resid_base)) || (jac_vals && (!J || !jac_src || !jac_add)) || (hes_vals && (!Hs || !lambda || !hes_ptr || !hes_src || !hes_obj))) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_rolling_assemble: an output was requested without its inputs / tables");
+        return NEMPC_EINVAL;
+    }
+    if (B == 0 || (!resid && !jac_vals && !hes_vals)) return NEMPC_OK;
+    const RollingTables tb{resid_base, jac_src, jac_add, hes_ptr, hes_src, hes_obj};
+    const long long per = (resid ? (long long)H * x : 0) + (jac_vals ? nnz_jac : 0) + (hes_vals ? nnz_hes : 0);
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((B * per + threads - 1) / threads, 148 * 16));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (io_dtype == NEMPC_F64)
+        nempc_rolling_assemble_kernel<double><<<grid, threads, 0, s>>>(tb, (const double*)z, (const double*)aux, (const double*)f, (const double*)J, (const double*)Hs,
+                                                                     (const double*)lambda, (const double*)obj_factor, obj_factor_scalar, (double*)resid,
+                                                                     (double*)jac_vals, (double*)hes_vals, H, x, dw, n, naux, nnz_jac, nnz_hes, B);
+    else
+        nempc_rolling_assemble_kernel<float><<<grid, threads, 0, s>>>(tb, (const float*)z, (const float*)aux, (const float*)f, (const float*)J, (const float*)Hs,
+                                                                    (const float*)lambda, (const float*)obj_factor, obj_factor_scalar, (float*)resid,
+                                                                    (float*)jac_vals, (float*)hes_vals, H, x, dw, n, naux, nnz_jac, nnz_hes, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "rolling assemble kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
     return NEMPC_OK;
 }
 

@@ -18,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 from ..engine import NlpEvaluator
-from ..model import CudaMLPModel, Model
+from ..model import CudaMLPModel, CudaMLPModelRollingInput, Model
 
 
 class Integrator:
@@ -60,16 +60,26 @@ class _CudaIntegrator(Integrator):
         if not isinstance(model, (Model,)):
             raise ValueError("The model provided isn't a Model object !")
         super().__init__(model, H, model.x_dim * H)
-        if not isinstance(model, CudaMLPModel):
+        if not isinstance(model, (CudaMLPModel, CudaMLPModelRollingInput)):
             raise ValueError("CUDA integrators need a CudaMLPModel (the network is fused into the integrator kernel)")
         self.DT = DT
         self.cache_mode = cache_mode
         self._cache, self._cache_size = [], max(1, int(cache_size))
+        self._exo_key, self._exo_token = None, None
+        self.rolling = isinstance(model, CudaMLPModelRollingInput)
+        if self.rolling:
+            # rolling-window (NARX) model: banded structure, its own evaluator (rolling.py); the history rows are read from the model at
+            # every evaluation (KerasTFModelRollingInput.set_prev_data is called between NMPC.next calls)
+            from ..rolling import RollingNlpEvaluator
+            self.evaluator = RollingNlpEvaluator(model.weights, model.x_dim, model.u_dim, H, self.KIND, model.rolling_window,
+                                                 forward_rolling=model.forward_rolling, activation=model.activation,
+                                                 compute_dtype=model.dtype, io_dtype="float64", device=model.device)
+            self.evaluator.prev_source = model
+            return
         self.evaluator = NlpEvaluator(model.weights, model.x_dim, model.u_dim, H, self.KIND, DT=DT,
                                       activation=model.activation, compute_dtype=model.dtype, io_dtype="float64",
                                       device=model.device, kernel=model.kernel,
                                       tvp_dim=model.tvp_dim or 0, p_dim=model.p_dim or 0)
-        self._exo_key, self._exo_token = None, None
 
     def _set_exogenous(self, p, tvp):
         """hand the model's tvp (H, tvp_dim) / p (p_dim,) rows to the evaluator when they changed (they are fixed during one solve:
@@ -133,6 +143,18 @@ class _CudaIntegrator(Integrator):
     def hessian(self, x, u, x0, p=None, tvp=None):
         H, xd, ud = self.H, self.model.x_dim, self.model.u_dim
         n = H * (xd + ud)
+        if self.rolling:
+            # banded model Hessian (H, x, n, n) over (x_{t-1} rows, u rows) -> shift the state index by one step (x_0 is data),
+            # the slicing of discret.py:61-81 / unity.py:61-81
+            xprev = np.concatenate([np.asarray(x0, np.float64).reshape(1, -1), np.asarray(x, np.float64)], axis=0)[:-1]
+            mh = self.model.hessian(xprev, np.asarray(u, np.float64)).reshape(-1, n, n)
+            out = np.zeros_like(mh)
+            sx = xd * H
+            out[:, :sx - xd, :sx - xd] = mh[:, xd:sx, xd:sx]
+            out[:, sx:, sx:] = mh[:, sx:, sx:]
+            out[:, :sx - xd, sx:] = mh[:, xd:sx, sx:]
+            out[:, sx:, :sx - xd] = mh[:, sx:, xd:sx]
+            return out
         blk = self.hessian_blocks(x, u, x0, p, tvp)
         out = np.zeros((H, xd, n, n))
         off = xd * H
@@ -150,6 +172,12 @@ class _CudaIntegrator(Integrator):
         H, xd, ud = self.H, self.model.x_dim, self.model.u_dim
         n = H * (xd + ud)
         m = np.zeros((n, n))
+        if self.rolling:
+            from ..rolling import rolling_structure
+            st = rolling_structure(H, xd, ud, self.model.rolling_window, self.KIND, None, self.model.forward_rolling)
+            m[st["hes_rows"], st["hes_cols"]] = 1.0
+            m[st["hes_cols"], st["hes_rows"]] = 1.0
+            return m
         for t in range(H):
             cu = slice(H * xd + t * ud, H * xd + (t + 1) * ud)
             m[cu, cu] = 1.0

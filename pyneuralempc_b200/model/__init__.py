@@ -138,3 +138,92 @@ class CudaMLPModel(Model):
             out[i, :, su, sx] = Hs[i, :, xd:, :xd]
             out[i, :, su, su] = Hs[i, :, xd:, xd:]
         return out
+
+
+class CudaMLPModelRollingInput(Model):
+    """Rolling-window (NARX) network on the GPU: the reference's ``KerasTFModelRollingInput`` (model/tensorflow.py:131-340) /
+    ``DiffDiscretJaxModelRollingWindow`` (model/jax.py:93-259).  Row ``i`` of a call reads the ``rolling_window`` latest rows of the
+    history-extended inputs (``set_prev_data`` provides the ``rolling_window - 1`` rows before the first one); the network has
+    ``rolling_window * (x_dim + u_dim)`` inputs ordered ``[x window | u window]``, oldest row first (newest first when
+    ``forward_rolling=False``).  Dense outputs have the layouts of ``CudaMLPModel`` with the band filled in:
+    ``jacobian`` (N x_dim, N (x_dim + u_dim)), ``hessian`` (N, x_dim, N d, N d); history columns are dropped like the reference does."""
+
+    def __init__(self, weights, x_dim: int, u_dim: int, p_dim=0, tvp_dim=0, rolling_window=2, forward_rolling=True, activation="tanh",
+                 dtype="float32", device=0, standardScaler=None):
+        if standardScaler is not None:
+            raise NotImplementedError("This feature isn't supported yet !")                      # tensorflow.py:134-135
+        if p_dim or tvp_dim:
+            raise NotImplementedError("rolling-window models with p / tvp inputs are not supported (the reference's own TODO, tensorflow.py:114)")
+        if not isinstance(rolling_window, int) or rolling_window < 1:
+            raise ValueError("Your rolling windows need to be an integer gretter than 1.")          # tensorflow.py:151-152
+        weights = [(np.asarray(W, np.float64), np.asarray(b, np.float64)) for W, b in weights]
+        if weights[-1][0].shape[1] != x_dim:                                                       # tensorflow.py:145-146
+            raise ValueError("Your Keras model do not provide a suitable output dim ! \n It must get the same dim as the state dim.")
+        if weights[0][0].shape[0] != rolling_window * (x_dim + u_dim):
+            raise ValueError("Your model do not provide a suitable input dim ! \n It must be rolling_window * (x_dim + u_dim).")
+        adopt_reference_base()
+        super().__init__(x_dim, u_dim, 0, 0)
+        self.weights, self.activation, self.dtype, self.device = weights, activation, dtype, device
+        self.rolling_window, self.forward_rolling = rolling_window, forward_rolling
+        self.prev_x, self.prev_u, self.prev_tvp = None, None, None
+        self._ev = None
+
+    def __getstate__(self):                                  # tensorflow.py:162-169
+        st = dict(self.__dict__)
+        st["_ev"], st["prev_x"], st["prev_u"], st["prev_tvp"] = None, None, None, None
+        return st
+
+    def set_prev_data(self, x_prev, u_prev, tvp_prev=None):   # tensorflow.py:174-185
+        w = self.rolling_window
+        x_prev, u_prev = np.asarray(x_prev, np.float64), np.asarray(u_prev, np.float64)
+        assert x_prev.shape == (w - 1, self.x_dim), f"Your x prev tensor must have the following shape {(w - 1, self.x_dim)} (received : {x_prev.shape})"
+        assert u_prev.shape == (w - 1, self.u_dim), f"Your u prev tensor must have the following shape {(w - 1, self.u_dim)} (received : {u_prev.shape})"
+        self.prev_x, self.prev_u = x_prev, u_prev
+
+    def evaluator(self):
+        if self._ev is None:
+            dw = self.rolling_window * (self.x_dim + self.u_dim)
+            self._ev = NlpEvaluator(self.weights, self.x_dim, dw - self.x_dim, 1, "unity", activation=self.activation,
+                                    compute_dtype=self.dtype, io_dtype="float64", device=self.device, kernel="generic")
+        return self._ev
+
+    def _rows(self, x, u):
+        """window rows (N, dw) of the network input and the (N, dw) column codes of its entries"""
+        from ..rolling import window_columns
+        assert (self.prev_x is not None) and (self.prev_u is not None), \
+            "You must give history window with set_prev_data before calling any inferance function."       # tensorflow.py:189
+        x, u = np.asarray(x, np.float64), np.asarray(u, np.float64)
+        N = x.shape[0]
+        code = window_columns(N, self.x_dim, self.u_dim, self.rolling_window, self.forward_rolling, model_level=True)
+        flat = np.concatenate([x.reshape(-1), u.reshape(-1)])
+        aux = np.concatenate([np.zeros(self.x_dim), self.prev_x.reshape(-1), self.prev_u.reshape(-1)])
+        zin = np.where(code >= 0, flat[np.clip(code, 0, None)], aux[np.clip(-1 - code, 0, None)])
+        return zin, code
+
+    def blocks(self, x, u, want_jac=True, want_hes=True):
+        zin, code = self._rows(x, u)
+        f, J, Hs = self.evaluator().model_eval(zin, want_jac, want_hes)
+        c = lambda t: None if t is None else t.cpu().numpy()
+        return c(f), c(J), c(Hs), code
+
+    def forward(self, x, u, p=None, tvp=None):
+        return self.blocks(x, u, False, False)[0]
+
+    def jacobian(self, x, u, p=None, tvp=None):
+        N, xd, d = np.asarray(x).shape[0], self.x_dim, self.x_dim + self.u_dim
+        _, J, _, code = self.blocks(x, u, True, False)
+        out = np.zeros((N * xd, N * d))
+        for i in range(N):
+            keep = code[i] >= 0
+            out[i * xd:(i + 1) * xd, code[i][keep]] = J[i][:, keep]
+        return out
+
+    def hessian(self, x, u, p=None, tvp=None):
+        N, xd, d = np.asarray(x).shape[0], self.x_dim, self.x_dim + self.u_dim
+        _, _, Hs, code = self.blocks(x, u, True, True)
+        out = np.zeros((N, xd, N * d, N * d))
+        for i in range(N):
+            keep = np.nonzero(code[i] >= 0)[0]
+            cols = code[i][keep]
+            out[i][:, cols[:, None], cols[None, :]] = Hs[i][:, keep[:, None], keep[None, :]]
+        return out

@@ -39,6 +39,9 @@ class CudaIpm(Optimizer):
         if problem.constraints_list:
             raise NotImplementedError("the on-device solver handles the integrator constraints and the DomainConstraint box only; "
                                       "use optimizer.TrustConstr / Slsqp / Ipopt with extra constraints")
+        if not hasattr(problem.ev, "solve"):
+            raise NotImplementedError("the on-device solver's Riccati sweep assumes the one-step band; rolling-window models go through "
+                                      "optimizer.TrustConstr / Slsqp / Ipopt")
         H = problem.integrator.H
         lb, ub = domain_constraint.get_lower_bounds(H), domain_constraint.get_upper_bounds(H)
         warm = (self.init_with_last_result and self.prev_result is not None) or problem.get_init_variables()[0] is not None

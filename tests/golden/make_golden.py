@@ -22,6 +22,9 @@ What is recorded (all float64 unless noted):
   ref_closed_loop_c1.npz  BASELINE config C1 as named (examples/lotka_volterra/run.py:38-87): the reference's own NMPC.next with its Slsqp
                           optimizer, H = 25, cost 1.1 * sum(u), u in [-1, 0.2], x_0 <= 1, LV fixture network, discrete and RK4 (DT 0.1)
                           integrators: iteration count, final cost, solution
+  ref_rolling_<kind>_w<w>.npz  rolling-window (NARX) models, SURVEY 8f rank 2: a window network (w (x+u) -> 10 -> 10 -> x) behind a subclass of
+                          the reference's Model with the layouts of KerasTFModelRollingInput (oracle/rolling_np.py restates
+                          model/tensorflow.py:112-340), through the reference's Discret / Unity integrators and IpoptProblem
 The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
 reference's ``Model`` (TensorFlow is not installed), so these files pin the integrator / IPOPT
 glue of the oracle, not TensorFlow's autodiff.
@@ -229,6 +232,49 @@ def record_closed_loop_c1(ref, lv, H=25):
     return out
 
 
+def record_rolling(ref, kind, w, forward_rolling, H=6, seed=800):
+    """reference integrator + IpoptProblem over a rolling-window model (banded model Jacobian / Hessian)"""
+    from oracle.rolling_np import RollingMLP
+    rng = np.random.default_rng(seed + w)
+    xd, ud = 2, 1
+    net = MLP.glorot([w * (xd + ud), 10, 10, xd], xd, w * (xd + ud) - xd, seed=30 + w)
+    roll = RollingMLP(net.weights, xd, ud, w, forward_rolling)
+
+    class RollingBackedModel(ref.model.base.Model):
+        def __init__(self):
+            super().__init__(xd, ud, 0, 0)
+
+        def forward(self, x, u, p=None, tvp=None):
+            return roll.forward(x, u)
+
+        def jacobian(self, x, u, p=None, tvp=None):
+            return roll.jacobian(x, u)
+
+        def hessian(self, x, u, p=None, tvp=None):
+            return roll.hessian(x, u)
+
+    x_prev, u_prev = rng.uniform(-1, 1, (w - 1, xd)), rng.uniform(-1, 1, (w - 1, ud))
+    roll.set_prev_data(x_prev, u_prev)
+    n, m = H * (xd + ud), H * xd
+    z, x0, lam, sigma = rng.uniform(-1, 1, n), rng.uniform(-1, 1, xd), rng.standard_normal(m), 0.8
+    sep = SeparableQuadraticObjective.tracking(H, xd, ud, rng.uniform(0.5, 2, xd), rng.uniform(0.1, 1, ud), x_ref=rng.uniform(-1, 1, (H, xd)))
+    integ = make_integrator(ref, kind, RollingBackedModel(), H)
+    np.random.seed(seed)
+    pb = ref.optimizer.ipopt.IpoptProblem(x0, ref_objective(ref, sep), [], integ, use_hessian=True)
+    out = dict(kind=kind, H=H, x_dim=xd, u_dim=ud, rolling_window=w, forward_rolling=forward_rolling, x_prev=x_prev, u_prev=u_prev,
+               z=z, x0=x0, lam=lam, sigma=sigma, obj_lin=sep.lin, obj_quad=sep.quad, obj_ref=sep.ref)
+    out.update({f"net_W{i}": W for i, (W, _) in enumerate(net.weights)})
+    out.update({f"net_b{i}": b for i, (_, b) in enumerate(net.weights)})
+    out["objective"], out["gradient"], out["constraints"], out["jacobian"] = pb.objective(z), pb.gradient(z), pb.constraints(z), pb.jacobian(z)
+    out["hes_rows"], out["hes_cols"] = pb.hessianstructure()
+    out["hessian_values"] = pb.hessian(z, lam, sigma)
+    states, u = z[:H * xd].reshape(H, xd), z[H * xd:].reshape(H, ud)
+    out["integrator_hessian"] = integ.hessian(states, u, x0)
+    xp = np.concatenate([x0[None], states])[:-1]
+    out["model_forward"], out["model_jacobian"], out["model_hessian"] = roll.forward(xp, u), roll.jacobian(xp, u), roll.hessian(xp, u)
+    return out
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -273,6 +319,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_rk4_w128_H6.npz"), **record_wide(ref, [3, 128, 128, 2], 2, 1, "rk4", 6, 700, 21))
     np.savez_compressed(os.path.join(HERE, "ref_discrete_w256_H6.npz"), **record_wide(ref, [5, 256, 256, 256, 4], 4, 1, "discrete", 6, 710, 22))
     np.savez_compressed(os.path.join(HERE, "ref_closed_loop_c1.npz"), **record_closed_loop_c1(ref, lv))
+    np.savez_compressed(os.path.join(HERE, "ref_rolling_discrete_w2.npz"), **record_rolling(ref, "discrete", 2, True))
+    np.savez_compressed(os.path.join(HERE, "ref_rolling_unity_w3.npz"), **record_rolling(ref, "unity", 3, False))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -54,7 +54,10 @@ def test_integrators_dense_interface_vs_reference_goldens(golden_dir, lv_weights
         assert integ.nb_contraints == 12
         assert _rel(integ.forward(s, u, x0), g["integrator_forward"]) < tol
         assert _rel(integ.jacobian(s, u, x0), g["integrator_jacobian"]) < tol
-        assert _rel(integ.hessian(s, u, x0), g["integrator_hessian"]) < tol
+        # per-output second derivatives: the golden is the float64 evaluation; a float32 evaluation of the same closed form IN NUMPY is
+        # already 1.25e-5 off by this metric at one entry of the unity case (4.7e-4 in an array whose maximum is 7e-2: float32
+        # cancellation, measured with oracle.blocks_np.step_blocks on a float32 MLP), so float32 gets 2e-5 here
+        assert _rel(integ.hessian(s, u, x0), g["integrator_hessian"]) < (2e-5 if dtype == "float32" else tol)
         np.testing.assert_array_equal(integ.hessianstructure(), g["integrator_structure"])
         assert integ.get_lower_bounds(H) == [0.0] * 12
     with pytest.raises(ValueError):

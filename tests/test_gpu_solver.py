@@ -54,19 +54,24 @@ def test_device_solver_matches_numpy_statement(kind, dims, x, u, H, DT, xb, lv_w
 
 
 def test_float32_network_and_large_batch(lv_weights):
-    """float32 network arithmetic (the reference's Keras precision) with the reference's acceptable tolerance 1e-4
-    (optimizer/ipopt.py:185); 2048 problems at once; every solution is feasible and within 1e-4 of the float64 optimum."""
+    """float32 network arithmetic (the reference's Keras precision) against float64, BOTH solved to the same KKT tolerance -- the reference's
+    acceptable tolerance 1e-4 (optimizer/ipopt.py:185) -- on 2048 problems at once.  The cost is flat (R = 0.1): a KKT error of 1e-4 leaves
+    ~2e-2 of slack in z whatever the arithmetic (tools/solver_precision_probe.py), so the two precisions are compared with each other, not
+    with a tighter solve: where they take the same number of iterations (99 % of the problems) the iterates agree to 1e-5, elsewhere
+    (one more or one fewer step across the same tolerance) to 1e-3, and the costs agree to 1e-5 relative everywhere."""
     mlp, obj, lb, ub, X0 = _setup("unity", "lv", 2, 1, 10, None, 0, lv_weights, B=2048)
     o32 = _ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=1e-4)
-    o64 = _ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-8)
+    o64 = _ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-4)
     assert (o32["status"].cpu().numpy() == 0).all() and (o64["status"].cpu().numpy() == 0).all()
     z32, z64 = o32["z"].cpu().numpy(), o64["z"].cpu().numpy()
-    assert np.abs(z32 - z64).max() < 5e-2                  # KKT error 1e-4 on a flat cost (R = 0.1) leaves ~1e-2 slack in z; costs agree below
+    same = (o32["iterations"] == o64["iterations"]).cpu().numpy()
+    dz = np.abs(z32 - z64).max(axis=1)
+    assert same.mean() > 0.97 and dz[same].max() < 1e-5 and dz.max() < 1e-3
     oe = BlockEvaluator(mlp, "unity", 10, objective=obj)
-    r32 = oe.evaluate(z32[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
-    r64 = oe.evaluate(z64[:64], X0[:64], None, 1.0, need_jac=False, need_hes=False)
+    r32 = oe.evaluate(z32[:256], X0[:256], None, 1.0, need_jac=False, need_hes=False)
+    r64 = oe.evaluate(z64[:256], X0[:256], None, 1.0, need_jac=False, need_hes=False)
     assert np.abs(r32["resid"]).max() < 1e-4
-    assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-3 * np.abs(r64["obj"]).max()
+    assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-5 * np.abs(r64["obj"]).max()
     its = o32["iterations"].cpu().numpy()
     assert its.mean() < 12 and int(its.max()) <= 60         # a few of the 2048 problems ride an active bound and need more IPM steps
 

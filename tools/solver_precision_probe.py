@@ -18,6 +18,14 @@ if __name__ == "__main__":
     o64 = T._ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-9)
     z64 = o64["z"].cpu().numpy()
     print("f64 tol 1e-9: converged", int((o64["status"] == 0).sum()), "iterations mean", float(o64["iterations"].double().mean()))
+    for tol in (1e-4, 1e-5, 3e-6):
+        a = T._ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=tol, max_iter=100)
+        b = T._ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=tol, max_iter=100)
+        ok = ((a["status"] == 0) & (b["status"] == 0)).cpu().numpy()
+        same_it = (a["iterations"] == b["iterations"]).cpu().numpy()
+        dz = np.abs(a["z"].cpu().numpy() - b["z"].cpu().numpy()).max(axis=1)
+        print(f"same tol {tol:g}: both converged {int(ok.sum())}, same iteration count {int(same_it.sum())}, max |z32 - z64| all {dz[ok].max():.3e}, "
+              f"where the counts agree {dz[ok & same_it].max():.3e}", flush=True)
     for comp in ("float64", "float32"):
         for tol in (1e-4, 1e-5, 3e-6, 1e-6, 3e-7):
             o = T._ev(mlp, "unity", 10, None, obj, comp).solve(X0, lb, ub, tol=tol, max_iter=100)
