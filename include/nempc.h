@@ -152,6 +152,23 @@ int nempc_model_eval(nempc_handle* h, int64_t N, const void* zin, void* f, void*
 int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const double* lin, const double* quad,
                          const double* ref, void* obj, void* grad, void* stream);
 
+/* ---- non-separable quadratic costs ------------------------------------------------------------------------------
+ * JAXObjectifFunc takes any scalar function (objective/jax.py:28-57).  Beyond the separable family of nempc_set_objective the device
+ * path evaluates GENERAL QUADRATIC costs f(z) = 1/2 z' P z + q' z + c with a sparse symmetric P: control-rate penalties
+ * (u_{t+1} - u_t)' S (u_{t+1} - u_t), full-matrix stage weights (x_t - r_t)' Q (x_t - r_t), a full terminal weight on x_H, cross terms.
+ *   nempc_quadform_eval   obj (B) / grad (B, n) of that cost; P as CSR over all n rows with BOTH triangles (p_ptr n+1, p_idx, p_val),
+ *                         q (n) and the table pointers are DEVICE arrays; z / obj / grad DEVICE arrays of io_dtype.
+ *   nempc_hessian_merge   sigma * P joins the Lagrangian Hessian (optimizer/ipopt.py:66-86) on the UNION pattern
+ *                         np.nonzero(np.tril(objective_map + integrator_map)) (ipopt.py:55-62):
+ *                         out_vals[b, s] = kern_vals[b, src_slot[s]] (src_slot[s] >= 0: the slot of the constraint part as nempc_eval
+ *                         wrote it on a handle WITHOUT a device objective) + obj_factor_b * p_val[s].
+ * Stateless, asynchronous on `stream`. */
+int nempc_quadform_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const int32_t* p_ptr, const int32_t* p_idx,
+                        const double* p_val, const double* q, double c, void* obj, void* grad, void* stream);
+int nempc_hessian_merge(int32_t io_dtype, int64_t B, int64_t nnz_kern, int64_t nnz_out, const void* kern_vals,
+                        const int32_t* src_slot, const double* p_val, const void* obj_factor, double obj_factor_scalar,
+                        void* out_vals, void* stream);
+
 /* ---- rolling-window (NARX) models ---------------------------------------------------------------
  * Replaces the window logic of KerasTFModelRollingInput / DiffDiscretJaxModelRollingWindow (model/tensorflow.py:112-340,
  * model/jax.py:93-259: rolling_input, _gather_input, the projection matrices of jacobian / hessian) together with the dense slicing

@@ -20,7 +20,8 @@ EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy",
            "nempc_set_objective", "nempc_set_exogenous", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
            "nempc_eval", "nempc_eval_host", "nempc_eval_blocks", "nempc_model_eval", "nempc_launch_count",
            "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve",
-           "nempc_abi_info", "nempc_source_hash", "nempc_rolling_gather", "nempc_rolling_assemble")
+           "nempc_abi_info", "nempc_source_hash", "nempc_rolling_gather", "nempc_rolling_assemble",
+           "nempc_quadform_eval", "nempc_hessian_merge")
 
 
 class NempcDesc(ctypes.Structure):
@@ -95,6 +96,8 @@ def load():
     lib.nempc_rolling_gather.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.nempc_rolling_assemble.argtypes = [i32, i64, i32, i32, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl,
                                            vp, vp, vp, vp]
+    lib.nempc_quadform_eval.argtypes = [i32, i64, i64, vp, vp, vp, vp, vp, dbl, vp, vp, vp]
+    lib.nempc_hessian_merge.argtypes = [i32, i64, i64, i64, vp, vp, vp, vp, dbl, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)                  # AttributeError here = the .so does not match include/nempc.h
     _lib = lib

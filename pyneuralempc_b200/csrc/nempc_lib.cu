@@ -89,6 +89,47 @@ __global__ void nempc_objective_kernel(const TIO* __restrict__ z, const double* 
     }
 }
 
+// objective value + gradient of a general quadratic cost f(z) = 1/2 z' P z + q' z + c with a sparse symmetric P (CSR over all n rows,
+// both triangles): rate penalties (u_{t+1} - u_t)' S (u_{t+1} - u_t), full-matrix stage / terminal weights, cross terms.  One warp per
+// problem, fixed summation order.  Replaces JAXObjectifFunc.forward / .gradient (objective/jax.py:28-41) for non-separable costs.
+template <typename TIO>
+__global__ void nempc_quadform_kernel(const TIO* __restrict__ z, const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                      const double* __restrict__ val, const double* __restrict__ q, double c,
+                                      TIO* __restrict__ obj, TIO* __restrict__ grad, int n, long long B) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = warp; b < B; b += nwarps) {
+        const TIO* zb = z + b * n;
+        double acc = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            double pz = 0.0;
+            for (int k = ptr[i]; k < ptr[i + 1]; ++k) pz += val[k] * (double)zb[idx[k]];
+            const double zi = (double)zb[i];
+            acc += zi * (0.5 * pz + q[i]);
+            if (grad) grad[b * n + i] = (TIO)(pz + q[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (obj && lane == 0) obj[b] = (TIO)(acc + c);
+    }
+}
+
+// Lagrangian-Hessian values on the UNION pattern of the constraint Hessian (what the evaluation kernels write, in their closed-form slot
+// order) and a constant objective Hessian P:  out[b, s] = kern[b, src[s]] (if src[s] >= 0) + obj_factor_b * pval[s]   (ipopt.py:66-86)
+template <typename TIO>
+__global__ void nempc_hessian_merge_kernel(const TIO* __restrict__ kern, const int32_t* __restrict__ src, const double* __restrict__ pval,
+                                           const TIO* __restrict__ sigma, double sigma_scalar, TIO* __restrict__ out,
+                                           long long nnz_kern, long long nnz_out, long long B) {
+    const long long total = B * nnz_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / nnz_out, s = i - b * nnz_out;
+        const int k = src[s];
+        const double sg = sigma ? (double)sigma[b] : sigma_scalar;
+        out[i] = (TIO)((k >= 0 ? (double)kern[b * nnz_kern + k] : 0.0) + sg * pval[s]);
+    }
+}
+
 // register-resident FMA loop: sustained FP32 / FP64 FMA-pipe throughput (the compute-roofline denominator)
 template <typename T>
 __global__ void nempc_fma_peak_kernel(T* out, int iters, T seed) {
@@ -1237,6 +1278,43 @@ extern "C" int nempc_objective_eval(int32_t io_dtype, int64_t B, int64_t n, cons
     else nempc_objective_kernel<float><<<grid, threads, 0, s>>>((const float*)z, lin, quad, ref, (float*)obj, (float*)grad, (int)n, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "objective kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+// ---- general quadratic objective: value / gradient, and the merge of its constant Hessian into the Lagrangian-Hessian values ---------
+extern "C" int nempc_quadform_eval(int32_t io_dtype, int64_t B, int64_t n, const void* z, const int32_t* p_ptr, const int32_t* p_idx,
+                                   const double* p_val, const double* q, double c, void* obj, void* grad, void* stream) {
+    if (B < 0 || n < 1 || !z || !p_ptr || !p_idx || !p_val || !q || (io_dtype != NEMPC_F32 && io_dtype != NEMPC_F64)) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_quadform_eval: bad argument");
+        return NEMPC_EINVAL;
+    }
+    if (B == 0 || (!obj && !grad)) return NEMPC_OK;
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((B * 32 + threads - 1) / threads, 148 * 16));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (io_dtype == NEMPC_F64) nempc_quadform_kernel<double><<<grid, threads, 0, s>>>((const double*)z, p_ptr, p_idx, p_val, q, c, (double*)obj, (double*)grad, (int)n, B);
+    else nempc_quadform_kernel<float><<<grid, threads, 0, s>>>((const float*)z, p_ptr, p_idx, p_val, q, c, (float*)obj, (float*)grad, (int)n, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "quadratic-form kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
+extern "C" int nempc_hessian_merge(int32_t io_dtype, int64_t B, int64_t nnz_kern, int64_t nnz_out, const void* kern_vals,
+                                   const int32_t* src_slot, const double* p_val, const void* obj_factor, double obj_factor_scalar,
+                                   void* out_vals, void* stream) {
+    if (B < 0 || nnz_out < 1 || nnz_kern < 0 || !src_slot || !p_val || !out_vals || (nnz_kern > 0 && !kern_vals) ||
+        (io_dtype != NEMPC_F32 && io_dtype != NEMPC_F64)) {
+        SET_ERR((nempc_handle*)nullptr, "nempc_hessian_merge: bad argument");
+        return NEMPC_EINVAL;
+    }
+    if (B == 0) return NEMPC_OK;
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((B * nnz_out + threads - 1) / threads, 148 * 16));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (io_dtype == NEMPC_F64) nempc_hessian_merge_kernel<double><<<grid, threads, 0, s>>>((const double*)kern_vals, src_slot, p_val, (const double*)obj_factor, obj_factor_scalar, (double*)out_vals, nnz_kern, nnz_out, B);
+    else nempc_hessian_merge_kernel<float><<<grid, threads, 0, s>>>((const float*)kern_vals, src_slot, p_val, (const float*)obj_factor, obj_factor_scalar, (float*)out_vals, nnz_kern, nnz_out, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { SET_ERR((nempc_handle*)nullptr, "Hessian merge kernel launch: %s", cudaGetErrorString(e)); return NEMPC_ECUDA; }
     return NEMPC_OK;
 }
 

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..objective import CudaSeparableObjective
+from ..objective import CudaQuadraticFormObjective, CudaSeparableObjective
 from .base import Optimizer, ProblemFactory, ProblemInterface, ProblemInterfaceHessianFree, initial_guess
 
 
@@ -37,10 +37,12 @@ class CudaIpoptProblem(ProblemInterface):
         self.ev = integrator.evaluator
         self._key, self._point = None, None
         self._device_objective = isinstance(objective_func, CudaSeparableObjective)
-        if self._device_objective:
+        self._quadform = isinstance(objective_func, CudaQuadraticFormObjective)       # non-separable quadratic: own kernels + Hessian merge
+        if self._device_objective or self._quadform:
             objective_func.prepare(self.H, self.x_dim, self.u_dim, p, tvp)
-        if not self._device_objective and use_hessian:
-            raise NotImplementedError("the Lagrangian-Hessian path needs a CudaSeparableObjective")
+        if not (self._device_objective or self._quadform) and use_hessian:
+            raise NotImplementedError("the Lagrangian-Hessian path needs a CudaSeparableObjective or a CudaQuadraticFormObjective")
+        self._merge = None
         self._bind()
         # extra (user, host-side) constraints: rows appended after the integrator's, ipopt.py:49-50, 93-94; their Jacobian rows are dense
         self._extra_dims = [int(np.size(c.get_lower_bounds(self.H))) for c in self.constraints_list]
@@ -59,6 +61,9 @@ class CudaIpoptProblem(ProblemInterface):
         self.integrator._set_exogenous(self.p, self.tvp)       # model inputs that stay fixed during this solve (controller.py:65-113)
         if self._device_objective:
             self.ev.set_objective(self.objective_func.lin, self.objective_func.quad, self.objective_func.ref)
+        elif self._quadform:
+            self.ev.set_objective(None, None, None)            # constraint pattern only: the cost's Hessian is merged in afterwards
+            self._merge = None
         self.ev.bound_to = self
         self._key, self._point = None, None
 
@@ -115,15 +120,34 @@ class CudaIpoptProblem(ProblemInterface):
             J = np.concatenate([J] + [c.jacobian(s, u, p=p, tvp=tvp) for c in self.constraints_list], axis=0)
         return J
 
+    def _merge_tables(self):
+        if self._merge is None:
+            import torch
+            self._bind()
+            r, c, src, pval = self.objective_func.merge_tables(self.ev.hes_rows, self.ev.hes_cols)
+            dev = self.ev.tdevice
+            self._merge = (r.astype(np.int64), c.astype(np.int64), torch.as_tensor(src, device=dev), torch.as_tensor(pval, device=dev))
+        return self._merge
+
     def hessianstructure(self):                                   # ipopt.py:55-62, analytic, same order
+        if self._quadform:
+            return self._merge_tables()[:2]
         return self.ev.hes_rows.astype(np.int64), self.ev.hes_cols.astype(np.int64)
 
     def hessian(self, x, lagrange, obj_factor):                   # ipopt.py:66-86
         self._bind()
         x = np.ascontiguousarray(x, np.float64)
-        out = self.ev.eval_host(x, self.x0, lam=np.asarray(lagrange, np.float64)[: self.ev.m], obj_factor=float(obj_factor),
-                                want=("hes",))
-        vals = out["hes"][0].copy()
+        if self._quadform:
+            import torch
+            _, _, src, pval = self._merge_tables()
+            dev = self.ev.tdevice
+            kern = self.ev.eval(torch.as_tensor(x[None], device=dev), torch.as_tensor(self.x0[None], device=dev),
+                                torch.as_tensor(np.asarray(lagrange, np.float64)[None, : self.ev.m], device=dev), 0.0, want=("hes",))["hes"]
+            vals = self.objective_func.merge_hessian(kern, src, pval, float(obj_factor))[0].cpu().numpy()
+        else:
+            out = self.ev.eval_host(x, self.x0, lam=np.asarray(lagrange, np.float64)[: self.ev.m], obj_factor=float(obj_factor),
+                                    want=("hes",))
+            vals = out["hes"][0].copy()
         if self.constraints_list:
             # ipopt.py:75-80: sum_i lagrange_i * ctr.hessian[i], gathered on the objective + integrator pattern (ipopt.py:55-62, 84-86:
             # entries of a constraint Hessian outside that pattern are dropped by the reference as well).  A constraint without a
@@ -134,7 +158,8 @@ class CudaIpoptProblem(ProblemInterface):
             for c, dim in zip(self.constraints_list, self._extra_dims):
                 if hasattr(c, "hessian"):
                     Hc = np.asarray(c.hessian(s, u, p=p, tvp=tvp), np.float64).reshape(dim, self.ev.n, self.ev.n)
-                    vals += np.einsum("i,ik->k", lam[off:off + dim], Hc[:, self.ev.hes_rows, self.ev.hes_cols])
+                    hr, hc = self.hessianstructure()
+                    vals += np.einsum("i,ik->k", lam[off:off + dim], Hc[:, hr, hc])
                 off += dim
         return vals
 

@@ -166,7 +166,7 @@ class RollingNlpEvaluator:
     def set_objective(self, lin=None, quad=None, ref=None):
         arrs = [None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64).ravel(), (self.n,))) for a in (lin, quad, ref)]
         self._objective = [np.zeros(self.n) if a is None else a for a in arrs]
-        self._obj_dev = [self._torch.as_tensor(a, dtype=self._torch.float64, device=self.tdevice) for a in self._objective]
+        self._obj_dev = [self._torch.as_tensor(np.array(a), dtype=self._torch.float64, device=self.tdevice) for a in self._objective]
         self.bound_to = None
         self._build(self._objective[1])
 
@@ -207,6 +207,8 @@ class RollingNlpEvaluator:
                 "You must give history window with set_prev_data before calling any inferance function."     # tensorflow.py:189
             xp, up = self.prev_source.prev_x, self.prev_source.prev_u
         parts = [x0]
+        if self.w == 1:
+            return x0
         for a, dim in ((xp, self.x_dim), (up, self.u_dim)):
             a = t.as_tensor(a, dtype=self.tdtype, device=self.tdevice).reshape(-1, (self.w - 1) * dim)
             parts.append(a.expand(B, -1) if a.shape[0] == 1 else a)

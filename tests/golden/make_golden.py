@@ -25,6 +25,9 @@ What is recorded (all float64 unless noted):
   ref_rolling_<kind>_w<w>.npz  rolling-window (NARX) models, SURVEY 8f rank 2: a window network (w (x+u) -> 10 -> 10 -> x) behind a subclass of
                           the reference's Model with the layouts of KerasTFModelRollingInput (oracle/rolling_np.py restates
                           model/tensorflow.py:112-340), through the reference's Discret / Unity integrators and IpoptProblem
+  ref_quadform_H6.npz     IpoptProblem callbacks with a NON-SEPARABLE quadratic cost (full stage / terminal weights, control-rate penalty,
+                          state-control cross term: oracle.objectives_np.QuadraticFormObjective behind the reference's ObjectiveFunc):
+                          the Hessian pattern is the union np.nonzero(np.tril(objective_map + integrator_map)) of ipopt.py:55-62
 The dynamics model handed to the reference is ``oracle.mlp_np.MLP`` wrapped in a subclass of the
 reference's ``Model`` (TensorFlow is not installed), so these files pin the integrator / IPOPT
 glue of the oracle, not TensorFlow's autodiff.
@@ -275,6 +278,33 @@ def record_rolling(ref, kind, w, forward_rolling, H=6, seed=800):
     return out
 
 
+def quadform_case(H, xd, ud, seed=900):
+    """the non-separable cost of ref_quadform_H6.npz (also rebuilt by the GPU test from the stored blocks)"""
+    rng = np.random.default_rng(seed)
+    A = lambda r, c: rng.uniform(-1, 1, (r, c))
+    spd = lambda k: (lambda M: M @ M.T + 0.1 * np.eye(k))(A(k, k))
+    return dict(Q=spd(xd), R=spd(ud), Qf=spd(xd), S=spd(ud), N=0.2 * A(xd, ud), x_ref=rng.uniform(-1, 1, (H, xd)), u_ref=rng.uniform(-1, 1, ud),
+                lin=0.3 * rng.uniform(-1, 1, H * (xd + ud)))
+
+
+def record_quadform(ref, lv, H=6, seed=900):
+    from oracle.objectives_np import QuadraticFormObjective
+    rng = np.random.default_rng(seed + 1)
+    xd, ud = lv.x_dim, lv.u_dim
+    n, m = H * (xd + ud), H * xd
+    blocks = quadform_case(H, xd, ud, seed)
+    qf = QuadraticFormObjective(H, xd, ud, **blocks)
+    integ = make_integrator(ref, "rk4", shim.make_reference_model(lv), H)
+    z, x0, lam, sigma = rng.uniform(-1, 1, n), rng.uniform(-1, 1, xd), rng.standard_normal(m), 0.65
+    np.random.seed(seed)
+    pb = ref.optimizer.ipopt.IpoptProblem(x0, ref_objective(ref, qf), [], integ, use_hessian=True)
+    r, c = pb.hessianstructure()
+    out = dict(H=H, DT=DT_RK4, z=z, x0=x0, lam=lam, sigma=sigma, objective=pb.objective(z), gradient=pb.gradient(z),
+               constraints=pb.constraints(z), jacobian=pb.jacobian(z), hes_rows=r, hes_cols=c, hessian_values=pb.hessian(z, lam, sigma))
+    out.update({f"cost_{k}": v for k, v in blocks.items()})
+    return out
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -319,6 +349,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_rk4_w128_H6.npz"), **record_wide(ref, [3, 128, 128, 2], 2, 1, "rk4", 6, 700, 21))
     np.savez_compressed(os.path.join(HERE, "ref_discrete_w256_H6.npz"), **record_wide(ref, [5, 256, 256, 256, 4], 4, 1, "discrete", 6, 710, 22))
     np.savez_compressed(os.path.join(HERE, "ref_closed_loop_c1.npz"), **record_closed_loop_c1(ref, lv))
+    np.savez_compressed(os.path.join(HERE, "ref_quadform_H6.npz"), **record_quadform(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_rolling_discrete_w2.npz"), **record_rolling(ref, "discrete", 2, True))
     np.savez_compressed(os.path.join(HERE, "ref_rolling_unity_w3.npz"), **record_rolling(ref, "unity", 3, False))
     for f in sorted(os.listdir(HERE)):

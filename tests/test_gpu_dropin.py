@@ -487,3 +487,70 @@ def test_problems_sharing_an_integrator_keep_their_own_cost_and_inputs(lv_weight
     ha, hb = pa.hessian(z, lam, 1.0), pb.hessian(z, lam, 1.0)
     assert np.abs(ha - hb).max() > 1e-3                                     # different quadratic weights on the diagonal
     assert _rel(pa.hessian(z, lam, 1.0), ha) < 1e-15
+
+
+def _quadform_blocks(g):
+    return {k[5:]: g[k] for k in g.files if k.startswith("cost_")}
+
+
+def test_non_separable_quadratic_cost_vs_reference_golden(golden_dir, lv_weights):
+    """JAXObjectifFunc takes any scalar function (objective/jax.py:28-57); beyond the separable family the device path evaluates general
+    quadratic costs: full stage / terminal weights, a control-rate penalty, a state-control cross term.  IpoptProblem callbacks recorded from
+    the unmodified reference (tests/golden/ref_quadform_H6.npz) -- the Hessian lives on the union pattern of ipopt.py:55-62."""
+    import torch
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaQuadraticFormObjective
+    from pyneuralempc_b200.optimizer.ipopt import CudaIpoptProblem
+    from oracle.objectives_np import QuadraticFormObjective
+    g = np.load(os.path.join(golden_dir, "ref_quadform_H6.npz"))
+    H = int(g["H"])
+    cost = CudaQuadraticFormObjective.from_blocks(H, 2, 1, **_quadform_blocks(g))
+    integ = I.RK4Integrator(CudaMLPModel(lv_weights, 2, 1, dtype="float64"), H, float(g["DT"]))
+    pb = CudaIpoptProblem(g["x0"], cost, [], integ, use_hessian=True)
+    z = g["z"]
+    r, c = pb.hessianstructure()
+    np.testing.assert_array_equal(r, g["hes_rows"]); np.testing.assert_array_equal(c, g["hes_cols"])
+    assert len(r) > len(integ.evaluator.hes_rows)                                        # rate penalty and terminal weight add entries
+    assert abs(pb.objective(z) - float(g["objective"])) < 1e-12 * max(1.0, abs(float(g["objective"])))
+    assert _rel(pb.gradient(z), g["gradient"]) < 1e-12
+    assert _rel(pb.constraints(z), g["constraints"]) < 1e-10
+    assert _rel(pb.hessian(z, g["lam"], float(g["sigma"])), g["hessian_values"]) < 1e-10
+    assert _rel(pb.hessian(z, g["lam"], 0.0) + float(g["sigma"]) * cost.P.toarray()[r, c], g["hessian_values"]) < 1e-10
+    # batched device evaluation of the cost against the literal definition
+    oq = QuadraticFormObjective(H, 2, 1, **_quadform_blocks(g))
+    rng = np.random.default_rng(4)
+    Z = rng.uniform(-1, 1, (37, 3 * H))
+    obj, grad = cost.eval_device(torch.as_tensor(Z).cuda())
+    ref_o = np.array([oq.forward(zz[:2 * H].reshape(H, 2), zz[2 * H:].reshape(H, 1)) for zz in Z])
+    ref_g = np.array([oq.gradient(zz[:2 * H].reshape(H, 2), zz[2 * H:].reshape(H, 1)) for zz in Z])
+    assert _rel(obj.cpu().numpy(), ref_o) < 1e-12 and _rel(grad.cpu().numpy(), ref_g) < 1e-12
+
+
+def test_rate_penalty_closed_loop_trust_constr_and_slsqp(lv_weights):
+    """a solve with a control-rate penalty (not expressible in the separable family): SLSQP and trust-constr on the CUDA callbacks reach the
+    optimum the same solvers reach on the oracle's dense callbacks, and the rate penalty visibly smooths the controls."""
+    from scipy.optimize import Bounds, minimize
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.objective import CudaQuadraticFormObjective
+    from pyneuralempc_b200.optimizer import Slsqp, TrustConstr
+    from oracle.objectives_np import QuadraticFormObjective
+    H = 10
+    x0 = np.array([0.66, -0.9])
+    model, integ, _, dom = _lv_setup(lv_weights, H)
+    blocks = dict(Q=np.array([[1.0, 0.3], [0.3, 1.0]]), R=np.array([[0.1]]), Qf=np.array([[4.0, 1.0], [1.0, 3.0]]), S=np.array([[2.0]]),
+                  x_ref=np.array([0.5, -0.7]))
+    cost = CudaQuadraticFormObjective.from_blocks(H, 2, 1, **blocks)
+    o_pb = DenseIpoptProblem(x0, QuadraticFormObjective(H, 2, 1, **blocks), DenseIntegrator(DenseModelView(MLP(lv_weights, 2, 1)), H, "unity"))
+    x_init = np.concatenate([np.tile(x0, H), np.zeros(H)])
+    ref = minimize(o_pb.objective, x_init, method="SLSQP", jac=o_pb.gradient, bounds=Bounds(dom.get_lower_bounds(H), dom.get_upper_bounds(H)),
+                   constraints=[{"type": "eq", "fun": o_pb.constraints, "jac": o_pb.jacobian}], options={"maxiter": 200, "ftol": 0.5e-6})
+    opt = Slsqp(verbose=0)
+    xs, us = NMPC(integ, cost, [dom], H, 0.1, optimizer=opt).next(x0)
+    assert xs is not None and opt.last_result.nit == ref.nit and abs(opt.last_result.fun - ref.fun) < 1e-6
+    opt2 = TrustConstr()
+    xs2, us2 = NMPC(integ, cost, [dom], H, 0.1, optimizer=opt2).next(x0)
+    assert xs2 is not None and abs(opt2.last_result.fun - ref.fun) < 1e-3 and np.abs(us2 - us).max() < 2e-2
+    free = CudaQuadraticFormObjective.from_blocks(H, 2, 1, **{**blocks, "S": None})
+    _, u_free = NMPC(integ, free, [dom], H, 0.1, optimizer=Slsqp(verbose=0)).next(x0)
+    assert np.abs(np.diff(us[:, 0])).sum() < 0.8 * np.abs(np.diff(u_free[:, 0])).sum()

@@ -70,3 +70,40 @@ def test_generalised_rk4_against_finite_differences(kind, dims, xd, ud, H):
 def test_reference_tril_nnz_formula():
     ev = BlockEvaluator(MLP.glorot([3, 4, 2], 2, 1), "rk4", 25, DT=0.1)
     assert len(ev.hes_rows) == 145 and len(ev.jac_rows) == 196
+
+
+def test_quadratic_form_objective_oracle_and_product_matrices_agree():
+    """non-separable quadratic costs: the oracle's literal cost definition, its separately assembled matrices and the product's
+    CudaQuadraticFormObjective.from_blocks (host-side scipy assembly) describe the same function"""
+    from oracle.objectives_np import QuadraticFormObjective
+    from pyneuralempc_b200.objective import CudaQuadraticFormObjective
+    rng = np.random.default_rng(0)
+    H, xd, ud = 5, 3, 2
+    A = lambda r, c: rng.standard_normal((r, c))
+    blocks = dict(Q=A(xd, xd), R=A(ud, ud), Qf=A(xd, xd), S=A(ud, ud), N=A(xd, ud), x_ref=rng.standard_normal((H, xd)),
+                  u_ref=rng.standard_normal(ud), lin=rng.standard_normal(H * (xd + ud)))
+    o = QuadraticFormObjective(H, xd, ud, **blocks)
+    s, u = rng.standard_normal((H, xd)), rng.standard_normal((H, ud))
+    g, Hd = o._numeric(s, u)
+    P, q, c = o.matrices()
+    z = np.concatenate([s.ravel(), u.ravel()])
+    assert abs(o.forward(s, u) - (0.5 * z @ P @ z + q @ z + c)) < 1e-11
+    np.testing.assert_allclose(g, o.gradient(s, u), atol=1e-11)
+    np.testing.assert_allclose(Hd, P, atol=1e-10)
+    prod = CudaQuadraticFormObjective.from_blocks(H, xd, ud, **blocks)
+    np.testing.assert_allclose(prod.P.toarray(), P, atol=1e-13)
+    np.testing.assert_allclose(prod.q, q, atol=1e-12)
+    assert abs(prod.c - c) < 1e-11
+    # union pattern = np.nonzero(np.tril(objective_map + integrator_map)) (ipopt.py:55-62)
+    from oracle import structure as S
+    hr, hc = S.hessian_structure(H, xd, ud, None)
+    r, cc, src, pval = prod.merge_tables(hr, hc)
+    m = np.zeros((len(z), len(z)))
+    m[hr, hc] = 1.0
+    m += np.tril(P != 0)
+    rr, rc = np.nonzero(m)
+    np.testing.assert_array_equal(r, rr); np.testing.assert_array_equal(cc, rc)
+    assert (src >= 0).sum() == len(hr) and np.array_equal(np.sort(src[src >= 0]), np.arange(len(hr)))
+    np.testing.assert_allclose(pval, P[r, cc], atol=1e-13)
+    with pytest.raises(ValueError):
+        CudaQuadraticFormObjective(np.triu(P) + 1.0)                                   # not symmetric
