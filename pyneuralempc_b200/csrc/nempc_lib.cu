@@ -385,14 +385,13 @@ static int tc_shape_id(const nempc_desc& d) {
     return -1;
 }
 
-// width-256 tensor-core kernel (nempc_wide.cuh): (x, u) instantiations; 2..4 hidden layers, all 256 wide; discrete / unity
+// width-256 tensor-core kernel (nempc_wide.cuh): (x, u) instantiations; 2..4 hidden layers, all 256 wide; discrete / unity / RK4
 struct WideShape { int x, u; };
 static const WideShape kWideShapes[] = {{12, 4}, {4, 1}, {2, 1}, {6, 2}};
 static const int kNumWideShapes = sizeof(kWideShapes) / sizeof(kWideShapes[0]);
 
 static int wide_shape_id(const nempc_desc& d) {
     if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
-    if (d.integrator == NEMPC_INTEG_RK4) return -1;
     if (d.n_layers - 1 < 2 || d.n_layers - 1 > NEMPC_WIDE_MAXHID) return -1;
     for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_WIDE_HW) return -1;
     for (int i = 0; i < kNumWideShapes; ++i)
@@ -988,12 +987,12 @@ template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO
     return NEMPC_EINVAL;
 }
 
-template <int X, int U, int MODE, typename TIO>
-static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    typedef WideCfg<X, U, MODE> C;
+template <int X, int U, int MODE, bool RK4, typename TIO>
+static int launch_wide_cfg(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
+    typedef WideCfg<X, U, MODE, RK4> C;
     auto kern = nempc_wide_kernel<C, TIO>;
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
-    StageTable<float> st = make_stage_table<float>(false, h->desc.dt);
+    StageTable<float> st = make_stage_table<float>(RK4, h->desc.dt);
     const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
     static const int grid_cap = getenv("NEMPC_WIDE_GRID") ? std::max(1, atoi(getenv("NEMPC_WIDE_GRID"))) : 1 << 30;      // experiments: fewer CTAs
     const long long npair = (nsup + 1) / 2;                                  // CTA pairs (clusters of two, cta_group::2 MMAs)
@@ -1009,6 +1008,10 @@ static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream
     CU(h, cudaGetLastError());
     h->launches++;
     return NEMPC_OK;
+}
+template <int X, int U, int MODE, typename TIO>
+static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
+    return h->desc.integrator == NEMPC_INTEG_RK4 ? launch_wide_cfg<X, U, MODE, true, TIO>(h, ar, s) : launch_wide_cfg<X, U, MODE, false, TIO>(h, ar, s);
 }
 template <int X, int U, typename TIO>
 static int launch_wide_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {

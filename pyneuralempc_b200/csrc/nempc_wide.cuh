@@ -66,8 +66,9 @@ inline size_t wide_img_index(int N, int K16, int img, int n, int k) {
     return ks * 32 * N + (img == 2 ? 16 * (size_t)N : 0) + in_img;
 }
 
-template <int X_, int U_, int MODE_> struct WideCfg {
+template <int X_, int U_, int MODE_, bool RK4_ = false> struct WideCfg {
     static constexpr int X = X_, U = U_, D = X + U, MODE = MODE_, HW = NEMPC_WIDE_HW;
+    static constexpr bool RK4 = RK4_;                                    // four stages: per-stage k_s, dk_s and adjoint weights in the scratch
     static constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
     static constexpr int DP = D <= 4 ? 4 : (D <= 8 ? 8 : 16);          // tangent rows per step (padded to a power of two)
     static constexpr int SPT = 128 / DP;                                 // steps per phase-C tile
@@ -88,7 +89,9 @@ template <int X_, int U_, int MODE_> struct WideCfg {
     static constexpr int OFF_SC = OFF_STG + STG_BYTES;
     static constexpr int TOTAL = OFF_SC + NEMPC_WIDE_EPI_WARPS * SC_WARP;
     static_assert(NSTAGE >= 4, "wide kernel: weight ring too shallow");
-    static constexpr long long SCRATCH_FLOATS = 2LL * NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;    // h_l and q_l of one super-tile
+    static constexpr long long SCRATCH_NET = 2LL * NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;       // h_l and q_l of one super-tile
+    // RK4: k_s [4][128][16], adjoint weights w [128][16], dk_s [3][128][16 columns][16], running sum_s c_s dk_s [128][16][16]
+    static constexpr long long SCRATCH_FLOATS = SCRATCH_NET + (RK4 ? 5LL * NEMPC_WIDE_SUP * 16 + 4LL * NEMPC_WIDE_SUP * 256 : 0);
     static_assert(D <= 16 && X <= 16, "x_dim + u_dim <= 16");
     static_assert(TOTAL <= 232448, "wide kernel: shared-memory map exceeds 227 KB");
 };
@@ -262,7 +265,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                   const NlpLayout L, const EvalArgs<TIO> ar, float* __restrict__ scratch_all) {
     using namespace widex;
     constexpr int X = C::X, U = C::U, D = C::D, DP = C::DP, SPT = C::SPT, SPW = C::SPW, HW = C::HW, NSTAGE = C::NSTAGE;
-    constexpr bool JAC = C::JAC, HES = C::HES;
+    constexpr bool JAC = C::JAC, HES = C::HES, RK4 = C::RK4;
     constexpr float INV = NEMPC_TC_LO_INV;                 // accumulators carry 2^11
     typedef typename WideOf<float, TIO>::type TW;
     extern __shared__ __align__(1024) unsigned char wide_smem[];
@@ -284,6 +287,10 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     const uint32_t rank = cluster_ctarank();                // 0 = leader (issues the MMAs of the pair)
     float* sa = scratch_all + (long long)blockIdx.x * C::SCRATCH_FLOATS;           // [128][MAXHID][HW]
     float* sq = sa + (long long)NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;
+    float* sks = sa + C::SCRATCH_NET;                                  // RK4 stage state, see WideCfg::SCRATCH_FLOATS
+    float* sw = sks + 4 * NEMPC_WIDE_SUP * 16;
+    float* sdk = sw + NEMPC_WIDE_SUP * 16;
+    float* sdkacc = sdk + 3 * NEMPC_WIDE_SUP * 256;
 
     const uint32_t bar0 = smem_u32(&bars[0]);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -443,79 +450,109 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     };
 
     // the pair works on super-tiles (2 i, 2 i + 1); both CTAs run the GEMM sequence of the fuller one (the leader's)
+    const int S = RK4 ? st.S : 1;                            // integrator stages: 1 (discrete / unity: a = 0, c = 1) or 4 (RK4)
     const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
     for (long long sup0 = 2 * (long long)(blockIdx.x >> 1); sup0 < nsup; sup0 += gridDim.x) {
         const long long step_base = (sup0 + rank) * NEMPC_WIDE_SUP;
         const long long left = ar.nsteps - step_base, left0 = ar.nsteps - sup0 * NEMPC_WIDE_SUP;
         const int nvalid = (int)(left < 0 ? 0 : (left < NEMPC_WIDE_SUP ? left : NEMPC_WIDE_SUP));
         const int nvalid_pair = (int)(left0 < NEMPC_WIDE_SUP ? left0 : NEMPC_WIDE_SUP);
-
-        // ============================ phase A: primal forward, row = step ========================================================
         const long long stepA = step_base + row;
         const bool validA = is_epi && row < nvalid;
         long long bA = 0; int tA = 0;
         if (validA) { bA = stepA / L.H; tA = (int)(stepA - bA * L.H); }
-        if (is_epi && sub == 0) {
-            float zr[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) zr[c] = 0.f;
-            if (validA) {
-                const TIO* zb = ar.z + bA * (long long)L.n;
-#pragma unroll
-                for (int c = 0; c < D; ++c)
-                    zr[c] = (float)(c < X ? ((tA == 0) ? ar.x0[bA * X + c] : zb[(tA - 1) * X + c]) : zb[L.H * X + tA * U + (c - X)]);
-            }
-            put_seed(zr);
-        }
-        publish();
-        for (int l = 0; l < nhid; ++l) {
-            gemm(l == 0 ? net.in_f : net.hid_f[l - 1], nopre, [&](const uint32_t dbase) {
-                const float* bl = bias + l * HW + 64 * sub;
-                float* dst = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
-                chunks(dbase, [&](const int qq, const uint32_t* vr) {
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(__uint_as_float(vr[i]), INV, bl[16 * qq + i]));
-                    if (HES) st16_global(dst + 16 * qq, v);                               // h_l: phase B needs it
-                    else if (JAC) {
-                        float s1[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) s1[i] = fmaf(-v[i], v[i], 1.f);
-                        st16_global(dst + 16 * qq, s1);                                   // s'(a_l) for phase C
-                    }
-                    uint32_t hi[8], lo[8];
-                    split16(v, hi, lo);
-                    tmem_st8(dbase + 64 * sub + 16 * qq, hi);
-                    tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
-                });
-            });
-            publish();
-        }
-        gemm(net.out_f, nopre, [&](const uint32_t dbase) {
-            if (sub != 0) return;
-            float v[16];
-            tmem_ld16(dbase, v);
-            tmem_ld_wait();
-            if (validA && ar.resid) {
-                const TIO* zb = ar.z + bA * (long long)L.n;
-#pragma unroll
-                for (int p = 0; p < X; ++p) {
-                    const TW xt = (TW)zb[tA * X + p];
-                    const TW xp = unity ? (TW)0 : (TW)((tA == 0) ? ar.x0[bA * X + p] : zb[(tA - 1) * X + p]);
-                    ar.resid[bA * L.m + tA * X + p] = (TIO)(xp + (TW)fmaf(v[p], INV, bout[p]) - xt);
-                }
-            }
-        });
 
-        // ============================ phase B: lambda-contracted adjoint, row = step =============================================
-        if (HES) {
+        // ============================ phase A: primal forward at stage s, row = step =============================================
+        // z_s = z + a_s E k_{s-1};  h_l = tanh(W_l^T h_{l-1} + b_l) -> scratch (keep_h: phase B needs h_l; else s'(a_l) for phase C);
+        // k_s -> sks[s] (RK4);  write_resid: the residual with sum_s c_s k_s
+        auto phaseA = [&](const int sg, const bool keep_h, const bool write_resid) {
+            if (is_epi && sub == 0) {
+                float zr[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) zr[c] = 0.f;
+                if (validA) {
+                    const TIO* zb = ar.z + bA * (long long)L.n;
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        zr[c] = (float)(c < X ? ((tA == 0) ? ar.x0[bA * X + c] : zb[(tA - 1) * X + c]) : zb[L.H * X + tA * U + (c - X)]);
+                    if (RK4 && sg > 0) {
+                        const float a_s = st.a[sg];
+                        const float* kp = sks + ((long long)(sg - 1) * NEMPC_WIDE_SUP + row) * 16;
+#pragma unroll
+                        for (int p = 0; p < X; ++p) zr[p] = fmaf(a_s, kp[p], zr[p]);
+                    }
+                }
+                put_seed(zr);
+            }
+            publish();
+            for (int l = 0; l < nhid; ++l) {
+                gemm(l == 0 ? net.in_f : net.hid_f[l - 1], nopre, [&](const uint32_t dbase) {
+                    const float* bl = bias + l * HW + 64 * sub;
+                    float* dst = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
+                    chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(__uint_as_float(vr[i]), INV, bl[16 * qq + i]));
+                        if (HES && keep_h) st16_global(dst + 16 * qq, v);                     // h_l: phase B needs it
+                        else if (JAC) {
+                            float s1[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) s1[i] = fmaf(-v[i], v[i], 1.f);
+                            st16_global(dst + 16 * qq, s1);                                   // s'(a_l) for phase C
+                        }
+                        uint32_t hi[8], lo[8];
+                        split16(v, hi, lo);
+                        tmem_st8(dbase + 64 * sub + 16 * qq, hi);
+                        tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                    });
+                });
+                publish();
+            }
+            gemm(net.out_f, nopre, [&](const uint32_t dbase) {
+                if (sub != 0) return;
+                float v[16];
+                tmem_ld16(dbase, v);
+                tmem_ld_wait();
+                float k[X];
+#pragma unroll
+                for (int p = 0; p < X; ++p) k[p] = fmaf(v[p], INV, bout[p]);
+                if (RK4) {
+                    float* kp = sks + ((long long)sg * NEMPC_WIDE_SUP + row) * 16;
+#pragma unroll
+                    for (int p = 0; p < X; ++p) kp[p] = k[p];
+                }
+                if (write_resid && validA && ar.resid) {
+                    const TIO* zb = ar.z + bA * (long long)L.n;
+#pragma unroll
+                    for (int p = 0; p < X; ++p) {
+                        float kacc = RK4 ? st.c[sg] * k[p] : k[p];
+                        if (RK4)
+                            for (int s2 = 0; s2 < sg; ++s2) kacc = fmaf(st.c[s2], sks[((long long)s2 * NEMPC_WIDE_SUP + row) * 16 + p], kacc);
+                        const TW xt = (TW)zb[tA * X + p];
+                        const TW xp = unity ? (TW)0 : (TW)((tA == 0) ? ar.x0[bA * X + p] : zb[(tA - 1) * X + p]);
+                        ar.resid[bA * L.m + tA * X + p] = (TIO)(xp + (TW)kacc - xt);
+                    }
+                }
+            });
+        };
+
+        // ============================ phase B: contracted adjoint at stage s, row = step ==========================================
+        // seed w_s = lambda (single stage) / c_{S-1} lambda (last RK4 stage) / the weights left in `sw` by the previous call (earlier
+        // stages);  want_in: continue through the input layer, J_s^T w_s, and leave  w_{s-1} = c_{s-1} lambda + a_s (J_s^T w_s)[:x]  in `sw`
+        auto phaseB = [&](const int sg, const bool want_in) {
             if (is_epi && sub == 0) {
                 float lr[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) lr[c] = 0.f;
                 if (validA) {
+                    if (RK4 && sg < S - 1) {
 #pragma unroll
-                    for (int p = 0; p < X; ++p) lr[p] = (float)ar.lam[bA * L.m + tA * X + p];
+                        for (int p = 0; p < X; ++p) lr[p] = sw[row * 16 + p];
+                    } else {
+                        const float cs = RK4 ? st.c[sg] : 1.f;
+#pragma unroll
+                        for (int p = 0; p < X; ++p) lr[p] = cs * (float)ar.lam[bA * L.m + tA * X + p];
+                    }
                 }
                 put_seed(lr);
             }
@@ -523,6 +560,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
             for (int l = nhid - 1; l >= 0; --l) {
                 // accumulator = g_l (adjoint with respect to h_l);  s'(a_l) -> sa (over h_l),  s''(a_l) g_l = -2 h_l s'(a_l) g_l -> sq;
                 // next operand u_l = s'(a_l) g_l
+                const bool more = l > 0 || want_in;
                 gemm(l == nhid - 1 ? net.out_b : net.hid_b[l], nopre, [&](const uint32_t dbase) {
                     float* ph = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
                     float* pq = sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
@@ -538,7 +576,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                         }
                         st16_global(ph + 16 * qq, h);
                         st16_global(pq + 16 * qq, cf);
-                        if (l > 0) {
+                        if (more) {
                             uint32_t hi[8], lo[8];
                             split16(u, hi, lo);
                             tmem_st8(dbase + 64 * sub + 16 * qq, hi);
@@ -546,13 +584,27 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                         }
                     });
                 });
-                if (l > 0) publish();
+                if (more) publish();
             }
-        }
-        epi_sync();                                        // the scratch of this super-tile is complete (bar.sync orders it at CTA scope)
+            if (RK4 && want_in) {
+                gemm(net.in_b, nopre, [&](const uint32_t dbase) {
+                    if (sub != 0) return;
+                    float v[16];
+                    tmem_ld16(dbase, v);
+                    tmem_ld_wait();
+                    const float a_s = st.a[sg], cprev = st.c[sg - 1];
+#pragma unroll
+                    for (int p = 0; p < X; ++p)
+                        sw[row * 16 + p] = validA ? fmaf(a_s, v[p] * INV, cprev * (float)ar.lam[bA * L.m + tA * X + p]) : 0.f;
+                });
+            }
+        };
 
-        // ============================ phase C: tangent forward (+ curvature), row = (step, tangent column) =========================
-        if (JAC) {
+        // ============================ phase C: tangent forward (+ curvature) at stage s, row = (step, tangent column) =================
+        // seed rows = columns of R_s = I + a_s E dk_{s-1} (identity for a single stage);  store_dk: leave dk_s = J_s R_s and the running
+        // sum_s c_s dk_s in the scratch;  write_jac: this is the last stage of the forward sweep;  curv: accumulate
+        // R_s^T (sum_p w_{s,p} Hess f_p) R_s;  first_hes: store the Hessian values (with the objective's), later stages add to them
+        auto phaseC = [&](const int sg, const bool curv, const bool first_hes, const bool write_jac, const bool store_dk) {
             const int ntile = (nvalid_pair + SPT - 1) / SPT;
             for (int ti = 0; ti < ntile; ++ti) {
                 const int sidx = ti * SPT + row / DP, cc = row % DP;          // step inside the super-tile, tangent column
@@ -565,6 +617,12 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     float e[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) e[c] = (c == cc && cc < D) ? 1.f : 0.f;
+                    if (RK4 && sg > 0 && validC) {
+                        const float a_s = st.a[sg];
+                        const float* dp = sdk + ((((long long)(sg - 1) * NEMPC_WIDE_SUP + sidx) * 16 + cc) * 16);
+#pragma unroll
+                        for (int p = 0; p < X; ++p) e[p] = fmaf(a_s, dp[p], e[p]);
+                    }
                     put_seed(e);
                 }
                 publish();
@@ -574,15 +632,15 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                              // while the MMAs run: this warp's s'(a_l) (x 2^-11: the accumulator's scale) and curvature coefficients (x 2^-22) of
                              // its SPW steps and 64 neurons, global scratch -> warp-private shared memory
                              for (int i = lane; i < SPW * 16; i += 32) {
-                                 const int sw = i >> 4, f4 = i & 15;
-                                 const long long o = ((long long)(sidx0 + sw) * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub + 4 * f4;
+                                 const int sw_ = i >> 4, f4 = i & 15;
+                                 const long long o = ((long long)(sidx0 + sw_) * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub + 4 * f4;
                                  float4 a = __ldcg(reinterpret_cast<const float4*>(sa + o));
                                  a.x *= INV; a.y *= INV; a.z *= INV; a.w *= INV;
-                                 *reinterpret_cast<float4*>(scs + sw * 64 + 4 * f4) = a;
-                                 if (HES) {
+                                 *reinterpret_cast<float4*>(scs + sw_ * 64 + 4 * f4) = a;
+                                 if (HES && curv) {
                                      float4 q = __ldcg(reinterpret_cast<const float4*>(sq + o));
                                      q.x *= INV * INV; q.y *= INV * INV; q.z *= INV * INV; q.w *= INV * INV;
-                                     *reinterpret_cast<float4*>(scs + (SPW + sw) * 64 + 4 * f4) = q;
+                                     *reinterpret_cast<float4*>(scs + (SPW + sw_) * 64 + 4 * f4) = q;
                                  }
                              }
                              __syncwarp();
@@ -590,7 +648,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                          [&](const uint32_t dbase) {
                              const float* s1row = scs + (lane / DP) * 64;
                              chunks(dbase, [&](const int qq, const uint32_t* vr) {
-                                 if (HES) gram_chunk<DP>(stg, vr, scs + SPW * 64, 16 * qq, acc, lane);      // raw tangent T_l (x 2^11)
+                                 if (HES && curv) gram_chunk<DP>(stg, vr, scs + SPW * 64, 16 * qq, acc, lane);      // raw tangent T_l (x 2^11)
                                  f2 v2[8];
 #pragma unroll
                                  for (int i4 = 0; i4 < 4; ++i4) {
@@ -612,28 +670,48 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     float v[16];
                     tmem_ld16(dbase, v);
                     tmem_ld_wait();
-                    if (validC && ar.jac) {
+                    if (!validC) return;
+                    float jv_[X];                                              // (sum_s c_s dk_s)[p][cc] up to this stage
+#pragma unroll
+                    for (int p = 0; p < X; ++p) jv_[p] = v[p] * INV;
+                    if (RK4) {
+                        const float c_s = st.c[sg];
+                        float* dacc = sdkacc + ((long long)sidx * 16 + cc) * 16;
+                        if (store_dk) {
+                            float* dp = sdk + ((((long long)sg * NEMPC_WIDE_SUP + sidx) * 16 + cc) * 16);
+#pragma unroll
+                            for (int p = 0; p < X; ++p) dp[p] = jv_[p];
+                        }
+                        if (store_dk || write_jac) {
+#pragma unroll
+                            for (int p = 0; p < X; ++p) {
+                                jv_[p] = sg == 0 ? c_s * jv_[p] : fmaf(c_s, jv_[p], dacc[p]);
+                                if (store_dk) dacc[p] = jv_[p];
+                            }
+                        }
+                    }
+                    if (write_jac && ar.jac) {
                         const long long step = step_base + sidx;
                         const long long b = step / L.H;
                         const int t = (int)(step - b * L.H);
                         TIO* jv = ar.jac + b * L.nnz_jac;
 #pragma unroll
                         for (int p = 0; p < X; ++p) {
-                            const TW val = (TW)(v[p] * INV) + ((!unity && cc == p) ? (TW)1 : (TW)0);
+                            const TW val = (TW)jv_[p] + ((!unity && cc == p) ? (TW)1 : (TW)0);
                             if (cc < X) { if (t > 0) jv[jac_slot_A(L, t, p, cc)] = (TIO)val; }
                             else jv[jac_slot_B(L, t, p, cc - X)] = (TIO)val;
                             if (cc == 0) jv[jac_slot_minus1(L, t, p)] = (TIO)-1;
                         }
                     }
                 });
-                if (HES) {
+                if (HES && curv) {
                     // ---- sum the four neuron quarters, scatter the lower triangle (same slots as nempc_generic.cuh) -----------------
                     epi_sync();                                    // `part` aliases the staging planes: every warp is done with its curvature
                     if (is_epi) {
                         constexpr int NB = DP / 4, LPS = NB * NB, ACTIVE = (32 / DP) * LPS;
                         if (lane < ACTIVE) {
-                            const int sw = lane / LPS, bl = lane % LPS, bi = bl / NB, bj = bl % NB;
-                            const int s8 = (32 * wq) / DP + sw;
+                            const int sw_ = lane / LPS, bl = lane % LPS, bi = bl / NB, bj = bl % NB;
+                            const int s8 = (32 * wq) / DP + sw_;
                             float* pp = part + ((sub * SPT + s8) * DP + 4 * bi) * DP + 4 * bj;
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
@@ -660,32 +738,52 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                             int slot;
                             if (a < X) {
                                 slot = hes_slot_xx(L, t, a, c);
-                                if (a == c && ar.quad) val += sig * (TW)2 * (TW)ar.quad[(t - 1) * X + a];
+                                if (first_hes && a == c && ar.quad) val += sig * (TW)2 * (TW)ar.quad[(t - 1) * X + a];
                             } else if (c < X) {
                                 slot = hes_slot_ux(L, t, a - X, c);
                             } else {
                                 slot = hes_slot_uu(L, t, a - X, c - X);
-                                if (a == c && ar.quad) val += sig * (TW)2 * (TW)ar.quad[L.H * X + t * U + (a - X)];
+                                if (first_hes && a == c && ar.quad) val += sig * (TW)2 * (TW)ar.quad[L.H * X + t * U + (a - X)];
                             }
-                            hv[slot] = (TIO)val;
+                            if (first_hes) hv[slot] = (TIO)val;
+                            else hv[slot] = (TIO)((TW)hv[slot] + val);             // later RK4 stages add their R_s^T M_s R_s (same thread every time)
                         }
-                        for (int idx = tid; idx < SPT * X; idx += NEMPC_WIDE_EPI_WARPS * 32) {   // objective-only diagonal of x_H
-                            const int s8 = idx / X, p = idx - s8 * X;
-                            const int sx = ti * SPT + s8;
-                            if (sx >= nvalid) continue;
-                            const long long step = step_base + sx;
-                            const long long b = step / L.H;
-                            const int t = (int)(step - b * L.H);
-                            if (t != L.H - 1 || L.hes_last_slot[p] < 0) continue;
-                            const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
-                            ar.hes[b * L.nnz_hes + L.hes_last_slot[p]] = (TIO)(sig * (TW)2 * (TW)ar.quad[(L.H - 1) * X + p]);
+                        if (first_hes) {
+                            for (int idx = tid; idx < SPT * X; idx += NEMPC_WIDE_EPI_WARPS * 32) {   // objective-only diagonal of x_H
+                                const int s8 = idx / X, p = idx - s8 * X;
+                                const int sx = ti * SPT + s8;
+                                if (sx >= nvalid) continue;
+                                const long long step = step_base + sx;
+                                const long long b = step / L.H;
+                                const int t = (int)(step - b * L.H);
+                                if (t != L.H - 1 || L.hes_last_slot[p] < 0) continue;
+                                const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
+                                ar.hes[b * L.nnz_hes + L.hes_last_slot[p]] = (TIO)(sig * (TW)2 * (TW)ar.quad[(L.H - 1) * X + p]);
+                            }
                         }
                     }
                     epi_sync();                                    // `part` is rewritten by the next tile
                 }
             }
+        };
+
+        // ============================ the stage schedule ==========================================================================
+        // single stage:  A, B, C.   RK4:  forward sweep  s = 0..2: A, C (tangents only: k_s, dk_s, R_{s+1});  last stage:
+        // A, B (w_3 = c_3 lambda, known up front), C with curvature (also the Jacobian);  backward sweep  s = 2..0: A (recomputed), B with
+        // w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}, C with curvature:  H = sum_s R_s^T (sum_p w_{s,p} Hess f_p(z_s)) R_s
+        // (one call site per phase, so that the three bodies stay inlined)
+        // (for a single stage everything below is a compile-time constant and the schedule collapses to A, B, C)
+        const int npass = RK4 ? ((HES && S > 1) ? 2 * S - 1 : S) : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int sg = RK4 ? (pass < S ? pass : 2 * S - 2 - pass) : 0;
+            const bool last = RK4 ? pass == S - 1 : true;
+            const bool second = RK4 ? pass >= S - 1 : true;              // second-order passes: the last stage and the backward sweep
+            phaseA(sg, second, last);
+            if (HES && second) phaseB(sg, RK4 && sg > 0);
+            epi_sync();                                    // the scratch of this stage is complete (bar.sync orders it at CTA scope)
+            if (JAC) phaseC(sg, second, last, last, !second);
+            epi_sync();                                    // the scratch is rewritten by the next stage / super-tile
         }
-        epi_sync();                                                // the scratch is rewritten by the next super-tile
     }
 
     WPROF_FLUSH;

@@ -19,6 +19,7 @@ What is recorded (all float64 unless noted):
                           integrator + IpoptProblem: pins the tcgen05 kernel of nempc_tc.cuh (TcCfg<2,1,2,...,128>) to the reference
   ref_discrete_w256_H6.npz  5 -> 256 -> 256 -> 256 -> 4 network through the reference's DiscretIntegrator + IpoptProblem: pins the
                           width-256 kernel of nempc_wide.cuh to the reference (its RK4 Hessian only runs for x_dim + u_dim == 3)
+  ref_rk4_w256_H6.npz     3 -> 256 -> 256 -> 2 network through the reference's RK4 integrator (two-sweep stage schedule of nempc_wide.cuh)
   ref_closed_loop_c1.npz  BASELINE config C1 as named (examples/lotka_volterra/run.py:38-87): the reference's own NMPC.next with its Slsqp
                           optimizer, H = 25, cost 1.1 * sum(u), u in [-1, 0.2], x_0 <= 1, LV fixture network, discrete and RK4 (DT 0.1)
                           integrators: iteration count, final cost, solution
@@ -348,6 +349,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_constraints_H6.npz"), **record_constraints(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_rk4_w128_H6.npz"), **record_wide(ref, [3, 128, 128, 2], 2, 1, "rk4", 6, 700, 21))
     np.savez_compressed(os.path.join(HERE, "ref_discrete_w256_H6.npz"), **record_wide(ref, [5, 256, 256, 256, 4], 4, 1, "discrete", 6, 710, 22))
+    np.savez_compressed(os.path.join(HERE, "ref_rk4_w256_H6.npz"), **record_wide(ref, [3, 256, 256, 2], 2, 1, "rk4", 6, 720, 23))
     np.savez_compressed(os.path.join(HERE, "ref_closed_loop_c1.npz"), **record_closed_loop_c1(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_quadform_H6.npz"), **record_quadform(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_rolling_discrete_w2.npz"), **record_rolling(ref, "discrete", 2, True))

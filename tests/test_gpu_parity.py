@@ -453,7 +453,8 @@ def _wide_golden(golden_dir, name):
     return g, mlp
 
 
-@pytest.mark.parametrize("name,kernel_tag", (("ref_rk4_w128_H6.npz", "nempc_tc_kernel"), ("ref_discrete_w256_H6.npz", "nempc_wide_kernel")))
+@pytest.mark.parametrize("name,kernel_tag", (("ref_rk4_w128_H6.npz", "nempc_tc_kernel"), ("ref_discrete_w256_H6.npz", "nempc_wide_kernel"),
+                                             ("ref_rk4_w256_H6.npz", "nempc_wide_kernel")))
 def test_tensor_core_kernels_against_reference_goldens(golden_dir, name, kernel_tag):
     """the two tcgen05 kernels pinned DIRECTLY to the unmodified reference (not only to the oracle): IpoptProblem callbacks of
     a 3-128-128-2 network under the reference's RK4 integrator (nempc_tc.cuh, TcCfg<2,1,2,...,128>) and of a 5-256-256-256-4 network
@@ -478,12 +479,16 @@ WIDE_CASES = [("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3),        # 
               ("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 37, 9),       # several super-tiles of 128 steps, ragged tail, odd tile pairing
               ("unity", [16, 256, 256, 12], 12, 4, 7, 2),
               ("discrete", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("discrete", [3, 256, 256, 2], 2, 1, 6, 4),
-              ("discrete", [8, 256, 256, 256, 6], 6, 2, 6, 4), ("unity", [3, 256, 256, 256, 2], 2, 1, 300, 3)]
+              ("discrete", [8, 256, 256, 256, 6], 6, 2, 6, 4), ("unity", [3, 256, 256, 256, 2], 2, 1, 300, 3),
+              # RK4: forward sweep (k_s, dk_s), last stage with curvature, backward sweep with w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}
+              ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3), ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 29, 10),
+              ("rk4", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("rk4", [3, 256, 256, 2], 2, 1, 50, 4), ("rk4", [8, 256, 256, 256, 6], 6, 2, 6, 4)]
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", WIDE_CASES)
 def test_wide_kernel_vs_oracle(kind, dims, xd, ud, H, B):
-    """width-256 tcgen05 kernel (adjoint form, streamed split-f16 weights, CTA pairs) against the float64 oracle, all request sets"""
+    """width-256 tcgen05 kernel (adjoint form, streamed split-f16 weights, CTA pairs; RK4 = two sweeps over the stages) against the
+    float64 oracle, all request sets"""
     import torch
     mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=len(dims) + H)
     ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)

@@ -106,7 +106,11 @@ if __name__ == "__main__":
         ok &= check([5, 256, 256, 256, 4], 4, 1, 11, 5, "discrete", seed=5)
         ok &= check([3, 256, 256, 2], 2, 1, 6, 4, "discrete", seed=6)
         ok &= check([8, 256, 256, 256, 6], 6, 2, 6, 4, "discrete", seed=7)
+        ok &= check([3, 256, 256, 2], 2, 1, 6, 4, "rk4", seed=8)
+        ok &= check([16, 256, 256, 256, 256, 12], 12, 4, 5, 3, "rk4", seed=9)
+        ok &= check([16, 256, 256, 256, 256, 12], 12, 4, 29, 10, "rk4", seed=10)
     print("ALL OK" if ok else "FAILURES", flush=True)
     if a.time:
         timing(a.time)
+        timing(max(64, a.time // 8), integ="rk4")
     sys.exit(0 if ok else 1)
