@@ -44,6 +44,8 @@ WORKLOADS = {
                desc="cart-pole MLP 5-128-128-128-4 tanh, RK4, H=100, B=16384 (BASELINE configs[2])"),
     "C4": dict(dims=[16, 256, 256, 256, 256, 12], x=12, u=4, integ="discrete", DT=None, H=200, B=65536,
                desc="quadrotor MLP 16-256x4-12, discrete, H=200, B=65536 (BASELINE configs[3])"),
+    "C4rk4": dict(dims=[16, 256, 256, 256, 256, 12], x=12, u=4, integ="rk4", DT=0.1, H=200, B=65536,
+                  desc="quadrotor MLP 16-256x4-12, RK4 DT=0.1, H=200, B=65536 (BASELINE configs[3] names no integrator: the RK4 variant)"),
 }
 
 
@@ -212,7 +214,7 @@ def tensor_roofline(ev, wl, steps_per_eval, k_ms, peaks):
     nmm = len(wl["dims"]) - 3
     hw = wl["dims"][1]
     if "nempc_wide" in ev.kernel_name:       # adjoint form: primal + adjoint + d tangent rows (RK4: two sweeps), 3 products
-        rows = (2 + d_in) if stages == 1 else (4 + 4 + 7 * d_in)
+        rows = (2 + d_in) if stages == 1 else (7 + 4 + 7 * d_in)      # RK4: 7 primal, 4 adjoint and 7 tangent passes (two sweeps over the stages)
         form = "adjoint form: %d GEMM rows per step" % rows
     else:                                    # forward second order: 1 + d + d(d+1)/2 rows per stage
         rows = (1 + d_in + d_in * (d_in + 1) // 2) * stages
@@ -284,7 +286,7 @@ def named_workload(name, world, rank, local, peaks, with_cpu, steps=3, e2e_cap=8
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(2):
+    for _ in range(1 if name == "C4rk4" else 2):
         ev.eval(z, x0, lam, 1.0, out=out)
     l0 = ev.launch_count
     ms = timed(lambda: ev.eval(z, x0, lam, 1.0, out=out), steps)
@@ -325,6 +327,48 @@ def named_workload(name, world, rank, local, peaks, with_cpu, steps=3, e2e_cap=8
             res["cpu_baseline"] = block_cpu_baseline(name)
         except Exception as exc:          # noqa: BLE001 -- never lose the line to a side measurement
             res["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: " + repr(exc)[:160]}
+    return res
+
+
+def c2_float64(world, rank, local, steps=10):
+    """C2 with FLOAT64 network arithmetic (the reference assembles in float64, optimizer/ipopt.py:66-86; this is the 1e-10 parity mode):
+    nempc_fast64_kernel against the measured FP64 FMA peak."""
+    import torch
+    import torch.distributed as dist
+    from pyneuralempc_b200 import NlpEvaluator
+    from pyneuralempc_b200.engine import measure_fma_peak
+    wl = WORKLOADS["C2"]
+    B = wl["B"]
+    mlp, obj, Z, X0, lam = make_problem(wl, B, seed=99 + rank)
+    ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"], compute_dtype="float64", io_dtype="float64", device=local)
+    ev.set_objective(obj.lin, obj.quad, obj.ref)
+    dev = ev.tdevice
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    z, x0, lm = t(Z), t(X0), t(lam)
+    out = ev.alloc_outputs(B)
+    for _ in range(3):
+        ev.eval(z, x0, lm, 1.0, out=out)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        ev.eval(z, x0, lm, 1.0, want=("resid", "jac", "hes"), out=out)
+    b.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    k_ms = float(tm.item())
+    peak = measure_fma_peak(local, "float64", 200)
+    flops = ev.flops_per_step * B * wl["H"]
+    res = {"workload": "C2 with float64 network arithmetic: " + wl["desc"], "metric": METRIC, "unit": UNIT, "n_gpus": world, "scaling": "weak",
+           "value": world * B * wl["H"] / (k_ms * 1e-3), "ms_per_eval": k_ms, "steps": steps, "dtype": "f64",
+           "roofline": {"bound": "fp64-fma", "kernel": ev.kernel_name, "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "peak_source": "measured live: register-resident DFMA loop (nempc_measure_fma_peak)",
+                        "kernel_ms": k_ms, "flops_per_horizon_step": ev.flops_per_step, "traffic": None}}
+    ev.close()
     return res
 
 
@@ -371,7 +415,7 @@ def gpu_run(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = WORKLOADS[args.workload]
-    if args.workload in ("C3", "C4"):
+    if args.workload in ("C3", "C4", "C4rk4"):
         # wide networks at their named batch: the fixed batch is split over the ranks (strong scaling), data generated on the device
         peaks = {}
         try:
@@ -500,7 +544,32 @@ def gpu_run(args):
         if world > 1:
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
             dist.all_reduce(conv, op=dist.ReduceOp.SUM)
+        # copy-inclusive: x0 from pinned host memory up, the solution (x_pred, u) and the status back into pinned host memory, every solve
+        x0_pin = torch.as_tensor(X0, dtype=torch.float64).pin_memory()
+        z_pin = torch.empty((B, ev.n), dtype=torch.float64).pin_memory()
+        st_pin = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def solve_e2e():
+            so_ = ev.solve(x0_pin.to(dev, non_blocking=True), lb, ub, **sopt)
+            z_pin.copy_(so_["z"], non_blocking=True)
+            st_pin.copy_(so_["status"], non_blocking=True)
+            torch.cuda.synchronize()
+            return int((st_pin == 0).sum())
+
+        solve_e2e()
+        barrier()
+        times_e = []
+        for _ in range(9):
+            t0 = time.perf_counter()
+            solve_e2e()
+            times_e.append(time.perf_counter() - t0)
+        tse = torch.tensor([statistics.median(times_e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tse, op=dist.ReduceOp.MAX)
         solves = {"metric": "mpc_solves_per_s", "value": world * B / float(ts.item()), "unit": "solves/s", "batch_per_gpu": B,
+                  "e2e": {"value": world * B / float(tse.item()), "unit": "solves/s", "ms_per_batch": float(tse.item()) * 1e3,
+                          "h2d_bytes_per_step": int(x0_pin.numel() * 8), "d2h_bytes_per_step": int(z_pin.numel() * 8 + st_pin.numel() * 4),
+                          "api": "NlpEvaluator.solve: x0 H2D from pinned memory, (x_pred, u) and status D2H into pinned memory inside the timed region"},
                   "ms_per_batch": float(ts.item()) * 1e3, "converged_frac": float(conv.item()) / (world * B),
                   "ipm_iterations_mean": float(so["iterations"].double().mean().item()), "outer_iterations": so["outer_iterations"],
                   "tol": sopt["tol"], "solver": "nempc_solve: primal-dual interior point, Riccati KKT sweep on the block-banded values, x0 device-resident",
@@ -518,11 +587,16 @@ def gpu_run(args):
         ev.close()                                      # release the headline workload's device buffers first
         del zs, x0s, lams, outs
         torch.cuda.empty_cache()
-        for nm in ("C3", "C4"):
+        for nm in ("C3", "C4", "C4rk4"):
             try:
-                side[nm] = named_workload(nm, world, rank, local, peaks_side, with_cpu=(world == 1 and not args.no_cpu_baseline))
+                side[nm] = named_workload(nm, world, rank, local, peaks_side, with_cpu=(world == 1 and not args.no_cpu_baseline),
+                                          steps=2 if nm == "C4rk4" else 3)
             except Exception as exc:                  # a side measurement must never cost the headline line
                 side[nm] = {"error": repr(exc)[:300]}
+        try:
+            side["C2_f64"] = c2_float64(world, rank, local)
+        except Exception as exc:                      # noqa: BLE001
+            side["C2_f64"] = {"error": repr(exc)[:300]}
         if rank == 0:
             try:
                 side["C1_callback"] = callback_latency(local)
@@ -591,7 +665,7 @@ def reference_run(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    if args.workload in ("C3", "C4"):
+    if args.workload in ("C3", "C4", "C4rk4"):
         # the reference's dense O(H^3) assembly needs 0.8 GB (C3) / 197 GB (C4) per problem: the O(H) block restatement is what can be timed
         b = block_cpu_baseline(args.workload, nprob=4)
         r = {"value": b["value"], "ms_per_step": 4 * wl["H"] / b["value"] * 1e3, "cores": 1, "sample": b["sample"]}

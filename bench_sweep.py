@@ -13,7 +13,8 @@ import numpy as np
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/sweep.csv")
-    ap.add_argument("--max-gflop", type=float, default=400.0, help="skip rows whose single evaluation exceeds this many GFLOP")
+    ap.add_argument("--max-seconds", type=float, default=1.5, help="skip rows whose single evaluation is expected to take longer (from the kernel's typical rate)")
+    ap.add_argument("--max-gb", type=float, default=60.0, help="skip rows whose inputs + outputs exceed this many GB")
     args = ap.parse_args()
     import torch
     from oracle.mlp_np import MLP
@@ -29,11 +30,17 @@ def main():
                 depth = 2 if width == 30 else 3
                 dims = [xd + ud] + [width] * depth + [xd]
                 mlp = MLP.glorot(dims, xd, ud, seed=0, dtype=np.float32)
-                for H in (10, 50, 200):
-                    for B in (1, 256, 4096, 65536):
+                for H in (10, 50, 200, 500):
+                    for B in (1, 256, 4096, 65536, 262144):
                         ev = NlpEvaluator(mlp.weights, xd, ud, H, integ, DT=0.1, compute_dtype=dtype, io_dtype="float64")
                         gflop = ev.flops_per_step * B * H / 1e9
-                        if gflop > args.max_gflop or B * ev.n * 8 > 2e9:
+                        kname = ("fast64" if "fast64" in ev.kernel_name else "fast" if "nempc_fast" in ev.kernel_name else
+                                 "wide" if "nempc_wide" in ev.kernel_name else "tc" if "tcgen05" in ev.kernel_name else "generic")
+                        if kname == "fast64" and B * H < 4096:
+                            kname = "generic"                    # AUTO hands small float64 batches to the generic kernel
+                        typical_tf = {"fast": 25.0, "fast64": 8.0, "wide": 90.0, "tc": 35.0, "generic": 2.0 if dtype == "float32" else 1.2}[kname]
+                        gbytes = B * (ev.n + ev.m * 2 + ev.nnz_jac + ev.nnz_hes) * 8 / 1e9
+                        if gflop / typical_tf / 1e3 > args.max_seconds or gbytes > args.max_gb:
                             ev.close(); continue
                         z = torch.as_tensor(rng.uniform(-1, 1, (B, ev.n))).cuda()
                         x0 = torch.as_tensor(rng.uniform(-1, 1, (B, xd))).cuda()
@@ -41,7 +48,7 @@ def main():
                         out = ev.alloc_outputs(B, ("resid", "jac", "hes"))
                         for _ in range(2):
                             ev.eval(z, x0, lam, 1.0, want=("resid", "jac", "hes"), out=out)
-                        reps = int(max(2, min(50, 20.0 / max(gflop, 1e-3))))
+                        reps = int(max(2, min(50, 20.0 * typical_tf / 25.0 / max(gflop, 1e-3))))
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         torch.cuda.synchronize(); a.record()
                         for _ in range(reps):
@@ -50,7 +57,7 @@ def main():
                         ms = a.elapsed_time(b) / reps
                         tf = gflop / ms
                         rows.append(dict(dtype=dtype, integrator=integ, width=width, depth=depth, x=xd, u=ud, H=H, B=B, steps=B * H,
-                                         kernel="fast" if "fast" in ev.kernel_name else ("tc" if "tcgen05" in ev.kernel_name else "generic"), ms=round(ms, 4),
+                                         kernel=kname, ms=round(ms, 4),
                                          steps_per_s=round(B * H / ms * 1e3), tflops=round(tf, 3), frac_of_fma_peak=round(tf / peak[dtype], 4)))
                         print(rows[-1], flush=True)
                         ev.close()

@@ -13,6 +13,7 @@
 
 #include "../../include/nempc.h"
 #include "nempc_fast.cuh"
+#include "nempc_fast64.cuh"
 #include "nempc_generic.cuh"
 #include "nempc_layout.h"
 #include "nempc_small.cuh"
@@ -318,6 +319,7 @@ struct nempc_handle {
     void* dW[NEMPC_MAXL] = {}; void* dWT[NEMPC_MAXL] = {}; void* db[NEMPC_MAXL] = {};
     double *dlin = nullptr, *dquad = nullptr, *dref = nullptr;
     int use_fast = 0; int fast_id = -1;
+    int fast64_id = -1; std::vector<unsigned char> fast64w;      // float64 register-resident kernel (nempc_fast64.cuh): Fast64Weights<...> blob
     int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr; float* d_tcwx = nullptr;   // tensor-core kernel: f16 weight images, f32 constants, first-layer rows of the exogenous inputs
     int use_wide = 0; int wide_id = -1; unsigned char* d_wblob = nullptr; float* d_wcb = nullptr; WideNet wnet{};    // width-256 tensor-core kernel: streamed operand images, biases
     float* wide_scratch = nullptr; size_t wide_scratch_bytes = 0;
@@ -364,6 +366,16 @@ static const int kNumFastShapes = sizeof(kFastShapes) / sizeof(kFastShapes[0]);
 
 static int fast_shape_id(const nempc_desc& d) {
     if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.n_layers != 3 || d.tvp_dim + d.p_dim > 0) return -1;
+    for (int i = 0; i < kNumFastShapes; ++i)
+        if (d.x_dim == kFastShapes[i].x && d.u_dim == kFastShapes[i].u && d.widths[0] == kFastShapes[i].h1 &&
+            d.widths[1] == kFastShapes[i].h2)
+            return i;
+    return -1;
+}
+
+// float64 arithmetic on the same small networks: nempc_fast64_kernel (float64 I/O only)
+static int fast64_shape_id(const nempc_desc& d) {
+    if (d.compute_dtype != NEMPC_F64 || d.io_dtype != NEMPC_F64 || d.activation != NEMPC_ACT_TANH || d.n_layers != 3 || d.tvp_dim + d.p_dim > 0) return -1;
     for (int i = 0; i < kNumFastShapes; ++i)
         if (d.x_dim == kFastShapes[i].x && d.u_dim == kFastShapes[i].u && d.widths[0] == kFastShapes[i].h1 &&
             d.widths[1] == kFastShapes[i].h2)
@@ -542,7 +554,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
 
     // kernel choice
     h->fast_id = fast_shape_id(D);
-    if (D.kernel == NEMPC_KERNEL_FAST && h->fast_id < 0) {
+    h->fast64_id = (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST) ? fast64_shape_id(D) : -1;
+    if (D.kernel == NEMPC_KERNEL_FAST && h->fast_id < 0 && h->fast64_id < 0) {
         SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_FAST requested but no register-resident instantiation matches this network");
         free_device(h); delete h; return NEMPC_EUNSUPPORTED;
     }
@@ -574,6 +587,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     char nm[224];
     if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
+    else if (h->fast64_id >= 0) snprintf(nm, sizeof nm, "nempc_fast64_kernel<x=%d,u=%d,h1=%d,h2=%d> f64 (thread/step, DFMA, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
+                                         D.kernel == NEMPC_KERNEL_AUTO ? "; generic kernel for small batches" : "");
     else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
     else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
@@ -611,6 +626,13 @@ template <typename T> static int upload_layer(nempc_handle* h, int l, int fin, i
     return NEMPC_OK;
 }
 
+template <int X, int U, int H1, int H2> static void fill_fast64(nempc_handle* h) {
+    typedef Fast64Weights<X, U, H1, H2> FW;
+    h->fast64w.assign(sizeof(FW) + 16, 0);
+    uintptr_t a = (reinterpret_cast<uintptr_t>(h->fast64w.data()) + 15) & ~(uintptr_t)15;
+    fill_fast64_weights<X, U, H1, H2>(*reinterpret_cast<FW*>(a), h->W[0].data(), h->bvec[0].data(), h->W[1].data(), h->bvec[1].data(),
+                                      h->W[2].data(), h->bvec[2].data());
+}
 template <int X, int U, int H1, int H2, int NCHUNK> static void fill_fast(nempc_handle* h) {
     typedef FastWeights<X, U, H1, H2, NCHUNK> FW;
     h->fastw.assign(sizeof(FW) + 16, 0);
@@ -729,6 +751,13 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
             case 0: fill_fast<2, 1, 30, 30, NEMPC_FAST_NCHUNK30>(h); break;
             case 1: fill_fast<2, 1, 32, 32, 2>(h); break;
             case 2: fill_fast<2, 1, 16, 16, 1>(h); break;
+        }
+    }
+    if (all && h->fast64_id >= 0) {
+        switch (h->fast64_id) {
+            case 0: fill_fast64<2, 1, 30, 30>(h); break;
+            case 1: fill_fast64<2, 1, 32, 32>(h); break;
+            case 2: fill_fast64<2, 1, 16, 16>(h); break;
         }
     }
     if (all && h->tc_id >= 0) { rc = upload_tc(h); if (rc) return rc; }
@@ -901,6 +930,53 @@ static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode,
     return NEMPC_OK;
 }
 
+// float64 arithmetic, register resident (nempc_fast64.cuh); JC = layer-2 neurons per register chunk
+#ifndef NEMPC_FAST64_MIN_STEPS
+#define NEMPC_FAST64_MIN_STEPS 4096      // below this many horizon steps one thread per step leaves the GPU empty: the generic kernel takes over
+#endif
+template <int X, int U, int H1, int H2, int JC>
+static int launch_fast64_shape(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
+    typedef Fast64Weights<X, U, H1, H2> FW;
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(h->fast64w.data()) + 15) & ~(uintptr_t)15;
+    const FW& w = *reinterpret_cast<const FW*>(a);
+    StageTable<double> st = make_stage_table<double>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
+    const int threads = NEMPC_FAST64_THREADS;
+    const long long blocks = std::max(1LL, (ar.nsteps + threads - 1) / threads);
+    const unsigned grid = (unsigned)std::min(blocks, (long long)h->sm_count * 64);
+    const size_t smem = (size_t)FastScratch<X, U, H1, H2>::count(mode) * threads * sizeof(double);
+    if (smem > 48 * 1024) {
+        static bool once = false;                        // opt in to > 48 KB of dynamic shared memory, once per instantiation
+        if (!once) {
+            CU(h, cudaFuncSetAttribute(nempc_fast64_kernel<X, U, H1, H2, JC, 2, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            once = true;
+        }
+    }
+    switch (mode) {
+        case 0: nempc_fast64_kernel<X, U, H1, H2, JC, 0, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        case 1: nempc_fast64_kernel<X, U, H1, H2, JC, 1, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+        default: nempc_fast64_kernel<X, U, H1, H2, JC, 2, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
+    }
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return NEMPC_OK;
+}
+static int launch_fast64(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
+    switch (h->fast64_id) {
+        case 0: return launch_fast64_shape<2, 1, 30, 30, 6>(h, ar, mode, s);
+        case 1: return launch_fast64_shape<2, 1, 32, 32, 8>(h, ar, mode, s);
+        case 2: return launch_fast64_shape<2, 1, 16, 16, 8>(h, ar, mode, s);
+    }
+    SET_ERR(h, "internal: bad fast64_id");
+    return NEMPC_EINVAL;
+}
+template <typename TIO> static bool take_fast64(nempc_handle*, const EvalArgs<TIO>&) { return false; }
+template <> bool take_fast64<double>(nempc_handle* h, const EvalArgs<double>& ar) {
+    static const long long min_steps = getenv("NEMPC_FAST64_MIN_STEPS") ? atoll(getenv("NEMPC_FAST64_MIN_STEPS")) : NEMPC_FAST64_MIN_STEPS;
+    return h->fast64_id >= 0 && (ar.nsteps >= min_steps || h->desc.kernel == NEMPC_KERNEL_FAST);
+}
+template <typename TIO> static int run_fast64(nempc_handle* h, const EvalArgs<TIO>&, int, cudaStream_t) { SET_ERR(h, "internal: fast64 needs float64 I/O"); return NEMPC_EINVAL; }
+template <> int run_fast64<double>(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) { return launch_fast64(h, ar, mode, s); }
+
 // small batches of the same networks: one WARP per horizon step (nempc_small.cuh) -- latency instead of throughput
 #ifndef NEMPC_SMALL_MAX_STEPS
 #define NEMPC_SMALL_MAX_STEPS 6144      // measured crossover with the thread-per-step kernel: 52 vs 63 us at 6400 steps, 91 vs 64 us at 12800
@@ -1044,7 +1120,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         const int mode = hes ? 2 : (jac ? 1 : 0);
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
-        int rc = h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
+        int rc = take_fast64<TIO>(h, ar) ? run_fast64<TIO>(h, ar, mode, s) : h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
                             : (h->use_tc ? launch_tc<TIO>(h, ar, mode, s) : (h->use_wide ? launch_wide<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s)));
         if (rc) return rc;
     }

@@ -543,3 +543,39 @@ def test_c4_properties_wide_kernel():
     for kr, kg in KEYS[:3]:
         assert _relerr(o1[kg][pick].cpu().numpy(), ref[kr]) < TOL32, (kg, _relerr(o1[kg][pick].cpu().numpy(), ref[kr]))
     ev.close()
+
+
+@pytest.mark.parametrize("kind", ("discrete", "unity", "rk4"))
+@pytest.mark.parametrize("h", (30, 32, 16))
+def test_float64_register_resident_kernel_vs_oracle(kind, h, lv_weights):
+    """nempc_fast64_kernel (thread per step, DFMA): the 1e-10 parity mode at register-resident speed"""
+    import torch
+    H, B = 50, 300
+    mlp = MLP(lv_weights, 2, 1) if h == 30 else MLP.glorot([3, h, h, 2], 2, 1, seed=h)
+    rng = np.random.default_rng(h + 1)
+    obj = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 0.5], [0.3], x_ref=rng.uniform(-1, 1, (H, 2)))
+    Z, X0 = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2))
+    lam, sig = rng.standard_normal((B, H * 2)), rng.uniform(0.5, 1.5, B)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    for kernel in ("auto", "fast"):
+        ev = _evaluator(mlp, kind, H, "float64", kernel, obj)
+        assert "nempc_fast64_kernel" in ev.kernel_name
+        got = _run(ev, Z, X0, lam, sig)
+        for kr, kg in KEYS:
+            assert _relerr(got[kg], ref[kr]) < TOL64, (kg, _relerr(got[kg], ref[kr]))
+        t = lambda a: torch.as_tensor(a).cuda()
+        o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+        o0 = ev.eval(t(Z), t(X0), want=("resid",))
+        torch.cuda.synchronize()
+        assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL64 and _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL64
+        ev.close()
+    # a forced register-resident evaluation of ONE small problem against the reference golden (auto would take the generic kernel here)
+    if h == 30 and kind == "rk4":
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rk4_H25.npz"))
+        gobj = SeparableQuadraticObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+        ev = _evaluator(mlp, "rk4", 25, "float64", "fast", gobj)
+        jr, jc = np.nonzero(g["jacobian"])
+        got = _run(ev, g["z"][None], g["x0"][None], g["lam"][None], np.asarray([float(g["sigma"])]))
+        assert _relerr(got["resid"][0], g["constraints"]) < TOL64 and _relerr(got["jac"][0], g["jacobian"][jr, jc]) < TOL64
+        assert _relerr(got["hes"][0], g["hessian_values"]) < TOL64
+        ev.close()
