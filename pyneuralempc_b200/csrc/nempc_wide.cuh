@@ -269,7 +269,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     constexpr float INV = NEMPC_TC_LO_INV;                 // accumulators carry 2^11
     typedef typename WideOf<float, TIO>::type TW;
     extern __shared__ __align__(1024) unsigned char wide_smem[];
-    __shared__ uint64_t bars[2 * C::NSTAGE + 2];
+    __shared__ uint64_t bars[2 * C::NSTAGE + 1 + 4];
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -295,12 +295,12 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     const uint32_t bar0 = smem_u32(&bars[0]);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    const uint32_t bar_dready = bar0 + 8u * (2 * NSTAGE), bar_aready = bar_dready + 8u;
+    const uint32_t bar_dready = bar0 + 8u * (2 * NSTAGE), bar_aready = bar_dready + 8u;   // bar_aready + 8 q: operand quarter q (K steps 4q .. 4q+3) is ready
     if (tid == 0) {
         // leader: a ring stage is full when its own TMA bytes have landed AND the peer forwarded the same for its half
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), rank == 0 ? 2 : 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_dready, 1);
-        mbar_init(bar_aready, 2 * NEMPC_WIDE_EPI_WARPS * 32);          // the epilogue threads of BOTH CTAs (used in the leader only)
+        for (int q = 0; q < 4; ++q) mbar_init(bar_aready + 8u * q, 2 * NEMPC_WIDE_EPI_WARPS);   // one arrival per epilogue warp of BOTH CTAs (used in the leader only)
         mbar_fence_init();
     }
     if (is_mma) tmem_alloc2(smem_u32(&tmem_holder), 512);
@@ -318,6 +318,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     const int nhid = net.nhid;
     uint32_t it = 0;            // ring iteration (producer / issuer)
     uint32_t g = 0;             // GEMM counter (all roles): A operand in region g & 1, accumulator in the other
+    uint32_t aphase = 0;        // issuer: phase bit of each operand-quarter barrier (quarters 1..3 only see the K = 256 GEMMs)
     auto areg = [&](uint32_t gg) { return (gg & 1u) ? 256u : 0u; };
     auto dreg = [&](uint32_t gg) { return (gg & 1u) ? 0u : 256u; };
 
@@ -330,75 +331,87 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         if (is_prod) {
             if (lane == 0) {
                 const uint32_t img = 16u * gm.n;                                               // one K-step image of this CTA's half of the rows
-                const unsigned char* src = blob + gm.off[rank];
-                for (uint32_t ks = 0; ks < gm.ksteps; ks += 2, ++it) {                         // pass 1: [hi | lo] of two K steps
-                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (ks + 1 < gm.ksteps ? 4u : 2u) * img;
-                    mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
-                    WPROF(8);
-                    mbar_expect_tx(bar_full(slot), bytes);
-                    bulk_g2s(ring + slot * C::STAGE_BYTES, src, bytes, bar_full(slot));
-                    src += bytes;
-                    WPROF(9);
-                }
-                for (uint32_t ks = 0; ks < gm.ksteps; ks += 4, ++it) {                         // pass 2: 2^11 hi of four K steps
-                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (gm.ksteps - ks < 4u ? gm.ksteps - ks : 4u) * img;
-                    mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
-                    WPROF(8);
-                    mbar_expect_tx(bar_full(slot), bytes);
-                    bulk_g2s(ring + slot * C::STAGE_BYTES, src, bytes, bar_full(slot));
-                    src += bytes;
-                    WPROF(9);
+                const unsigned char* src0 = blob + gm.off[rank];
+                const uint32_t main0 = gm.ksteps * 2u * img;                                   // the 2^11 hi images follow the [hi | lo] pairs of all K steps
+                for (uint32_t k0 = 0; k0 < gm.ksteps; k0 += 4) {                               // operand quarter by quarter, in the order the issuer consumes
+                    const uint32_t k1 = k0 + 4u < gm.ksteps ? k0 + 4u : gm.ksteps;
+                    for (uint32_t ks = k0; ks < k1; ks += 2, ++it) {                           // corrections: [hi | lo] of two K steps
+                        const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (ks + 1 < k1 ? 4u : 2u) * img;
+                        mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
+                        WPROF(8);
+                        mbar_expect_tx(bar_full(slot), bytes);
+                        bulk_g2s(ring + slot * C::STAGE_BYTES, src0 + ks * 2u * img, bytes, bar_full(slot));
+                        WPROF(9);
+                    }
+                    {                                                                          // main products: 2^11 hi of the quarter's K steps
+                        const uint32_t slot = it % NSTAGE, round = it / NSTAGE, bytes = (k1 - k0) * img;
+                        mbar_wait(bar_empty(slot), (round & 1u) ^ 1u);
+                        WPROF(8);
+                        mbar_expect_tx(bar_full(slot), bytes);
+                        bulk_g2s(ring + slot * C::STAGE_BYTES, src0 + main0 + k0 * img, bytes, bar_full(slot));
+                        WPROF(9);
+                        ++it;
+                    }
                 }
             }
             __syncwarp();
         } else if (is_mma) {
             if (rank == 0) {
-                // the whole warp runs the loop (converged: operands stay in uniform registers), one elected lane issues
+                // the whole warp runs the loop (converged: operands stay in uniform registers), one elected lane issues.
+                // The A operand arrives QUARTER BY QUARTER (64 neurons = 4 K steps): the epilogue of the previous layer publishes a quarter as
+                // soon as it is converted, so these MMAs run under the rest of that epilogue.  Within a quarter the corrections go first.
                 WPROF(2);
-                mbar_wait(bar_aready, g & 1u);
-                fence_after_sync();
-                WPROF(0); WPROF_COUNT(3);
+                WPROF_COUNT(3);
                 const uint32_t ta = tmem + areg(g), td = tmem + dreg(g);
                 const uint32_t idesc = make_idesc_f16(256, (int)gm.n);
                 const uint32_t lbo = 8u * gm.n, img = 16u * gm.n;                               // per-CTA half: n / 2 rows
-                for (uint32_t ks = 0; ks < gm.ksteps; ks += 2, ++it) {                         // corrections first: the accumulator is still small
-                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
-                    mbar_wait(bar_full(slot), round & 1u);
+                for (uint32_t k0 = 0; k0 < gm.ksteps; k0 += 4) {
+                    const uint32_t k1 = k0 + 4u < gm.ksteps ? k0 + 4u : gm.ksteps, q = k0 >> 2;
+                    mbar_wait(bar_aready + 8u * q, (aphase >> q) & 1u);
+                    aphase ^= 1u << q;
                     fence_after_sync();
-                    WPROF(1);
-                    const uint32_t sb = ring + slot * C::STAGE_BYTES;
-                    if (elect_one()) {
-                        mma2_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);      // A_lo W_hi
-                        mma2_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);           // A_hi W_lo
-                        if (ks + 1 < gm.ksteps) {
-                            mma2_f16_ts(td, ta + 16u * ks + 24u, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);
-                            mma2_f16_ts(td, ta + 16u * ks + 16u, make_desc_kmajor(sb + 3u * img, lbo, 128), idesc, 1);
+                    WPROF(0);
+                    for (uint32_t ks = k0; ks < k1; ks += 2, ++it) {
+                        const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
+                        mbar_wait(bar_full(slot), round & 1u);
+                        fence_after_sync();
+                        WPROF(1);
+                        const uint32_t sb = ring + slot * C::STAGE_BYTES;
+                        if (elect_one()) {
+                            mma2_f16_ts(td, ta + 16u * ks + 8u, make_desc_kmajor(sb, lbo, 128), idesc, ks != 0);      // A_lo W_hi
+                            mma2_f16_ts(td, ta + 16u * ks, make_desc_kmajor(sb + img, lbo, 128), idesc, 1);           // A_hi W_lo
+                            if (ks + 1 < k1) {
+                                mma2_f16_ts(td, ta + 16u * ks + 24u, make_desc_kmajor(sb + 2u * img, lbo, 128), idesc, 1);
+                                mma2_f16_ts(td, ta + 16u * ks + 16u, make_desc_kmajor(sb + 3u * img, lbo, 128), idesc, 1);
+                            }
+                            mma2_commit(bar_empty(slot));
                         }
-                        mma2_commit(bar_empty(slot));
+                        __syncwarp();
+                        WPROF(2);
                     }
-                    __syncwarp();
-                    WPROF(2);
-                }
-                for (uint32_t ks = 0; ks < gm.ksteps; ks += 4, ++it) {                         // main products A_hi (2^11 W_hi)
-                    const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
-                    mbar_wait(bar_full(slot), round & 1u);
-                    fence_after_sync();
-                    WPROF(1);
-                    const uint32_t sb = ring + slot * C::STAGE_BYTES;
-                    if (elect_one()) {
+                    {                                                                          // main products A_hi (2^11 W_hi)
+                        const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
+                        mbar_wait(bar_full(slot), round & 1u);
+                        fence_after_sync();
+                        WPROF(1);
+                        const uint32_t sb = ring + slot * C::STAGE_BYTES;
+                        if (elect_one()) {
 #pragma unroll
-                        for (uint32_t j = 0; j < 4; ++j)
-                            if (ks + j < gm.ksteps) mma2_f16_ts(td, ta + 16u * (ks + j), make_desc_kmajor(sb + j * img, lbo, 128), idesc, 1);
-                        mma2_commit(bar_empty(slot));
+                            for (uint32_t j = 0; j < 4; ++j)
+                                if (k0 + j < k1) mma2_f16_ts(td, ta + 16u * (k0 + j), make_desc_kmajor(sb + j * img, lbo, 128), idesc, 1);
+                            mma2_commit(bar_empty(slot));
+                        }
+                        __syncwarp();
+                        WPROF(2);
+                        ++it;
                     }
-                    __syncwarp();
-                    WPROF(2);
                 }
                 if (elect_one()) mma2_commit(bar_dready);
                 __syncwarp();
             } else if (lane == 0) {
                 // peer CTA: tell the leader when this CTA's half of a ring stage has landed
-                const uint32_t nst = (gm.ksteps + 1) / 2 + (gm.ksteps + 3) / 4;
+                uint32_t nst = 0;
+                for (uint32_t k0 = 0; k0 < gm.ksteps; k0 += 4) nst += ((k0 + 4u < gm.ksteps ? 4u : gm.ksteps - k0) + 1u) / 2u + 1u;
                 for (uint32_t i = 0; i < nst; ++i, ++it) {
                     const uint32_t slot = it % NSTAGE, round = it / NSTAGE;
                     mbar_wait(bar_full(slot), round & 1u);
@@ -420,9 +433,16 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     };
     auto nopre = []() {};
     // epilogue role: this thread's part of the A operand of GEMM g (region areg(g)) is written
-    auto publish = [&]() {
-        if (is_epi) { tmem_st_wait(); fence_before_sync(); mbar_arrive_cluster(aready_leader); }
+    // quarter q (K steps 4q .. 4q+3 = neurons [64 q, 64 q + 64)) of the A operand of GEMM g is written: one arrival per warp
+    auto publish_q = [&](const int q) {
+        if (is_epi) {
+            tmem_st_wait();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(aready_leader + 8u * q);
+        }
     };
+    auto publish = [&]() { publish_q(0); };                // K = 16 operands (seeds) have one quarter
     auto epi_sync = [&]() { if (is_epi) asm volatile("bar.sync 1, %0;" ::"n"(NEMPC_WIDE_EPI_WARPS * 32) : "memory"); };
     // K = 16 operand (one K step): hi pairs in columns [0, 8), lo pairs in [8, 16) of region areg(g); written by the quarter-0 warps
     auto put_seed = [&](const float* v16) {
@@ -432,21 +452,27 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         tmem_st8(a, hi);
         tmem_st8(a + 8, lo);
     };
-    // the four 16-neuron chunks of this warp's quarter, the next chunk's accumulator in flight while `body(chunk, registers)` runs
-    auto chunks = [&](const uint32_t dbase, auto&& body) {
+    // this warp's 16-neuron chunk of EVERY 64-neuron quarter (columns 64 q + 16 sub), quarter by quarter, the next chunk's accumulator in flight
+    // while `body(q, registers)` runs; `feeds`: the body converted the chunk into operand form -- the quarter is published right away
+    auto chunks = [&](const uint32_t dbase, const bool feeds, auto&& body) {
         uint32_t va[16], vb[16];
-        tmem_ld16_nowait(dbase + 64 * sub, va);
+        const uint32_t c0 = dbase + 16 * sub;
+        tmem_ld16_nowait(c0, va);
         tmem_ld_wait(); tmem_ld_pin(va);
-        tmem_ld16_nowait(dbase + 64 * sub + 16, vb);
+        tmem_ld16_nowait(c0 + 64, vb);
         body(0, va);
+        if (feeds) publish_q(0);
         tmem_ld_wait(); tmem_ld_pin(vb);
-        tmem_ld16_nowait(dbase + 64 * sub + 32, va);
+        tmem_ld16_nowait(c0 + 128, va);
         body(1, vb);
+        if (feeds) publish_q(1);
         tmem_ld_wait(); tmem_ld_pin(va);
-        tmem_ld16_nowait(dbase + 64 * sub + 48, vb);
+        tmem_ld16_nowait(c0 + 192, vb);
         body(2, va);
+        if (feeds) publish_q(2);
         tmem_ld_wait(); tmem_ld_pin(vb);
         body(3, vb);
+        if (feeds) publish_q(3);
     };
 
     // the pair works on super-tiles (2 i, 2 i + 1); both CTAs run the GEMM sequence of the fuller one (the leader's)
@@ -487,26 +513,25 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
             publish();
             for (int l = 0; l < nhid; ++l) {
                 gemm(l == 0 ? net.in_f : net.hid_f[l - 1], nopre, [&](const uint32_t dbase) {
-                    const float* bl = bias + l * HW + 64 * sub;
-                    float* dst = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
-                    chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                    const float* bl = bias + l * HW + 16 * sub;
+                    float* dst = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 16 * sub;
+                    chunks(dbase, true, [&](const int qq, const uint32_t* vr) {
                         float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(__uint_as_float(vr[i]), INV, bl[16 * qq + i]));
-                        if (HES && keep_h) st16_global(dst + 16 * qq, v);                     // h_l: phase B needs it
+                        for (int i = 0; i < 16; ++i) v[i] = tanh_acc(fmaf(__uint_as_float(vr[i]), INV, bl[64 * qq + i]));
+                        if (HES && keep_h) st16_global(dst + 64 * qq, v);                     // h_l: phase B needs it
                         else if (JAC) {
                             float s1[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) s1[i] = fmaf(-v[i], v[i], 1.f);
-                            st16_global(dst + 16 * qq, s1);                                   // s'(a_l) for phase C
+                            st16_global(dst + 64 * qq, s1);                                   // s'(a_l) for phase C
                         }
                         uint32_t hi[8], lo[8];
                         split16(v, hi, lo);
-                        tmem_st8(dbase + 64 * sub + 16 * qq, hi);
-                        tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                        tmem_st8(dbase + 64 * qq + 16 * sub, hi);
+                        tmem_st8(dbase + 64 * qq + 16 * sub + 8, lo);
                     });
                 });
-                publish();
             }
             gemm(net.out_f, nopre, [&](const uint32_t dbase) {
                 if (sub != 0) return;
@@ -562,11 +587,11 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 // next operand u_l = s'(a_l) g_l
                 const bool more = l > 0 || want_in;
                 gemm(l == nhid - 1 ? net.out_b : net.hid_b[l], nopre, [&](const uint32_t dbase) {
-                    float* ph = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
-                    float* pq = sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub;
-                    chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                    float* ph = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 16 * sub;
+                    float* pq = sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 16 * sub;
+                    chunks(dbase, more, [&](const int qq, const uint32_t* vr) {
                         float h[16], u[16], cf[16];
-                        ld16_global_cg(ph + 16 * qq, h);
+                        ld16_global_cg(ph + 64 * qq, h);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float hv = h[i], s1 = fmaf(-hv, hv, 1.f);
@@ -574,17 +599,16 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                             cf[i] = -2.f * hv * u[i];
                             h[i] = s1;
                         }
-                        st16_global(ph + 16 * qq, h);
-                        st16_global(pq + 16 * qq, cf);
+                        st16_global(ph + 64 * qq, h);
+                        st16_global(pq + 64 * qq, cf);
                         if (more) {
                             uint32_t hi[8], lo[8];
                             split16(u, hi, lo);
-                            tmem_st8(dbase + 64 * sub + 16 * qq, hi);
-                            tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                            tmem_st8(dbase + 64 * qq + 16 * sub, hi);
+                            tmem_st8(dbase + 64 * qq + 16 * sub + 8, lo);
                         }
                     });
                 });
-                if (more) publish();
             }
             if (RK4 && want_in) {
                 gemm(net.in_b, nopre, [&](const uint32_t dbase) {
@@ -630,10 +654,10 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     gemm(l == 0 ? net.in_f : net.hid_f[l - 1],
                          [&]() {
                              // while the MMAs run: this warp's s'(a_l) (x 2^-11: the accumulator's scale) and curvature coefficients (x 2^-22) of
-                             // its SPW steps and 64 neurons, global scratch -> warp-private shared memory
+                             // its SPW steps and 64 neurons (chunk `sub` of every quarter), global scratch -> warp-private shared memory
                              for (int i = lane; i < SPW * 16; i += 32) {
                                  const int sw_ = i >> 4, f4 = i & 15;
-                                 const long long o = ((long long)(sidx0 + sw_) * NEMPC_WIDE_MAXHID + l) * HW + 64 * sub + 4 * f4;
+                                 const long long o = ((long long)(sidx0 + sw_) * NEMPC_WIDE_MAXHID + l) * HW + 64 * (f4 >> 2) + 16 * sub + 4 * (f4 & 3);
                                  float4 a = __ldcg(reinterpret_cast<const float4*>(sa + o));
                                  a.x *= INV; a.y *= INV; a.z *= INV; a.w *= INV;
                                  *reinterpret_cast<float4*>(scs + sw_ * 64 + 4 * f4) = a;
@@ -647,7 +671,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                          },
                          [&](const uint32_t dbase) {
                              const float* s1row = scs + (lane / DP) * 64;
-                             chunks(dbase, [&](const int qq, const uint32_t* vr) {
+                             chunks(dbase, true, [&](const int qq, const uint32_t* vr) {
                                  if (HES && curv) gram_chunk<DP>(stg, vr, scs + SPW * 64, 16 * qq, acc, lane);      // raw tangent T_l (x 2^11)
                                  f2 v2[8];
 #pragma unroll
@@ -658,12 +682,11 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                                  }
                                  uint32_t hi[8], lo[8];
                                  split16p(v2, hi, lo);
-                                 tmem_st8(dbase + 64 * sub + 16 * qq, hi);
-                                 tmem_st8(dbase + 64 * sub + 16 * qq + 8, lo);
+                                 tmem_st8(dbase + 64 * qq + 16 * sub, hi);
+                                 tmem_st8(dbase + 64 * qq + 16 * sub + 8, lo);
                              });
                              __syncwarp();                                      // `scs` is rewritten for the next layer
                          });
-                    publish();
                 }
                 gemm(net.out_f, nopre, [&](const uint32_t dbase) {
                     if (sub != 0) return;
