@@ -8,9 +8,11 @@
 //   phase B  contracted adjoint      128 steps per row tile   g_{l-1} = W_l (s'(a_l) * g_l),  seed g_L = W_out w       (w = lambda for the
 //            single-stage integrators, the stage weight w_s of SURVEY 7.3 for RK4)      -> q_l = -2 h_l g_l to the scratch
 //   phase C  tangent forward         128 / DP steps per tile, DP tangent rows per step (seed rows R_s, identity for discrete):
-//            T_l = W_l^T V_{l-1},  V_l = s'(a_l) * T_l;  J R = W_out^T V_L;  curvature  sum_l T_l^T diag(s''(a_l) g_l) T_l  with
-//            s''(a) g = (q s'),  accumulated as 4x4 register blocks on the FFMA2 pipe from a warp-private shared-memory staging of T_l
-//            (a warp owns all DP rows of its steps, so no cross-warp traffic until the final sum over the four neuron quarters).
+//            T_l = W_l^T V_{l-1},  V_l = s'(a_l) * T_l;  J R = W_out^T V_L;  curvature  sum_l T_l^T diag(s''(a_l) g_l) T_l  =  sum_l U_l V_l^T
+//            with U_l = (-2 h_l g_l) * T_l: per 16-neuron chunk the warp stages the split-f16 rows of U and V in its own shared-memory planes
+//            and accumulates the 16 x 16 blocks with warp-level mma.sync.m16n8k16 (three products, as in the big GEMMs) -- a warp owns all DP
+//            rows of its steps, so there is no cross-warp traffic until the final sum over the four 16-neuron slices of each quarter.
+//            (-DNEMPC_WIDE_GRAM_MMA=0 keeps the first version: 4x4 register blocks on the FFMA2 pipe, 1.44x slower on C4.)
 //   RK4: sweep 1 over the stages (A, C without curvature: k_s, dk_s = J_s R_s, R_{s+1} = I + a_{s+1} E dk_s), sweep 2 backwards
 //   (B with w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}, C with curvature): H = sum_s R_s^T (sum_p w_{s,p} Hess f_p(z_s)) R_s.
 //
@@ -29,10 +31,13 @@
 //     scaling with the CTA count).  So two CTAs of a cluster work on two 128-row tiles as ONE M = 256 MMA: each CTA streams only its
 //     half of the B rows (tcgen05.mma.cta_group::2 exchanges the halves between the two SMs), which halves the bytes per SM and row.
 //     The two CTAs run the same GEMM sequence on their own super-tile (a CTA without work runs it on zero rows).
-//   * roles per CTA: 16 epilogue warps (lane = row; warp w: lane quadrant w & 3, neuron quarter w >> 2), one TMA producer thread
+//   * the operand is handed over QUARTER BY QUARTER: an epilogue warp converts its 16-neuron slice of every 64-neuron quarter in turn and
+//     arrives on that quarter's barrier, the issuer consumes quarter q (K steps 4q .. 4q+3, corrections first within the quarter) as soon as
+//     all 32 warps of the pair have arrived: the MMAs of layer l+1 run under the rest of the epilogue of layer l.
+//   * roles per CTA: 16 epilogue warps (lane = row; warp w: lane quadrant w & 3, 16-neuron slice w >> 2 of each quarter), one TMA producer thread
 //     (warp 16) that runs ahead through the ring, and in warp 17 the MMA-issuing thread (leader CTA) or a thread that forwards the
 //     peer's ring-full signals to the leader.  mbarriers only: ring full (leader: own TMA + peer's forward) / empty and accumulator
-//     ready (tcgen05.commit multicast to both CTAs), operand ready (2 x 512 arrivals on the leader's barrier, the peer's arrive remotely).
+//     ready (tcgen05.commit multicast to both CTAs), operand-quarter ready (2 x 16 warp arrivals on the leader's barriers, the peer's arrive remotely).
 #pragma once
 #include "nempc_fast.cuh"
 #include "nempc_generic.cuh"
@@ -46,6 +51,9 @@
 #endif
 #define NEMPC_WIDE_MAXHID 4
 #define NEMPC_WIDE_SUP 128                      // steps per super-tile (= rows of a phase A / B tile)
+#ifndef NEMPC_WIDE_GRAM_MMA
+#define NEMPC_WIDE_GRAM_MMA 1                  // curvature blocks on the warp-level tensor path (mma.sync, split-f16) instead of FFMA2
+#endif
 
 // one streamed operand of a GEMM with n rows and `ksteps` K steps of 16, cut in two halves of nh = n / 2 rows (CTA r of the pair
 // streams rows [r nh, (r + 1) nh) from off[r]); an image of one K step = [K chunk 0..1][nh][8 halves] = 32 nh bytes:
@@ -75,7 +83,11 @@ template <int X_, int U_, int MODE_, bool RK4_ = false> struct WideCfg {
     static constexpr int NTILE = NEMPC_WIDE_SUP / SPT;                   // phase-C tiles per super-tile
     static constexpr int STAGE_BYTES = 128 * (HW / 2);                   // four K-step images of one CTA's half of the B rows
     static constexpr int C_FLOATS = NEMPC_WIDE_MAXHID * HW + 16;        // biases, output bias
+#if NEMPC_WIDE_GRAM_MMA
+    static constexpr int STG_WARP = HES ? 4 * 1024 : 0;                  // per-warp staging of a 32-row x 16-neuron chunk: f16 planes U_hi, U_lo, V_hi, V_lo, [K half][row][8 halves]
+#else
     static constexpr int STG_WARP = HES ? 4 * 32 * 16 : 0;              // per-warp staging of a 32-row x 16-neuron chunk of T_l (4 planes of 32 granules)
+#endif
     static constexpr int SPW = 32 / DP;                                  // steps per epilogue warp in phase C
     static constexpr int SC_WARP = JAC ? (HES ? 2 : 1) * SPW * 64 * 4 : 0;   // per-warp copy of s'(a_l) (and the curvature coefficients) of its steps and neuron quarter
     static constexpr int PART_BYTES = HES ? 4 * SPT * DP * DP * 4 : 0;  // [4 quarters][SPT][DP][DP] partial curvature: aliases the staging area
@@ -239,6 +251,48 @@ __device__ __forceinline__ void gram_chunk(float* stg, const uint32_t* T, const 
         }
     }
     __syncwarp();
+}
+
+// ---- curvature blocks on the warp-level tensor path ----------------------------------------------------------------------------
+// G[a][b] += sum_j U[a][j] V[b][j] over the 16 neurons of a chunk, for the two 16-row tiles of the warp (U = (-2 h g) T, V = s' T, so
+// that U V = s'' g T T), as split-f16 mma.sync.m16n8k16 products:  U_hi V_hi  into accM,  U_lo V_hi + U_hi V_lo  (both carry 2^11) into
+// accC;  G = accM + 2^-11 accC.  The rows reach the fragment layout through the warp's staging planes and ldmatrix:
+//   plane p (0 U_hi, 1 U_lo, 2 V_hi, 3 V_lo) = 1 KB:  [K half kh][row r][8 halves]  (16 B per row: conflict-free stores and ldmatrix rows)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t* r) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, const uint32_t b0, const uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// accM / accC: [tile 0..1][column half 0..1][4] in the m16n8 accumulator layout (rows lane/4 and lane/4 + 8, columns 2 (lane%4), +1)
+__device__ __forceinline__ void gram_mma_chunk(const uint32_t stg_addr, uint4* stg, const uint32_t* uhi, const uint32_t* ulo,
+                                               const uint32_t* vhi, const uint32_t* vlo, float* accM, float* accC, const int lane) {
+    stg[0 * 64 + lane] = make_uint4(uhi[0], uhi[1], uhi[2], uhi[3]); stg[0 * 64 + 32 + lane] = make_uint4(uhi[4], uhi[5], uhi[6], uhi[7]);
+    stg[1 * 64 + lane] = make_uint4(ulo[0], ulo[1], ulo[2], ulo[3]); stg[1 * 64 + 32 + lane] = make_uint4(ulo[4], ulo[5], ulo[6], ulo[7]);
+    stg[2 * 64 + lane] = make_uint4(vhi[0], vhi[1], vhi[2], vhi[3]); stg[2 * 64 + 32 + lane] = make_uint4(vhi[4], vhi[5], vhi[6], vhi[7]);
+    stg[3 * 64 + lane] = make_uint4(vlo[0], vlo[1], vlo[2], vlo[3]); stg[3 * 64 + 32 + lane] = make_uint4(vlo[4], vlo[5], vlo[6], vlo[7]);
+    __syncwarp();
+    const int mi = lane >> 3, rr = lane & 7;
+    // A fragments: matrices (rows 0-7, kh 0), (rows 8-15, kh 0), (rows 0-7, kh 1), (rows 8-15, kh 1);  B fragments of both column halves:
+    // (rows 0-7, kh 0), (rows 0-7, kh 1), (rows 8-15, kh 0), (rows 8-15, kh 1)
+    const uint32_t offA = (uint32_t)(((mi >> 1) * 32 + 8 * (mi & 1) + rr) * 16);
+    const uint32_t offB = (uint32_t)(((mi & 1) * 32 + 8 * (mi >> 1) + rr) * 16);
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+        uint32_t ah[4], al[4], bh[4], bl[4];
+        ldmatrix_x4(stg_addr + 0 * 1024 + offA + tile * 256, ah);
+        ldmatrix_x4(stg_addr + 1 * 1024 + offA + tile * 256, al);
+        ldmatrix_x4(stg_addr + 2 * 1024 + offB + tile * 256, bh);
+        ldmatrix_x4(stg_addr + 3 * 1024 + offB + tile * 256, bl);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mma_16816(accM + (tile * 2 + h) * 4, ah, bh[2 * h], bh[2 * h + 1]);
+            mma_16816(accC + (tile * 2 + h) * 4, al, bh[2 * h], bh[2 * h + 1]);
+            mma_16816(accC + (tile * 2 + h) * 4, ah, bl[2 * h], bl[2 * h + 1]);
+        }
+    }
+    __syncwarp();                                              // the planes are rewritten by the next chunk
 }
 }  // namespace widex
 
@@ -595,8 +649,9 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float hv = h[i], s1 = fmaf(-hv, hv, 1.f);
-                            u[i] = s1 * (__uint_as_float(vr[i]) * INV);
-                            cf[i] = -2.f * hv * u[i];
+                            const float gv = __uint_as_float(vr[i]) * INV;
+                            u[i] = s1 * gv;
+                            cf[i] = NEMPC_WIDE_GRAM_MMA ? -2.f * hv * gv : -2.f * hv * u[i];     // -2 h g (times s' T below), or s''(a) g = -2 h s' g
                             h[i] = s1;
                         }
                         st16_global(ph + 64 * qq, h);
@@ -634,9 +689,15 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 const int sidx = ti * SPT + row / DP, cc = row % DP;          // step inside the super-tile, tangent column
                 const int sidx0 = ti * SPT + (32 * wq) / DP;                  // first step of this warp
                 const bool validC = is_epi && sidx < nvalid && cc < D;
+#if NEMPC_WIDE_GRAM_MMA
+                float accM[16], accC[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { accM[i] = 0.f; accC[i] = 0.f; }
+#else
                 f2 acc[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[i] = pk(0.f, 0.f);
+#endif
                 if (is_epi && sub == 0) {
                     float e[16];
 #pragma unroll
@@ -663,7 +724,8 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                                  *reinterpret_cast<float4*>(scs + sw_ * 64 + 4 * f4) = a;
                                  if (HES && curv) {
                                      float4 q = __ldcg(reinterpret_cast<const float4*>(sq + o));
-                                     q.x *= INV * INV; q.y *= INV * INV; q.z *= INV * INV; q.w *= INV * INV;
+                                     constexpr float QS = NEMPC_WIDE_GRAM_MMA ? INV : INV * INV;     // one raw tangent factor (2^11) or two
+                                     q.x *= QS; q.y *= QS; q.z *= QS; q.w *= QS;
                                      *reinterpret_cast<float4*>(scs + (SPW + sw_) * 64 + 4 * f4) = q;
                                  }
                              }
@@ -672,7 +734,9 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                          [&](const uint32_t dbase) {
                              const float* s1row = scs + (lane / DP) * 64;
                              chunks(dbase, true, [&](const int qq, const uint32_t* vr) {
+#if !NEMPC_WIDE_GRAM_MMA
                                  if (HES && curv) gram_chunk<DP>(stg, vr, scs + SPW * 64, 16 * qq, acc, lane);      // raw tangent T_l (x 2^11)
+#endif
                                  f2 v2[8];
 #pragma unroll
                                  for (int i4 = 0; i4 < 4; ++i4) {
@@ -684,6 +748,22 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                                  split16p(v2, hi, lo);
                                  tmem_st8(dbase + 64 * qq + 16 * sub, hi);
                                  tmem_st8(dbase + 64 * qq + 16 * sub + 8, lo);
+#if NEMPC_WIDE_GRAM_MMA
+                                 if (HES && curv) {
+                                     // U = (-2 h g) T (true scale: the coefficient row carries 2^-11), split like V; G += U V^T on the tensor path
+                                     const float* krow = scs + (SPW + lane / DP) * 64 + 16 * qq;
+                                     f2 u2[8];
+#pragma unroll
+                                     for (int i4 = 0; i4 < 4; ++i4) {
+                                         const float4 k4 = *reinterpret_cast<const float4*>(krow + 4 * i4);
+                                         u2[2 * i4] = mul2(pk(__uint_as_float(vr[4 * i4]), __uint_as_float(vr[4 * i4 + 1])), pk(k4.x, k4.y));
+                                         u2[2 * i4 + 1] = mul2(pk(__uint_as_float(vr[4 * i4 + 2]), __uint_as_float(vr[4 * i4 + 3])), pk(k4.z, k4.w));
+                                     }
+                                     uint32_t uhi[8], ulo[8];
+                                     split16p(u2, uhi, ulo);
+                                     gram_mma_chunk(smem_u32(stg), reinterpret_cast<uint4*>(stg), uhi, ulo, hi, lo, accM, accC, lane);
+                                 }
+#endif
                              });
                              __syncwarp();                                      // `scs` is rewritten for the next layer
                          });
@@ -730,6 +810,24 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 if (HES && curv) {
                     // ---- sum the four neuron quarters, scatter the lower triangle (same slots as nempc_generic.cuh) -----------------
                     epi_sync();                                    // `part` aliases the staging planes: every warp is done with its curvature
+#if NEMPC_WIDE_GRAM_MMA
+                    if (is_epi) {
+                        // accumulator fragments -> [quarter][step][DP][DP]: entry (R, Cc) of a 16-row tile is kept when row and column belong to the same step
+#pragma unroll
+                        for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int R = 16 * tile + (lane >> 2) + 8 * (e >> 1), Cc = 16 * tile + 8 * h + 2 * (lane & 3) + (e & 1);
+                                    if (R / DP == Cc / DP) {
+                                        const int s8 = (32 * wq) / DP + R / DP;
+                                        const int ai = (tile * 2 + h) * 4 + e;
+                                        part[((sub * SPT + s8) * DP + R % DP) * DP + Cc % DP] = fmaf(accC[ai], INV, accM[ai]);
+                                    }
+                                }
+                    }
+#else
                     if (is_epi) {
                         constexpr int NB = DP / 4, LPS = NB * NB, ACTIVE = (32 / DP) * LPS;
                         if (lane < ACTIVE) {
@@ -742,6 +840,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                                 for (int k = 0; k < 4; ++k) pp[i * DP + k] = f2lo(acc[i * 4 + k]) + f2hi(acc[i * 4 + k]);
                         }
                     }
+#endif
                     epi_sync();
                     if (is_epi && ar.hes) {
                         for (int idx = tid; idx < SPT * DP * DP; idx += NEMPC_WIDE_EPI_WARPS * 32) {
