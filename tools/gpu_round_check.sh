@@ -20,7 +20,7 @@ cap() {   # name, kernel regex, skip, command...
         python profiles/ncu_lines.py /tmp/${name}.ncu-rep 45 > $O/${TAG}_${name}_lines.md 2>> $O/${TAG}_ncu_${name}.log
     fi
 }
-cap wide_kernel nempc_wide_kernel 3 python tools/wide_check.py --no-check --time 2048
+cap wide_kernel nempc_wide_kernel 9 python tools/wide_check.py --no-check --time 2048
 cap fast64_kernel nempc_fast64_kernel 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-solver
 cap fast_kernel nempc_fast_kernel 4 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-solver --no-side-workloads
 cap tc_kernel nempc_tc_kernel 1 python bench.py --workload C3 --steps 1 --warmup 1 --no-cpu-baseline
