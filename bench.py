@@ -67,26 +67,62 @@ def make_problem(wl, B, seed=1234):
 # ------------------------------------------------------------------------------------------------------
 # CPU baseline: the dense reference-literal port (oracle/dense_ref.py) on host cores
 # ------------------------------------------------------------------------------------------------------
-def _cpu_problem_eval(args):
-    """one problem, one iterate: objective, gradient, constraints, dense Jacobian, Lagrangian Hessian
-    (reference optimizer/ipopt.py callbacks over the dense O(H^3) integrator arrays)."""
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    wl, z, x0, lam = args
-    from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem
-    from oracle.mlp_np import MLP, DenseModelView
+def reference_usable(wl):
+    """the reference's own classes can run this workload on the CPU: its package (sources in the build container, bytecode from
+    oracle/_ref on the GPU box) is importable and its RK4 Hessian supports the shape (x_dim + u_dim == 3 only: integrator/rk4.py:246)."""
+    from oracle import shim
+    return shim.reference_available() and (wl["integ"] != "rk4" or wl["x"] + wl["u"] == 3)
+
+
+def _reference_problem(wl):
+    """the UNMODIFIED reference's integrator + IpoptProblem factory for this workload (network evaluated by oracle.mlp_np: TensorFlow is
+    not installable); cached per process"""
+    from oracle import shim
+    from oracle.mlp_np import MLP
     from oracle.objectives_np import SeparableQuadraticObjective
+    ref = shim.load_reference()
+    mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+    sep = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
+
+    class Obj(ref.objective.base.ObjectiveFunc):
+        def forward(self, states, u, p=None, tvp=None): return sep.forward(states, u)
+        def gradient(self, states, u, p=None, tvp=None): return sep.gradient(states, u)
+        def hessian(self, states, u, p=None, tvp=None): return sep.hessian(states, u)
+        def hessianstructure(self, H, model): return sep.hessianstructure(H, model)
+
+    model = shim.make_reference_model(mlp)
+    if wl["integ"] == "rk4":
+        integ = ref.integrator.rk4.RK4Integrator(model, wl["H"], wl["DT"])
+    elif wl["integ"] == "unity":
+        integ = ref.integrator.unity.UnityIntegrator(model, wl["H"])
+    else:
+        integ = ref.integrator.discret.DiscretIntegrator(model, wl["H"])
+    integ.hessianstructure()                # structure probing is a one-off in the reference (cached on the integrator)
+    return lambda x0: ref.optimizer.ipopt.IpoptProblem(x0, Obj(), [], integ, use_hessian=True)
+
+
+def _cpu_problem_eval(args):
+    """one problem, one iterate: objective, gradient, constraints, dense Jacobian, Lagrangian Hessian -- the reference's
+    optimizer/ipopt.py callbacks over its dense O(H^3) integrator arrays (use_ref: the reference's own classes; else the literal port)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    wl, z, x0, lam, use_ref = args
     cache = _cpu_problem_eval.__dict__.setdefault("cache", {})
-    key = json.dumps(wl, sort_keys=True)
+    key = json.dumps(wl, sort_keys=True) + str(use_ref)
     if key not in cache:
-        mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
-        obj = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
-        integ = DenseIntegrator(DenseModelView(mlp), wl["H"], "discrete" if wl["integ"] == "discrete" else wl["integ"], DT=wl["DT"])
-        integ.hessianstructure()            # structure probing is a one-off in the reference too (cached)
-        cache[key] = (obj, integ)
-    obj, integ = cache[key]
-    pb = DenseIpoptProblem(x0, obj, integ)
+        if use_ref:
+            cache[key] = _reference_problem(wl)
+        else:
+            from oracle.dense_ref import DenseIntegrator, DenseIpoptProblem
+            from oracle.mlp_np import MLP, DenseModelView
+            from oracle.objectives_np import SeparableQuadraticObjective
+            mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+            obj = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
+            integ = DenseIntegrator(DenseModelView(mlp), wl["H"], "discrete" if wl["integ"] == "discrete" else wl["integ"], DT=wl["DT"])
+            integ.hessianstructure()            # structure probing is a one-off in the reference too (cached)
+            cache[key] = lambda x0, obj=obj, integ=integ: DenseIpoptProblem(x0, obj, integ)
+    pb = cache[key](x0)
     pb.objective(z); pb.gradient(z); pb.constraints(z); pb.jacobian(z)
-    return float(pb.hessian(z, lam, 1.0).sum())
+    return float(np.sum(pb.hessian(z, lam, 1.0)))
 
 
 def solver_bounds(wl):
@@ -137,27 +173,29 @@ def cpu_reference_run(wl_name, sample, steps, warmup, procs=None, budget_s=None)
     import multiprocessing as mp
     wl = {k: v for k, v in WORKLOADS[wl_name].items() if k != "desc"}
     procs = procs or os.cpu_count() or 1
+    use_ref = reference_usable(wl)
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         _, _, Z, X0, lam = make_problem(wl, max(sample, 4 * procs))
         for _ in range(max(1, min(warmup, 3))):
-            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i]) for i in range(procs)], chunksize=1)   # per-process caches
+            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i], use_ref) for i in range(procs)], chunksize=1)   # per-process caches
         if budget_s:
             t0 = time.perf_counter()
-            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i]) for i in range(2 * procs)], chunksize=1)
+            pool.map(_cpu_problem_eval, [(wl, Z[i], X0[i], lam[i], use_ref) for i in range(2 * procs)], chunksize=1)
             per_problem = (time.perf_counter() - t0) / (2 * procs)          # wall seconds per problem with all workers busy
             sample = int(max(procs, min(wl["B"], 512, budget_s / max(1, steps) / per_problem)))
             _, _, Z, X0, lam = make_problem(wl, sample)
-        jobs = [(wl, Z[i], X0[i], lam[i]) for i in range(sample)]
+        jobs = [(wl, Z[i], X0[i], lam[i], use_ref) for i in range(sample)]
         chunk = max(1, sample // (procs * 4))
         t0 = time.perf_counter()
         for _ in range(steps):
             pool.map(_cpu_problem_eval, jobs, chunksize=chunk)
         dt = time.perf_counter() - t0
     ms = dt / steps * 1e3
-    return dict(value=sample * wl["H"] / (dt / steps), ms_per_step=ms, cores=procs,
-                sample=f"{sample} of {wl['B']} problems per step ({sample * wl['H']} horizon-steps), dense reference-literal port "
-                       f"(oracle/dense_ref.py: O(H^3) dense Jacobian/Hessian like integrator/rk4.py + optimizer/ipopt.py), float32 network")
+    how = ("the reference's own integrator + IpoptProblem (unmodified pyNeuralEMPC, bytecode in oracle/_ref; network evaluated by oracle.mlp_np: TensorFlow is absent)"
+           if use_ref else "dense reference-literal port (oracle/dense_ref.py: O(H^3) dense Jacobian/Hessian like integrator/rk4.py + optimizer/ipopt.py)")
+    return dict(value=sample * wl["H"] / (dt / steps), ms_per_step=ms, cores=procs, kind="reference" if use_ref else "port",
+                sample=f"{sample} of {wl['B']} problems per step ({sample * wl['H']} horizon-steps), {how}, float32 network")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -638,7 +676,7 @@ def gpu_run(args):
                             "--cpu-sample", str(args.cpu_sample)] + (["--no-solver"] if args.no_solver else []), capture_output=True, text=True)
         try:
             c = json.loads(r.stdout.strip().splitlines()[-1])
-            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+            cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c.get("kind", "port"), "sample": c["sample"]}
             if solves is not None and "solver" in c:
                 solves["cpu_baseline"] = c["solver"]
         except (ValueError, IndexError):
@@ -668,14 +706,14 @@ def reference_run(args):
     if args.workload in ("C3", "C4", "C4rk4"):
         # the reference's dense O(H^3) assembly needs 0.8 GB (C3) / 197 GB (C4) per problem: the O(H) block restatement is what can be timed
         b = block_cpu_baseline(args.workload, nprob=4)
-        r = {"value": b["value"], "ms_per_step": 4 * wl["H"] / b["value"] * 1e3, "cores": 1, "sample": b["sample"]}
+        r = {"value": b["value"], "ms_per_step": 4 * wl["H"] / b["value"] * 1e3, "cores": 1, "sample": b["sample"], "kind": "port"}
     else:
         r = cpu_reference_run(args.workload, args.cpu_sample, max(1, args.steps), max(1, args.warmup), budget_s=args.cpu_budget)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "note": "reference CPU algorithm (oracle port; TensorFlow/JAX/cyipopt are not installable here), bounded sample per step"},
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "config": {"workload": args.workload + ": " + wl["desc"], "note": "reference CPU path (the reference's own integrator + IpoptProblem where its bytecode is present, else the oracle port; TensorFlow/JAX/cyipopt are not installable here), bounded sample per step"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r.get("kind", "port"), "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -1,9 +1,11 @@
 """Import the UNMODIFIED reference package from ``/root/reference`` with its absent
-third-party imports stubbed.  TEST INFRASTRUCTURE ONLY; only usable in the build
-container (``/root/reference`` does not exist on the GPU box), so nothing that runs under
-``-m gpu``, ``smoke()`` or ``bench.py`` may call it.  Used by
-``tests/golden/make_golden.py`` to record what the real reference computes and by the
-container-only tests in ``tests/test_reference_live.py``.
+third-party imports stubbed.  TEST / BASELINE INFRASTRUCTURE ONLY.  In the build container the
+package is imported from its sources; on the GPU box (no ``/root/reference``) from the bytecode
+``oracle/build_ref.py`` compiled into ``oracle/_ref/`` -- nothing under ``-m gpu`` or ``smoke()``
+reads either, ``bench.py --impl reference`` and the ``cpu_baseline`` leg use the bytecode to time
+the reference's own integrators and ``IpoptProblem``.  Used by ``tests/golden/make_golden.py`` to
+record what the real reference computes and by the container-only tests in
+``tests/test_reference_live.py``.
 
 What gets stubbed and why:
   tensorflow  ``model/tensorflow.py:1,5,77,112`` needs ``tf.function`` (identity here) and
@@ -21,10 +23,21 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("NEMPC_REFERENCE_ROOT", "/root/reference")
+# the same package compiled to bytecode by oracle/build_ref.py (git-ignored build output that travels to the GPU box)
+BYTECODE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def reference_available():
+    """the source tree (build container) or its compiled bytecode (GPU box) is importable"""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyNeuralEMPC")) or os.path.isdir(os.path.join(BYTECODE_ROOT, "pyNeuralEMPC"))
+
+
+def source_tree_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyNeuralEMPC"))
+
+
+def import_root():
+    return REFERENCE_ROOT if source_tree_available() else BYTECODE_ROOT
 
 
 def _stub(name):
@@ -53,8 +66,9 @@ def load_reference():
     if getattr(jax, "__nempc_stub__", False):
         jax.numpy = jnp
     _stub("cyipopt")
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = import_root()
+    if root not in sys.path:
+        sys.path.insert(0, root)
     return importlib.import_module("pyNeuralEMPC")
 
 

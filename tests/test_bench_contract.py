@@ -19,7 +19,11 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "problems per step" in cb["sample"]
+    # "reference" = the unmodified reference's integrator + IpoptProblem (sources here, bytecode under oracle/_ref on the GPU box); "port"
+    # only where neither is present
+    from oracle import shim
+    assert cb["kind"] == ("reference" if shim.reference_available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "problems per step" in cb["sample"]
     assert d["config"]["workload"].startswith("C2")
 
 

@@ -12,7 +12,7 @@ from oracle import shim
 from oracle.dense_ref import DenseIntegrator
 from oracle.mlp_np import MLP, DenseModelView, load_lv_fixture_npz
 
-pytestmark = pytest.mark.skipif(not shim.reference_available(), reason="/root/reference is not present on this machine")
+pytestmark = pytest.mark.skipif(not shim.source_tree_available(), reason="/root/reference is not present on this machine")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -80,3 +80,26 @@ def test_cuda_model_passes_the_reference_isinstance_check(lv_weights):
     assert isinstance(m, ref.model.base.Model) and isinstance(m, Model)
     integ = ref.integrator.discret.DiscretIntegrator(m, 5)
     assert integ.model is m and integ.H == 5
+
+
+def test_reference_bytecode_build_and_sourceless_import(tmp_path):
+    """oracle/build_ref.py: the reference compiled to bytecode (what travels to the GPU box under oracle/_ref) imports without its sources
+    and computes what the source tree computes"""
+    import subprocess
+    import sys
+    from oracle.build_ref import build_reference_bytecode
+    out = tmp_path / "_ref"
+    n = build_reference_bytecode(out=str(out))
+    assert n >= 15 and (out / "pyNeuralEMPC" / "integrator" / "rk4.pyc").exists()
+    assert not list(out.rglob("*.py"))                                   # bytecode only: no reference source is copied
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import shim; shim.REFERENCE_ROOT = '/nonexistent'; shim.BYTECODE_ROOT = %r;"
+            "ref = shim.load_reference(); assert ref.__file__.endswith('.pyc'), ref.__file__;"
+            "from oracle.mlp_np import MLP, load_lv_fixture_npz;"
+            "mlp = MLP(load_lv_fixture_npz(%r), 2, 1);"
+            "integ = ref.integrator.rk4.RK4Integrator(shim.make_reference_model(mlp), 6, 0.1);"
+            "g = np.load(%r); z = g['z'];"
+            "print(float(np.abs(integ.forward(z[:12].reshape(6, 2), z[12:].reshape(6, 1), g['x0']) - g['integrator_forward']).max()))") % (
+        os.path.dirname(HERE), str(out), os.path.join(HERE, "golden", "lv_mlp_weights.npz"), os.path.join(HERE, "golden", "ref_rk4_H6.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert float(r.stdout.strip().splitlines()[-1]) == 0.0
