@@ -264,7 +264,18 @@ def tensor_roofline(ev, wl, steps_per_eval, k_ms, peaks):
             "kernel_ms": k_ms, "flops_per_horizon_step": ev.flops_per_step, "bytes_per_horizon_step": ev.bytes_per_step(),
             "executed_mma_tflops": executed / (k_ms * 1e-3) / 1e12, "executed_over_algorithmic": executed / flops,
             "hbm_achieved_gbs": ev.bytes_per_step() * steps_per_eval / (k_ms * 1e-3) / 1e9,
-            "note": "tcgen05 kind::f16, split operands; " + form + "; see DESIGN.md 5.4 / 5.8", "traffic": None}
+            "note": "tcgen05 kind::f16, split operands; " + form + "; see DESIGN.md 5.4 / 5.8", "traffic": wide_traffic(ev, wl, steps_per_eval)}
+
+
+def wide_traffic(ev, wl, steps_per_eval):
+    """DRAM bytes per launch of the wide kernel from the committed ncu capture (bytes per horizon step x steps of this launch), or None"""
+    if "nempc_wide" not in ev.kernel_name or wl["integ"] == "rk4":
+        return None
+    try:
+        per_step = json.load(open(os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json"))).get("C4_per_horizon_step")
+    except (OSError, ValueError):
+        return None
+    return None if per_step is None else per_step * steps_per_eval
 
 
 def block_cpu_baseline(name, nprob=2):

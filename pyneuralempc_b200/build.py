@@ -8,7 +8,9 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.environ.get("NEMPC_LIB_PATH") or os.path.join(CSRC, "libnempc.so")   # env override: kernel-variant experiments
-SOURCES = ["nempc_lib.cu"]
+SOURCES = ["nempc_lib.cu", "nempc_fast64_tu.cu"]
+# per-source extra flags (see the header of nempc_fast64_tu.cu)
+SOURCE_FLAGS = {"nempc_fast64_tu.cu": ["--split-compile=0"]}
 HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_fast64.cuh", "nempc_small.cuh", "nempc_tc.cuh", "nempc_wide.cuh", "nempc_rolling.cuh", "nempc_tc_ptx.cuh", "nempc_solver.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -18,6 +20,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # development only: the code it produces measured 8 % slower on nempc_wide_kernel and 2 % slower on nempc_fast_kernel (B200, round 2).
 if os.environ.get("NEMPC_BUILD_SPLIT"):
     NVCC_FLAGS = NVCC_FLAGS + ["--split-compile=0"]
+if os.environ.get("NEMPC_NVCC_EXTRA"):                 # kernel-variant experiments, e.g. "-DNEMPC_FAST64_SMEM_WEIGHTS=1"
+    NVCC_FLAGS = NVCC_FLAGS + os.environ["NEMPC_NVCC_EXTRA"].split()
 
 
 def find_nvcc():
@@ -52,11 +56,27 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     sh = source_hash()
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [f'-DNEMPC_SOURCE_HASH="{sh}"', "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    nvcc = find_nvcc()
+    import tempfile
+    objdir = tempfile.mkdtemp(prefix="nempc_build_")
+    common = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + [f'-DNEMPC_SOURCE_HASH="{sh}"']
+    procs = []
+    for src in SOURCES:                                    # the translation units compile side by side, then one link
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + common + [fl for fl in SOURCE_FLAGS.get(src, []) if fl not in common] + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    logs = []
+    for obj, pr in procs:
+        out, _ = pr.communicate()
+        logs.append(out)
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + out)
+    link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [o for o, _ in procs],
+                          capture_output=True, text=True)
+    if link.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + link.stdout + link.stderr)
+    proc = type("R", (), {"stderr": "\n".join(logs)})()
+    shutil.rmtree(objdir, ignore_errors=True)
     with open(LIB_PATH + ".srchash", "w") as fh:
         fh.write(sh + "\n")
     if verbose:

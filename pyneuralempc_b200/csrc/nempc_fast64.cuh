@@ -5,8 +5,9 @@
 //
 // Same mathematics and the same loop structure as nempc_fast.cuh (the "forward-only per-output" second-order chain of
 // integrator/rk4.py:113-285: no stored stage state), without the f32x2 packing:
-//   * weights are a __grid_constant__ kernel parameter (25 - 28 KB of doubles incl. the pre-multiplied W2 W3 and W1 (x) W1 tables): the
-//     neuron loops are warp-uniform, so every weight is a uniform 64-bit constant load feeding a DFMA -- no shared-memory staging;
+//   * weights (25 - 28 KB of doubles incl. the pre-multiplied W2 W3 and W1 (x) W1 tables) arrive as a __grid_constant__ kernel parameter and
+//     are copied to shared memory once per CTA: the neuron loops are warp-uniform, so every weight is ONE broadcast LDS.64 (reading them
+//     straight from the constant bank measured 14 % slower: the image overflows the immediate-constant cache);
 //   * layer-2 pre-activations (value + d tangent rows) accumulate in registers for JC output neurons at a time and are consumed on the
 //     fly (output value, local Jacobian, curvature, adjoint seed);
 //   * cold per-thread state (layer-1 activations, s'(a2), per-output Hessian accumulators: 84 doubles) sits in an [element][thread]
@@ -324,12 +325,31 @@ __device__ __forceinline__ void fast64_step(const Fast64Weights<X, U, H1, H2>& w
 #ifndef NEMPC_FAST64_THREADS
 #define NEMPC_FAST64_THREADS 128
 #endif
+#ifndef NEMPC_FAST64_SMEM_WEIGHTS
+#define NEMPC_FAST64_SMEM_WEIGHTS 1      // copy the weight image to shared memory and read it with broadcast LDS.64 (0: constant bank -- the 26 KB image
+                                         // overflows the immediate-constant cache: hit rate 73 %, 0.29 instead of 0.33 of the FP64 peak on C2)
+#endif
 template <int X, int U, int H1, int H2, int JC, int MODE, typename TIO>
 __global__ void __launch_bounds__(NEMPC_FAST64_THREADS)
 nempc_fast64_kernel(const __grid_constant__ Fast64Weights<X, U, H1, H2> w, const StageTable<double> st, const NlpLayout L, const EvalArgs<TIO> ar) {
     extern __shared__ __align__(16) unsigned char fast64_smem[];
+#if NEMPC_FAST64_SMEM_WEIGHTS
+    typedef Fast64Weights<X, U, H1, H2> FW;
+    constexpr int WB = (int)((sizeof(FW) + 15) / 16 * 16);
+    {
+        const double* src = reinterpret_cast<const double*>(&w);
+        double* dst = reinterpret_cast<double*>(fast64_smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(FW) / 8); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const FW& ws = *reinterpret_cast<const FW*>(fast64_smem);
+    double* scr = reinterpret_cast<double*>(fast64_smem + WB) + threadIdx.x;
+    for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps; step += (long long)gridDim.x * blockDim.x)
+        fast64_step<X, U, H1, H2, JC, MODE, TIO>(ws, st, L, ar, step, scr, (int)blockDim.x);
+#else
     double* scr = reinterpret_cast<double*>(fast64_smem) + threadIdx.x;
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps; step += (long long)gridDim.x * blockDim.x)
         fast64_step<X, U, H1, H2, JC, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+#endif
 }
 #endif  // __CUDACC__

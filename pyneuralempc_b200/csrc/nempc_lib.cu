@@ -742,6 +742,7 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
     h->W[layer].assign(W, W + (size_t)fin * fout);
     h->bvec[layer].assign(b, b + fout);
     CU(h, cudaSetDevice(h->desc.device));
+    CU(h, cudaDeviceSynchronize());                       // evaluations still in flight on a caller's stream read the old weight images
     int rc = h->desc.compute_dtype == NEMPC_F64 ? upload_layer<double>(h, layer, fin, fout) : upload_layer<float>(h, layer, fin, fout);
     if (rc) return rc;
     h->wset[layer] = true;
@@ -776,6 +777,7 @@ extern "C" int nempc_set_objective(nempc_handle* h, const double* lin, const dou
     h->has_objective = true;
     rebuild_layout(h);
     CU(h, cudaSetDevice(h->desc.device));
+    CU(h, cudaDeviceSynchronize());                       // evaluations / solves still in flight on a caller's stream read the old cost
     if (!h->dlin) {
         CU(h, cudaMalloc(&h->dlin, n * sizeof(double)));
         CU(h, cudaMalloc(&h->dquad, n * sizeof(double)));
@@ -930,44 +932,21 @@ static int launch_fast_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode,
     return NEMPC_OK;
 }
 
-// float64 arithmetic, register resident (nempc_fast64.cuh); JC = layer-2 neurons per register chunk
+// float64 arithmetic, register resident (nempc_fast64.cuh): the kernels live in their own translation unit (nempc_fast64_tu.cu, see
+// build.py) behind this one internal entry point
 #ifndef NEMPC_FAST64_MIN_STEPS
 #define NEMPC_FAST64_MIN_STEPS 4096      // below this many horizon steps one thread per step leaves the GPU empty: the generic kernel takes over
 #endif
-template <int X, int U, int H1, int H2, int JC>
-static int launch_fast64_shape(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
-    typedef Fast64Weights<X, U, H1, H2> FW;
+int nempc_fast64_launch(int shape_id, int mode, const void* weights, const StageTable<double>& st, const NlpLayout& L, const EvalArgs<double>& ar,
+                        int sm_count, cudaStream_t s);
+static int launch_fast64(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
     const uintptr_t a = (reinterpret_cast<uintptr_t>(h->fast64w.data()) + 15) & ~(uintptr_t)15;
-    const FW& w = *reinterpret_cast<const FW*>(a);
     StageTable<double> st = make_stage_table<double>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
-    const int threads = NEMPC_FAST64_THREADS;
-    const long long blocks = std::max(1LL, (ar.nsteps + threads - 1) / threads);
-    const unsigned grid = (unsigned)std::min(blocks, (long long)h->sm_count * 64);
-    const size_t smem = (size_t)FastScratch<X, U, H1, H2>::count(mode) * threads * sizeof(double);
-    if (smem > 48 * 1024) {
-        static bool once = false;                        // opt in to > 48 KB of dynamic shared memory, once per instantiation
-        if (!once) {
-            CU(h, cudaFuncSetAttribute(nempc_fast64_kernel<X, U, H1, H2, JC, 2, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            once = true;
-        }
-    }
-    switch (mode) {
-        case 0: nempc_fast64_kernel<X, U, H1, H2, JC, 0, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
-        case 1: nempc_fast64_kernel<X, U, H1, H2, JC, 1, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
-        default: nempc_fast64_kernel<X, U, H1, H2, JC, 2, double><<<grid, threads, smem, s>>>(w, st, h->lay, ar); break;
-    }
-    CU(h, cudaGetLastError());
+    const int rc = nempc_fast64_launch(h->fast64_id, mode, reinterpret_cast<const void*>(a), st, h->lay, ar, h->sm_count, s);
+    if (rc == -1) { SET_ERR(h, "internal: bad fast64_id"); return NEMPC_EINVAL; }
+    if (rc != 0) { SET_ERR(h, "nempc_fast64_kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return NEMPC_ECUDA; }
     h->launches++;
     return NEMPC_OK;
-}
-static int launch_fast64(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
-    switch (h->fast64_id) {
-        case 0: return launch_fast64_shape<2, 1, 30, 30, 6>(h, ar, mode, s);
-        case 1: return launch_fast64_shape<2, 1, 32, 32, 8>(h, ar, mode, s);
-        case 2: return launch_fast64_shape<2, 1, 16, 16, 8>(h, ar, mode, s);
-    }
-    SET_ERR(h, "internal: bad fast64_id");
-    return NEMPC_EINVAL;
 }
 template <typename TIO> static bool take_fast64(nempc_handle*, const EvalArgs<TIO>&) { return false; }
 template <> bool take_fast64<double>(nempc_handle* h, const EvalArgs<double>& ar) {

@@ -640,6 +640,8 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 // accumulator = g_l (adjoint with respect to h_l);  s'(a_l) -> sa (over h_l),  s''(a_l) g_l = -2 h_l s'(a_l) g_l -> sq;
                 // next operand u_l = s'(a_l) g_l
                 const bool more = l > 0 || want_in;
+                // (fetching h_l of the next chunk while the MMAs run / the previous chunk is processed was tried: the 16 extra live registers
+                // cost more than the hidden latency returns -- 118 -> 125 ms on C4 at B = 16384)
                 gemm(l == nhid - 1 ? net.out_b : net.hid_b[l], nopre, [&](const uint32_t dbase) {
                     float* ph = sa + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 16 * sub;
                     float* pq = sq + ((long long)row * NEMPC_WIDE_MAXHID + l) * HW + 16 * sub;
