@@ -71,7 +71,13 @@ def reference_usable(wl):
     """the reference's own classes can run this workload on the CPU: its package (sources in the build container, bytecode from
     oracle/_ref on the GPU box) is importable and its RK4 Hessian supports the shape (x_dim + u_dim == 3 only: integrator/rk4.py:246)."""
     from oracle import shim
-    return shim.reference_available() and (wl["integ"] != "rk4" or wl["x"] + wl["u"] == 3)
+    if not shim.reference_available() or not (wl["integ"] != "rk4" or wl["x"] + wl["u"] == 3):
+        return False
+    try:                                                   # a broken / partial copy must not cost the CPU leg: fall back to the port
+        ref = shim.load_reference()
+        return hasattr(ref.optimizer.ipopt, "IpoptProblem") and hasattr(ref.integrator.rk4, "RK4Integrator")
+    except Exception:                                      # noqa: BLE001
+        return False
 
 
 def _reference_problem(wl):

@@ -24,12 +24,12 @@ import types
 
 REFERENCE_ROOT = os.environ.get("NEMPC_REFERENCE_ROOT", "/root/reference")
 # the same package compiled to bytecode by oracle/build_ref.py (git-ignored build output that travels to the GPU box)
-BYTECODE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+BYTECODE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyNeuralEMPC_bytecode.zip")
 
 
 def reference_available():
     """the source tree (build container) or its compiled bytecode (GPU box) is importable"""
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyNeuralEMPC")) or os.path.isdir(os.path.join(BYTECODE_ROOT, "pyNeuralEMPC"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyNeuralEMPC")) or os.path.isfile(BYTECODE_ROOT)
 
 
 def source_tree_available():

@@ -995,96 +995,46 @@ template <typename TIO> static int launch_fast(nempc_handle* h, const EvalArgs<T
     return NEMPC_EINVAL;
 }
 
-template <int X, int U, int NHID, int HW, int MODE, typename TIO>
-static int launch_tc_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    typedef TcCfg<X, U, NHID, MODE, HW> C;
-    auto kern = nempc_tc_kernel<C, TIO>;
-    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+// tensor-core kernels: compiled in their own translation units (nempc_tc_tu.cu, nempc_wide_tu.cu; build.py compiles the units side by
+// side) behind internal entry points -- 0, a cudaError_t, or -1 for an unknown shape
+int nempc_tc_launch(int tc_id, int mode, int io_f64, const void* img, const float* cb, const float* wx, const StageTable<float>& st,
+                    const NlpLayout& L, const void* ar, int tvp_dim, int p_dim, int sm_count, cudaStream_t s);
+size_t nempc_wide_scratch_floats(int wide_id, int mode, int rk4);
+int nempc_wide_launch(int wide_id, int mode, int rk4, int io_f64, const unsigned char* blob, const float* cb, const WideNet& net,
+                      const StageTable<float>& st, const NlpLayout& L, const void* ar, float* scratch, int sm_count, cudaStream_t s);
+
+template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
     StageTable<float> st = make_stage_table<float>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
-    const long long ntiles = (ar.nsteps + C::SPT - 1) / C::SPT;
-    const unsigned grid = (unsigned)std::max(1LL, std::min((ntiles + C::NG - 1) / C::NG, (long long)h->sm_count));     // NG tiles in flight per CTA
     EvalArgs<TIO> ax = ar;
     if (h->n_ext > 0) {
         int rc = bind_exogenous(h, ax, false);
         if (rc) return rc;
     }
-    kern<<<grid, NEMPC_TC_THREADS, C::TOTAL, s>>>((const __half*)h->d_tcimg, h->d_tccb, st, h->lay, ax, h->d_tcwx, h->desc.tvp_dim, h->desc.p_dim);
-    CU(h, cudaGetLastError());
+    const int rc = nempc_tc_launch(h->tc_id, mode, sizeof(TIO) == 8, h->d_tcimg, h->d_tccb, h->d_tcwx, st, h->lay, &ax, h->desc.tvp_dim, h->desc.p_dim,
+                                   h->sm_count, s);
+    if (rc == -1) { SET_ERR(h, "internal: bad tc_id"); return NEMPC_EINVAL; }
+    if (rc != 0) { SET_ERR(h, "nempc_tc_kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return NEMPC_ECUDA; }
     h->launches++;
     return NEMPC_OK;
 }
-template <int X, int U, int NHID, int HW, typename TIO>
-static int launch_tc_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    switch (mode) {
-        case 0: return launch_tc_mode<X, U, NHID, HW, 0, TIO>(h, ar, s);
-        case 1: return launch_tc_mode<X, U, NHID, HW, 1, TIO>(h, ar, s);
-        default: return launch_tc_mode<X, U, NHID, HW, 2, TIO>(h, ar, s);
-    }
-}
-template <typename TIO> static int launch_tc(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    switch (h->tc_id) {                                    // index into kTcShapes
-        case 0: return launch_tc_shape<4, 1, 3, 128, TIO>(h, ar, mode, s);
-        case 1: return launch_tc_shape<4, 1, 2, 128, TIO>(h, ar, mode, s);
-        case 2: return launch_tc_shape<2, 1, 3, 128, TIO>(h, ar, mode, s);
-        case 3: return launch_tc_shape<2, 1, 2, 128, TIO>(h, ar, mode, s);
-        case 4: return launch_tc_shape<3, 1, 3, 128, TIO>(h, ar, mode, s);
-        case 5: return launch_tc_shape<3, 1, 2, 128, TIO>(h, ar, mode, s);
-        case 6: return launch_tc_shape<4, 2, 3, 128, TIO>(h, ar, mode, s);
-        case 7: return launch_tc_shape<4, 2, 2, 128, TIO>(h, ar, mode, s);
-        case 8: return launch_tc_shape<4, 1, 3, 64, TIO>(h, ar, mode, s);
-        case 9: return launch_tc_shape<4, 1, 2, 64, TIO>(h, ar, mode, s);
-        case 10: return launch_tc_shape<2, 1, 3, 64, TIO>(h, ar, mode, s);
-        case 11: return launch_tc_shape<2, 1, 2, 64, TIO>(h, ar, mode, s);
-        case 12: return launch_tc_shape<2, 1, 3, 32, TIO>(h, ar, mode, s);
-        case 13: return launch_tc_shape<4, 1, 3, 32, TIO>(h, ar, mode, s);
-    }
-    SET_ERR(h, "internal: bad tc_id");
-    return NEMPC_EINVAL;
-}
 
-template <int X, int U, int MODE, bool RK4, typename TIO>
-static int launch_wide_cfg(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    typedef WideCfg<X, U, MODE, RK4> C;
-    auto kern = nempc_wide_kernel<C, TIO>;
-    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
-    StageTable<float> st = make_stage_table<float>(RK4, h->desc.dt);
-    const long long nsup = (ar.nsteps + NEMPC_WIDE_SUP - 1) / NEMPC_WIDE_SUP;
-    static const int grid_cap = getenv("NEMPC_WIDE_GRID") ? std::max(1, atoi(getenv("NEMPC_WIDE_GRID"))) : 1 << 30;      // experiments: fewer CTAs
-    const long long npair = (nsup + 1) / 2;                                  // CTA pairs (clusters of two, cta_group::2 MMAs)
-    const unsigned grid = 2u * (unsigned)std::max(1LL, std::min(npair, (long long)std::min(h->sm_count, grid_cap) / 2));
-    const size_t need = (size_t)h->sm_count * C::SCRATCH_FLOATS * sizeof(float);      // h_l, q_l of one super-tile per CTA (L2-resident)
+template <typename TIO> static int launch_wide(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
+    const int rk4 = h->desc.integrator == NEMPC_INTEG_RK4;
+    const size_t fl = nempc_wide_scratch_floats(h->wide_id, mode, rk4);
+    if (fl == 0) { SET_ERR(h, "internal: bad wide_id"); return NEMPC_EINVAL; }
+    const size_t need = (size_t)h->sm_count * fl * sizeof(float);      // h_l, q_l (and the RK4 stage state) of one super-tile per CTA
     if (need > h->wide_scratch_bytes) {
         CU(h, cudaStreamSynchronize(s));
         cudaFree(h->wide_scratch); h->wide_scratch = nullptr; h->wide_scratch_bytes = 0;
         CU(h, cudaMalloc((void**)&h->wide_scratch, need));
         h->wide_scratch_bytes = need;
     }
-    kern<<<grid, NEMPC_WIDE_THREADS, C::TOTAL, s>>>(h->d_wblob, h->d_wcb, h->wnet, st, h->lay, ar, h->wide_scratch);
-    CU(h, cudaGetLastError());
+    StageTable<float> st = make_stage_table<float>(rk4 != 0, h->desc.dt);
+    const int rc = nempc_wide_launch(h->wide_id, mode, rk4, sizeof(TIO) == 8, h->d_wblob, h->d_wcb, h->wnet, st, h->lay, &ar, h->wide_scratch, h->sm_count, s);
+    if (rc == -1) { SET_ERR(h, "internal: bad wide_id"); return NEMPC_EINVAL; }
+    if (rc != 0) { SET_ERR(h, "nempc_wide_kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return NEMPC_ECUDA; }
     h->launches++;
     return NEMPC_OK;
-}
-template <int X, int U, int MODE, typename TIO>
-static int launch_wide_mode(nempc_handle* h, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    return h->desc.integrator == NEMPC_INTEG_RK4 ? launch_wide_cfg<X, U, MODE, true, TIO>(h, ar, s) : launch_wide_cfg<X, U, MODE, false, TIO>(h, ar, s);
-}
-template <int X, int U, typename TIO>
-static int launch_wide_shape(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    switch (mode) {
-        case 0: return launch_wide_mode<X, U, 0, TIO>(h, ar, s);
-        case 1: return launch_wide_mode<X, U, 1, TIO>(h, ar, s);
-        default: return launch_wide_mode<X, U, 2, TIO>(h, ar, s);
-    }
-}
-template <typename TIO> static int launch_wide(nempc_handle* h, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
-    switch (h->wide_id) {                                  // index into kWideShapes
-        case 0: return launch_wide_shape<12, 4, TIO>(h, ar, mode, s);
-        case 1: return launch_wide_shape<4, 1, TIO>(h, ar, mode, s);
-        case 2: return launch_wide_shape<2, 1, TIO>(h, ar, mode, s);
-        case 3: return launch_wide_shape<6, 2, TIO>(h, ar, mode, s);
-    }
-    SET_ERR(h, "internal: bad wide_id");
-    return NEMPC_EINVAL;
 }
 
 template <typename TIO>
@@ -1556,27 +1506,6 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     if (outer_iterations) *outer_iterations = it;
     return NEMPC_OK;
 }
-
-#ifdef NEMPC_TC_PROFILE
-// development builds only: cycles per phase of nempc_tc_kernel summed over all CTAs (thread 0's clock), then reset
-extern "C" int nempc_debug_tc_profile(unsigned long long* out16) {
-    if (cudaDeviceSynchronize() != cudaSuccess) return NEMPC_ECUDA;
-    if (cudaMemcpyFromSymbol(out16, nempc_tc_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return NEMPC_ECUDA;
-    unsigned long long z[16] = {};
-    cudaMemcpyToSymbol(nempc_tc_prof, z, sizeof z);
-    return NEMPC_OK;
-}
-#endif
-
-#ifdef NEMPC_WIDE_PROFILE
-extern "C" int nempc_debug_wide_profile(unsigned long long* out16) {
-    if (cudaDeviceSynchronize() != cudaSuccess) return NEMPC_ECUDA;
-    if (cudaMemcpyFromSymbol(out16, nempc_wide_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return NEMPC_ECUDA;
-    unsigned long long z[16] = {};
-    cudaMemcpyToSymbol(nempc_wide_prof, z, sizeof z);
-    return NEMPC_OK;
-}
-#endif
 
 // ---- introspection ------------------------------------------------------------------------------------------------
 extern "C" int64_t nempc_launch_count(const nempc_handle* h) { return h ? h->launches : 0; }

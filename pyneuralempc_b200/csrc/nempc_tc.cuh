@@ -111,7 +111,7 @@ inline size_t tc_img_index(int n, int k, int hw = NEMPC_TC_HW) { return (size_t)
 #if defined(__CUDACC__)
 // -DNEMPC_TC_PROFILE: thread 0 of every CTA accumulates the cycles between phase boundaries (development builds only)
 #ifdef NEMPC_TC_PROFILE
-__device__ unsigned long long nempc_tc_prof[16];
+static __device__ unsigned long long nempc_tc_prof[16];
 #define TC_PROF_DECL long long prof_t0 = clock64(); unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define TC_PROF(i) do { const long long t_ = clock64(); prof_acc[i] += (unsigned long long)(t_ - prof_t0); prof_t0 = t_; } while (0)
 #define TC_PROF_FLUSH do { if (tid == 0) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&nempc_tc_prof[i_], prof_acc[i_]); } while (0)

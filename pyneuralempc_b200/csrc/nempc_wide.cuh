@@ -301,7 +301,7 @@ __device__ __forceinline__ void gram_mma_chunk(const uint32_t stg_addr, uint4* s
 //   4 epilogue thread 0: pre   5 wait accumulator   6 epilogue body   7 between GEMMs (publish, seeds, scatter)
 //   8 producer: wait free slot   9 producer: issue
 #ifdef NEMPC_WIDE_PROFILE
-__device__ unsigned long long nempc_wide_prof[16];
+static __device__ unsigned long long nempc_wide_prof[16];
 #define WPROF_DECL long long wp_t = clock64(); unsigned long long wp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define WPROF(i) do { const long long t_ = clock64(); wp_acc[i] += (unsigned long long)(t_ - wp_t); wp_t = t_; } while (0)
 #define WPROF_COUNT(i) do { wp_acc[i] += 1; } while (0)

@@ -90,8 +90,10 @@ def test_reference_bytecode_build_and_sourceless_import(tmp_path):
     from oracle.build_ref import build_reference_bytecode
     out = tmp_path / "_ref"
     n = build_reference_bytecode(out=str(out))
-    assert n >= 15 and (out / "pyNeuralEMPC" / "integrator" / "rk4.pyc").exists()
-    assert not list(out.rglob("*.py"))                                   # bytecode only: no reference source is copied
+    import zipfile
+    names = zipfile.ZipFile(out / "pyNeuralEMPC_bytecode.zip").namelist()
+    assert n >= 15 and "pyNeuralEMPC/integrator/rk4.pyc" in names
+    assert all(nm.endswith(".pyc") for nm in names) and not list(out.rglob("*.py"))     # bytecode only: no reference source is copied
     code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import shim; shim.REFERENCE_ROOT = '/nonexistent'; shim.BYTECODE_ROOT = %r;"
             "ref = shim.load_reference(); assert ref.__file__.endswith('.pyc'), ref.__file__;"
             "from oracle.mlp_np import MLP, load_lv_fixture_npz;"
@@ -99,7 +101,7 @@ def test_reference_bytecode_build_and_sourceless_import(tmp_path):
             "integ = ref.integrator.rk4.RK4Integrator(shim.make_reference_model(mlp), 6, 0.1);"
             "g = np.load(%r); z = g['z'];"
             "print(float(np.abs(integ.forward(z[:12].reshape(6, 2), z[12:].reshape(6, 1), g['x0']) - g['integrator_forward']).max()))") % (
-        os.path.dirname(HERE), str(out), os.path.join(HERE, "golden", "lv_mlp_weights.npz"), os.path.join(HERE, "golden", "ref_rk4_H6.npz"))
+        os.path.dirname(HERE), str(out / "pyNeuralEMPC_bytecode.zip"), os.path.join(HERE, "golden", "lv_mlp_weights.npz"), os.path.join(HERE, "golden", "ref_rk4_H6.npz"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-800:]
     assert float(r.stdout.strip().splitlines()[-1]) == 0.0
