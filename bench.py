@@ -755,9 +755,12 @@ def main():
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_worker:
+        # the solver leg first: importing the reference (shim) leaves stub `tensorflow` / `jax` modules in sys.modules, and SciPy's
+        # array-API dispatch then probes them on every call (measured: SLSQP 30x slower in that process)
+        solver = None if args.no_solver else cpu_solver_run(args.workload)
         out = cpu_reference_run(args.workload, args.cpu_sample, 2, 1)
-        if not args.no_solver:
-            out["solver"] = cpu_solver_run(args.workload)
+        if solver is not None:
+            out["solver"] = solver
         print(json.dumps(out))
         return
     if args.impl == "reference":
