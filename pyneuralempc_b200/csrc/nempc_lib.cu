@@ -321,7 +321,7 @@ struct nempc_handle {
     int use_fast = 0; int fast_id = -1;
     int fast64_id = -1; std::vector<unsigned char> fast64w;      // float64 register-resident kernel (nempc_fast64.cuh): Fast64Weights<...> blob
     int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr; float* d_tcwx = nullptr;   // tensor-core kernel: f16 weight images, f32 constants, first-layer rows of the exogenous inputs
-    int use_wide = 0; int wide_id = -1; unsigned char* d_wblob = nullptr; float* d_wcb = nullptr; WideNet wnet{};    // width-256 tensor-core kernel: streamed operand images, biases
+    int use_wide = 0; int wide_hes = 0; int wide_id = -1; unsigned char* d_wblob = nullptr; float* d_wcb = nullptr; WideNet wnet{};    // width-256 tensor-core kernel: streamed operand images, biases
     float* wide_scratch = nullptr; size_t wide_scratch_bytes = 0;
     std::vector<unsigned char> fastw;            // FastWeights<...> blob
     SlotLayout sl{};
@@ -398,16 +398,16 @@ static int tc_shape_id(const nempc_desc& d) {
 }
 
 // width-256 tensor-core kernel (nempc_wide.cuh): (x, u) instantiations; 2..4 hidden layers, all 256 wide; discrete / unity / RK4
-struct WideShape { int x, u; };
-static const WideShape kWideShapes[] = {{12, 4}, {4, 1}, {2, 1}, {6, 2}};
+struct WideShape { int x, u, hw; };
+static const WideShape kWideShapes[] = {{12, 4, 256}, {4, 1, 256}, {2, 1, 256}, {6, 2, 256}, {4, 1, 128}, {2, 1, 128}};
 static const int kNumWideShapes = sizeof(kWideShapes) / sizeof(kWideShapes[0]);
 
 static int wide_shape_id(const nempc_desc& d) {
     if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
     if (d.n_layers - 1 < 2 || d.n_layers - 1 > NEMPC_WIDE_MAXHID) return -1;
-    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != NEMPC_WIDE_HW) return -1;
+    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
     for (int i = 0; i < kNumWideShapes; ++i)
-        if (d.x_dim == kWideShapes[i].x && d.u_dim == kWideShapes[i].u) return i;
+        if (d.x_dim == kWideShapes[i].x && d.u_dim == kWideShapes[i].u && d.widths[0] == kWideShapes[i].hw) return i;
     return -1;
 }
 
@@ -561,13 +561,18 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     }
     h->use_fast = (h->fast_id >= 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_FAST)) ? 1 : 0;
     h->tc_id = tc_shape_id(D);
-    if (D.kernel == NEMPC_KERNEL_TC && h->tc_id < 0 && wide_shape_id(D) < 0) {
-        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32, tanh, hidden width %d, 64 or 32)", NEMPC_TC_HW);
-        free_device(h); delete h; return NEMPC_EUNSUPPORTED;
-    }
+    // hidden width 128 is served by two tensor-core kernels: the forward second-order one (nempc_tc.cuh) and the adjoint-form one
+    // (nempc_wide.cuh, instantiated for (4,1) and (2,1)).  Measured on 5-128x3-4, H=100, B=8192 (tools/c3_compare.py): RK4 29.6 vs 39.0 ms
+    // (tc wins), discrete with Hessian 9.0 vs 6.6 ms (adjoint form wins), Jacobian only 2.3 vs 3.1 ms (tc wins).  So the handle keeps
+    // both images and the single-stage integrators send their Hessian evaluations to the adjoint-form kernel.
+    // NEMPC_WIDE128 = 0 never / 1 always / unset: as measured.
+    int wide128 = -1;
+    if (getenv("NEMPC_WIDE128")) wide128 = atoi(getenv("NEMPC_WIDE128"));
+    if (wide128 == 1 && D.widths[0] == 128 && wide_shape_id(D) >= 0) h->tc_id = -1;
     h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
     h->wide_id = wide_shape_id(D);
     h->use_wide = (h->wide_id >= 0 && !h->use_fast && !h->use_tc && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
+    h->wide_hes = (h->use_tc && h->wide_id >= 0 && wide128 != 0 && D.integrator != NEMPC_INTEG_RK4) ? 1 : 0;
 
     // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
     int sum_h = 0, hmax = 0;
@@ -584,13 +589,14 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     else h->smem_bytes = per_slot * slots;
     h->slots = slots;
 
-    char nm[224];
+    char nm[288];
     if (h->use_fast) snprintf(nm, sizeof nm, "nempc_fast_kernel<x=%d,u=%d,h1=%d,h2=%d> f32 (thread/step, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
     else if (h->fast64_id >= 0) snprintf(nm, sizeof nm, "nempc_fast64_kernel<x=%d,u=%d,h1=%d,h2=%d> f64 (thread/step, DFMA, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                                          D.kernel == NEMPC_KERNEL_AUTO ? "; generic kernel for small batches" : "");
     else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
-    else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
+    else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem%s)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0],
+                                 h->wide_hes ? "; Hessian evaluations on the adjoint-form nempc_wide_kernel<hw=128>" : "");
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");
     h->kname = nm;
     *out = h;
@@ -680,7 +686,7 @@ static int upload_tc(nempc_handle* h) {
 
 // streamed operand images of nempc_wide_kernel: per GEMM and K step [2^11 hi | hi | lo] x [K chunk] x [n] x [8 halves]
 static int upload_wide(nempc_handle* h) {
-    const int nhid = h->L - 1, HW = NEMPC_WIDE_HW, x = h->desc.x_dim, d = h->d;
+    const int nhid = h->L - 1, HW = h->desc.widths[0], x = h->desc.x_dim, d = h->d;
     std::vector<__half> blob;
     bool range_ok = true;
     // Bm(n, k): row n of the B operand, contraction index k
@@ -762,7 +768,7 @@ extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W
         }
     }
     if (all && h->tc_id >= 0) { rc = upload_tc(h); if (rc) return rc; }
-    if (all && h->use_wide) { rc = upload_wide(h); if (rc) return rc; }
+    if (all && (h->use_wide || h->wide_hes)) { rc = upload_wide(h); if (rc) return rc; }
     return NEMPC_OK;
 }
 
@@ -1050,7 +1056,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
         int rc = take_fast64<TIO>(h, ar) ? run_fast64<TIO>(h, ar, mode, s) : h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
-                            : (h->use_tc ? launch_tc<TIO>(h, ar, mode, s) : (h->use_wide ? launch_wide<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s)));
+                            : (h->use_tc ? ((h->wide_hes && mode == 2) ? launch_wide<TIO>(h, ar, mode, s) : launch_tc<TIO>(h, ar, mode, s)) : (h->use_wide ? launch_wide<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s)));
         if (rc) return rc;
     }
     if (obj || grad) {

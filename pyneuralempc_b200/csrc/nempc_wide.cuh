@@ -74,8 +74,10 @@ inline size_t wide_img_index(int N, int K16, int img, int n, int k) {
     return ks * 32 * N + (img == 2 ? 16 * (size_t)N : 0) + in_img;
 }
 
-template <int X_, int U_, int MODE_, bool RK4_ = false> struct WideCfg {
-    static constexpr int X = X_, U = U_, D = X + U, MODE = MODE_, HW = NEMPC_WIDE_HW;
+template <int X_, int U_, int MODE_, bool RK4_ = false, int HW_ = NEMPC_WIDE_HW> struct WideCfg {
+    static constexpr int X = X_, U = U_, D = X + U, MODE = MODE_, HW = HW_;      // hidden width 256 (C4 class) or 128 (C3 class)
+    static constexpr int NQ = HW / 64;                                     // 64-neuron operand quarters (= groups of 4 K steps) per hidden layer
+    static_assert(HW == 256 || HW == 128, "hidden width 256 or 128");
     static constexpr bool RK4 = RK4_;                                    // four stages: per-stage k_s, dk_s and adjoint weights in the scratch
     static constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
     static constexpr int DP = D <= 4 ? 4 : (D <= 8 ? 8 : 16);          // tangent rows per step (padded to a power of two)
@@ -517,16 +519,18 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         body(0, va);
         if (feeds) publish_q(0);
         tmem_ld_wait(); tmem_ld_pin(vb);
-        tmem_ld16_nowait(c0 + 128, va);
+        if constexpr (C::NQ == 4) tmem_ld16_nowait(c0 + 128, va);
         body(1, vb);
         if (feeds) publish_q(1);
-        tmem_ld_wait(); tmem_ld_pin(va);
-        tmem_ld16_nowait(c0 + 192, vb);
-        body(2, va);
-        if (feeds) publish_q(2);
-        tmem_ld_wait(); tmem_ld_pin(vb);
-        body(3, vb);
-        if (feeds) publish_q(3);
+        if constexpr (C::NQ == 4) {
+            tmem_ld_wait(); tmem_ld_pin(va);
+            tmem_ld16_nowait(c0 + 192, vb);
+            body(2, va);
+            if (feeds) publish_q(2);
+            tmem_ld_wait(); tmem_ld_pin(vb);
+            body(3, vb);
+            if (feeds) publish_q(3);
+        }
     };
 
     // the pair works on super-tiles (2 i, 2 i + 1); both CTAs run the GEMM sequence of the fuller one (the leader's)
@@ -718,8 +722,8 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                          [&]() {
                              // while the MMAs run: this warp's s'(a_l) (x 2^-11: the accumulator's scale) and curvature coefficients (x 2^-22) of
                              // its SPW steps and 64 neurons (chunk `sub` of every quarter), global scratch -> warp-private shared memory
-                             for (int i = lane; i < SPW * 16; i += 32) {
-                                 const int sw_ = i >> 4, f4 = i & 15;
+                             for (int i = lane; i < SPW * 4 * C::NQ; i += 32) {
+                                 const int sw_ = i / (4 * C::NQ), f4 = i % (4 * C::NQ);
                                  const long long o = ((long long)(sidx0 + sw_) * NEMPC_WIDE_MAXHID + l) * HW + 64 * (f4 >> 2) + 16 * sub + 4 * (f4 & 3);
                                  float4 a = __ldcg(reinterpret_cast<const float4*>(sa + o));
                                  a.x *= INV; a.y *= INV; a.z *= INV; a.w *= INV;

@@ -12,9 +12,9 @@
 struct WideArgs { int wide_id, rk4, query; const unsigned char* blob; const float* cb; const WideNet* net; const StageTable<float>* st; const NlpLayout* L;
                   float* scratch; int sm_count; };
 
-template <int X, int U, int MODE, bool RK4, typename TIO>
+template <int X, int U, int MODE, bool RK4, typename TIO, int HW>
 static int launch_wide_cfg(const WideArgs& t, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    typedef WideCfg<X, U, MODE, RK4> C;
+    typedef WideCfg<X, U, MODE, RK4, HW> C;
     auto kern = nempc_wide_kernel<C, TIO>;
     if (t.query) return (int)C::SCRATCH_FLOATS;            // (fits an int: < 2^31 floats)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL);
@@ -26,16 +26,16 @@ static int launch_wide_cfg(const WideArgs& t, const EvalArgs<TIO>& ar, cudaStrea
     kern<<<grid, NEMPC_WIDE_THREADS, C::TOTAL, s>>>(t.blob, t.cb, *t.net, *t.st, *t.L, ar, t.scratch);
     return (int)cudaGetLastError();
 }
-template <int X, int U, int MODE, typename TIO>
+template <int X, int U, int MODE, typename TIO, int HW>
 static int launch_wide_mode(const WideArgs& t, const EvalArgs<TIO>& ar, cudaStream_t s) {
-    return t.rk4 ? launch_wide_cfg<X, U, MODE, true, TIO>(t, ar, s) : launch_wide_cfg<X, U, MODE, false, TIO>(t, ar, s);
+    return t.rk4 ? launch_wide_cfg<X, U, MODE, true, TIO, HW>(t, ar, s) : launch_wide_cfg<X, U, MODE, false, TIO, HW>(t, ar, s);
 }
-template <int X, int U, typename TIO>
+template <int X, int U, typename TIO, int HW = NEMPC_WIDE_HW>
 static int launch_wide_shape(const WideArgs& t, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
     switch (mode) {
-        case 0: return launch_wide_mode<X, U, 0, TIO>(t, ar, s);
-        case 1: return launch_wide_mode<X, U, 1, TIO>(t, ar, s);
-        default: return launch_wide_mode<X, U, 2, TIO>(t, ar, s);
+        case 0: return launch_wide_mode<X, U, 0, TIO, HW>(t, ar, s);
+        case 1: return launch_wide_mode<X, U, 1, TIO, HW>(t, ar, s);
+        default: return launch_wide_mode<X, U, 2, TIO, HW>(t, ar, s);
     }
 }
 template <typename TIO> static int launch_wide(const WideArgs& t, const EvalArgs<TIO>& ar, int mode, cudaStream_t s) {
@@ -44,6 +44,8 @@ template <typename TIO> static int launch_wide(const WideArgs& t, const EvalArgs
         case 1: return launch_wide_shape<4, 1, TIO>(t, ar, mode, s);
         case 2: return launch_wide_shape<2, 1, TIO>(t, ar, mode, s);
         case 3: return launch_wide_shape<6, 2, TIO>(t, ar, mode, s);
+        case 4: return launch_wide_shape<4, 1, TIO, 128>(t, ar, mode, s);       // hidden width 128 (C3 class)
+        case 5: return launch_wide_shape<2, 1, TIO, 128>(t, ar, mode, s);
     }
     return -1;
 }

@@ -579,3 +579,30 @@ def test_float64_register_resident_kernel_vs_oracle(kind, h, lv_weights):
         assert _relerr(got["resid"][0], g["constraints"]) < TOL64 and _relerr(got["jac"][0], g["jacobian"][jr, jc]) < TOL64
         assert _relerr(got["hes"][0], g["hessian_values"]) < TOL64
         ev.close()
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,B", [("rk4", [5, 128, 128, 128, 4], 4, 1, 13, 7), ("discrete", [5, 128, 128, 4], 4, 1, 9, 30),
+                                                ("unity", [3, 128, 128, 128, 2], 2, 1, 25, 11), ("rk4", [3, 128, 128, 2], 2, 1, 50, 5)])
+def test_adjoint_form_kernel_at_hidden_width_128(kind, dims, xd, ud, H, B, monkeypatch):
+    """nempc_wide_kernel<..., HW = 128>: by default the single-stage integrators send their Hessian evaluations there (1.37x faster than the
+    forward second-order kernel on that case) while RK4 and Jacobian-only calls stay on nempc_tc_kernel; NEMPC_WIDE128=1 routes everything
+    to it, =0 nothing.  All three routings against the oracle."""
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=len(dims) + H)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    for setting in (None, "1", "0"):
+        if setting is None:
+            monkeypatch.delenv("NEMPC_WIDE128", raising=False)
+        else:
+            monkeypatch.setenv("NEMPC_WIDE128", setting)
+        ev = _evaluator(mlp, kind, H, "float32", "auto", obj)
+        name = ev.kernel_name
+        if setting == "1":
+            assert name.startswith("nempc_wide_kernel") and "x128" in name
+        elif setting == "0":
+            assert name.startswith("nempc_tc_kernel") and "nempc_wide_kernel" not in name
+        else:
+            assert name.startswith("nempc_tc_kernel") and (("nempc_wide_kernel" in name) == (kind != "rk4"))
+        got = _run(ev, Z, X0, lam, sig)
+        for kr, kg in KEYS:
+            assert _relerr(got[kg], ref[kr]) < TOL32, (setting, kg, _relerr(got[kg], ref[kr]))
+        ev.close()
