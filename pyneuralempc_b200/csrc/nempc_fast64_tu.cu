@@ -9,6 +9,9 @@
 #include "nempc_generic.cuh"
 #include "nempc_fast64.cuh"
 
+#ifndef NEMPC_FAST64_JC30
+#define NEMPC_FAST64_JC30 10       // layer-2 neurons per register chunk of the 30-wide networks (tools/fast64_variants.sh: 5 / 6 / 10 / 15 -> 0.31 / 0.33 / 0.34 / 0.34 of the FP64 peak at 128 threads; 96 or 64 threads per CTA: 0.26 - 0.29)
+#endif
 template <int X, int U, int H1, int H2, int JC>
 static int launch_shape(int mode, const void* weights, const StageTable<double>& st, const NlpLayout& L, const EvalArgs<double>& ar, int sm_count,
                         cudaStream_t s) {
@@ -42,7 +45,7 @@ static int launch_shape(int mode, const void* weights, const StageTable<double>&
 int nempc_fast64_launch(int shape_id, int mode, const void* weights, const StageTable<double>& st, const NlpLayout& L, const EvalArgs<double>& ar,
                         int sm_count, cudaStream_t s) {
     switch (shape_id) {
-        case 0: return launch_shape<2, 1, 30, 30, 6>(mode, weights, st, L, ar, sm_count, s);
+        case 0: return launch_shape<2, 1, 30, 30, NEMPC_FAST64_JC30>(mode, weights, st, L, ar, sm_count, s);
         case 1: return launch_shape<2, 1, 32, 32, 8>(mode, weights, st, L, ar, sm_count, s);
         case 2: return launch_shape<2, 1, 16, 16, 8>(mode, weights, st, L, ar, sm_count, s);
     }
