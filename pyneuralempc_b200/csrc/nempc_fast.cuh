@@ -52,6 +52,18 @@ __device__ __forceinline__ float fast_tanh(float x) {
     p = fmaf(ax * x2, p, ax);
     return copysignf(ax < 0.25f ? p : big, x);
 }
+// the register-resident kernel's variant, 11 instructions instead of 15 (60 tanh per RK4 stage are ~4 % of its instructions): the MUFU
+// formula on the signed argument (saturates by itself) for |x| >= 1/8 -- relative error <= 1e-6 there -- and x - x^3/3 + 2 x^5/15 below
+// (truncation 17/315 x^7: 2e-7 relative at 1/8)
+__device__ __forceinline__ float fast_tanh_lv(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float big = fmaf(-2.0f, r, 1.0f);
+    const float x2 = x * x;
+    const float p = fmaf(x2 * x, fmaf(x2, 0.13333333333333333f, -0.3333333333333333f), x);
+    return x2 < 0.015625f ? p : big;
+}
 #else
 struct f2 { float lo, hi; };
 inline f2 pk(float lo, float hi) { f2 r; r.lo = lo; r.hi = hi; return r; }
@@ -66,6 +78,11 @@ inline float fast_tanh(float x) {
     p = fmaf(x2, p, -0.3333333333333333f);
     p = fmaf(ax * x2, p, ax);
     return copysignf(ax < 0.25f ? p : big, x);
+}
+inline float fast_tanh_lv(float x) {
+    const float e = exp2f(x * 2.885390081777927f), big = fmaf(-2.0f, 1.0f / (e + 1.0f), 1.0f), x2 = x * x;
+    const float p = fmaf(x2 * x, fmaf(x2, 0.13333333333333333f, -0.3333333333333333f), x);
+    return x2 < 0.015625f ? p : big;
 }
 #endif
 
@@ -178,7 +195,7 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
         for (int i = 0; i < H1; ++i) {
             const nf4 w1 = w.W1T[i];
             const float a1 = fmaf(w1.x, zs[0], fmaf(w1.y, zs[1], fmaf(w1.z, zs[2], w1.w)));
-            scr[(SC::H1_OFF + i) * sstride] = fast_tanh(a1);
+            scr[(SC::H1_OFF + i) * sstride] = fast_tanh_lv(a1);
         }
 
         // packed state: k2 = (k[0],k[1]), J2[c] = (J[0][c],J[1][c]) [pairs over outputs p], M2[p][e/2] [pairs over e]
@@ -229,7 +246,7 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
 #pragma unroll
             for (int jj = 0; jj < JC; ++jj) {
                 const float a2 = (jj & 1) ? f2hi(acc[0][jj / 2]) : f2lo(acc[0][jj / 2]);
-                const float t2 = fast_tanh(a2);
+                const float t2 = fast_tanh_lv(a2);
                 f2 w3[XP];
 #pragma unroll
                 for (int q = 0; q < XP; ++q) {
