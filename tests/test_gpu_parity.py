@@ -480,6 +480,7 @@ WIDE_CASES = [("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3),        # 
               ("unity", [16, 256, 256, 12], 12, 4, 7, 2),
               ("discrete", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("discrete", [3, 256, 256, 2], 2, 1, 6, 4),
               ("discrete", [8, 256, 256, 256, 6], 6, 2, 6, 4), ("unity", [3, 256, 256, 256, 2], 2, 1, 300, 3),
+              ("discrete", [16, 256, 256, 12], 12, 4, 1, 1), ("rk4", [16, 256, 256, 12], 12, 4, 1, 1),      # one horizon step in the whole launch
               # RK4: forward sweep (k_s, dk_s), last stage with curvature, backward sweep with w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}
               ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3), ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 29, 10),
               ("rk4", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("rk4", [3, 256, 256, 2], 2, 1, 50, 4), ("rk4", [8, 256, 256, 256, 6], 6, 2, 6, 4)]
