@@ -134,3 +134,42 @@ def test_jax_objectif_func_identifies_the_shipped_costs():
         JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum(np.diff(u[:, 0]) ** 2)).prepare(H, xd, ud)     # rate penalty: cross terms
     with pytest.raises(NotImplementedError):
         JAXObjectifFunc(lambda x, u, p=None, tvp=None: np.sum(x ** 4)).prepare(H, xd, ud)
+
+
+def _dense_stack(rng, dims):
+    return [(rng.standard_normal((a, b)).astype(np.float32), rng.standard_normal(b).astype(np.float32)) for a, b in zip(dims[:-1], dims[1:])]
+
+
+def test_h5lite_reads_keras_h5_and_keras_archive(tmp_path):
+    """the dependency-free HDF5 reader (pyneuralempc_b200/h5lite.py) and the .h5 / .keras importers on files built by the test-side
+    mini writer (tests/h5mini_writer.py): weights, layer order, activations, error paths"""
+    import h5mini_writer as W
+    from pyneuralempc_b200 import h5lite
+    from pyneuralempc_b200.model.tensorflow import KerasTFModel
+    rng = np.random.default_rng(0)
+    ws = _dense_stack(rng, [3, 30, 30, 2])
+    p = W.write_keras_h5(str(tmp_path / "m.h5"), ws, ["tanh", "tanh", "linear"])
+    f = h5lite.H5File(p)
+    assert sorted(f.members()) == ["model_config_blob", "model_weights"]
+    assert [n.decode() for n in f.attributes(f.members()["model_weights"])["layer_names"]] == ["dense", "dense_1", "dense_2"]
+    got, act = importers.from_keras_h5(p)
+    assert act == "tanh" and len(got) == 3
+    for (Wg, bg), (Wr, br) in zip(got, ws):
+        np.testing.assert_array_equal(Wg, Wr.astype(np.float64)); np.testing.assert_array_equal(bg, br.astype(np.float64))
+    m = KerasTFModel(p, x_dim=2, u_dim=1)
+    assert m.activation == "tanh" and m.weights[1][0].shape == (30, 30)
+    # a weights-only file (save_weights) carries no config: the activation has to be given
+    p2 = W.write_keras_h5(str(tmp_path / "w.h5"), ws, None, with_config=False)
+    with pytest.raises(ValueError):
+        importers.from_keras_h5(p2)
+    assert importers.from_keras_h5(p2, "softplus")[1] == "softplus"
+    # relu stack through the Keras-3 archive
+    ws2 = _dense_stack(rng, [5, 16, 16, 16, 4])
+    p3 = W.write_keras_archive(str(tmp_path / "m.keras"), ws2, ["relu", "relu", "relu", "linear"])
+    got3, act3 = importers.load_any(p3)
+    assert act3 == "relu" and [w.shape for w, _ in got3] == [(5, 16), (16, 16), (16, 16), (16, 4)]
+    np.testing.assert_array_equal(got3[2][0], ws2[2][0].astype(np.float64))
+    with pytest.raises(ValueError):
+        h5lite.H5File(b"not an hdf5 file at all")
+    with pytest.raises(ValueError):
+        importers.load_any(str(tmp_path / "m.unknown"))
