@@ -607,3 +607,37 @@ def test_adjoint_form_kernel_at_hidden_width_128(kind, dims, xd, ud, H, B, monke
         for kr, kg in KEYS:
             assert _relerr(got[kg], ref[kr]) < TOL32, (setting, kg, _relerr(got[kg], ref[kr]))
         ev.close()
+
+
+def test_c4_named_size_full_batch():
+    """BASELINE config C4 at its NAMED size (16 -> 256 x 4 -> 12, H = 200, B = 65 536: 13.1 M horizon steps, 37 GB of values in one launch):
+    structural entries over the whole batch, a sample of problems against the oracle, and a sub-batch evaluated alone must reproduce its
+    slice of the big launch bit for bit (the rows of a GEMM tile do not see each other, wherever a step lands in the tiling)."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 80e9:
+        pytest.skip("needs ~45 GB of device memory")
+    H, B, xd, ud = 200, 65536, 12, 4
+    mlp = MLP.glorot([16, 256, 256, 256, 256, 12], xd, ud, seed=0, dtype=np.float32)
+    n, m = H * (xd + ud), H * xd
+    ev = _evaluator(mlp, "discrete", H, "float32", "auto")
+    assert "nempc_wide_kernel" in ev.kernel_name
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7)
+    z = torch.rand((B, n), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    x0 = torch.rand((B, xd), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    lam = torch.randn((B, m), dtype=torch.float64, device="cuda", generator=gen)
+    out = ev.eval(z, x0, lam, 0.0, want=("resid", "jac", "hes"))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out["hes"]).all()) and bool(torch.isfinite(out["jac"]).all())
+    minus1 = torch.as_tensor(np.nonzero((ev.jac_cols < H * xd) & (ev.jac_cols // xd == ev.jac_rows // xd))[0]).cuda()
+    assert len(minus1) == m and bool((out["jac"][:, minus1] == -1.0).all())
+    lo, hi = 1000, 1512                                       # 200 000 steps in: not aligned to the 128-step tiles
+    sub = ev.eval(z[lo:hi].contiguous(), x0[lo:hi].contiguous(), lam[lo:hi].contiguous(), 0.0, want=("resid", "jac", "hes"))
+    for k in ("resid", "jac", "hes"):
+        assert torch.equal(sub[k], out[k][lo:hi]), k
+    pick = [0, 31337, B - 1]
+    ref = BlockEvaluator(mlp, "discrete", H, DT=0.1).evaluate(z[pick].cpu().numpy(), x0[pick].cpu().numpy(), lam[pick].cpu().numpy(), 0.0)
+    for kr, kg in KEYS[:3]:
+        assert _relerr(out[kg][pick].cpu().numpy(), ref[kr]) < TOL32, (kg, _relerr(out[kg][pick].cpu().numpy(), ref[kr]))
+    ev.close()
+    del out, z, lam
+    torch.cuda.empty_cache()
