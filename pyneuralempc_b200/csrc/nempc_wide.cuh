@@ -94,14 +94,16 @@ template <int X_, int U_, int MODE_, bool RK4_ = false, int HW_ = NEMPC_WIDE_HW>
     static constexpr int SC_WARP = JAC ? (HES ? 2 : 1) * SPW * 64 * 4 : 0;   // per-warp copy of s'(a_l) (and the curvature coefficients) of its steps and neuron quarter
     static constexpr int PART_BYTES = HES ? 4 * SPT * DP * DP * 4 : 0;  // [4 quarters][SPT][DP][DP] partial curvature: aliases the staging area
     static constexpr int STG_BYTES = NEMPC_WIDE_EPI_WARPS * STG_WARP > PART_BYTES ? NEMPC_WIDE_EPI_WARPS * STG_WARP : PART_BYTES;
-    static constexpr int FIXED = C_FLOATS * 4 + STG_BYTES + NEMPC_WIDE_EPI_WARPS * SC_WARP;
+    static constexpr int LS_BYTES = HES ? NEMPC_WIDE_SUP * 4 : 0;        // per-step multiplier scale of the super-tile (see phase B)
+    static constexpr int FIXED = C_FLOATS * 4 + STG_BYTES + NEMPC_WIDE_EPI_WARPS * SC_WARP + LS_BYTES;
     static constexpr int NSTAGE = (232448 - 1024 - FIXED) / STAGE_BYTES < 10 ? (232448 - 1024 - FIXED) / STAGE_BYTES : 10;
     static constexpr int OFF_RING = 0;
     static constexpr int OFF_C = OFF_RING + NSTAGE * STAGE_BYTES;
     static constexpr int OFF_STG = OFF_C + C_FLOATS * 4;
     static constexpr int OFF_PART = OFF_STG;
     static constexpr int OFF_SC = OFF_STG + STG_BYTES;
-    static constexpr int TOTAL = OFF_SC + NEMPC_WIDE_EPI_WARPS * SC_WARP;
+    static constexpr int OFF_LS = OFF_SC + NEMPC_WIDE_EPI_WARPS * SC_WARP;
+    static constexpr int TOTAL = OFF_LS + LS_BYTES;
     static_assert(NSTAGE >= 4, "wide kernel: weight ring too shallow");
     static constexpr long long SCRATCH_NET = 2LL * NEMPC_WIDE_SUP * NEMPC_WIDE_MAXHID * HW;       // h_l and q_l of one super-tile
     // RK4: k_s [4][128][16], adjoint weights w [128][16], dk_s [3][128][16 columns][16], running sum_s c_s dk_s [128][16][16]
@@ -339,6 +341,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
     float* stg = reinterpret_cast<float*>(wide_smem + C::OFF_STG + (is_epi ? warp : 0) * C::STG_WARP);
     float* scs = reinterpret_cast<float*>(wide_smem + C::OFF_SC + (is_epi ? warp : 0) * C::SC_WARP);   // [s' 2^-11 | coef 2^-22][SPW][64]
     float* part = reinterpret_cast<float*>(wide_smem + C::OFF_PART);
+    float* lscale = reinterpret_cast<float*>(wide_smem + C::OFF_LS);      // [128] max |lambda| of each step of the super-tile
     // per-CTA scratch: sa = h_l (phase A -> B), overwritten by s'(a_l) (phase B, or phase A when no Hessian is wanted); sq = s''(a_l) g_l
     const uint32_t rank = cluster_ctarank();                // 0 = leader (issues the MMAs of the pair)
     float* sa = scratch_all + (long long)blockIdx.x * C::SCRATCH_FLOATS;           // [128][MAXHID][HW]
@@ -627,12 +630,22 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 float lr[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) lr[c] = 0.f;
+                // The adjoint is linear in the multipliers and travels through f16-split operands (range 6e-5 .. 6e4 for full precision), while an
+                // NLP solver's multipliers range over many decades: every step works with lambda / max|lambda| and its Hessian block is scaled
+                // back in the scatter (all RK4 stage weights of a step derive from the same lambda, so one scale per step serves them all)
+                float lmax = 0.f;
+                if (validA) {
+#pragma unroll
+                    for (int p = 0; p < X; ++p) lmax = fmaxf(lmax, fabsf((float)ar.lam[bA * L.m + tA * X + p]));
+                }
+                const float linv = lmax > 0.f ? 1.f / lmax : 0.f;
+                lscale[row] = lmax;
                 if (validA) {
                     if (RK4 && sg < S - 1) {
 #pragma unroll
                         for (int p = 0; p < X; ++p) lr[p] = sw[row * 16 + p];
                     } else {
-                        const float cs = RK4 ? st.c[sg] : 1.f;
+                        const float cs = (RK4 ? st.c[sg] : 1.f) * linv;
 #pragma unroll
                         for (int p = 0; p < X; ++p) lr[p] = cs * (float)ar.lam[bA * L.m + tA * X + p];
                     }
@@ -677,7 +690,8 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     float v[16];
                     tmem_ld16(dbase, v);
                     tmem_ld_wait();
-                    const float a_s = st.a[sg], cprev = st.c[sg - 1];
+                    const float lmax = lscale[row];
+                    const float a_s = st.a[sg], cprev = st.c[sg - 1] * (lmax > 0.f ? 1.f / lmax : 0.f);
 #pragma unroll
                     for (int p = 0; p < X; ++p)
                         sw[row * 16 + p] = validA ? fmaf(a_s, v[p] * INV, cprev * (float)ar.lam[bA * L.m + tA * X + p]) : 0.f;
@@ -862,7 +876,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                             for (int k = 0; k < 4; ++k) sum += part[((k * SPT + s8) * DP + a) * DP + c];
                             TIO* hv = ar.hes + b * L.nnz_hes;
                             const TW sig = ar.sigma ? (TW)ar.sigma[b] : (TW)ar.sigma_scalar;
-                            TW val = (TW)sum;
+                            TW val = (TW)sum * (TW)lscale[sx];                      // back to the step's multiplier scale
                             int slot;
                             if (a < X) {
                                 slot = hes_slot_xx(L, t, a, c);

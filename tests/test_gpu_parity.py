@@ -641,3 +641,26 @@ def test_c4_named_size_full_batch():
     ev.close()
     del out, z, lam
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind", ("discrete", "rk4"))
+@pytest.mark.parametrize("scale", (1e6, 1e-7))
+def test_wide_kernel_over_the_range_of_solver_multipliers(kind, scale):
+    """IPOPT's multipliers span many decades, the adjoint of the width-256 kernel travels through f16-split operands: each step works with
+    lambda / max|lambda| and scales its Hessian block back, so 1e6 x and 1e-7 x the usual multipliers (and a step with lambda = 0, and one
+    whose multipliers differ by 1e6 among themselves) give the same RELATIVE accuracy"""
+    dims, xd, ud, H, B = [16, 256, 256, 12], 12, 4, 7, 3
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B, seed=17)
+    lam = lam * scale
+    lam[0, :xd] = 0.0                                          # a step without multipliers
+    lam[1, xd:2 * xd] *= np.logspace(0, 6, xd)                 # a step whose multipliers span six decades
+    obj.quad[:] = 0.0                                          # the constraint part alone: the cost's diagonal would mask small entries
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float32", "auto", obj)
+    assert "nempc_wide_kernel" in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    assert np.isfinite(got["hes"]).all()
+    for b in range(B):                                         # per problem: the blocks of problem 1 are 1e6 x larger than the others'
+        assert _relerr(got["hes"][b], ref["hes_vals"][b]) < TOL32, (b, _relerr(got["hes"][b], ref["hes_vals"][b]))
+    assert _relerr(got["jac"], ref["jac_vals"]) < TOL32
+    ev.close()
