@@ -142,3 +142,26 @@ def test_solver_on_the_tensor_core_kernel():
     assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-4 * max(1.0, np.abs(r64["obj"]).max())
     assert np.abs(z32 - z64).max() < 1e-2
     assert (z32 >= lb - 1e-9).all() and (z32 <= ub + 1e-9).all()
+
+
+def test_solver_on_the_wide_kernel():
+    """nempc_solve with the width-256 tcgen05 evaluation kernel (quadrotor-class network 16-256-256-12, discrete): the interior-point
+    iterates feed multipliers of every magnitude back into the adjoint-form kernel; the solutions are feasible and agree with the
+    float64 generic-kernel solve to the solver tolerance."""
+    from pyneuralempc_b200 import NlpEvaluator
+    H, B = 6, 12
+    mlp, obj, lb, ub, X0 = _setup("discrete", [16, 256, 256, 12], 12, 4, H, None, 5.0, None, B=B)
+    wd = NlpEvaluator(mlp.weights, 12, 4, H, "discrete", compute_dtype="float32", io_dtype="float64", kernel="auto")
+    wd.set_objective(obj.lin, obj.quad, obj.ref)
+    assert "nempc_wide_kernel" in wd.kernel_name
+    o32 = wd.solve(X0, lb, ub, tol=1e-5)
+    o64 = _ev(mlp, "discrete", H, None, obj, "float64").solve(X0, lb, ub, tol=1e-8)
+    assert (o32["status"].cpu().numpy() == 0).all() and (o64["status"].cpu().numpy() == 0).all()
+    z32, z64 = o32["z"].cpu().numpy(), o64["z"].cpu().numpy()
+    oe = BlockEvaluator(mlp, "discrete", H, objective=obj)
+    r32 = oe.evaluate(z32, X0, None, 1.0, need_jac=False, need_hes=False)
+    r64 = oe.evaluate(z64, X0, None, 1.0, need_jac=False, need_hes=False)
+    assert np.abs(r32["resid"]).max() < 1e-5
+    assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-4 * max(1.0, np.abs(r64["obj"]).max())
+    assert np.abs(z32 - z64).max() < 1e-2
+    assert (z32 >= lb - 1e-9).all() and (z32 <= ub + 1e-9).all()
