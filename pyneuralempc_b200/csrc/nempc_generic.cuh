@@ -102,6 +102,9 @@ template <typename TIO> struct EvalArgs {
     // (MODEL mode: sample i at tvp + i * tvp_dim), p row of problem b at p + b * p_bstride; a stride of 0 shares one set between problems
     const double* tvp; const double* p;
     long long tvp_bstride, p_bstride;
+    // optional gate (the batched solver): problem b is evaluated only where gate[b] == gate_value (null: every problem).  Honoured by the
+    // register-resident f32 kernel and the objective kernel; the other kernels evaluate everything (their callers ignore the surplus).
+    const int* gate; int gate_value;
 };
 
 template <typename A, typename B> struct WideOf { typedef double type; };

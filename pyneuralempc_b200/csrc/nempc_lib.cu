@@ -63,8 +63,10 @@ nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2, NCHUNK> w, c
     // cold per-thread state (layer-1 activations, per-output Hessian accumulators): [element][thread], bank = thread
     float* scr = reinterpret_cast<float*>(nempc_smem) + threadIdx.x;
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps;
-         step += (long long)gridDim.x * blockDim.x)
+         step += (long long)gridDim.x * blockDim.x) {
+        if (ar.gate && ar.gate[step / L.H] != ar.gate_value) continue;          // batched solver: problems that are done are not re-evaluated
         fast_step<X, U, H1, H2, NCHUNK, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+    }
 }
 
 // objective value + gradient of f(z) = sum lin_i z_i + quad_i (z_i - ref_i)^2 : one warp per problem,
@@ -72,11 +74,13 @@ nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2, NCHUNK> w, c
 template <typename TIO>
 __global__ void nempc_objective_kernel(const TIO* __restrict__ z, const double* __restrict__ lin,
                                        const double* __restrict__ quad, const double* __restrict__ ref,
-                                       TIO* __restrict__ obj, TIO* __restrict__ grad, int n, long long B) {
+                                       TIO* __restrict__ obj, TIO* __restrict__ grad, int n, long long B,
+                                       const int* __restrict__ gate = nullptr, int gate_value = 0) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long b = warp; b < B; b += nwarps) {
+        if (gate && gate[b] != gate_value) continue;
         double acc = 0.0;
         for (int i = lane; i < n; i += 32) {
             const double zi = (double)z[b * n + i];
@@ -333,6 +337,7 @@ struct nempc_handle {
     // staging for eval_host
     void* st_buf[10] = {}; size_t st_cap[10] = {};
     long long launches = 0;
+    const int* gate = nullptr; int gate_value = 0;   // set by nempc_solve around its internal evaluations (EvalArgs::gate)
     // exogenous model inputs (nempc_set_exogenous): device copies, rows held, and the problem offset of the chunk being issued
     int n_ext = 0; double *d_tvp = nullptr, *d_p = nullptr; size_t tvp_cap = 0, p_cap = 0;
     long long tvp_rows = 0, p_rows = 0, exo_base = 0;
@@ -1052,6 +1057,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         ar.sigma_scalar = sigma; ar.quad = h->has_objective ? h->dquad : nullptr;
         ar.resid = (TIO*)resid; ar.jac = (TIO*)jac; ar.hes = (TIO*)hes;
         ar.nsteps = (long long)B * h->desc.horizon;
+        ar.gate = h->gate; ar.gate_value = h->gate_value;
         const int mode = hes ? 2 : (jac ? 1 : 0);
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
@@ -1064,7 +1070,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         const int threads = 256;
         const long long warps_needed = B;
         const unsigned grid = (unsigned)std::max(1LL, std::min((warps_needed * 32 + threads - 1) / threads, (long long)h->sm_count * 16));
-        nempc_objective_kernel<TIO><<<grid, threads, 0, s>>>((const TIO*)z, h->dlin, h->dquad, h->dref, (TIO*)obj, (TIO*)grad, h->lay.n, B);
+        nempc_objective_kernel<TIO><<<grid, threads, 0, s>>>((const TIO*)z, h->dlin, h->dquad, h->dref, (TIO*)obj, (TIO*)grad, h->lay.n, B, h->gate, h->gate_value);
         CU(h, cudaGetLastError());
         h->launches++;
     }
@@ -1475,7 +1481,9 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     CU(h, cudaGetLastError()); h->launches++;
     int it = 0;
     for (; it < o.max_iter; ++it) {
+        h->gate = w.status; h->gate_value = NEMPC_ST_RUNNING;           // converged / failed problems are not re-evaluated
         rc = nempc_eval(h, B, w.z, x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)s);
+        h->gate = nullptr;
         if (rc) return rc;
         CU(h, cudaMemsetAsync(h->sv_counts, 0, 2 * sizeof(int), s));
         if (staged_smem) kkt_staged<<<(unsigned)((B + staged_wpb - 1) / staged_wpb), 32 * staged_wpb, staged_smem, s>>>(L, w, o, B, h->sv_counts);
@@ -1487,7 +1495,9 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
         int trial = 0;
         do {
             if (o.max_backtrack > 0) {
+                h->gate = w.accepted; h->gate_value = 0;               // only the problems whose step is not accepted yet need the trial point
                 rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
+                h->gate = nullptr;
                 if (rc) return rc;
                 CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
                 if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, s>>>(L, w, o, B, h->sv_counts);
