@@ -26,6 +26,7 @@ What is recorded (all float64 unless noted):
   ref_rolling_<kind>_w<w>.npz  rolling-window (NARX) models, SURVEY 8f rank 2: a window network (w (x+u) -> 10 -> 10 -> x) behind a subclass of
                           the reference's Model with the layouts of KerasTFModelRollingInput (oracle/rolling_np.py restates
                           model/tensorflow.py:112-340), through the reference's Discret / Unity integrators and IpoptProblem
+  ref_receding_horizon.npz  six receding-horizon steps of the reference's NMPC + warm-started Slsqp (unity transcription, H = 15, tracking cost)
   ref_quadform_H6.npz     IpoptProblem callbacks with a NON-SEPARABLE quadratic cost (full stage / terminal weights, control-rate penalty,
                           state-control cross term: oracle.objectives_np.QuadraticFormObjective behind the reference's ObjectiveFunc):
                           the Hessian pattern is the union np.nonzero(np.tril(objective_map + integrator_map)) of ipopt.py:55-62
@@ -306,6 +307,37 @@ def record_quadform(ref, lv, H=6, seed=900):
     return out
 
 
+def record_receding_horizon(ref, lv, H=15, nsteps=6):
+    """receding-horizon run of the reference's NMPC (unity transcription, Slsqp warm-started from the shifted previous solution,
+    optimizer/slsqp.py:155-160): the plant is the network itself, x_{k+1} = first predicted state; per step: iterations, cost, control"""
+    from scipy.optimize import minimize as sp_minimize
+    sep = SeparableQuadraticObjective.tracking(H, 2, 1, [1.0, 1.0], [0.1], x_ref=np.array([0.5, -0.7]))
+    dom = ref.constraints.DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])
+    seen = []
+
+    def spy(*a, **kw):
+        r = sp_minimize(*a, **kw)
+        seen.append(r)
+        return r
+
+    ref.optimizer.slsqp.minimize = spy
+    try:
+        integ = make_integrator(ref, "unity", shim.make_reference_model(lv), H)
+        opt = ref.optimizer.slsqp.Slsqp(verbose=0, init_with_last_result=True)
+        mpc = ref.controller.NMPC(integ, ref_objective(ref, sep), [dom], H, DT_RK4, optimizer=opt)
+        x = np.array([0.66, -0.9])
+        xs, us, nits, funs = [x.copy()], [], [], []
+        for _ in range(nsteps):
+            pred, u = mpc.next(x)
+            nits.append(seen[-1].nit); funs.append(seen[-1].fun); us.append(u[0].copy())
+            x = np.asarray(pred[0], np.float64)
+            xs.append(x.copy())
+    finally:
+        ref.optimizer.slsqp.minimize = sp_minimize
+    return dict(H=H, nsteps=nsteps, obj_lin=sep.lin, obj_quad=sep.quad, obj_ref=sep.ref, x_traj=np.array(xs), u_traj=np.array(us),
+                nit=np.array(nits), fun=np.array(funs), minimize_calls=len(seen))
+
+
 def main():
     ref = shim.load_reference()
     h5 = os.path.join(shim.REFERENCE_ROOT, "examples", "lotka_volterra", "nn_model.h5")
@@ -351,6 +383,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_discrete_w256_H6.npz"), **record_wide(ref, [5, 256, 256, 256, 4], 4, 1, "discrete", 6, 710, 22))
     np.savez_compressed(os.path.join(HERE, "ref_rk4_w256_H6.npz"), **record_wide(ref, [3, 256, 256, 2], 2, 1, "rk4", 6, 720, 23))
     np.savez_compressed(os.path.join(HERE, "ref_closed_loop_c1.npz"), **record_closed_loop_c1(ref, lv))
+    np.savez_compressed(os.path.join(HERE, "ref_receding_horizon.npz"), **record_receding_horizon(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_quadform_H6.npz"), **record_quadform(ref, lv))
     np.savez_compressed(os.path.join(HERE, "ref_rolling_discrete_w2.npz"), **record_rolling(ref, "discrete", 2, True))
     np.savez_compressed(os.path.join(HERE, "ref_rolling_unity_w3.npz"), **record_rolling(ref, "unity", 3, False))

@@ -554,3 +554,45 @@ def test_rate_penalty_closed_loop_trust_constr_and_slsqp(lv_weights):
     free = CudaQuadraticFormObjective.from_blocks(H, 2, 1, **{**blocks, "S": None})
     _, u_free = NMPC(integ, free, [dom], H, 0.1, optimizer=Slsqp(verbose=0)).next(x0)
     assert np.abs(np.diff(us[:, 0])).sum() < 0.8 * np.abs(np.diff(u_free[:, 0])).sum()
+
+
+def test_receding_horizon_run_matches_the_reference(golden_dir, lv_weights):
+    """six receding-horizon steps (plant = the network, x_{k+1} = first predicted state) with the warm-started Slsqp of the reference
+    (init_with_last_result, optimizer/slsqp.py:155-160), recorded from the UNMODIFIED reference's NMPC (ref_receding_horizon.npz):
+    the CUDA controller takes the same number of SLSQP iterations at every step and applies the same controls"""
+    import scipy.optimize
+    from pyneuralempc_b200 import integrator as I
+    from pyneuralempc_b200.constraints import DomainConstraint
+    from pyneuralempc_b200.controller import NMPC
+    from pyneuralempc_b200.model import CudaMLPModel
+    from pyneuralempc_b200.objective import CudaSeparableObjective
+    from pyneuralempc_b200.optimizer import Slsqp
+    from pyneuralempc_b200.optimizer import slsqp as slsqp_mod
+    g = np.load(os.path.join(golden_dir, "ref_receding_horizon.npz"))
+    H = int(g["H"])
+    integ = I.UnityIntegrator(CudaMLPModel(lv_weights, 2, 1, dtype="float64"), H)
+    obj = CudaSeparableObjective(g["obj_lin"], g["obj_quad"], g["obj_ref"])
+    dom = DomainConstraint(states_constraint=[[-np.inf, 1.0], [-np.inf, np.inf]], control_constraint=[[-1.0, 0.2]])
+    seen = []
+
+    def spy(*a, **kw):
+        r = scipy.optimize.minimize(*a, **kw)
+        seen.append(r)
+        return r
+
+    old = slsqp_mod.minimize
+    slsqp_mod.minimize = spy
+    try:
+        mpc = NMPC(integ, obj, [dom], H, 0.1, optimizer=Slsqp(verbose=0, init_with_last_result=True))
+        x = g["x_traj"][0].copy()
+        for k in range(int(g["nsteps"])):
+            pred, u = mpc.next(x)
+            assert pred is not None
+            assert seen[-1].nit == int(g["nit"][k]), (k, seen[-1].nit, int(g["nit"][k]))
+            assert abs(seen[-1].fun - float(g["fun"][k])) < 1e-6
+            assert np.abs(u[0] - g["u_traj"][k]).max() < 1e-6
+            x = np.asarray(pred[0], np.float64)
+            assert np.abs(x - g["x_traj"][k + 1]).max() < 1e-6
+    finally:
+        slsqp_mod.minimize = old
+    assert len(seen) == int(g["minimize_calls"])
