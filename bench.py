@@ -284,6 +284,41 @@ def wide_traffic(ev, wl, steps_per_eval):
     return None if per_step is None else per_step * steps_per_eval
 
 
+def _cpu_block_chunk(args):
+    """a chunk of problems through the O(H) per-step block restatement (oracle/blocks_np.py): the best-effort vectorised CPU path"""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    wl, Z, X0, lam = args
+    from oracle.blocks_np import BlockEvaluator
+    from oracle.mlp_np import MLP
+    from oracle.objectives_np import SeparableQuadraticObjective
+    cache = _cpu_block_chunk.__dict__.setdefault("cache", {})
+    key = json.dumps(wl, sort_keys=True)
+    if key not in cache:
+        mlp = MLP.glorot(wl["dims"], wl["x"], wl["u"], seed=0, dtype=np.float32)
+        obj = SeparableQuadraticObjective.tracking(wl["H"], wl["x"], wl["u"], np.linspace(1.0, 2.0, wl["x"]), np.linspace(0.1, 0.2, wl["u"]))
+        cache[key] = BlockEvaluator(mlp, wl["integ"], wl["H"], DT=wl["DT"], objective=obj)
+    out = cache[key].evaluate(Z, X0, lam, 1.0)
+    return float(out["hes_vals"].sum())
+
+
+def cpu_blocks_run(wl_name, per_proc=64, procs=None):
+    """SURVEY 8d "R2": the same evaluation restated in O(H) per-step blocks + sparse assembly (what the kernels compute), vectorised numpy,
+    one process per core -- reported so that the speed-up is not inflated by the O(H^3) density of the reference's own assembly."""
+    import multiprocessing as mp
+    wl = {k: v for k, v in WORKLOADS[wl_name].items() if k != "desc"}
+    procs = procs or os.cpu_count() or 1
+    _, _, Z, X0, lam = make_problem(wl, per_proc * procs)
+    jobs = [(wl, Z[i * per_proc:(i + 1) * per_proc], X0[i * per_proc:(i + 1) * per_proc], lam[i * per_proc:(i + 1) * per_proc]) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_cpu_block_chunk, [(wl, Z[:2], X0[:2], lam[:2])] * procs, chunksize=1)      # per-process caches, imports
+        t0 = time.perf_counter()
+        pool.map(_cpu_block_chunk, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    return dict(value=per_proc * procs * wl["H"] / dt, unit=UNIT, cores=procs, kind="port",
+                sample=f"{per_proc * procs} of {wl['B']} problems, O(H) per-step block restatement of the reference algorithm (oracle/blocks_np.py, vectorised numpy, "
+                       f"one process per core): the best-effort CPU path, without the reference's O(H^3) dense assembly")
+
+
 def block_cpu_baseline(name, nprob=2):
     """CPU figure beside a wide workload: the O(H) per-step block restatement (oracle/blocks_np.py, numpy, one core) on `nprob`
     problems.  The reference's own dense path is O(H^3): 0.8 GB per problem for C3, 197 GB for C4 -- not runnable."""
@@ -696,6 +731,7 @@ def gpu_run(args):
             cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c.get("kind", "port"), "sample": c["sample"]}
             if solves is not None and "solver" in c:
                 solves["cpu_baseline"] = c["solver"]
+            cpu["vectorised_port"] = c.get("blocks")       # SURVEY 8d "R2": best-effort vectorised CPU path beside the reference-literal one
         except (ValueError, IndexError):
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -758,7 +794,9 @@ def main():
         # the solver leg first: importing the reference (shim) leaves stub `tensorflow` / `jax` modules in sys.modules, and SciPy's
         # array-API dispatch then probes them on every call (measured: SLSQP 30x slower in that process)
         solver = None if args.no_solver else cpu_solver_run(args.workload)
+        blocks = cpu_blocks_run(args.workload)
         out = cpu_reference_run(args.workload, args.cpu_sample, 2, 1)
+        out["blocks"] = blocks
         if solver is not None:
             out["solver"] = solver
         print(json.dumps(out))
