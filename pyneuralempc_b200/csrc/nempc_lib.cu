@@ -411,9 +411,14 @@ static int wide_shape_id(const nempc_desc& d) {
     if (d.compute_dtype != NEMPC_F32 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
     if (d.n_layers - 1 < 2 || d.n_layers - 1 > NEMPC_WIDE_MAXHID) return -1;
     for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
-    for (int i = 0; i < kNumWideShapes; ++i)
+    if (d.widths[0] != 256 && d.widths[0] != 128) return -1;
+    static const bool force_rt = getenv("NEMPC_WIDE_RUNTIME_SHAPES") && atoi(getenv("NEMPC_WIDE_RUNTIME_SHAPES")) != 0;      // experiments
+    for (int i = 0; i < kNumWideShapes && !force_rt; ++i)
         if (d.x_dim == kWideShapes[i].x && d.u_dim == kWideShapes[i].u && d.widths[0] == kWideShapes[i].hw) return i;
-    return -1;
+    // any other shape with x_dim + u_dim <= 16: instantiations that read the dimensions at run time (nempc_wide_tu.cu)
+    const int dd = d.x_dim + d.u_dim;
+    if (dd > 16) return -1;
+    return 100 + (d.widths[0] == 128 ? 3 : 0) + (dd <= 4 ? 0 : (dd <= 8 ? 1 : 2));
 }
 
 extern "C" const char* nempc_version(void) { return "nempc 0.2 (sm_100a)"; }
@@ -599,7 +604,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
     else if (h->fast64_id >= 0) snprintf(nm, sizeof nm, "nempc_fast64_kernel<x=%d,u=%d,h1=%d,h2=%d> f64 (thread/step, DFMA, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                                          D.kernel == NEMPC_KERNEL_AUTO ? "; generic kernel for small batches" : "");
-    else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0]);
+    else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring%s)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0],
+                               h->wide_id >= 100 ? "; dimensions read at run time" : "");
     else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem%s)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0],
                                  h->wide_hes ? "; Hessian evaluations on the adjoint-form nempc_wide_kernel<hw=128>" : "");
     else snprintf(nm, sizeof nm, "nempc_generic_kernel<%s,dmax=%d> tps=%d slots=%d %s", D.compute_dtype == NEMPC_F64 ? "f64" : "f32", h->dmax, h->tps, h->slots, h->global_ws ? "global-ws" : "smem-ws");

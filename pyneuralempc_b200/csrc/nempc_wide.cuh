@@ -74,13 +74,17 @@ inline size_t wide_img_index(int N, int K16, int img, int n, int k) {
     return ks * 32 * N + (img == 2 ? 16 * (size_t)N : 0) + in_img;
 }
 
-template <int X_, int U_, int MODE_, bool RK4_ = false, int HW_ = NEMPC_WIDE_HW> struct WideCfg {
-    static constexpr int X = X_, U = U_, D = X + U, MODE = MODE_, HW = HW_;      // hidden width 256 (C4 class) or 128 (C3 class)
+// X_ = U_ = 0: x_dim / u_dim are read from the layout at run time (any x_dim + u_dim <= DPR_ <= 16); the thin per-step loops then run to 16
+// under a predicate, everything else is the same code
+template <int X_, int U_, int MODE_, bool RK4_ = false, int HW_ = NEMPC_WIDE_HW, int DPR_ = 16> struct WideCfg {
+    static constexpr int X = X_, U = U_, D = X_ ? X_ + U_ : DPR_, MODE = MODE_, HW = HW_;      // hidden width 256 (C4 class) or 128 (C3 class)
+    static constexpr int XM = X_ ? X_ : 16;                                // bound of the unrolled per-output loops
     static constexpr int NQ = HW / 64;                                     // 64-neuron operand quarters (= groups of 4 K steps) per hidden layer
     static_assert(HW == 256 || HW == 128, "hidden width 256 or 128");
     static constexpr bool RK4 = RK4_;                                    // four stages: per-stage k_s, dk_s and adjoint weights in the scratch
     static constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
     static constexpr int DP = D <= 4 ? 4 : (D <= 8 ? 8 : 16);          // tangent rows per step (padded to a power of two)
+    static_assert(X_ != 0 || DPR_ == 4 || DPR_ == 8 || DPR_ == 16, "run-time shapes: tangent rows 4, 8 or 16");
     static constexpr int SPT = 128 / DP;                                 // steps per phase-C tile
     static constexpr int NTILE = NEMPC_WIDE_SUP / SPT;                   // phase-C tiles per super-tile
     static constexpr int STAGE_BYTES = 128 * (HW / 2);                   // four K-step images of one CTA's half of the B rows
@@ -322,7 +326,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NEMPC_WIDE_THREADS, 
 nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restrict__ cblk, const WideNet net, const StageTable<float> st,
                   const NlpLayout L, const EvalArgs<TIO> ar, float* __restrict__ scratch_all) {
     using namespace widex;
-    constexpr int X = C::X, U = C::U, D = C::D, DP = C::DP, SPT = C::SPT, SPW = C::SPW, HW = C::HW, NSTAGE = C::NSTAGE;
+    constexpr int XM = C::XM, DP = C::DP, SPT = C::SPT, SPW = C::SPW, HW = C::HW, NSTAGE = C::NSTAGE;
+    const int X = C::X ? C::X : L.x, U = C::X ? C::U : L.u, D = X + U;        // compile-time constants for the listed shapes
+#define WIDE_FOR_X(p) _Pragma("unroll") for (int p = 0; p < XM; ++p) if (p < X)
     constexpr bool JAC = C::JAC, HES = C::HES, RK4 = C::RK4;
     constexpr float INV = NEMPC_TC_LO_INV;                 // accumulators carry 2^11
     typedef typename WideOf<float, TIO>::type TW;
@@ -560,13 +566,12 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 if (validA) {
                     const TIO* zb = ar.z + bA * (long long)L.n;
 #pragma unroll
-                    for (int c = 0; c < D; ++c)
-                        zr[c] = (float)(c < X ? ((tA == 0) ? ar.x0[bA * X + c] : zb[(tA - 1) * X + c]) : zb[L.H * X + tA * U + (c - X)]);
+                    for (int c = 0; c < 16; ++c)
+                        if (c < D) zr[c] = (float)(c < X ? ((tA == 0) ? ar.x0[bA * X + c] : zb[(tA - 1) * X + c]) : zb[L.H * X + tA * U + (c - X)]);
                     if (RK4 && sg > 0) {
                         const float a_s = st.a[sg];
                         const float* kp = sks + ((long long)(sg - 1) * NEMPC_WIDE_SUP + row) * 16;
-#pragma unroll
-                        for (int p = 0; p < X; ++p) zr[p] = fmaf(a_s, kp[p], zr[p]);
+                        WIDE_FOR_X(p) zr[p] = fmaf(a_s, kp[p], zr[p]);
                     }
                 }
                 put_seed(zr);
@@ -599,18 +604,15 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 float v[16];
                 tmem_ld16(dbase, v);
                 tmem_ld_wait();
-                float k[X];
-#pragma unroll
-                for (int p = 0; p < X; ++p) k[p] = fmaf(v[p], INV, bout[p]);
+                float k[XM];
+                WIDE_FOR_X(p) k[p] = fmaf(v[p], INV, bout[p]);
                 if (RK4) {
                     float* kp = sks + ((long long)sg * NEMPC_WIDE_SUP + row) * 16;
-#pragma unroll
-                    for (int p = 0; p < X; ++p) kp[p] = k[p];
+                    WIDE_FOR_X(p) kp[p] = k[p];
                 }
                 if (write_resid && validA && ar.resid) {
                     const TIO* zb = ar.z + bA * (long long)L.n;
-#pragma unroll
-                    for (int p = 0; p < X; ++p) {
+                    WIDE_FOR_X(p) {
                         float kacc = RK4 ? st.c[sg] * k[p] : k[p];
                         if (RK4)
                             for (int s2 = 0; s2 < sg; ++s2) kacc = fmaf(st.c[s2], sks[((long long)s2 * NEMPC_WIDE_SUP + row) * 16 + p], kacc);
@@ -635,19 +637,16 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                 // back in the scatter (all RK4 stage weights of a step derive from the same lambda, so one scale per step serves them all)
                 float lmax = 0.f;
                 if (validA) {
-#pragma unroll
-                    for (int p = 0; p < X; ++p) lmax = fmaxf(lmax, fabsf((float)ar.lam[bA * L.m + tA * X + p]));
+                    WIDE_FOR_X(p) lmax = fmaxf(lmax, fabsf((float)ar.lam[bA * L.m + tA * X + p]));
                 }
                 const float linv = lmax > 0.f ? 1.f / lmax : 0.f;
                 lscale[row] = lmax;
                 if (validA) {
                     if (RK4 && sg < S - 1) {
-#pragma unroll
-                        for (int p = 0; p < X; ++p) lr[p] = sw[row * 16 + p];
+                        WIDE_FOR_X(p) lr[p] = sw[row * 16 + p];
                     } else {
                         const float cs = (RK4 ? st.c[sg] : 1.f) * linv;
-#pragma unroll
-                        for (int p = 0; p < X; ++p) lr[p] = cs * (float)ar.lam[bA * L.m + tA * X + p];
+                        WIDE_FOR_X(p) lr[p] = cs * (float)ar.lam[bA * L.m + tA * X + p];
                     }
                 }
                 put_seed(lr);
@@ -692,8 +691,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     tmem_ld_wait();
                     const float lmax = lscale[row];
                     const float a_s = st.a[sg], cprev = st.c[sg - 1] * (lmax > 0.f ? 1.f / lmax : 0.f);
-#pragma unroll
-                    for (int p = 0; p < X; ++p)
+                    WIDE_FOR_X(p)
                         sw[row * 16 + p] = validA ? fmaf(a_s, v[p] * INV, cprev * (float)ar.lam[bA * L.m + tA * X + p]) : 0.f;
                 });
             }
@@ -725,8 +723,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     if (RK4 && sg > 0 && validC) {
                         const float a_s = st.a[sg];
                         const float* dp = sdk + ((((long long)(sg - 1) * NEMPC_WIDE_SUP + sidx) * 16 + cc) * 16);
-#pragma unroll
-                        for (int p = 0; p < X; ++p) e[p] = fmaf(a_s, dp[p], e[p]);
+                        WIDE_FOR_X(p) e[p] = fmaf(a_s, dp[p], e[p]);
                     }
                     put_seed(e);
                 }
@@ -794,20 +791,17 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                     tmem_ld16(dbase, v);
                     tmem_ld_wait();
                     if (!validC) return;
-                    float jv_[X];                                              // (sum_s c_s dk_s)[p][cc] up to this stage
-#pragma unroll
-                    for (int p = 0; p < X; ++p) jv_[p] = v[p] * INV;
+                    float jv_[XM];                                             // (sum_s c_s dk_s)[p][cc] up to this stage
+                    WIDE_FOR_X(p) jv_[p] = v[p] * INV;
                     if (RK4) {
                         const float c_s = st.c[sg];
                         float* dacc = sdkacc + ((long long)sidx * 16 + cc) * 16;
                         if (store_dk) {
                             float* dp = sdk + ((((long long)sg * NEMPC_WIDE_SUP + sidx) * 16 + cc) * 16);
-#pragma unroll
-                            for (int p = 0; p < X; ++p) dp[p] = jv_[p];
+                            WIDE_FOR_X(p) dp[p] = jv_[p];
                         }
                         if (store_dk || write_jac) {
-#pragma unroll
-                            for (int p = 0; p < X; ++p) {
+                            WIDE_FOR_X(p) {
                                 jv_[p] = sg == 0 ? c_s * jv_[p] : fmaf(c_s, jv_[p], dacc[p]);
                                 if (store_dk) dacc[p] = jv_[p];
                             }
@@ -818,8 +812,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
                         const long long b = step / L.H;
                         const int t = (int)(step - b * L.H);
                         TIO* jv = ar.jac + b * L.nnz_jac;
-#pragma unroll
-                        for (int p = 0; p < X; ++p) {
+                        WIDE_FOR_X(p) {
                             const TW val = (TW)jv_[p] + ((!unity && cc == p) ? (TW)1 : (TW)0);
                             if (cc < X) { if (t > 0) jv[jac_slot_A(L, t, p, cc)] = (TIO)val; }
                             else jv[jac_slot_B(L, t, p, cc - X)] = (TIO)val;
@@ -928,6 +921,7 @@ nempc_wide_kernel(const unsigned char* __restrict__ blob, const float* __restric
         }
     }
 
+#undef WIDE_FOR_X
     WPROF_FLUSH;
     fence_before_sync();
     __syncthreads();

@@ -483,7 +483,12 @@ WIDE_CASES = [("discrete", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3),        # 
               ("discrete", [16, 256, 256, 12], 12, 4, 1, 1), ("rk4", [16, 256, 256, 12], 12, 4, 1, 1),      # one horizon step in the whole launch
               # RK4: forward sweep (k_s, dk_s), last stage with curvature, backward sweep with w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}
               ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 5, 3), ("rk4", [16, 256, 256, 256, 256, 12], 12, 4, 29, 10),
-              ("rk4", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("rk4", [3, 256, 256, 2], 2, 1, 50, 4), ("rk4", [8, 256, 256, 256, 6], 6, 2, 6, 4)]
+              ("rk4", [5, 256, 256, 256, 4], 4, 1, 11, 5), ("rk4", [3, 256, 256, 2], 2, 1, 50, 4), ("rk4", [8, 256, 256, 256, 6], 6, 2, 6, 4),
+              # shapes without a specialised instantiation: dimensions read at run time, 4 / 8 / 16 tangent rows
+              ("discrete", [4, 256, 256, 3], 3, 1, 9, 4), ("rk4", [4, 256, 256, 3], 3, 1, 9, 4), ("unity", [2, 256, 256, 1], 1, 1, 6, 3),
+              ("discrete", [7, 256, 256, 256, 5], 5, 2, 8, 3), ("rk4", [7, 256, 256, 5], 5, 2, 8, 3),
+              ("discrete", [12, 256, 256, 10], 10, 2, 5, 3), ("rk4", [14, 256, 256, 256, 8], 8, 6, 7, 3), ("unity", [16, 256, 256, 9], 9, 7, 5, 2),
+              ("discrete", [16, 256, 256, 16], 16, 0, 4, 2) if False else ("discrete", [16, 256, 256, 15], 15, 1, 4, 2)]
 
 
 @pytest.mark.parametrize("kind,dims,xd,ud,H,B", WIDE_CASES)
