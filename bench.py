@@ -663,7 +663,26 @@ def gpu_run(args):
                   "ms_per_batch": float(ts.item()) * 1e3, "converged_frac": float(conv.item()) / (world * B),
                   "ipm_iterations_mean": float(so["iterations"].double().mean().item()), "outer_iterations": so["outer_iterations"],
                   "tol": sopt["tol"], "solver": "nempc_solve: primal-dual interior point, Riccati KKT sweep on the block-banded values, x0 device-resident",
-                  "bounds": "u in [-1, 0.2] (run.py:72-74), states free"}
+                  "bounds": "u in [-1, 0.2] (run.py:72-74), states free",
+                  "loop": "device: one CUDA graph, nested WHILE nodes (cudaGraphSetConditional)" if so.get("used_graph") else "host-issued kernels, one synchronisation per iteration",
+                  "unaccepted_steps": so.get("unaccepted_steps")}
+        if rank == 0:
+            # ONE problem (what a closed-loop controller solves per sample): latency with the device-side loop and with the host-issued one
+            one = {}
+            for mode, name in (("1", "device_loop_ms"), ("0", "host_loop_ms")):
+                os.environ["NEMPC_SOLVE_GRAPH"] = mode
+                for _ in range(3):
+                    ev.solve(x0d[:1], lb, ub, **sopt)
+                tt = []
+                for _ in range(15):
+                    t0 = time.perf_counter()
+                    s1 = ev.solve(x0d[:1], lb, ub, **sopt)
+                    torch.cuda.synchronize()
+                    tt.append(time.perf_counter() - t0)
+                one[name] = statistics.median(tt) * 1e3
+                one["iterations"] = int(s1["iterations"][0].item())
+            os.environ.pop("NEMPC_SOLVE_GRAPH", None)
+            solves["single_problem"] = one
     ev_name, ev_flops, ev_bytes = ev.kernel_name, ev.flops_per_step, ev.bytes_per_step()
     side = None
     if args.workload == "C2" and not args.no_side_workloads:

@@ -67,7 +67,7 @@ typedef struct nempc_handle nempc_handle;
 const char* nempc_version(void);
 /* ABI generation of the library (NEMPC_ABI_VERSION at its build) and the sizes of the two structs it was compiled with; a binding
  * compares them with its own after dlopen (a stale libnempc.so would otherwise misread nempc_desc / nempc_solver_opts). */
-#define NEMPC_ABI_VERSION 3
+#define NEMPC_ABI_VERSION 4
 int32_t nempc_abi_info(int32_t* desc_bytes, int32_t* solver_opts_bytes);
 /* hash of the CUDA sources the binary was built from ("unknown" for a build outside pyneuralempc_b200/build.py) */
 const char* nempc_source_hash(void);
@@ -210,6 +210,13 @@ int nempc_solver_defaults(nempc_solver_opts* opts);
 int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const double* lb, const double* ub, void* z, int32_t use_init,
                 void* lambda, int32_t* status, int32_t* iterations, double* kkt_error, const nempc_solver_opts* opts,
                 int32_t* outer_iterations, void* stream);
+/* Statistics of the last nempc_solve on this handle.  used_graph: 1 when the whole iteration loop ran on the device as ONE CUDA graph
+ * (two nested WHILE nodes driven by cudaGraphSetConditional: no host synchronisation between the kernels of an iteration; environment
+ * NEMPC_SOLVE_GRAPH = 0 never / 1 from the second solve with unchanged batch size, options and workspace (default) / 2 from the first),
+ * 0 when the host issued the kernels.  Both produce the same bits.  unaccepted_steps: steps over all problems that were taken although no
+ * line-search trial within max_backtrack halvings passed the Armijo test (the last halved step is applied; a large count with status 1
+ * says the tolerance is below what the network's float32 arithmetic resolves). */
+int nempc_solve_stats(const nempc_handle* h, int32_t* used_graph, int64_t* unaccepted_steps);
 
 /* ---- introspection -------------------------------------------------------------------------------------- */
 int64_t nempc_launch_count(const nempc_handle* h);   /* kernels launched by this handle so far */

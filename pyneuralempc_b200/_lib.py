@@ -14,12 +14,12 @@ F32, F64 = 0, 1
 INTEGRATORS = {"discrete": 0, "unity": 1, "rk4": 2}
 ACTIVATIONS = {"tanh": 0, "sigmoid": 1, "softplus": 2, "relu": 3}
 KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
-ABI_VERSION = 3                             # NEMPC_ABI_VERSION of include/nempc.h this binding was written against
+ABI_VERSION = 4                             # NEMPC_ABI_VERSION of include/nempc.h this binding was written against
 
 EXPORTS = ("nempc_version", "nempc_last_error", "nempc_create", "nempc_destroy", "nempc_set_weights",
            "nempc_set_objective", "nempc_set_exogenous", "nempc_structure_counts", "nempc_structure_fill", "nempc_dims", "nempc_structure",
            "nempc_eval", "nempc_eval_host", "nempc_eval_blocks", "nempc_model_eval", "nempc_launch_count",
-           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve",
+           "nempc_kernel_name", "nempc_flops_per_step", "nempc_measure_fma_peak", "nempc_objective_eval", "nempc_solver_defaults", "nempc_solve", "nempc_solve_stats",
            "nempc_abi_info", "nempc_source_hash", "nempc_rolling_gather", "nempc_rolling_assemble",
            "nempc_quadform_eval", "nempc_hessian_merge")
 
@@ -93,6 +93,7 @@ def load():
     lib.nempc_objective_eval.argtypes = [i32, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.nempc_solver_defaults.argtypes = [ctypes.POINTER(SolverOpts)]
     lib.nempc_solve.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, ctypes.POINTER(SolverOpts), ctypes.POINTER(i32), vp]
+    lib.nempc_solve_stats.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64)]
     lib.nempc_rolling_gather.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.nempc_rolling_assemble.argtypes = [i32, i64, i32, i32, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl,
                                            vp, vp, vp, vp]

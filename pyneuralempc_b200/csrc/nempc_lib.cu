@@ -65,7 +65,7 @@ nempc_fast_kernel(const __grid_constant__ FastWeights<X, U, H1, H2, NCHUNK> w, c
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps;
          step += (long long)gridDim.x * blockDim.x) {
         if (ar.gate && ar.gate[step / L.H] != ar.gate_value) continue;          // batched solver: problems that are done are not re-evaluated
-        fast_step<X, U, H1, H2, NCHUNK, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+        fast_step<X, U, H1, H2, NCHUNK, MODE, TIO>(w, st, L, ar, step, scr, NEMPC_FAST_THREADS);   // compile-time scratch stride (the launch uses exactly this block size): LDS / STS with immediate offsets, 2.8 % fewer instructions
     }
 }
 
@@ -233,10 +233,12 @@ nempc_ipm_kkt_staged_kernel(const NlpLayout L, const SolverWs w, const SolverOpt
 }
 
 // iterate update, one thread per (problem, variable): same arithmetic as ipm_update_problem, coalesced
-__global__ void nempc_ipm_update_flat_kernel(const NlpLayout L, const SolverWs w, long long B) {
+// `counts` (device-side iteration loop, see nempc_solve): counts[0] == 0 means every problem converged or failed in this iteration's KKT
+// kernel -- the host loop leaves BEFORE the update, the captured loop runs the update kernels as no-ops
+__global__ void nempc_ipm_update_flat_kernel(const NlpLayout L, const SolverWs w, long long B, const int* counts) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int n = L.n, m = L.m;
-    if (idx >= B * n) return;
+    if (idx >= B * n || (counts && counts[0] == 0)) return;
     const long long b = idx / n;
     const int i = (int)(idx - b * n);
     if (w.status[b] != NEMPC_ST_RUNNING) return;
@@ -248,9 +250,31 @@ __global__ void nempc_ipm_update_flat_kernel(const NlpLayout L, const SolverWs w
     if (nempc_finite(w.ub[i])) { const double d = w.ub[i] - zi; w.zU[idx] = fmin(fmax(w.zU[idx] + aD * w.dzU[idx], mu / (ks * d)), ks * mu / d); }
     if (i < m) { const long long j = b * m + i; w.lam[j] += a * (w.lamn[j] - w.lam[j]); }
 }
-__global__ void nempc_ipm_count_iter_kernel(const SolverWs w, long long B) {
+// stats[NEMPC_SV_LSX] counts the steps that were taken although no line-search trial passed the Armijo test (the step of the last halving
+// is applied as in the numpy statement; nempc_solve_stats reports how often that happened)
+__global__ void nempc_ipm_count_iter_kernel(const SolverWs w, long long B, const int* counts, int* stats) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B && w.status[b] == NEMPC_ST_RUNNING) w.iters[b] += 1;
+    if (counts && counts[0] == 0) return;
+    if (b < B && w.status[b] == NEMPC_ST_RUNNING) {
+        w.iters[b] += 1;
+        if (!w.accepted[b]) atomicAdd(stats + NEMPC_SV_LSX, 1);
+    }
+}
+// ---- device-side iteration loop: the conditions of the two host loops of nempc_solve, evaluated by one thread between the kernels of a
+// CUDA graph whose WHILE nodes they drive (cudaGraphSetConditional) ------------------------------------------------------------------------
+__global__ void nempc_ipm_ls_begin_kernel(cudaGraphConditionalHandle inner, int* stats, int max_backtrack) {
+    stats[NEMPC_SV_TRIAL] = 0;
+    cudaGraphSetConditional(inner, max_backtrack > 0 ? 1u : 0u);
+}
+__global__ void nempc_ipm_ls_cond_kernel(cudaGraphConditionalHandle inner, int* stats, int max_backtrack) {
+    const int t = ++stats[NEMPC_SV_TRIAL];
+    stats[NEMPC_SV_TRIALS_TOTAL] += 1;
+    cudaGraphSetConditional(inner, (t < max_backtrack && stats[0] > 0 && stats[1] > 0) ? 1u : 0u);
+}
+__global__ void nempc_ipm_outer_cond_kernel(cudaGraphConditionalHandle outer, int* stats, int max_iter) {
+    unsigned go = 0;
+    if (stats[0] > 0) { const int it = ++stats[NEMPC_SV_IT]; go = it < max_iter ? 1u : 0u; }      // stats[0] == 0: the host loop's `break`
+    cudaGraphSetConditional(outer, go);
 }
 
 // line search, ONE WARP PER PROBLEM: |c|_1 and the barrier terms (a logarithm per bounded variable) are computed on 32 lanes into
@@ -347,6 +371,10 @@ struct nempc_handle {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     // solver workspace
     void* sv_buf = nullptr; size_t sv_cap = 0; double *sv_lb = nullptr, *sv_ub = nullptr; int* sv_counts = nullptr; int* sv_counts_host = nullptr;
+    // nempc_solve's iteration loop as a CUDA graph with two nested WHILE nodes, replayed while (batch, options, workspace) stay the same
+    struct SolveKey { int64_t B; const void* buf; int32_t max_iter, max_backtrack; double od[11]; bool operator==(const SolveKey& o) const { return memcmp(this, &o, sizeof(SolveKey)) == 0; } };
+    SolveKey sk{}; int sk_seen = 0; cudaGraphExec_t sk_exec = nullptr; bool sk_disabled = false; long long sk_launches_kkt = 3, sk_launches_trial = 3;
+    int sv_last_graph = 0; long long sv_last_lsx = 0, sv_last_trials = 0;
     std::string err, kname;
 };
 
@@ -514,6 +542,7 @@ static void free_device(nempc_handle* h) {
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->hk_exec) cudaGraphExecDestroy(h->hk_exec);
+    if (h->sk_exec) cudaGraphExecDestroy(h->sk_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int i = 0; i < 3; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -747,9 +776,14 @@ static int upload_wide(nempc_handle* h) {
 }
 
 // kernel parameters (weights of the register-resident kernel, the sparse layout) are baked into a captured graph by value
+static void drop_solve_graph(nempc_handle* h) {
+    if (h->sk_exec) { cudaGraphExecDestroy(h->sk_exec); h->sk_exec = nullptr; }
+    h->sk_seen = 0;
+}
 static void drop_host_graph(nempc_handle* h) {
     if (h->hk_exec) { cudaGraphExecDestroy(h->hk_exec); h->hk_exec = nullptr; }
     h->hk_seen = 0;
+    drop_solve_graph(h);
 }
 
 extern "C" int nempc_set_weights(nempc_handle* h, int32_t layer, const double* W, const double* b) {
@@ -1425,26 +1459,30 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
         o.bound_push = opts->bound_push; o.eta = opts->eta; o.reg_init = opts->reg_init; o.reg_max = opts->reg_max;
     }
     // ---- workspace -------------------------------------------------------------------------------------------------------
+    // The iterate and x0 live in the handle's own workspace (copied in / out around the loop): every pointer the loop's kernels see is then
+    // a function of (workspace, B) alone, so the captured loop below can be replayed for any caller buffers.
     const size_t n = L.n, m = L.m, nj = (size_t)L.nnz_jac, nh = (size_t)L.nnz_hes, Hux = (size_t)L.H * L.u * L.x, Hu = (size_t)L.H * L.u;
-    const size_t per = 9 * n + 4 * m + nj + nh + Hux + Hu + 2 /*obj, objt*/ + 7 /*scalars*/ + 2 /*3 ints, padded*/;
+    const size_t per = 10 * n + 4 * m + nj + nh + Hux + Hu + L.x + 2 /*obj, objt*/ + 7 /*scalars*/ + 2 /*3 ints, padded*/;
     const size_t need = per * (size_t)B * sizeof(double);
     if (need > h->sv_cap) {
         CU(h, cudaStreamSynchronize(s));
+        drop_solve_graph(h);
         cudaFree(h->sv_buf); h->sv_buf = nullptr; h->sv_cap = 0;
         CU(h, cudaMalloc(&h->sv_buf, need));
         h->sv_cap = need;
     }
     if (!h->sv_lb) {
         CU(h, cudaMalloc(&h->sv_lb, n * sizeof(double))); CU(h, cudaMalloc(&h->sv_ub, n * sizeof(double)));
-        CU(h, cudaMalloc(&h->sv_counts, 2 * sizeof(int))); CU(h, cudaMallocHost(&h->sv_counts_host, 2 * sizeof(int)));
+        CU(h, cudaMalloc(&h->sv_counts, NEMPC_SV_COUNT * sizeof(int))); CU(h, cudaMallocHost(&h->sv_counts_host, NEMPC_SV_COUNT * sizeof(int)));
     }
     CU(h, cudaMemcpyAsync(h->sv_lb, lb, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->sv_ub, ub, n * sizeof(double), cudaMemcpyHostToDevice, s));
     double* p = (double*)h->sv_buf;
     auto take = [&](size_t cnt) { double* r = p; p += cnt * (size_t)B; return r; };
     SolverWs w{};
-    w.x0 = (const double*)x0; w.lb = h->sv_lb; w.ub = h->sv_ub;
-    w.z = (double*)z; w.lam = take(m); w.zL = take(n); w.zU = take(n);
+    double* x0w = take(L.x);
+    w.x0 = x0w; w.lb = h->sv_lb; w.ub = h->sv_ub;
+    w.z = take(n); w.lam = take(m); w.zL = take(n); w.zU = take(n);
     w.dz = take(n); w.lamn = take(m); w.dzL = take(n); w.dzU = take(n);
     w.grad = take(n); w.resid = take(m); w.jac = take(nj); w.hes = take(nh); w.obj = take(1);
     w.zt = take(n); w.residt = take(m); w.objt = take(1);
@@ -1452,6 +1490,8 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     w.mu = take(1); w.nu = take(1); w.alpha = take(1); w.alphaD = take(1); w.phi0 = take(1); w.dphi = take(1); w.err = take(1);
     int* ip = (int*)take(2);
     w.status = ip; w.iters = ip + B; w.accepted = ip + 2 * B;
+    CU(h, cudaMemcpyAsync(x0w, x0, (size_t)B * L.x * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (use_init) CU(h, cudaMemcpyAsync(w.z, z, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     const int threads = 128;
     const unsigned grid = (unsigned)((B + threads - 1) / threads);
     // KKT kernel instance: exact (x_dim, u_dim) instantiations for the common small systems, run-time dimensions otherwise;
@@ -1483,49 +1523,155 @@ extern "C" int nempc_solve(nempc_handle* h, int64_t B, const void* x0, const dou
     const char* force = getenv("NEMPC_KKT_STAGED");
     if (force && force[0] == '0') staged_smem = 0;
     if (staged_smem > 48 * 1024) CU(h, cudaFuncSetAttribute(kkt_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
+    int* const cnt = h->sv_counts;
+    // ---- the three segments of one outer iteration, issued on stream `cs` (directly, or while it is being captured) -----------------------
+    // A: evaluation at the iterate -> KKT step;  T: one line-search trial;  U: take the step
+    auto seg_kkt = [&](cudaStream_t cs) -> int {
+        h->gate = w.status; h->gate_value = NEMPC_ST_RUNNING;           // converged / failed problems are not re-evaluated
+        const int r = nempc_eval(h, B, w.z, w.x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)cs);
+        h->gate = nullptr;
+        if (r) return r;
+        CU(h, cudaMemsetAsync(cnt, 0, 2 * sizeof(int), cs));
+        if (staged_smem) kkt_staged<<<(unsigned)((B + staged_wpb - 1) / staged_wpb), 32 * staged_wpb, staged_smem, cs>>>(L, w, o, B, cnt);
+        else kkt_plain<<<grid, threads, 0, cs>>>(L, w, o, B, cnt);
+        CU(h, cudaGetLastError()); h->launches++;
+        return NEMPC_OK;
+    };
+    auto seg_trial = [&](cudaStream_t cs) -> int {
+        h->gate = w.accepted; h->gate_value = 0;               // only the problems whose step is not accepted yet need the trial point
+        const int r = nempc_eval(h, B, w.zt, w.x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)cs);
+        h->gate = nullptr;
+        if (r) return r;
+        CU(h, cudaMemsetAsync(cnt + 1, 0, sizeof(int), cs));
+        if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, cs>>>(L, w, o, B, cnt);
+        else nempc_ipm_linesearch_kernel<<<grid, threads, 0, cs>>>(L, w, o, B, cnt);
+        CU(h, cudaGetLastError()); h->launches++;
+        return NEMPC_OK;
+    };
+    auto seg_update = [&](cudaStream_t cs, const int* gate_counts) -> int {
+        const long long tot = (long long)B * L.n;
+        nempc_ipm_update_flat_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, cs>>>(L, w, B, gate_counts);
+        nempc_ipm_count_iter_kernel<<<grid, threads, 0, cs>>>(w, B, gate_counts, cnt);
+        CU(h, cudaGetLastError()); h->launches += 2;
+        return NEMPC_OK;
+    };
+    CU(h, cudaMemsetAsync(cnt, 0, NEMPC_SV_COUNT * sizeof(int), s));
     nempc_ipm_init_kernel<<<grid, threads, 0, s>>>(L, w, o, B, use_init);
     CU(h, cudaGetLastError()); h->launches++;
     int it = 0;
-    for (; it < o.max_iter; ++it) {
-        h->gate = w.status; h->gate_value = NEMPC_ST_RUNNING;           // converged / failed problems are not re-evaluated
-        rc = nempc_eval(h, B, w.z, x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)s);
-        h->gate = nullptr;
-        if (rc) return rc;
-        CU(h, cudaMemsetAsync(h->sv_counts, 0, 2 * sizeof(int), s));
-        if (staged_smem) kkt_staged<<<(unsigned)((B + staged_wpb - 1) / staged_wpb), 32 * staged_wpb, staged_smem, s>>>(L, w, o, B, h->sv_counts);
-        else kkt_plain<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
-        CU(h, cudaGetLastError()); h->launches++;
-        // After a KKT step every running problem needs at least one line-search trial, so the first trial is issued WITHOUT waiting
-        // for the counters (one host synchronisation per iteration instead of two); further trials only when some problem backtracks.
-        // When nothing is running any more the trial is a wasted residual evaluation, once per solve.
-        int trial = 0;
-        do {
-            if (o.max_backtrack > 0) {
-                h->gate = w.accepted; h->gate_value = 0;               // only the problems whose step is not accepted yet need the trial point
-                rc = nempc_eval(h, B, w.zt, x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
-                h->gate = nullptr;
-                if (rc) return rc;
-                CU(h, cudaMemsetAsync(h->sv_counts + 1, 0, sizeof(int), s));
-                if (ls_smem <= 48 * 1024) nempc_ipm_linesearch_warp_kernel<<<(unsigned)((B + 7) / 8), 256, ls_smem, s>>>(L, w, o, B, h->sv_counts);
-                else nempc_ipm_linesearch_kernel<<<grid, threads, 0, s>>>(L, w, o, B, h->sv_counts);
-                CU(h, cudaGetLastError()); h->launches++;
-            }
-            CU(h, cudaMemcpyAsync(h->sv_counts_host, h->sv_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // ---- device-side loop: both host loops below as WHILE nodes of ONE CUDA graph (no host synchronisation and no launch latency between
+    // the ~10 kernels of an iteration: what a single problem's solve time consists of).  NEMPC_SOLVE_GRAPH: 0 = never, 1 (default) = from
+    // the second solve with the same (batch, options, workspace) on, 2 = from the first (a warm-up evaluation sizes the kernels' scratch).
+    const char* gm = getenv("NEMPC_SOLVE_GRAPH");
+    const int graph_mode = gm ? atoi(gm) : 1;
+    nempc_handle::SolveKey key;
+    memset(&key, 0, sizeof key);
+    key.B = B; key.buf = h->sv_buf; key.max_iter = o.max_iter; key.max_backtrack = o.max_backtrack;
+    const double od[11] = {o.tol, o.mu_init, o.mu_min, o.kappa_eps, o.kappa_mu, o.theta_mu, o.tau_min, o.bound_push, o.eta, o.reg_init, o.reg_max};
+    memcpy(key.od, od, sizeof od);
+    if (!(key == h->sk)) { drop_solve_graph(h); h->sk = key; }
+    h->sk_seen++;
+    bool used_graph = false;
+    if (graph_mode > 0 && o.max_iter > 0 && !h->sk_disabled && !h->sk_exec && (graph_mode >= 2 || h->sk_seen >= 2)) {
+        if (h->sk_seen < 2) {                    // first solve with this key: one evaluation of each kind outside the capture (allocations)
+            rc = nempc_eval(h, B, w.z, w.x0, w.lam, nullptr, 1.0, w.resid, w.jac, w.hes, w.obj, w.grad, (void*)s);
+            if (!rc) rc = nempc_eval(h, B, w.z, w.x0, nullptr, nullptr, 1.0, w.residt, nullptr, nullptr, w.objt, nullptr, (void*)s);
+            if (rc) return rc;
             CU(h, cudaStreamSynchronize(s));
-        } while (++trial < o.max_backtrack && h->sv_counts_host[0] > 0 && h->sv_counts_host[1] > 0);
-        if (h->sv_counts_host[0] == 0) break;                      // every problem converged or failed
-        {
-            const long long tot = (long long)B * L.n;
-            nempc_ipm_update_flat_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(L, w, B);
-            nempc_ipm_count_iter_kernel<<<grid, threads, 0, s>>>(w, B);
         }
-        CU(h, cudaGetLastError()); h->launches += 2;
+        const long long l0 = h->launches;
+        cudaStream_t cs = h->stream;
+        cudaGraph_t g = nullptr, tmp = nullptr;
+        cudaGraphConditionalHandle hO = 0, hI = 0;
+        bool ok = cudaGraphCreate(&g, 0) == cudaSuccess;
+        ok = ok && cudaGraphConditionalHandleCreate(&hO, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+        ok = ok && cudaGraphConditionalHandleCreate(&hI, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+        cudaGraphNodeParams pO = {cudaGraphNodeTypeConditional};
+        pO.type = cudaGraphNodeTypeConditional; pO.conditional.handle = hO; pO.conditional.type = cudaGraphCondTypeWhile; pO.conditional.size = 1;
+        cudaGraphNode_t nO = nullptr, nI = nullptr;
+        ok = ok && cudaGraphAddNode(&nO, g, nullptr, 0, &pO) == cudaSuccess;
+        cudaGraph_t bodyO = ok ? pO.conditional.phGraph_out[0] : nullptr, bodyI = nullptr;
+        bool capturing = false;
+        if (ok) { ok = cudaStreamBeginCaptureToGraph(cs, bodyO, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess; capturing = ok; }
+        if (ok) ok = seg_kkt(cs) == NEMPC_OK;
+        h->sk_launches_kkt = h->launches - l0;
+        if (ok) { nempc_ipm_ls_begin_kernel<<<1, 1, 0, cs>>>(hI, cnt, o.max_backtrack); ok = cudaGetLastError() == cudaSuccess; }
+        if (ok) {                                // the inner WHILE node goes between the segments: after what was captured so far, before the rest
+            cudaStreamCaptureStatus st; cudaGraph_t cg = nullptr; const cudaGraphNode_t* deps = nullptr; size_t nd = 0;
+            ok = cudaStreamGetCaptureInfo_v2(cs, &st, nullptr, &cg, &deps, &nd) == cudaSuccess && st == cudaStreamCaptureStatusActive;
+            cudaGraphNodeParams pI = {cudaGraphNodeTypeConditional};
+            pI.type = cudaGraphNodeTypeConditional; pI.conditional.handle = hI; pI.conditional.type = cudaGraphCondTypeWhile; pI.conditional.size = 1;
+            ok = ok && cudaGraphAddNode(&nI, cg, deps, nd, &pI) == cudaSuccess;
+            if (ok) bodyI = pI.conditional.phGraph_out[0];
+            ok = ok && cudaStreamUpdateCaptureDependencies(cs, &nI, 1, cudaStreamSetCaptureDependencies) == cudaSuccess;
+        }
+        if (ok) ok = seg_update(cs, cnt) == NEMPC_OK;
+        if (ok) { nempc_ipm_outer_cond_kernel<<<1, 1, 0, cs>>>(hO, cnt, o.max_iter); ok = cudaGetLastError() == cudaSuccess; }
+        if (capturing) { const bool ended = cudaStreamEndCapture(cs, &tmp) == cudaSuccess; ok = ok && ended; capturing = false; }
+        if (ok) { ok = cudaStreamBeginCaptureToGraph(cs, bodyI, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess; capturing = ok; }
+        const long long l1 = h->launches;
+        if (ok) ok = seg_trial(cs) == NEMPC_OK;
+        h->sk_launches_trial = h->launches - l1;
+        if (ok) { nempc_ipm_ls_cond_kernel<<<1, 1, 0, cs>>>(hI, cnt, o.max_backtrack); ok = cudaGetLastError() == cudaSuccess; }
+        if (capturing) { const bool ended = cudaStreamEndCapture(cs, &tmp) == cudaSuccess; ok = ok && ended; }
+        h->gate = nullptr;
+        h->launches = l0;
+        if (ok) ok = cudaGraphInstantiate(&h->sk_exec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (!ok) {                               // the captured loop is an optimisation: keep the host loop for good on this handle
+            cudaGetLastError();
+            if (h->sk_exec) { cudaGraphExecDestroy(h->sk_exec); h->sk_exec = nullptr; }
+            h->sk_disabled = true;
+        }
+    }
+    if (graph_mode > 0 && h->sk_exec && !h->sk_disabled) {
+        CU(h, cudaGraphLaunch(h->sk_exec, s));
+        used_graph = true;
+    } else {
+        for (; it < o.max_iter; ++it) {
+            rc = seg_kkt(s);
+            if (rc) return rc;
+            // After a KKT step every running problem needs at least one line-search trial, so the first trial is issued WITHOUT waiting
+            // for the counters (one host synchronisation per iteration instead of two); further trials only when some problem backtracks.
+            // When nothing is running any more the trial is a wasted residual evaluation, once per solve.
+            int trial = 0;
+            do {
+                if (o.max_backtrack > 0) {
+                    rc = seg_trial(s);
+                    if (rc) return rc;
+                }
+                CU(h, cudaMemcpyAsync(h->sv_counts_host, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+                CU(h, cudaStreamSynchronize(s));
+            } while (++trial < o.max_backtrack && h->sv_counts_host[0] > 0 && h->sv_counts_host[1] > 0);
+            if (h->sv_counts_host[0] == 0) break;                      // every problem converged or failed
+            rc = seg_update(s, nullptr);
+            if (rc) return rc;
+        }
     }
     nempc_ipm_finish_kernel<<<grid, threads, 0, s>>>(w, B, status, iterations, kkt_error);
     CU(h, cudaGetLastError()); h->launches++;
+    CU(h, cudaMemcpyAsync(z, w.z, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (lambda) CU(h, cudaMemcpyAsync(lambda, w.lam, (size_t)B * m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(h->sv_counts_host, cnt, NEMPC_SV_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
+    if (used_graph) {
+        it = h->sv_counts_host[NEMPC_SV_IT];
+        // kernels the graph ran: per outer iteration segment A + ls_begin + the two update kernels + outer_cond, per trial segment T + ls_cond
+        const long long outer_runs = std::min<long long>(it + 1, o.max_iter);
+        h->launches += outer_runs * (h->sk_launches_kkt + 4) + (long long)h->sv_counts_host[NEMPC_SV_TRIALS_TOTAL] * (h->sk_launches_trial + 1);
+    }
+    h->sv_last_graph = used_graph ? 1 : 0;
+    h->sv_last_lsx = h->sv_counts_host[NEMPC_SV_LSX];
+    h->sv_last_trials = used_graph ? h->sv_counts_host[NEMPC_SV_TRIALS_TOTAL] : -1;
     if (outer_iterations) *outer_iterations = it;
+    return NEMPC_OK;
+}
+
+/* statistics of the last nempc_solve on this handle */
+extern "C" int nempc_solve_stats(const nempc_handle* h, int32_t* used_graph, int64_t* unaccepted_steps) {
+    if (!h) return NEMPC_EINVAL;
+    if (used_graph) *used_graph = h->sv_last_graph;
+    if (unaccepted_steps) *unaccepted_steps = h->sv_last_lsx;
     return NEMPC_OK;
 }
 

@@ -19,6 +19,9 @@
 #define NEMPC_SOLVER_UM 16
 
 enum : int { NEMPC_ST_RUNNING = -1, NEMPC_ST_CONVERGED = 0, NEMPC_ST_MAXITER = 1, NEMPC_ST_FAILED = 2 };
+// slots of the solver's device counters (nempc_handle::sv_counts): [0] problems still running after the KKT kernel, [1] problems whose line-search
+// trial was not accepted, then the state of the device-side iteration loop and the statistics nempc_solve_stats reports
+enum : int { NEMPC_SV_RUNNING = 0, NEMPC_SV_NOTACC = 1, NEMPC_SV_TRIAL = 2, NEMPC_SV_IT = 3, NEMPC_SV_LSX = 4, NEMPC_SV_TRIALS_TOTAL = 5, NEMPC_SV_COUNT = 8 };
 
 struct SolverOpts {
     int max_iter, max_backtrack;

@@ -300,7 +300,9 @@ class NlpEvaluator:
         x0: (B, x_dim) initial states (numpy or CUDA tensor); lb / ub: length-n bound vectors in ``DomainConstraint``
         order (``get_lower_bounds(H)``), +-inf allowed; z_init: optional (B, n) warm start.  options: fields of
         ``nempc_solver_opts`` (max_iter, tol, mu_init, ...).  Returns a dict of CUDA tensors ``z`` (B,n), ``lam`` (B,m),
-        ``status`` (0 converged / 1 iteration limit / 2 failed), ``iterations``, ``kkt_error`` and ``outer_iterations``."""
+        ``status`` (0 converged / 1 iteration limit / 2 failed), ``iterations``, ``kkt_error``, ``outer_iterations``, and the
+        ``nempc_solve_stats`` of the call: ``used_graph`` (the iteration loop ran on the device as one CUDA graph) and
+        ``unaccepted_steps`` (steps taken although the line search ran out of halvings)."""
         torch = self._torch
         if self.io_dtype != "float64":
             raise ValueError("solve() needs io_dtype='float64'")
@@ -332,7 +334,10 @@ class NlpEvaluator:
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         self._check(self.lib.nempc_solve(self._h, B, _vp(x0), p(lb), p(ub), _vp(z), int(z_init is not None), _vp(lam), _vp(status),
                                          _vp(iters), _vp(kkt), ctypes.byref(opts), ctypes.byref(outer), ctypes.c_void_p(s)), "nempc_solve")
-        return dict(z=z, lam=lam, status=status, iterations=iters, kkt_error=kkt, outer_iterations=outer.value)
+        used_graph, unacc = ctypes.c_int32(), ctypes.c_int64()
+        self._check(self.lib.nempc_solve_stats(self._h, ctypes.byref(used_graph), ctypes.byref(unacc)), "nempc_solve_stats")
+        return dict(z=z, lam=lam, status=status, iterations=iters, kkt_error=kkt, outer_iterations=outer.value,
+                    used_graph=bool(used_graph.value), unaccepted_steps=int(unacc.value))
 
     def host_io_bytes(self, B, want=("resid", "jac", "hes", "obj", "grad"), with_lambda=True):
         s = 8 if self.io_dtype == "float64" else 4

@@ -165,3 +165,58 @@ def test_solver_on_the_wide_kernel():
     assert np.abs(r32["obj"] - r64["obj"]).max() < 1e-4 * max(1.0, np.abs(r64["obj"]).max())
     assert np.abs(z32 - z64).max() < 1e-2
     assert (z32 >= lb - 1e-9).all() and (z32 <= ub + 1e-9).all()
+
+
+@pytest.mark.parametrize("kind,dims,x,u,H,DT,xb", [CASES[0], CASES[1], CASES[3]])
+def test_device_side_loop_gives_the_bits_of_the_host_loop(kind, dims, x, u, H, DT, xb, lv_weights, monkeypatch):
+    """The iteration loop as ONE CUDA graph (two nested WHILE nodes, conditions set by kernels: no host synchronisation inside a solve)
+    must reproduce the host-issued loop bit for bit: same iterates, multipliers, iteration counts, outer iterations -- on the first solve
+    (NEMPC_SOLVE_GRAPH=2), on a replay with other caller buffers and another x0, with a warm start, and when the iteration limit cuts the
+    loop short."""
+    mlp, obj, lb, ub, X0 = _setup(kind, dims, x, u, H, DT, xb, lv_weights, B=7)
+    X1 = X0[::-1].copy() * 0.9
+    ev = _ev(mlp, kind, H, DT, obj)
+
+    def run(mode, X, **kw):
+        monkeypatch.setenv("NEMPC_SOLVE_GRAPH", str(mode))
+        o = ev.solve(X, lb, ub, **kw)
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in o.items()}
+
+    def same(a, b):
+        for k in ("z", "lam", "status", "iterations", "kkt_error"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        assert a["outer_iterations"] == b["outer_iterations"] and a["unaccepted_steps"] == b["unaccepted_steps"]
+
+    h0, h1 = run(0, X0), run(0, X1)
+    assert not h0["used_graph"] and (h0["status"] == 0).all()
+    g0 = run(2, X0)                                    # captured on this call
+    assert g0["used_graph"]
+    same(h0, g0)
+    g1 = run(1, X1)                                    # replay: other x0, other (freshly allocated) output tensors
+    assert g1["used_graph"]
+    same(h1, g1)
+    same(run(0, X1, z_init=h0["z"]), run(1, X1, z_init=h0["z"]))          # warm start
+    hc, gc = run(0, X0, max_iter=3), run(2, X0, max_iter=3)               # other options: new graph; the limit ends the loop
+    assert gc["used_graph"] and gc["outer_iterations"] == 3 and (gc["status"] == 1).any()
+    same(hc, gc)
+    hb, gb = run(0, X0, max_backtrack=0), run(2, X0, max_backtrack=0)     # no line search: the inner loop never runs
+    same(hb, gb)
+    # default mode: host loop on the first solve with a key, graph from the second on
+    ev2 = _ev(mlp, kind, H, DT, obj)
+    monkeypatch.delenv("NEMPC_SOLVE_GRAPH")
+    a = ev2.solve(X0, lb, ub); b = ev2.solve(X0, lb, ub)
+    assert not a["used_graph"] and b["used_graph"]
+    np.testing.assert_array_equal(a["z"].cpu().numpy(), b["z"].cpu().numpy())
+    ev2.set_objective(obj.lin, obj.quad * 2.0, obj.ref)                   # new cost: the captured loop is dropped, not replayed
+    c = ev2.solve(X0, lb, ub)
+    assert not c["used_graph"] and np.abs(c["z"].cpu().numpy() - b["z"].cpu().numpy()).max() > 1e-6
+
+
+def test_unaccepted_steps_are_counted(lv_weights):
+    """a float32 network under a tolerance its arithmetic cannot resolve: the line search runs out of halvings; the solver applies the last
+    halved step (as its numpy statement does) and REPORTS how often that happened instead of doing so silently"""
+    mlp, obj, lb, ub, X0 = _setup("unity", "lv", 2, 1, 10, None, 0, lv_weights, B=64)
+    ok = _ev(mlp, "unity", 10, None, obj, "float64").solve(X0, lb, ub, tol=1e-6)
+    assert ok["unaccepted_steps"] == 0 and (ok["status"].cpu().numpy() == 0).all()
+    hard = _ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=1e-13, max_iter=40, max_backtrack=4)
+    assert hard["unaccepted_steps"] > 0 and (hard["status"].cpu().numpy() == 1).any()
