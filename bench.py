@@ -420,15 +420,20 @@ def named_workload(name, world, rank, local, peaks, with_cpu, steps=3, e2e_cap=8
     return res
 
 
-def c2_float64(world, rank, local, steps=10):
-    """C2 with FLOAT64 network arithmetic (the reference assembles in float64, optimizer/ipopt.py:66-86; this is the 1e-10 parity mode):
-    nempc_fast64_kernel against the measured FP64 FMA peak."""
+def c2_float64(world, rank, local, steps=10, name="C2"):
+    """C2 (or, name="C3", the cart-pole class at its named batch split over the ranks) with FLOAT64 network arithmetic (the reference assembles
+    in float64, optimizer/ipopt.py:66-86; this is the 1e-10 parity mode): nempc_fast64_kernel / the DMMA path against the measured FP64 FMA
+    peak (B200's FP64 tensor cores have the rate of its FP64 FMA pipe, so one denominator serves both)."""
     import torch
     import torch.distributed as dist
     from pyneuralempc_b200 import NlpEvaluator
     from pyneuralempc_b200.engine import measure_fma_peak
-    wl = WORKLOADS["C2"]
+    from pyneuralempc_b200.sharding import shard_range
+    wl = WORKLOADS[name]
     B = wl["B"]
+    if name != "C2":
+        lo, hi = shard_range(B, rank, world)
+        B = hi - lo
     mlp, obj, Z, X0, lam = make_problem(wl, B, seed=99 + rank)
     ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"], compute_dtype="float64", io_dtype="float64", device=local)
     ev.set_objective(obj.lin, obj.quad, obj.ref)
@@ -453,9 +458,11 @@ def c2_float64(world, rank, local, steps=10):
     k_ms = float(tm.item())
     peak = measure_fma_peak(local, "float64", 200)
     flops = ev.flops_per_step * B * wl["H"]
-    res = {"workload": "C2 with float64 network arithmetic: " + wl["desc"], "metric": METRIC, "unit": UNIT, "n_gpus": world, "scaling": "weak",
-           "value": world * B * wl["H"] / (k_ms * 1e-3), "ms_per_eval": k_ms, "steps": steps, "dtype": "f64",
-           "roofline": {"bound": "fp64-fma", "kernel": ev.kernel_name, "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+    tot = world * B if name == "C2" else wl["B"]
+    res = {"workload": name + " with float64 network arithmetic: " + wl["desc"], "metric": METRIC, "unit": UNIT, "n_gpus": world,
+           "scaling": "weak" if name == "C2" else "strong",
+           "value": tot * wl["H"] / (k_ms * 1e-3), "ms_per_eval": k_ms, "steps": steps, "dtype": "f64",
+           "roofline": {"bound": "fp64-fma" if name == "C2" else "fp64 tensor (DMMA) = fp64-fma rate", "kernel": ev.kernel_name, "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                         "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "peak_source": "measured live: register-resident DFMA loop (nempc_measure_fma_peak)",
                         "kernel_ms": k_ms, "flops_per_horizon_step": ev.flops_per_step, "traffic": None}}
     ev.close()
@@ -706,6 +713,10 @@ def gpu_run(args):
             side["C2_f64"] = c2_float64(world, rank, local)
         except Exception as exc:                      # noqa: BLE001
             side["C2_f64"] = {"error": repr(exc)[:300]}
+        try:
+            side["C3_f64"] = c2_float64(world, rank, local, steps=2, name="C3")
+        except Exception as exc:                      # noqa: BLE001
+            side["C3_f64"] = {"error": repr(exc)[:300]}
         if rank == 0:
             try:
                 side["C1_callback"] = callback_latency(local)

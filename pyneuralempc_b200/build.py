@@ -8,10 +8,10 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.environ.get("NEMPC_LIB_PATH") or os.path.join(CSRC, "libnempc.so")   # env override: kernel-variant experiments
-SOURCES = ["nempc_lib.cu", "nempc_tc_tu.cu", "nempc_wide_tu.cu", "nempc_wide_rt_tu.cu", "nempc_fast64_tu.cu"]
+SOURCES = ["nempc_lib.cu", "nempc_tc_tu.cu", "nempc_wide_tu.cu", "nempc_wide_rt_tu.cu", "nempc_fast64_tu.cu", "nempc_dmma_tu.cu"]
 # per-source extra flags (see the header of nempc_fast64_tu.cu)
 SOURCE_FLAGS = {"nempc_fast64_tu.cu": ["--split-compile=0"]}
-HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_fast64.cuh", "nempc_small.cuh", "nempc_tc.cuh", "nempc_wide.cuh", "nempc_wide_launch.cuh", "nempc_rolling.cuh", "nempc_tc_ptx.cuh", "nempc_solver.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
+HEADERS = ["nempc_generic.cuh", "nempc_fast.cuh", "nempc_fast64.cuh", "nempc_small.cuh", "nempc_tc.cuh", "nempc_wide.cuh", "nempc_wide_launch.cuh", "nempc_dmma.cuh", "nempc_rolling.cuh", "nempc_tc_ptx.cuh", "nempc_solver.cuh", "nempc_layout.h", os.path.join("..", "..", "include", "nempc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,0 +1,359 @@
+// Float64 tensor-core path for wide tanh networks (hidden layers all HW = 128 or 64 wide): the reference assembles in float64
+// (optimizer/ipopt.py:66-86) and a Keras model built with float64 layers evaluates in it; this is the 1e-10 mode of the C3 class
+// (cart-pole 5 -> 128 x 3 -> 4) at tensor-core speed.  B200 keeps full-rate FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64: the
+// tcgen05 family has no f64 kind), so the hidden-to-hidden layers run as warp-level DMMA GEMMs; everything else is DFMA.
+//
+// Formulation: FORWARD second order, as nempc_tc.cuh -- per horizon step and integrator stage the network is evaluated on a stack of
+// RPS = 1 + d + d(d+1)/2 rows (activations, first-order tangents V[., c], second-order tangents Q[., (c,c2)]); every row goes through the
+// same weights, so a hidden-to-hidden layer is ONE GEMM [MT rows x HW] x [HW x HW] for SPT = MT / RPS steps at once:
+//   * the row tile A (MT x HW doubles, 132 KB at MT = HW = 128) stays in shared memory for the life of a tile and is updated in place;
+//   * the weights of the layer stream from L2 through a three-slot cp.async ring of 16-row chunks (they are 128 KB per layer: tile and
+//     weights do not fit together), one __syncthreads per chunk;
+//   * 8 warps, warp tile 32 x 64 at HW = 128: 32 m8n8k4 accumulators (128 registers) per lane, 12 shared-memory fragment loads per 32 DMMAs;
+//   * epilogue per (step, neuron): bias, tanh, s', s'', V = s' dV, Q = s' dQ + s'' dV_c dV_c2, written back as the next operand tile;
+//   * first layer (K = d) and output layer (N = x) are thin: DFMA, the output contraction with warp shuffles.
+// The kernel is a pure NETWORK kernel: zin (N, d) -> k = f(zin) (N, x), local Jacobian J (N, x, d), per-output local Hessians M (N, x, NS)
+// (lower triangle e = c(c+1)/2 + c2).  The integrator's stage algebra (dk = J R, h_s = R^T M R + a_s J h_{s-1}, R_{s+1} = I + a_{s+1} E dk;
+// reference integrator/rk4.py:113-285, discret.py:32-81, unity.py:34-81) and the scatter into the block-banded value arrays run in a second,
+// thread-per-step kernel between the stages (nempc_dmma_stage_kernel); the few hundred bytes per step that travel between the two kernels
+// through L2 are noise next to 5.6 MFLOP per step.
+#pragma once
+#include "nempc_generic.cuh"
+
+struct DmmaNet {
+    int d, x, nhid;                                   // inputs, outputs, hidden layers (all HW wide)
+    const double* W[NEMPC_MAXL];                      // [in][out] (Keras kernel layout), W[0] (d x HW), W[1..nhid-1] (HW x HW), W[nhid] (HW x x)
+    const double* b[NEMPC_MAXL];
+};
+
+template <int HW_> struct DmmaCfg {
+    static constexpr int HW = HW_, MT = 128, THREADS = 256;
+    static constexpr int LDA = HW + 4;                // row stride of the tile (doubles): fragment loads of 8 rows x 4 columns fall on 32 distinct banks
+    static constexpr int LDW = HW + 8;                // row stride of a weight chunk: 4 rows x 8 columns likewise
+    static constexpr int KC = 16, NSLOT = 3;          // ring: chunks of 16 weight rows
+    static constexpr int WGN = HW / 64, WGM = 8 / WGN;          // warp grid (8 warps): warp tile (MT / WGM) x 64
+    static constexpr int WM = MT / WGM, WN = 64, MI = WM / 8, NI = WN / 8;
+    static constexpr int A_DOUBLES = MT * LDA, RING_DOUBLES = NSLOT * KC * LDW;
+    static constexpr int Z_DOUBLES = MT * 16;         // inputs of the tile's steps (d <= 16)
+    static constexpr size_t SMEM = (size_t)(A_DOUBLES + RING_DOUBLES + Z_DOUBLES) * sizeof(double);
+    static_assert(HW == 128 || HW == 64, "hidden width 128 or 64");
+    static_assert(SMEM <= 232448, "shared-memory map exceeds 227 KB");
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void dmma_cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void dmma_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void dmma_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows: 1 (mode 0), 1 + d (mode 1), 1 + d + d(d+1)/2 (mode 2) per step, kind-major inside the tile: row = kind * spt + step
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long long N, int mode, double* __restrict__ fo, double* __restrict__ Jo,
+                      double* __restrict__ Mo) {
+    constexpr int HW = C::HW, MT = C::MT, LDA = C::LDA, LDW = C::LDW, KC = C::KC, NSLOT = C::NSLOT, MI = C::MI, NI = C::NI;
+    extern __shared__ __align__(16) unsigned char dmma_smem[];
+    double* A = reinterpret_cast<double*>(dmma_smem);
+    double* ring = A + C::A_DOUBLES;
+    double* zs = ring + C::RING_DOUBLES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = net.d, x = net.x, ns = d * (d + 1) / 2;
+    const int rps = 1 + (mode >= 1 ? d : 0) + (mode >= 2 ? ns : 0);
+    const int spt = MT / rps, rows = spt * rps;
+    const int wm0 = (warp / C::WGN) * C::WM, wn0 = (warp % C::WGN) * C::WN;
+    const int g = lane >> 2, q = lane & 3;
+    for (int i = tid; i < C::A_DOUBLES; i += C::THREADS) A[i] = 0.0;                 // padding rows stay zero for the life of the CTA
+    const long long ntiles = (N + spt - 1) / spt;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * spt;
+        const int nst = (int)((N - s0) < spt ? (N - s0) : spt);
+        __syncthreads();                                                             // previous tile's output contraction is done with A
+        for (int i = tid; i < spt * d; i += C::THREADS) zs[i] = (i < nst * d) ? zin[s0 * d + i] : 0.0;
+        __syncthreads();
+        // ---- first layer (K = d): DFMA ------------------------------------------------------------------------------------------
+        for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
+            const int sl = idx / HW, j = idx - sl * HW;
+            double a = net.b[0][j];
+            for (int c = 0; c < d; ++c) a = fma(net.W[0][c * HW + j], zs[sl * d + c], a);
+            const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
+            A[sl * LDA + j] = h;
+            if (mode >= 1) {
+                for (int c = 0; c < d; ++c) {
+                    const double wc = net.W[0][c * HW + j];
+                    A[((1 + c) * spt + sl) * LDA + j] = sp * wc;
+                    if (mode >= 2)
+                        for (int c2 = 0; c2 <= c; ++c2) A[((1 + d + c * (c + 1) / 2 + c2) * spt + sl) * LDA + j] = spp * wc * net.W[0][c2 * HW + j];
+                }
+            }
+        }
+        // ---- hidden-to-hidden layers: DMMA GEMM + epilogue --------------------------------------------------------------------------
+        for (int l = 1; l < net.nhid; ++l) {
+            const double* __restrict__ Wl = net.W[l];
+            double acc[MI][NI][2];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+            auto issue_chunk = [&](int kc) {                                         // weight rows [kc KC, +KC) -> ring slot kc % NSLOT
+                double* dst = ring + (kc % NSLOT) * (KC * LDW);
+                constexpr int V = HW / 2;                                            // 16-byte pieces per row
+                for (int i = tid; i < KC * V; i += C::THREADS) {
+                    const int r = i / V, v = i - r * V;
+                    dmma_cp_async16(dst + r * LDW + 2 * v, Wl + (size_t)(kc * KC + r) * HW + 2 * v);
+                }
+                dmma_cp_commit();
+            };
+            constexpr int NCH = HW / KC;
+            issue_chunk(0);
+            issue_chunk(1);
+            for (int kc = 0; kc < NCH; ++kc) {
+                if (kc + 1 < NCH) dmma_cp_wait<1>(); else dmma_cp_wait<0>();
+                __syncthreads();                            // chunk kc has landed for every thread; everyone is done with chunk kc - 1 (and, for kc = 0, with writing A)
+                if (kc + 2 < NCH) issue_chunk(kc + 2);      // its slot held chunk kc - 1
+                const double* wch = ring + (kc % NSLOT) * (KC * LDW);
+#pragma unroll
+                for (int kk = 0; kk < KC / 4; ++kk) {
+                    double af[MI], bf[NI];
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) af[mi] = A[(wm0 + mi * 8 + g) * LDA + kc * KC + kk * 4 + q];
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) bf[ni] = wch[(kk * 4 + q) * LDW + wn0 + ni * 8 + g];
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                }
+            }
+            __syncthreads();                                // every warp has read its A fragments: the tile can be overwritten
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni)
+                    *reinterpret_cast<double2*>(&A[(wm0 + mi * 8 + g) * LDA + wn0 + ni * 8 + 2 * q]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            __syncthreads();
+            const double* __restrict__ bl = net.b[l];
+            for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
+                const int sl = idx / HW, j = idx - sl * HW;
+                const double a = A[sl * LDA + j] + bl[j];
+                const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
+                A[sl * LDA + j] = h;
+                if (mode >= 1) {
+                    double tg[16];
+                    for (int c = 0; c < d; ++c) {
+                        double* pa = &A[((1 + c) * spt + sl) * LDA + j];
+                        tg[c] = *pa;
+                        *pa = sp * tg[c];
+                    }
+                    if (mode >= 2)
+                        for (int c = 0; c < d; ++c)
+                            for (int c2 = 0; c2 <= c; ++c2) {
+                                double* pa = &A[((1 + d + c * (c + 1) / 2 + c2) * spt + sl) * LDA + j];
+                                *pa = fma(sp, *pa, spp * tg[c] * tg[c2]);
+                            }
+                }
+            }
+            // (the __syncthreads at the top of the next layer's first chunk / before the output contraction orders these writes)
+        }
+        __syncthreads();
+        // ---- output layer (N = x): each warp contracts its rows with W_out, lanes over neurons, shuffle reduction ---------------------
+        {
+            constexpr int JP = HW / 32;
+            const double* __restrict__ Wo = net.W[net.nhid];
+            for (int r = warp; r < rows; r += 8) {
+                const int kind = r / spt, sl = r - kind * spt;
+                if (sl >= nst) continue;                                            // warp-uniform
+                double av[JP];
+#pragma unroll
+                for (int i = 0; i < JP; ++i) av[i] = A[r * LDA + lane + 32 * i];
+                for (int p = 0; p < x; ++p) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < JP; ++i) sacc = fma(av[i], Wo[(size_t)(lane + 32 * i) * x + p], sacc);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (lane == 0) {
+                        const long long st = s0 + sl;
+                        if (kind == 0) fo[st * x + p] = sacc + net.b[net.nhid][p];
+                        else if (kind <= d) Jo[(st * x + p) * d + (kind - 1)] = sacc;
+                        else Mo[(st * x + p) * ns + (kind - 1 - d)] = sacc;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- stage algebra + scatter: one thread per horizon step -----------------------------------------------------------------------------
+// per-step state that lives across the stages (doubles): kprev X | kacc X | Rt X*D | dkacc X*D | hprev 2 x X*NS (stage s writes half s & 1 and
+// reads h_{s-1} of every output from the other half) | hacc X*NS
+template <int X, int U> struct DmmaState {
+    static constexpr int D = X + U, NS = D * (D + 1) / 2;
+    static constexpr int KPREV = 0, KACC = X, RT = 2 * X, DKACC = RT + X * D, HPREV = DKACC + X * D, HACC = HPREV + 2 * X * NS, COUNT = HACC + X * NS;
+};
+
+// stage < 0: initialise (zin = z of the step); otherwise consume the network outputs of stage `stage`
+template <int X, int U>
+__global__ void __launch_bounds__(128)
+nempc_dmma_stage_kernel(const StageTable<double> st, const NlpLayout L, const EvalArgs<double> ar, long long base, long long N, int mode, int stage,
+                        double* __restrict__ zin, const double* __restrict__ fo, const double* __restrict__ Jo, const double* __restrict__ Mo,
+                        double* __restrict__ state) {
+    typedef DmmaState<X, U> S;
+    constexpr int D = S::D, NS = S::NS;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const long long step = base + i;
+    const long long b = step / L.H;
+    const int t = (int)(step - b * L.H);
+    const double* zb = ar.z + b * (long long)L.n;
+    double z[D];
+#pragma unroll
+    for (int c = 0; c < X; ++c) z[c] = (t == 0) ? ar.x0[b * X + c] : zb[(t - 1) * X + c];
+#pragma unroll
+    for (int c = 0; c < U; ++c) z[X + c] = zb[L.H * X + t * U + c];
+    double* sp = state + i * S::COUNT;
+    if (stage < 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) zin[i * D + c] = z[c];
+        return;
+    }
+    const bool JAC = mode >= 1, HES = mode >= 2, first = stage == 0, last = stage + 1 == st.S;
+    const double a_s = st.a[stage], c_s = st.c[stage];
+    double k[X], J[X][D], Rt[X][D];
+#pragma unroll
+    for (int p = 0; p < X; ++p) {
+        k[p] = fo[i * X + p];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            J[p][c] = JAC ? Jo[(i * X + p) * D + c] : 0.0;
+            Rt[p][c] = first ? (p == c ? 1.0 : 0.0) : sp[S::RT + p * D + c];
+        }
+    }
+#define NEMPC_RF(kk, cc) ((kk) < X ? Rt[(kk) < X ? (kk) : 0][cc] : ((kk) == (cc) ? 1.0 : 0.0))
+    double dk[X][D], dkacc[X][D];
+    if (JAC) {
+#pragma unroll
+        for (int p = 0; p < X; ++p)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double a = (c >= X) ? J[p][c] : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < X; ++kk) a = fma(J[p][kk], Rt[kk][c], a);
+                dk[p][c] = a;
+                dkacc[p][c] = fma(c_s, a, first ? 0.0 : sp[S::DKACC + p * D + c]);
+                if (!last) sp[S::DKACC + p * D + c] = dkacc[p][c];
+            }
+    }
+    if (HES) {
+#pragma unroll
+        for (int p = 0; p < X; ++p) {
+            double M[NS], tm[D][D];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) M[e] = Mo[(i * X + p) * NS + e];
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int l2 = 0; l2 < D; ++l2) a = fma(M[l2 <= kk ? kk * (kk + 1) / 2 + l2 : l2 * (l2 + 1) / 2 + kk], NEMPC_RF(l2, c), a);
+                    tm[kk][c] = a;
+                }
+#pragma unroll
+            for (int a2 = 0; a2 < D; ++a2)
+#pragma unroll
+                for (int c = 0; c <= a2; ++c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) a = fma(NEMPC_RF(kk, a2), tm[kk][c], a);
+                    const int e = a2 * (a2 + 1) / 2 + c;
+                    // + a_s sum_k J[p][k] h_{s-1}[k]: h_{s-1} of EVERY output is needed, so the new h_s goes to the other half of a double buffer
+                    if (!first) {
+#pragma unroll
+                        for (int kk = 0; kk < X; ++kk) a = fma(a_s * J[p][kk], sp[S::HPREV + ((stage & 1) ? 0 : X * NS) + kk * NS + e], a);
+                    }
+                    sp[S::HPREV + ((stage & 1) ? X * NS : 0) + p * NS + e] = a;
+                    double* ha = sp + S::HACC + p * NS + e;
+                    *ha = fma(c_s, a, first ? 0.0 : *ha);
+                }
+        }
+    }
+#undef NEMPC_RF
+    double kacc[X];
+#pragma unroll
+    for (int p = 0; p < X; ++p) {
+        kacc[p] = fma(c_s, k[p], first ? 0.0 : sp[S::KACC + p]);
+        sp[S::KACC + p] = kacc[p];
+    }
+    if (!last) {
+        const double an = st.a[stage + 1];
+#pragma unroll
+        for (int p = 0; p < X; ++p) {
+            zin[i * D + p] = fma(an, k[p], z[p]);
+#pragma unroll
+            for (int c = 0; c < D; ++c) sp[S::RT + p * D + c] = JAC ? fma(an, dk[p][c], (p == c) ? 1.0 : 0.0) : 0.0;
+        }
+        return;
+    }
+    // ---- outputs (the scatter of nempc_fast.cuh, in double) -------------------------------------------------------------------------
+    const bool unity = (ar.flags & NEMPC_UNITY) != 0;
+    if (ar.resid) {
+#pragma unroll
+        for (int p = 0; p < X; ++p) {
+            const double xt = zb[t * X + p];
+            const double xp = unity ? 0.0 : z[p];
+            ar.resid[b * L.m + t * X + p] = xp + kacc[p] - xt;
+        }
+    }
+    if (JAC && ar.jac) {
+        double* jv = ar.jac + b * L.nnz_jac;
+#pragma unroll
+        for (int p = 0; p < X; ++p) {
+            jv[jac_slot_minus1(L, t, p)] = -1.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const double v = dkacc[p][c] + ((!unity && c == p) ? 1.0 : 0.0);
+                if (c < X) { if (t > 0) jv[jac_slot_A(L, t, p, c)] = v; }
+                else jv[jac_slot_B(L, t, p, c - X)] = v;
+            }
+        }
+    }
+    if (HES && ar.hes) {
+        double* hv = ar.hes + b * L.nnz_hes;
+        const double sig = ar.sigma ? ar.sigma[b] : ar.sigma_scalar;
+        double lam[X];
+#pragma unroll
+        for (int p = 0; p < X; ++p) lam[p] = ar.lam[b * L.m + t * X + p];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int c = 0; c <= a; ++c) {
+                if (t == 0 && c < X) continue;
+                double acc = 0.0;
+#pragma unroll
+                for (int p = 0; p < X; ++p) acc = fma(lam[p], sp[S::HACC + p * NS + a * (a + 1) / 2 + c], acc);
+                double v = acc;
+                int slot;
+                if (a < X) {
+                    slot = hes_slot_xx(L, t, a, c);
+                    if (a == c && ar.quad) v += sig * 2.0 * ar.quad[(t - 1) * X + a];
+                } else if (c < X) {
+                    slot = hes_slot_ux(L, t, a - X, c);
+                } else {
+                    slot = hes_slot_uu(L, t, a - X, c - X);
+                    if (a == c && ar.quad) v += sig * 2.0 * ar.quad[L.H * X + t * U + (a - X)];
+                }
+                hv[slot] = v;
+            }
+        if (t == L.H - 1) {
+#pragma unroll
+            for (int p = 0; p < X; ++p)
+                if (L.hes_last_slot[p] >= 0) hv[L.hes_last_slot[p]] = sig * 2.0 * ar.quad[(L.H - 1) * X + p];
+        }
+    }
+}
+#endif

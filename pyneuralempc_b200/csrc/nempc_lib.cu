@@ -349,6 +349,7 @@ struct nempc_handle {
     int use_fast = 0; int fast_id = -1;
     int fast64_id = -1; std::vector<unsigned char> fast64w;      // float64 register-resident kernel (nempc_fast64.cuh): Fast64Weights<...> blob
     int use_tc = 0; int tc_id = -1; void* d_tcimg = nullptr; float* d_tccb = nullptr; float* d_tcwx = nullptr;   // tensor-core kernel: f16 weight images, f32 constants, first-layer rows of the exogenous inputs
+    int dmma_id = -1; double* dmma_scratch = nullptr; size_t dmma_scratch_doubles = 0;      // float64 DMMA path: network outputs + stage state of one chunk of steps
     int use_wide = 0; int wide_hes = 0; int wide_id = -1; unsigned char* d_wblob = nullptr; float* d_wcb = nullptr; WideNet wnet{};    // width-256 tensor-core kernel: streamed operand images, biases
     float* wide_scratch = nullptr; size_t wide_scratch_bytes = 0;
     std::vector<unsigned char> fastw;            // FastWeights<...> blob
@@ -449,6 +450,20 @@ static int wide_shape_id(const nempc_desc& d) {
     return 100 + (d.widths[0] == 128 ? 3 : 0) + (dd <= 4 ? 0 : (dd <= 8 ? 1 : 2));
 }
 
+// float64 tensor-core (DMMA) path (nempc_dmma.cuh): (x, u) instantiations of the stage kernel; 2..4 tanh hidden layers, all 128 or 64 wide
+struct DmmaShape { int x, u; };
+static const DmmaShape kDmmaShapes[] = {{2, 1}, {3, 1}, {4, 1}, {4, 2}, {6, 2}};
+static const int kNumDmmaShapes = sizeof(kDmmaShapes) / sizeof(kDmmaShapes[0]);
+static int dmma_shape_id(const nempc_desc& d) {
+    if (d.compute_dtype != NEMPC_F64 || d.io_dtype != NEMPC_F64 || d.activation != NEMPC_ACT_TANH || d.tvp_dim + d.p_dim > 0) return -1;
+    if (d.n_layers - 1 < 2 || d.n_layers - 1 > 4) return -1;
+    for (int l = 0; l + 1 < d.n_layers; ++l) if (d.widths[l] != d.widths[0]) return -1;
+    if (d.widths[0] != 128 && d.widths[0] != 64) return -1;
+    for (int i = 0; i < kNumDmmaShapes; ++i)
+        if (d.x_dim == kDmmaShapes[i].x && d.u_dim == kDmmaShapes[i].u) return i;
+    return -1;
+}
+
 extern "C" const char* nempc_version(void) { return "nempc 0.2 (sm_100a)"; }
 #ifndef NEMPC_SOURCE_HASH
 #define NEMPC_SOURCE_HASH "unknown"
@@ -542,6 +557,7 @@ static void free_device(nempc_handle* h) {
     cudaFree(h->sv_buf); cudaFree(h->sv_lb); cudaFree(h->sv_ub); cudaFree(h->sv_counts); if (h->sv_counts_host) cudaFreeHost(h->sv_counts_host);
     for (int i = 0; i < 10; ++i) cudaFree(h->st_buf[i]);
     if (h->hk_exec) cudaGraphExecDestroy(h->hk_exec);
+    cudaFree(h->dmma_scratch);
     if (h->sk_exec) cudaGraphExecDestroy(h->sk_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int i = 0; i < 3; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -609,9 +625,14 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
     if (getenv("NEMPC_WIDE128")) wide128 = atoi(getenv("NEMPC_WIDE128"));
     if (wide128 == 1 && D.widths[0] == 128 && wide_shape_id(D) >= 0) h->tc_id = -1;
     h->use_tc = (h->tc_id >= 0 && !h->use_fast && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
+    h->dmma_id = (!h->use_fast && h->fast64_id < 0 && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? dmma_shape_id(D) : -1;
     h->wide_id = wide_shape_id(D);
     h->use_wide = (h->wide_id >= 0 && !h->use_fast && !h->use_tc && (D.kernel == NEMPC_KERNEL_AUTO || D.kernel == NEMPC_KERNEL_TC)) ? 1 : 0;
     h->wide_hes = (h->use_tc && h->wide_id >= 0 && wide128 != 0 && D.integrator != NEMPC_INTEG_RK4) ? 1 : 0;
+    if (D.kernel == NEMPC_KERNEL_TC && !h->use_tc && !h->use_wide && h->dmma_id < 0) {
+        SET_ERR((nempc_handle*)nullptr, "NEMPC_KERNEL_TC requested but no tensor-core instantiation matches this network (f32: tanh, hidden layers all 256 / 128 / 64 / 32 wide; f64: all 128 / 64 wide)");
+        free_device(h); delete h; return NEMPC_EUNSUPPORTED;
+    }
 
     // generic launch geometry (also used by eval_blocks / model_eval of fast handles)
     int sum_h = 0, hmax = 0;
@@ -633,6 +654,8 @@ extern "C" int nempc_create(const nempc_desc* desc, nempc_handle** out) {
                               D.kernel == NEMPC_KERNEL_AUTO ? "; warp/step nempc_small_kernel for small batches" : "");
     else if (h->fast64_id >= 0) snprintf(nm, sizeof nm, "nempc_fast64_kernel<x=%d,u=%d,h1=%d,h2=%d> f64 (thread/step, DFMA, weights in constant bank%s)", D.x_dim, D.u_dim, D.widths[0], D.widths[1],
                                          D.kernel == NEMPC_KERNEL_AUTO ? "; generic kernel for small batches" : "");
+    else if (h->dmma_id >= 0) snprintf(nm, sizeof nm, "nempc_dmma_net_kernel<hidden=%dx%d> f64 DMMA m8n8k4 (forward second order, weights streamed through a cp.async ring) + nempc_dmma_stage_kernel<x=%d,u=%d>%s",
+                                      D.n_layers - 1, D.widths[0], D.x_dim, D.u_dim, D.kernel == NEMPC_KERNEL_AUTO ? "; generic kernel for small batches" : "");
     else if (h->use_wide) snprintf(nm, sizeof nm, "nempc_wide_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (adjoint form, weights streamed through a TMA ring%s)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0],
                                h->wide_id >= 100 ? "; dimensions read at run time" : "");
     else if (h->use_tc) snprintf(nm, sizeof nm, "nempc_tc_kernel<x=%d,u=%d,hidden=%dx%d> tcgen05 split-f16 (forward second order, weights resident in smem%s)", D.x_dim, D.u_dim, D.n_layers - 1, D.widths[0],
@@ -1088,6 +1111,41 @@ template <typename TIO> static int launch_wide(nempc_handle* h, const EvalArgs<T
     return NEMPC_OK;
 }
 
+// float64 tensor-core path (nempc_dmma_tu.cu)
+#include "nempc_dmma.cuh"
+size_t nempc_dmma_scratch_doubles(int shape_id, long long nsteps);
+int nempc_dmma_launch(int shape_id, int hw, int mode, const DmmaNet& net, const StageTable<double>& st, const NlpLayout& L, const EvalArgs<double>& ar,
+                      double* scratch, int sm_count, cudaStream_t s, int* launches);
+#ifndef NEMPC_DMMA_MIN_STEPS
+#define NEMPC_DMMA_MIN_STEPS 512         // below this many horizon steps the row tiles leave most SMs empty: the generic kernel takes over
+#endif
+template <typename TIO> static bool take_dmma(nempc_handle*, const EvalArgs<TIO>&) { return false; }
+template <> bool take_dmma<double>(nempc_handle* h, const EvalArgs<double>& ar) {
+    static const long long min_steps = getenv("NEMPC_DMMA_MIN_STEPS") ? atoll(getenv("NEMPC_DMMA_MIN_STEPS")) : NEMPC_DMMA_MIN_STEPS;
+    return h->dmma_id >= 0 && (ar.nsteps >= min_steps || h->desc.kernel == NEMPC_KERNEL_TC);
+}
+template <typename TIO> static int run_dmma(nempc_handle*, const EvalArgs<TIO>&, int, cudaStream_t) { return NEMPC_EINVAL; }
+template <> int run_dmma<double>(nempc_handle* h, const EvalArgs<double>& ar, int mode, cudaStream_t s) {
+    const size_t need = nempc_dmma_scratch_doubles(h->dmma_id, ar.nsteps);
+    if (need == 0) { SET_ERR(h, "internal: bad dmma_id"); return NEMPC_EINVAL; }
+    if (need > h->dmma_scratch_doubles) {
+        CU(h, cudaStreamSynchronize(s));
+        cudaFree(h->dmma_scratch); h->dmma_scratch = nullptr; h->dmma_scratch_doubles = 0;
+        CU(h, cudaMalloc((void**)&h->dmma_scratch, need * sizeof(double)));
+        h->dmma_scratch_doubles = need;
+    }
+    DmmaNet net{};
+    net.d = h->d; net.x = h->desc.x_dim; net.nhid = h->L - 1;
+    for (int l = 0; l < h->L; ++l) { net.W[l] = (const double*)h->dW[l]; net.b[l] = (const double*)h->db[l]; }
+    StageTable<double> st = make_stage_table<double>(h->desc.integrator == NEMPC_INTEG_RK4, h->desc.dt);
+    int launches = 0;
+    const int rc = nempc_dmma_launch(h->dmma_id, h->desc.widths[0], mode, net, st, h->lay, ar, h->dmma_scratch, h->sm_count, s, &launches);
+    h->launches += launches;
+    if (rc == -1) { SET_ERR(h, "internal: bad dmma shape"); return NEMPC_EINVAL; }
+    if (rc != 0) { SET_ERR(h, "nempc_dmma kernels: %s", cudaGetErrorString((cudaError_t)rc)); return NEMPC_ECUDA; }
+    return NEMPC_OK;
+}
+
 template <typename TIO>
 static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, const void* lambda, const void* obj_factor,
                   double sigma, void* resid, void* jac, void* hes, void* obj, void* grad, cudaStream_t s) {
@@ -1101,7 +1159,7 @@ static int eval_t(nempc_handle* h, int64_t B, const void* z, const void* x0, con
         const int mode = hes ? 2 : (jac ? 1 : 0);
         ar.flags = (mode >= 1 ? NEMPC_WANT_JAC : 0) | (mode >= 2 ? NEMPC_WANT_HES : 0) |
                    (h->desc.integrator == NEMPC_INTEG_UNITY ? NEMPC_UNITY : 0);
-        int rc = take_fast64<TIO>(h, ar) ? run_fast64<TIO>(h, ar, mode, s) : h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
+        int rc = take_fast64<TIO>(h, ar) ? run_fast64<TIO>(h, ar, mode, s) : take_dmma<TIO>(h, ar) ? run_dmma<TIO>(h, ar, mode, s) : h->use_fast ? launch_fast<TIO>(h, ar, mode, s)
                             : (h->use_tc ? ((h->wide_hes && mode == 2) ? launch_wide<TIO>(h, ar, mode, s) : launch_tc<TIO>(h, ar, mode, s)) : (h->use_wide ? launch_wide<TIO>(h, ar, mode, s) : launch_generic<TIO>(h, ar, false, s)));
         if (rc) return rc;
     }

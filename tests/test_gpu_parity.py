@@ -669,3 +669,67 @@ def test_wide_kernel_over_the_range_of_solver_multipliers(kind, scale):
         assert _relerr(got["hes"][b], ref["hes_vals"][b]) < TOL32, (b, _relerr(got["hes"][b], ref["hes_vals"][b]))
     assert _relerr(got["jac"], ref["jac_vals"]) < TOL32
     ev.close()
+
+
+DMMA_CASES = [("rk4", [5, 128, 128, 128, 4], 4, 1, 7, 9), ("discrete", [3, 128, 128, 2], 2, 1, 5, 30), ("unity", [4, 64, 64, 3], 3, 1, 6, 11),
+              ("rk4", [6, 64, 64, 64, 64, 4], 4, 2, 5, 13), ("discrete", [8, 128, 128, 6], 6, 2, 4, 40), ("rk4", [8, 128, 128, 128, 6], 6, 2, 3, 7),
+              ("rk4", [3, 128, 128, 128, 128, 2], 2, 1, 50, 12), ("discrete", [5, 64, 64, 4], 4, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("kind,dims,xd,ud,H,B", DMMA_CASES)
+def test_float64_tensor_core_path_vs_oracle(kind, dims, xd, ud, H, B):
+    """nempc_dmma_net_kernel (FP64 tensor cores, mma.sync.m8n8k4.f64) + nempc_dmma_stage_kernel: the 1e-10 parity mode of the wide tanh networks;
+    all three output sets (residual only / + Jacobian / + Hessian run different row stacks), tiles that end inside a problem, the generic
+    kernel as a second opinion"""
+    import torch
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z, X0, lam, sig)
+    ev = _evaluator(mlp, kind, H, "float64", "tc", obj)
+    assert "nempc_dmma_net_kernel" in ev.kernel_name and "DMMA" in ev.kernel_name
+    np.testing.assert_array_equal(ev.hes_rows, BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).hes_rows)
+    got = _run(ev, Z, X0, lam, sig)
+    for kr, kg in KEYS:
+        assert _relerr(got[kg], ref[kr]) < TOL64, (kg, _relerr(got[kg], ref[kr]))
+    t = lambda a: torch.as_tensor(a).cuda()
+    o1 = ev.eval(t(Z), t(X0), want=("resid", "jac"))
+    o0 = ev.eval(t(Z), t(X0), want=("resid",))
+    torch.cuda.synchronize()
+    assert _relerr(o1["jac"].cpu().numpy(), ref["jac_vals"]) < TOL64 and _relerr(o1["resid"].cpu().numpy(), ref["resid"]) < TOL64
+    assert _relerr(o0["resid"].cpu().numpy(), ref["resid"]) < TOL64
+    gen = _run(_evaluator(mlp, kind, H, "float64", "generic", obj), Z, X0, lam, sig)
+    for _, kg in KEYS:
+        assert _relerr(got[kg], gen[kg]) < TOL64, kg
+    ev.close()
+
+
+def test_float64_tensor_core_path_dispatch_and_chunks():
+    """AUTO sends float64 wide networks to the DMMA path from 512 horizon steps on (generic below); a batch above one scratch chunk
+    (2^18 steps) is evaluated chunk by chunk -- problems on both sides of the chunk boundary against the oracle; unsupported shapes are
+    refused under kernel='tc' and served by the generic kernel under 'auto'"""
+    import torch
+    from pyneuralempc_b200._lib import NempcError
+    H, B = 100, 2700                                             # 270 000 steps > 262 144
+    mlp, obj, _, _, _, _ = _problem([3, 64, 64, 2], 2, 1, H, 1)
+    rng = np.random.default_rng(5)
+    Z, X0, lam = rng.uniform(-1, 1, (B, H * 3)), rng.uniform(-1, 1, (B, 2)), rng.standard_normal((B, H * 2))
+    ev = _evaluator(mlp, "rk4", H, "float64", "auto", obj)
+    assert "nempc_dmma_net_kernel" in ev.kernel_name
+    t = lambda a: torch.as_tensor(a).cuda()
+    out = ev.eval(t(Z), t(X0), t(lam), 1.0)
+    torch.cuda.synchronize()
+    assert ev.launch_count == 2 * 9 + 1                          # two chunks x (init + 4 network + 4 stage kernels) + objective
+    pick = np.array([0, 1, 2620, 2621, 2622, 2699])              # 2621 * 100 = 262 100: problem 2621 straddles the chunk boundary
+    ref = BlockEvaluator(mlp, "rk4", H, DT=0.1, objective=obj).evaluate(Z[pick], X0[pick], lam[pick], 1.0)
+    for kr, kg in KEYS:
+        assert _relerr(out[kg][torch.as_tensor(pick).cuda()].cpu().numpy(), ref[kr]) < TOL64, kg
+    n0 = ev.launch_count
+    small = ev.eval(t(Z[:2]), t(X0[:2]), t(lam[:2]), 1.0)        # 200 steps: generic kernel (one launch + objective)
+    torch.cuda.synchronize()
+    assert ev.launch_count - n0 == 2
+    for kr, kg in KEYS:
+        assert _relerr(small[kg].cpu().numpy(), ref[kr][:2]) < TOL64, kg
+    ev.close()
+    m2 = MLP.glorot([3, 128, 96, 2], 2, 1, seed=2)
+    with pytest.raises(NempcError):
+        _evaluator(m2, "rk4", 5, "float64", "tc")
+    assert "generic" in _evaluator(m2, "rk4", 5, "float64", "auto").kernel_name

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--integ", default="")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--want", default="resid,jac,hes")
+    ap.add_argument("--compute", default="float32")
     args = ap.parse_args()
     import torch
     from bench import WORKLOADS, make_problem
@@ -28,7 +29,7 @@ def main():
     if args.integ: wl["integ"] = args.integ
     B = args.batch or wl["B"]
     mlp, obj, Z, X0, lam = make_problem({k: v for k, v in wl.items() if k != "desc"}, B)
-    ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"] or 0.1, compute_dtype="float32",
+    ev = NlpEvaluator(mlp.weights, wl["x"], wl["u"], wl["H"], wl["integ"], DT=wl["DT"] or 0.1, compute_dtype=args.compute,
                       io_dtype="float64", kernel=args.kernel)
     ev.set_objective(obj.lin, obj.quad, obj.ref)
     want = tuple(args.want.split(","))
