@@ -11,7 +11,8 @@
 //     weights do not fit together), one __syncthreads per chunk;
 //   * 8 warps, warp tile 32 x 64 at HW = 128: 32 m8n8k4 accumulators (128 registers) per lane, 12 shared-memory fragment loads per 32 DMMAs;
 //   * epilogue per (step, neuron): bias, tanh, s', s'', V = s' dV, Q = s' dQ + s'' dV_c dV_c2, written back as the next operand tile;
-//   * first layer (K = d) and output layer (N = x) are thin: DFMA, the output contraction with warp shuffles.
+//   * the first layer (K = d) is DFMA; the output layer (N = x <= 8) is one more DMMA pass over the tile against W_out padded to 8 columns,
+//     whose accumulator fragments go straight to global memory (a shuffle-reduced DFMA contraction took 29 % of the kernel, profiles/r2r).
 // The kernel is a pure NETWORK kernel: zin (N, d) -> k = f(zin) (N, x), local Jacobian J (N, x, d), per-output local Hessians M (N, x, NS)
 // (lower triangle e = c(c+1)/2 + c2).  The integrator's stage algebra (dk = J R, h_s = R^T M R + a_s J h_{s-1}, R_{s+1} = I + a_{s+1} E dk;
 // reference integrator/rk4.py:113-285, discret.py:32-81, unity.py:34-81) and the scatter into the block-banded value arrays run in a second,
@@ -29,13 +30,14 @@ struct DmmaNet {
 template <int HW_> struct DmmaCfg {
     static constexpr int HW = HW_, MT = 128, THREADS = 256;
     static constexpr int LDA = HW + 4;                // row stride of the tile (doubles): fragment loads of 8 rows x 4 columns fall on 32 distinct banks
-    static constexpr int LDW = HW + 8;                // row stride of a weight chunk: 4 rows x 8 columns likewise
+    static constexpr int LDW = HW + 4;                // row stride of a weight chunk: a half-warp's 4 rows x 4 columns likewise (HW + 8 measured a two-way conflict)
+    static constexpr int LDO = 12, O_DOUBLES = HW * LDO;  // output weights, zero-padded to 8 columns (row stride 12: conflict-free fragments)
     static constexpr int KC = 16, NSLOT = 3;          // ring: chunks of 16 weight rows
     static constexpr int WGN = HW / 64, WGM = 8 / WGN;          // warp grid (8 warps): warp tile (MT / WGM) x 64
     static constexpr int WM = MT / WGM, WN = 64, MI = WM / 8, NI = WN / 8;
     static constexpr int A_DOUBLES = MT * LDA, RING_DOUBLES = NSLOT * KC * LDW;
     static constexpr int Z_DOUBLES = MT * 16;         // inputs of the tile's steps (d <= 16)
-    static constexpr size_t SMEM = (size_t)(A_DOUBLES + RING_DOUBLES + Z_DOUBLES) * sizeof(double);
+    static constexpr size_t SMEM = (size_t)(A_DOUBLES + RING_DOUBLES + Z_DOUBLES + O_DOUBLES) * sizeof(double);
     static_assert(HW == 128 || HW == 64, "hidden width 128 or 64");
     static_assert(SMEM <= 232448, "shared-memory map exceeds 227 KB");
 };
@@ -52,7 +54,7 @@ __device__ __forceinline__ void dmma_cp_commit() { asm volatile("cp.async.commit
 template <int N> __device__ __forceinline__ void dmma_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // rows: 1 (mode 0), 1 + d (mode 1), 1 + d + d(d+1)/2 (mode 2) per step, kind-major inside the tile: row = kind * spt + step
-template <class C>
+template <class C, int D>
 __global__ void __launch_bounds__(C::THREADS, 1)
 nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long long N, int mode, double* __restrict__ fo, double* __restrict__ Jo,
                       double* __restrict__ Mo) {
@@ -62,32 +64,42 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
     double* ring = A + C::A_DOUBLES;
     double* zs = ring + C::RING_DOUBLES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = net.d, x = net.x, ns = d * (d + 1) / 2;
+    constexpr int d = D, ns = D * (D + 1) / 2;
+    const int x = net.x;
+    double* wos = zs + C::Z_DOUBLES;
     const int rps = 1 + (mode >= 1 ? d : 0) + (mode >= 2 ? ns : 0);
     const int spt = MT / rps, rows = spt * rps;
     const int wm0 = (warp / C::WGN) * C::WM, wn0 = (warp % C::WGN) * C::WN;
     const int g = lane >> 2, q = lane & 3;
     for (int i = tid; i < C::A_DOUBLES; i += C::THREADS) A[i] = 0.0;                 // padding rows stay zero for the life of the CTA
+    for (int i = tid; i < HW * C::LDO; i += C::THREADS) { const int j = i / C::LDO, p = i - j * C::LDO; wos[i] = p < x ? net.W[net.nhid][(size_t)j * x + p] : 0.0; }
     const long long ntiles = (N + spt - 1) / spt;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long s0 = tile * spt;
         const int nst = (int)((N - s0) < spt ? (N - s0) : spt);
         __syncthreads();                                                             // previous tile's output contraction is done with A
-        for (int i = tid; i < spt * d; i += C::THREADS) zs[i] = (i < nst * d) ? zin[s0 * d + i] : 0.0;
+        for (int i = tid; i < spt * D; i += C::THREADS) zs[i] = (i < nst * D) ? zin[s0 * D + i] : 0.0;
         __syncthreads();
         // ---- first layer (K = d): DFMA ------------------------------------------------------------------------------------------
         for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
             const int sl = idx / HW, j = idx - sl * HW;
-            double a = net.b[0][j];
-            for (int c = 0; c < d; ++c) a = fma(net.W[0][c * HW + j], zs[sl * d + c], a);
+            double a = net.b[0][j], w0[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) { w0[c] = net.W[0][c * HW + j]; a = fma(w0[c], zs[sl * D + c], a); }
             const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
-            A[sl * LDA + j] = h;
+            double* col = A + sl * LDA + j;
+            const int rs = spt * LDA;                                                // distance between the row kinds of one step
+            col[0] = h;
             if (mode >= 1) {
-                for (int c = 0; c < d; ++c) {
-                    const double wc = net.W[0][c * HW + j];
-                    A[((1 + c) * spt + sl) * LDA + j] = sp * wc;
-                    if (mode >= 2)
-                        for (int c2 = 0; c2 <= c; ++c2) A[((1 + d + c * (c + 1) / 2 + c2) * spt + sl) * LDA + j] = spp * wc * net.W[0][c2 * HW + j];
+#pragma unroll
+                for (int c = 0; c < D; ++c) col[(1 + c) * rs] = sp * w0[c];
+                if (mode >= 2) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const double sw = spp * w0[c];
+#pragma unroll
+                        for (int c2 = 0; c2 <= c; ++c2) col[(1 + D + c * (c + 1) / 2 + c2) * rs] = sw * w0[c2];
+                    }
                 }
             }
         }
@@ -139,48 +151,65 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
             const double* __restrict__ bl = net.b[l];
             for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
                 const int sl = idx / HW, j = idx - sl * HW;
-                const double a = A[sl * LDA + j] + bl[j];
-                const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
-                A[sl * LDA + j] = h;
+                double* col = A + sl * LDA + j;
+                const int rs = spt * LDA;
+                const double a = col[0] + bl[j];
+                double tg[D], qv[ns];
                 if (mode >= 1) {
-                    double tg[16];
-                    for (int c = 0; c < d; ++c) {
-                        double* pa = &A[((1 + c) * spt + sl) * LDA + j];
-                        tg[c] = *pa;
-                        *pa = sp * tg[c];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) tg[c] = col[(1 + c) * rs];
+                    if (mode >= 2) {
+#pragma unroll
+                        for (int e = 0; e < ns; ++e) qv[e] = col[(1 + D + e) * rs];
                     }
-                    if (mode >= 2)
-                        for (int c = 0; c < d; ++c)
-                            for (int c2 = 0; c2 <= c; ++c2) {
-                                double* pa = &A[((1 + d + c * (c + 1) / 2 + c2) * spt + sl) * LDA + j];
-                                *pa = fma(sp, *pa, spp * tg[c] * tg[c2]);
-                            }
+                }
+                const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
+                col[0] = h;
+                if (mode >= 1) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) col[(1 + c) * rs] = sp * tg[c];
+                    if (mode >= 2) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            const double st = spp * tg[c];
+#pragma unroll
+                            for (int c2 = 0; c2 <= c; ++c2) { const int e = c * (c + 1) / 2 + c2; col[(1 + D + e) * rs] = fma(sp, qv[e], st * tg[c2]); }
+                        }
+                    }
                 }
             }
             // (the __syncthreads at the top of the next layer's first chunk / before the output contraction orders these writes)
         }
         __syncthreads();
-        // ---- output layer (N = x): each warp contracts its rows with W_out, lanes over neurons, shuffle reduction ---------------------
+        // ---- output layer (N = x <= 8): one DMMA pass, two row blocks of 8 per warp, two K halves each (four independent accumulator chains) ----
         {
-            constexpr int JP = HW / 32;
-            const double* __restrict__ Wo = net.W[net.nhid];
-            for (int r = warp; r < rows; r += 8) {
+            double oc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+            const int mt0 = warp * (MT / 64);                                        // MT / 8 row blocks over 8 warps
+#pragma unroll 4
+            for (int k4 = 0; k4 < HW / 8; ++k4) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int kb = (hf * (HW / 8) + k4) * 4;
+                    const double bfr = wos[(kb + q) * C::LDO + g];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) dmma_m8n8k4(oc[mi][hf][0], oc[mi][hf][1], A[((mt0 + mi) * 8 + g) * LDA + kb + q], bfr);
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int r = (mt0 + mi) * 8 + g;
                 const int kind = r / spt, sl = r - kind * spt;
-                if (sl >= nst) continue;                                            // warp-uniform
-                double av[JP];
+                if (r < rows && sl < nst) {
+                    const long long st = s0 + sl;
 #pragma unroll
-                for (int i = 0; i < JP; ++i) av[i] = A[r * LDA + lane + 32 * i];
-                for (int p = 0; p < x; ++p) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int i = 0; i < JP; ++i) sacc = fma(av[i], Wo[(size_t)(lane + 32 * i) * x + p], sacc);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                    if (lane == 0) {
-                        const long long st = s0 + sl;
-                        if (kind == 0) fo[st * x + p] = sacc + net.b[net.nhid][p];
-                        else if (kind <= d) Jo[(st * x + p) * d + (kind - 1)] = sacc;
-                        else Mo[(st * x + p) * ns + (kind - 1 - d)] = sacc;
+                    for (int i = 0; i < 2; ++i) {
+                        const int p = 2 * q + i;
+                        if (p < x) {
+                            const double v = oc[mi][0][i] + oc[mi][1][i];
+                            if (kind == 0) fo[st * x + p] = v + net.b[net.nhid][p];
+                            else if (kind <= d) Jo[(st * x + p) * d + (kind - 1)] = v;
+                            else Mo[(st * x + p) * ns + (kind - 1 - d)] = v;
+                        }
                     }
                 }
             }

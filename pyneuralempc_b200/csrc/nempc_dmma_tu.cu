@@ -21,7 +21,7 @@ static int launch_shape(int mode, const DmmaNet& net, const StageTable<double>& 
     constexpr int D = X + U, NS = D * (D + 1) / 2;
     static bool once = false;
     if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(nempc_dmma_net_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(nempc_dmma_net_kernel<C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
         once = true;
     }
@@ -35,7 +35,7 @@ static int launch_shape(int mode, const DmmaNet& net, const StageTable<double>& 
         nempc_dmma_stage_kernel<X, U><<<sgrid, 128, 0, s>>>(st, L, ar, base, N, mode, -1, zin, fo, Jo, Mo, state);
         ++*launches;
         for (int stage = 0; stage < st.S; ++stage) {
-            nempc_dmma_net_kernel<C><<<ngrid, C::THREADS, C::SMEM, s>>>(net, zin, N, mode, fo, Jo, Mo);
+            nempc_dmma_net_kernel<C, D><<<ngrid, C::THREADS, C::SMEM, s>>>(net, zin, N, mode, fo, Jo, Mo);
             nempc_dmma_stage_kernel<X, U><<<sgrid, 128, 0, s>>>(st, L, ar, base, N, mode, stage, zin, fo, Jo, Mo, state);
             *launches += 2;
         }
