@@ -5,11 +5,12 @@
 //
 // Formulation: FORWARD second order, as nempc_tc.cuh -- per horizon step and integrator stage the network is evaluated on a stack of
 // RPS = 1 + d + d(d+1)/2 rows (activations, first-order tangents V[., c], second-order tangents Q[., (c,c2)]); every row goes through the
-// same weights, so a hidden-to-hidden layer is ONE GEMM [MT rows x HW] x [HW x HW] for SPT = MT / RPS steps at once:
-//   * the row tile A (MT x HW doubles, 132 KB at MT = HW = 128) stays in shared memory for the life of a tile and is updated in place;
-//   * the weights of the layer stream from L2 through a three-slot cp.async ring of 16-row chunks (they are 128 KB per layer: tile and
-//     weights do not fit together), one __syncthreads per chunk;
-//   * 8 warps, warp tile 32 x 64 at HW = 128: 32 m8n8k4 accumulators (128 registers) per lane, 12 shared-memory fragment loads per 32 DMMAs;
+// same weights, so a hidden-to-hidden layer is ONE GEMM [64 rows x HW] x [HW x HW] for SPT = 64 / RPS steps at once:
+//   * one persistent CTA per SM, TWO GROUPS of 4 warps, each group with its own 64-row tile A (in place in shared memory for the life of a
+//     tile), weight ring and named barrier -- while one group runs an epilogue the other keeps the DMMA pipe busy;
+//   * the weights of the layer stream from L2 through a three-slot cp.async ring of 8-row chunks per group (a layer is 128 KB: tiles and
+//     weights do not fit together), one group barrier per chunk;
+//   * warp tile 32 x 64 at HW = 128: 32 m8n8k4 accumulators (128 registers) per lane, 12 shared-memory fragment loads per 32 DMMAs;
 //   * epilogue per (step, neuron): bias, tanh, s', s'', V = s' dV, Q = s' dQ + s'' dV_c dV_c2, written back as the next operand tile;
 //   * the first layer (K = d) is DFMA; the output layer (N = x <= 8) is one more DMMA pass over the tile against W_out padded to 8 columns,
 //     whose accumulator fragments go straight to global memory (a shuffle-reduced DFMA contraction took 29 % of the kernel, profiles/r2r).
@@ -28,16 +29,20 @@ struct DmmaNet {
 };
 
 template <int HW_> struct DmmaCfg {
-    static constexpr int HW = HW_, MT = 128, THREADS = 256;
-    static constexpr int LDA = HW + 4;                // row stride of the tile (doubles): fragment loads of 8 rows x 4 columns fall on 32 distinct banks
-    static constexpr int LDW = HW + 4;                // row stride of a weight chunk: a half-warp's 4 rows x 4 columns likewise (HW + 8 measured a two-way conflict)
+    // TWO GROUPS of 128 threads per CTA, each with its own 64-row tile, weight ring and named barrier: while one group runs an epilogue
+    // (tanh, chain rule: DFMA) the other keeps the DMMA pipe busy -- the overlap a second CTA per SM would give (a second CTA does not fit:
+    // registers).  One tile of 128 rows measured 72 % DMMA-pipe activity, serialised GEMM / epilogue phases (profiles/r2r).
+    static constexpr int HW = HW_, NG = 2, GT = 128, THREADS = NG * GT, MT = 64;   // MT: rows per GROUP tile
+    static constexpr int LDA = HW + 4;                // row stride of the tile (doubles): a half-warp's fragment loads (4 rows x 4 columns) fall on distinct banks
+    static constexpr int LDW = HW + 4;                // row stride of a weight chunk: likewise (HW + 8 measured a two-way conflict)
     static constexpr int LDO = 12, O_DOUBLES = HW * LDO;  // output weights, zero-padded to 8 columns (row stride 12: conflict-free fragments)
-    static constexpr int KC = 16, NSLOT = 3;          // ring: chunks of 16 weight rows
-    static constexpr int WGN = HW / 64, WGM = 8 / WGN;          // warp grid (8 warps): warp tile (MT / WGM) x 64
+    static constexpr int KC = 8, NSLOT = 3;           // ring: chunks of 8 weight rows, three slots per group
+    static constexpr int WGN = HW / 64, WGM = 4 / WGN;          // warp grid of a group (4 warps): warp tile (MT / WGM) x 64
     static constexpr int WM = MT / WGM, WN = 64, MI = WM / 8, NI = WN / 8;
-    static constexpr int A_DOUBLES = MT * LDA, RING_DOUBLES = NSLOT * KC * LDW;
-    static constexpr int Z_DOUBLES = MT * 16;         // inputs of the tile's steps (d <= 16)
-    static constexpr size_t SMEM = (size_t)(A_DOUBLES + RING_DOUBLES + Z_DOUBLES + O_DOUBLES) * sizeof(double);
+    static constexpr int A_DOUBLES = MT * LDA, RING_DOUBLES = NSLOT * KC * LDW;      // per group
+    static constexpr int Z_DOUBLES = MT * 8;          // inputs of the tile's steps (d <= 8), per group
+    static constexpr int G_DOUBLES = A_DOUBLES + RING_DOUBLES + Z_DOUBLES;
+    static constexpr size_t SMEM = (size_t)(NG * G_DOUBLES + O_DOUBLES) * sizeof(double);
     static_assert(HW == 128 || HW == 64, "hidden width 128 or 64");
     static_assert(SMEM <= 232448, "shared-memory map exceeds 227 KB");
 };
@@ -58,30 +63,33 @@ template <class C, int D>
 __global__ void __launch_bounds__(C::THREADS, 1)
 nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long long N, int mode, double* __restrict__ fo, double* __restrict__ Jo,
                       double* __restrict__ Mo) {
-    constexpr int HW = C::HW, MT = C::MT, LDA = C::LDA, LDW = C::LDW, KC = C::KC, NSLOT = C::NSLOT, MI = C::MI, NI = C::NI;
+    constexpr int HW = C::HW, MT = C::MT, LDA = C::LDA, LDW = C::LDW, KC = C::KC, NSLOT = C::NSLOT, MI = C::MI, NI = C::NI, GT = C::GT;
+    static_assert(D <= 8, "input width");
     extern __shared__ __align__(16) unsigned char dmma_smem[];
-    double* A = reinterpret_cast<double*>(dmma_smem);
+    const int grp = threadIdx.x / GT, tid = threadIdx.x - grp * GT, lane = tid & 31, warp = tid >> 5;      // group-local thread / warp index
+    double* A = reinterpret_cast<double*>(dmma_smem) + grp * C::G_DOUBLES;
     double* ring = A + C::A_DOUBLES;
     double* zs = ring + C::RING_DOUBLES;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* wos = reinterpret_cast<double*>(dmma_smem) + C::NG * C::G_DOUBLES;
     constexpr int d = D, ns = D * (D + 1) / 2;
     const int x = net.x;
-    double* wos = zs + C::Z_DOUBLES;
     const int rps = 1 + (mode >= 1 ? d : 0) + (mode >= 2 ? ns : 0);
     const int spt = MT / rps, rows = spt * rps;
     const int wm0 = (warp / C::WGN) * C::WM, wn0 = (warp % C::WGN) * C::WN;
     const int g = lane >> 2, q = lane & 3;
-    for (int i = tid; i < C::A_DOUBLES; i += C::THREADS) A[i] = 0.0;                 // padding rows stay zero for the life of the CTA
-    for (int i = tid; i < HW * C::LDO; i += C::THREADS) { const int j = i / C::LDO, p = i - j * C::LDO; wos[i] = p < x ? net.W[net.nhid][(size_t)j * x + p] : 0.0; }
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(C::GT) : "memory"); };        // barrier of this group only
+    for (int i = tid; i < C::A_DOUBLES; i += GT) A[i] = 0.0;                         // padding rows stay zero for the life of the CTA
+    for (int i = threadIdx.x; i < HW * C::LDO; i += C::THREADS) { const int j = i / C::LDO, p = i - j * C::LDO; wos[i] = p < x ? net.W[net.nhid][(size_t)j * x + p] : 0.0; }
+    __syncthreads();                                                                 // the only CTA-wide barrier: the groups run on their own from here
     const long long ntiles = (N + spt - 1) / spt;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * C::NG + grp; tile < ntiles; tile += (long long)gridDim.x * C::NG) {
         const long long s0 = tile * spt;
         const int nst = (int)((N - s0) < spt ? (N - s0) : spt);
-        __syncthreads();                                                             // previous tile's output contraction is done with A
-        for (int i = tid; i < spt * D; i += C::THREADS) zs[i] = (i < nst * D) ? zin[s0 * D + i] : 0.0;
-        __syncthreads();
+        gsync();                                                                     // previous tile's output pass is done with A
+        for (int i = tid; i < spt * D; i += GT) zs[i] = (i < nst * D) ? zin[s0 * D + i] : 0.0;
+        gsync();
         // ---- first layer (K = d): DFMA ------------------------------------------------------------------------------------------
-        for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
+        for (int idx = tid; idx < spt * HW; idx += GT) {
             const int sl = idx / HW, j = idx - sl * HW;
             double a = net.b[0][j], w0[D];
 #pragma unroll
@@ -114,7 +122,7 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
             auto issue_chunk = [&](int kc) {                                         // weight rows [kc KC, +KC) -> ring slot kc % NSLOT
                 double* dst = ring + (kc % NSLOT) * (KC * LDW);
                 constexpr int V = HW / 2;                                            // 16-byte pieces per row
-                for (int i = tid; i < KC * V; i += C::THREADS) {
+                for (int i = tid; i < KC * V; i += GT) {
                     const int r = i / V, v = i - r * V;
                     dmma_cp_async16(dst + r * LDW + 2 * v, Wl + (size_t)(kc * KC + r) * HW + 2 * v);
                 }
@@ -125,7 +133,7 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
             issue_chunk(1);
             for (int kc = 0; kc < NCH; ++kc) {
                 if (kc + 1 < NCH) dmma_cp_wait<1>(); else dmma_cp_wait<0>();
-                __syncthreads();                            // chunk kc has landed for every thread; everyone is done with chunk kc - 1 (and, for kc = 0, with writing A)
+                gsync();                                    // chunk kc has landed for every thread of the group; everyone is done with chunk kc - 1 (and, for kc = 0, with writing A)
                 if (kc + 2 < NCH) issue_chunk(kc + 2);      // its slot held chunk kc - 1
                 const double* wch = ring + (kc % NSLOT) * (KC * LDW);
 #pragma unroll
@@ -141,15 +149,15 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
                         for (int ni = 0; ni < NI; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
                 }
             }
-            __syncthreads();                                // every warp has read its A fragments: the tile can be overwritten
+            gsync();                                        // every warp has read its A fragments: the tile can be overwritten
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < NI; ++ni)
                     *reinterpret_cast<double2*>(&A[(wm0 + mi * 8 + g) * LDA + wn0 + ni * 8 + 2 * q]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-            __syncthreads();
+            gsync();
             const double* __restrict__ bl = net.b[l];
-            for (int idx = tid; idx < spt * HW; idx += C::THREADS) {
+            for (int idx = tid; idx < spt * HW; idx += GT) {
                 const int sl = idx / HW, j = idx - sl * HW;
                 double* col = A + sl * LDA + j;
                 const int rs = spt * LDA;
@@ -178,13 +186,13 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
                     }
                 }
             }
-            // (the __syncthreads at the top of the next layer's first chunk / before the output contraction orders these writes)
+            // (the group barrier at the top of the next layer's first chunk / before the output pass orders these writes)
         }
-        __syncthreads();
+        gsync();
         // ---- output layer (N = x <= 8): one DMMA pass, two row blocks of 8 per warp, two K halves each (four independent accumulator chains) ----
         {
             double oc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-            const int mt0 = warp * (MT / 64);                                        // MT / 8 row blocks over 8 warps
+            const int mt0 = warp * 2;                                                // MT / 8 = 8 row blocks over the group's 4 warps
 #pragma unroll 4
             for (int k4 = 0; k4 < HW / 8; ++k4) {
 #pragma unroll

@@ -31,7 +31,7 @@ static int launch_shape(int mode, const DmmaNet& net, const StageTable<double>& 
         double* zin = scratch; double* fo = zin + N * D; double* Jo = fo + N * X; double* Mo = Jo + N * X * D; double* state = Mo + N * X * NS;
         const unsigned sgrid = (unsigned)((N + 127) / 128);
         const long long ntiles = (N + spt - 1) / spt;
-        const unsigned ngrid = (unsigned)std::min<long long>(ntiles, sm_count);
+        const unsigned ngrid = (unsigned)std::min<long long>((ntiles + C::NG - 1) / C::NG, sm_count);      // persistent CTAs, one row tile per group
         nempc_dmma_stage_kernel<X, U><<<sgrid, 128, 0, s>>>(st, L, ar, base, N, mode, -1, zin, fo, Jo, Mo, state);
         ++*launches;
         for (int stage = 0; stage < st.S; ++stage) {
