@@ -8,7 +8,7 @@
 // same weights, so a hidden-to-hidden layer is ONE GEMM [64 rows x HW] x [HW x HW] for SPT = 64 / RPS steps at once:
 //   * one persistent CTA per SM, TWO GROUPS of 4 warps, each group with its own 64-row tile A (in place in shared memory for the life of a
 //     tile), weight ring and named barrier -- while one group runs an epilogue the other keeps the DMMA pipe busy;
-//   * the weights of the layer stream from L2 through a three-slot cp.async ring of 8-row chunks per group (a layer is 128 KB: tiles and
+//   * the weights of the layer stream from L2 through a two-slot cp.async ring of 16-row chunks per group (a layer is 128 KB: tiles and
 //     weights do not fit together), one group barrier per chunk;
 //   * warp tile 32 x 64 at HW = 128: 32 m8n8k4 accumulators (128 registers) per lane, 12 shared-memory fragment loads per 32 DMMAs;
 //   * epilogue per (step, neuron): bias, tanh, s', s'', V = s' dV, Q = s' dQ + s'' dV_c dV_c2, written back as the next operand tile;
@@ -36,7 +36,7 @@ template <int HW_> struct DmmaCfg {
     static constexpr int LDA = HW + 4;                // row stride of the tile (doubles): a half-warp's fragment loads (4 rows x 4 columns) fall on distinct banks
     static constexpr int LDW = HW + 4;                // row stride of a weight chunk: likewise (HW + 8 measured a two-way conflict)
     static constexpr int LDO = 12, O_DOUBLES = HW * LDO;  // output weights, zero-padded to 8 columns (row stride 12: conflict-free fragments)
-    static constexpr int KC = 8, NSLOT = 3;           // ring: chunks of 8 weight rows, three slots per group
+    static constexpr int KC = 16, NSLOT = 2;          // ring: chunks of 16 weight rows, two slots per group (chunk kc + 1 streams in under the DMMAs of chunk kc: 8 group barriers per layer; 8-row chunks in three slots measured the same)
     static constexpr int WGN = HW / 64, WGM = 4 / WGN;          // warp grid of a group (4 warps): warp tile (MT / WGM) x 64
     static constexpr int WM = MT / WGM, WN = 64, MI = WM / 8, NI = WN / 8;
     static constexpr int A_DOUBLES = MT * LDA, RING_DOUBLES = NSLOT * KC * LDW;      // per group
@@ -130,11 +130,10 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
             };
             constexpr int NCH = HW / KC;
             issue_chunk(0);
-            issue_chunk(1);
             for (int kc = 0; kc < NCH; ++kc) {
-                if (kc + 1 < NCH) dmma_cp_wait<1>(); else dmma_cp_wait<0>();
+                dmma_cp_wait<0>();
                 gsync();                                    // chunk kc has landed for every thread of the group; everyone is done with chunk kc - 1 (and, for kc = 0, with writing A)
-                if (kc + 2 < NCH) issue_chunk(kc + 2);      // its slot held chunk kc - 1
+                if (kc + 1 < NCH) issue_chunk(kc + 1);      // its slot held chunk kc - 1
                 const double* wch = ring + (kc % NSLOT) * (KC * LDW);
 #pragma unroll
                 for (int kk = 0; kk < KC / 4; ++kk) {
@@ -157,31 +156,46 @@ nempc_dmma_net_kernel(const DmmaNet net, const double* __restrict__ zin, long lo
                     *reinterpret_cast<double2*>(&A[(wm0 + mi * 8 + g) * LDA + wn0 + ni * 8 + 2 * q]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             gsync();
             const double* __restrict__ bl = net.b[l];
-            for (int idx = tid; idx < spt * HW; idx += GT) {
-                const int sl = idx / HW, j = idx - sl * HW;
-                double* col = A + sl * LDA + j;
+            // IL steps of one column in flight per thread: the chain tanh -> s' -> s'' is ~100 dependent DFMA-class instructions and an epilogue
+            // has only this group's four warps to hide them (measured neutral on C3: the kernel is bound by the DMMA pipe, 3/4 busy)
+            constexpr int IL = (D <= 6) ? 2 : 1;
+            for (int idx = tid; idx < spt * HW; idx += IL * GT) {
+                double* col[IL]; bool on[IL];
+                double a[IL], tg[IL][D], qv[IL][ns];
                 const int rs = spt * LDA;
-                const double a = col[0] + bl[j];
-                double tg[D], qv[ns];
-                if (mode >= 1) {
 #pragma unroll
-                    for (int c = 0; c < D; ++c) tg[c] = col[(1 + c) * rs];
-                    if (mode >= 2) {
+                for (int u = 0; u < IL; ++u) {
+                    const int id = idx + u * GT;
+                    on[u] = id < spt * HW;
+                    const int sl = on[u] ? id / HW : 0, j = on[u] ? id - sl * HW : 0;
+                    col[u] = A + sl * LDA + j;
+                    a[u] = col[u][0] + bl[j];
+                    if (mode >= 1) {
 #pragma unroll
-                        for (int e = 0; e < ns; ++e) qv[e] = col[(1 + D + e) * rs];
+                        for (int c = 0; c < D; ++c) tg[u][c] = col[u][(1 + c) * rs];
+                        if (mode >= 2) {
+#pragma unroll
+                            for (int e = 0; e < ns; ++e) qv[u][e] = col[u][(1 + D + e) * rs];
+                        }
                     }
                 }
-                const double h = tanh(a), sp = fma(-h, h, 1.0), spp = -2.0 * h * sp;
-                col[0] = h;
-                if (mode >= 1) {
+                double h[IL], sp[IL], spp[IL];
 #pragma unroll
-                    for (int c = 0; c < D; ++c) col[(1 + c) * rs] = sp * tg[c];
-                    if (mode >= 2) {
+                for (int u = 0; u < IL; ++u) { h[u] = tanh(a[u]); sp[u] = fma(-h[u], h[u], 1.0); spp[u] = -2.0 * h[u] * sp[u]; }
 #pragma unroll
-                        for (int c = 0; c < D; ++c) {
-                            const double st = spp * tg[c];
+                for (int u = 0; u < IL; ++u) {
+                    if (!on[u]) continue;
+                    col[u][0] = h[u];
+                    if (mode >= 1) {
 #pragma unroll
-                            for (int c2 = 0; c2 <= c; ++c2) { const int e = c * (c + 1) / 2 + c2; col[(1 + D + e) * rs] = fma(sp, qv[e], st * tg[c2]); }
+                        for (int c = 0; c < D; ++c) col[u][(1 + c) * rs] = sp[u] * tg[u][c];
+                        if (mode >= 2) {
+#pragma unroll
+                            for (int c = 0; c < D; ++c) {
+                                const double st = spp[u] * tg[u][c];
+#pragma unroll
+                                for (int c2 = 0; c2 <= c; ++c2) { const int e = c * (c + 1) / 2 + c2; col[u][(1 + D + e) * rs] = fma(sp[u], qv[u][e], st * tg[u][c2]); }
+                            }
                         }
                     }
                 }

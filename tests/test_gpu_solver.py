@@ -220,3 +220,29 @@ def test_unaccepted_steps_are_counted(lv_weights):
     assert ok["unaccepted_steps"] == 0 and (ok["status"].cpu().numpy() == 0).all()
     hard = _ev(mlp, "unity", 10, None, obj, "float32").solve(X0, lb, ub, tol=1e-13, max_iter=40, max_backtrack=4)
     assert hard["unaccepted_steps"] > 0 and (hard["status"].cpu().numpy() == 1).any()
+
+
+def test_solver_on_the_float64_tensor_core_path(monkeypatch):
+    """nempc_solve over the FP64 tensor-core evaluation path (nempc_dmma_net_kernel + stage kernel; 5-128-128-4, RK4, 768 horizon steps per
+    evaluation), host-issued and as the captured device-side loop: same bits between the two loop modes, and the iterates of the generic
+    float64 kernel to rounding (the GEMM sums in another order)"""
+    from pyneuralempc_b200 import NlpEvaluator
+    H, B = 12, 64
+    mlp, obj, lb, ub, X0 = _setup("rk4", [5, 128, 128, 4], 4, 1, H, 0.05, 5.0, None, B=B)
+    dm = NlpEvaluator(mlp.weights, 4, 1, H, "rk4", DT=0.05, compute_dtype="float64", io_dtype="float64", kernel="auto")
+    dm.set_objective(obj.lin, obj.quad, obj.ref)
+    assert "nempc_dmma_net_kernel" in dm.kernel_name
+    monkeypatch.setenv("NEMPC_SOLVE_GRAPH", "0")
+    a = dm.solve(X0, lb, ub, tol=1e-8)
+    monkeypatch.setenv("NEMPC_SOLVE_GRAPH", "2")
+    b = dm.solve(X0, lb, ub, tol=1e-8)
+    assert not a["used_graph"] and b["used_graph"]
+    for k in ("z", "lam", "iterations", "status"):
+        np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
+    ge = NlpEvaluator(mlp.weights, 4, 1, H, "rk4", DT=0.05, compute_dtype="float64", io_dtype="float64", kernel="generic")
+    ge.set_objective(obj.lin, obj.quad, obj.ref)
+    monkeypatch.setenv("NEMPC_SOLVE_GRAPH", "0")
+    c = ge.solve(X0, lb, ub, tol=1e-8)
+    assert (a["status"].cpu().numpy() == 0).all() and (c["status"].cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(a["iterations"].cpu().numpy(), c["iterations"].cpu().numpy())
+    np.testing.assert_allclose(a["z"].cpu().numpy(), c["z"].cpu().numpy(), atol=1e-9)

@@ -24,4 +24,5 @@ cap wide_kernel nempc_wide_kernel 9 python tools/wide_check.py --no-check --time
 cap fast64_kernel nempc_fast64_kernel 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-solver
 cap fast_kernel nempc_fast_kernel 4 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-solver --no-side-workloads
 cap tc_kernel nempc_tc_kernel 1 python bench.py --workload C3 --steps 1 --warmup 1 --no-cpu-baseline
+cap dmma_net_kernel nempc_dmma_net 5 python tools/time_eval.py --workload C3 --compute float64 --batch 2048 --reps 1
 ls -la $O | tail -20

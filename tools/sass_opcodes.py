@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode histogram of libnempc.so (cuobjdump -sass): the evidence that the tensor-core kernels issue tcgen05 MMAs
 (UTCHMMA), read / write tensor memory (LDTM / STTM), stream weights with the TMA unit (UBLKCP = cp.async.bulk, UTMALDG = tensor-map
-loads), and that the register-resident kernel runs on packed FFMA2.  Kernels are grouped by family (template arguments dropped).
+loads), that the register-resident kernel runs on packed FFMA2, and that the float64 wide-network path runs on the
+FP64 tensor cores (DMMA) fed by cp.async (LDGSTS).  Kernels are grouped by family (template arguments dropped).
 
   python tools/sass_opcodes.py [path/to/libnempc.so] > profiles/<round>_sass_opcodes.md"""
 import collections
@@ -11,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OPS = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "FMUL2", "DFMA", "HMMA", "MUFU", "LDCU", "LDS", "STS",
+OPS = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "FMUL2", "DFMA", "DMMA", "LDGSTS", "HMMA", "MUFU", "LDCU", "LDS", "STS",
        "LDG", "STG", "BAR", "SHFL")
 
 
