@@ -15,6 +15,8 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.csv")
     ap.add_argument("--max-seconds", type=float, default=1.5, help="skip rows whose single evaluation is expected to take longer (from the kernel's typical rate)")
     ap.add_argument("--max-gb", type=float, default=60.0, help="skip rows whose inputs + outputs exceed this many GB")
+    ap.add_argument("--dtypes", default="float32,float64")
+    ap.add_argument("--widths", default="30,32,64,128,256,512")
     args = ap.parse_args()
     import torch
     from oracle.mlp_np import MLP
@@ -23,9 +25,9 @@ def main():
     peak = {"float32": measure_fma_peak(0, "float32", 200), "float64": measure_fma_peak(0, "float64", 200)}
     rows = []
     rng = np.random.default_rng(0)
-    for dtype in ("float32", "float64"):
+    for dtype in args.dtypes.split(","):
         for integ in ("discrete", "rk4"):
-            for width in (30, 32, 64, 128, 256, 512):
+            for width in [int(w) for w in args.widths.split(",")]:
                 xd, ud = (2, 1) if width < 64 else (4, 1)
                 depth = 2 if width == 30 else 3
                 dims = [xd + ud] + [width] * depth + [xd]
@@ -34,11 +36,11 @@ def main():
                     for B in (1, 256, 4096, 65536, 262144):
                         ev = NlpEvaluator(mlp.weights, xd, ud, H, integ, DT=0.1, compute_dtype=dtype, io_dtype="float64")
                         gflop = ev.flops_per_step * B * H / 1e9
-                        kname = ("fast64" if "fast64" in ev.kernel_name else "fast" if "nempc_fast" in ev.kernel_name else
+                        kname = ("dmma" if "nempc_dmma" in ev.kernel_name else "fast64" if "fast64" in ev.kernel_name else "fast" if "nempc_fast" in ev.kernel_name else
                                  "wide" if "nempc_wide" in ev.kernel_name else "tc" if "tcgen05" in ev.kernel_name else "generic")
-                        if kname == "fast64" and B * H < 4096:
+                        if (kname == "fast64" and B * H < 4096) or (kname == "dmma" and B * H < 512):
                             kname = "generic"                    # AUTO hands small float64 batches to the generic kernel
-                        typical_tf = {"fast": 25.0, "fast64": 8.0, "wide": 90.0, "tc": 35.0, "generic": 2.0 if dtype == "float32" else 1.2}[kname]
+                        typical_tf = {"dmma": 8.0, "fast": 25.0, "fast64": 8.0, "wide": 90.0, "tc": 35.0, "generic": 2.0 if dtype == "float32" else 1.2}[kname]
                         gbytes = B * (ev.n + ev.m * 2 + ev.nnz_jac + ev.nnz_hes) * 8 / 1e9
                         if gflop / typical_tf / 1e3 > args.max_seconds or gbytes > args.max_gb:
                             ev.close(); continue
