@@ -226,6 +226,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, timeout=3.0):
+        """block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation takes driver locks) must not fall into
+        the timed region, where it delayed kernel launches of rank 0 by ~1 ms in a 5 ms region (profiles/r2s_bench_n2.json)"""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -558,12 +565,14 @@ def gpu_run(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
-        step(i)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    for i in range(max(3, args.warmup)):
+        step(i)
+    if rank == 0:
+        sampler.wait_ready()
+    barrier()
     l0 = ev.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
