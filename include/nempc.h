@@ -43,7 +43,9 @@ enum { NEMPC_INTEG_DISCRETE = 0,   /* x_{t-1} + f - x_t        integrator/discre
        NEMPC_INTEG_RK4 = 2 };      /* classical RK4, ZOH on u  integrator/rk4.py:57-83      */
 enum { NEMPC_ACT_TANH = 0, NEMPC_ACT_SIGMOID = 1, NEMPC_ACT_SOFTPLUS = 2, NEMPC_ACT_RELU = 3 };
 enum { NEMPC_KERNEL_AUTO = 0, NEMPC_KERNEL_GENERIC = 1, NEMPC_KERNEL_FAST = 2,
-       NEMPC_KERNEL_TC = 3 };      /* tcgen05 tensor-core kernel: f32 tanh networks whose hidden layers are all 128 (or all 64) wide */
+       NEMPC_KERNEL_TC = 3 };      /* tensor-core kernels: f32 tanh networks whose hidden layers are all 256 / 128 / 64 / 32 wide (tcgen05, split-f16 operands),
+                                      f64 tanh networks whose hidden layers are all 128 / 64 wide (FP64 tensor cores, mma.sync.m8n8k4.f64); nempc_create
+                                      returns NEMPC_EUNSUPPORTED when no instantiation matches */
 
 typedef struct nempc_desc {
     int32_t x_dim, u_dim;                /* model/base.py:4-9 */
