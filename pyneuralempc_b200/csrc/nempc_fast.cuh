@@ -86,6 +86,15 @@ inline float fast_tanh_lv(float x) {
 }
 #endif
 
+// NEMPC_FAST_CONTRACT_LAST = 1: the LAST integrator stage (the only one of the discrete / unity integrators) contracts the multipliers into
+// the layer-1 adjoint -- w_S = c_S lambda is known there, so ONE adjoint row (15 FFMA2 per layer-1 neuron against the W2 pairs of the forward
+// loop) replaces the two per-output rows (30 against the W2 W3 table), and the stage algebra runs once instead of per output.  The earlier
+// RK4 stages need the Jacobians of later stages for their multipliers (w_s = c_s lambda + a_{s+1} J_{s+1,x}^T w_{s+1}) and keep the
+// per-output chain.
+#ifndef NEMPC_FAST_CONTRACT_LAST
+#define NEMPC_FAST_CONTRACT_LAST 1
+#endif
+
 // 16-byte weight quad: read as ONE uniform 128-bit constant load (LDCU.128) and consumed as two FFMA2 operand pairs
 struct alignas(16) nf4 { float x, y, z, w; };
 
@@ -158,6 +167,7 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
     typedef FastScratch<X, U, H1, H2> SC;
     constexpr int D = X + U, NS = D * (D + 1) / 2, JC = FW::JC, NR = (MODE >= 1) ? 1 + D : 1;
     constexpr bool JAC = MODE >= 1, HES = MODE >= 2;
+    static_assert(!NEMPC_FAST_CONTRACT_LAST || JC % 2 == 0, "the contracted adjoint pairs the layer-2 neurons inside a register chunk");
     typedef typename WideOf<float, TIO>::type TW;
     const bool unity = (ar.flags & NEMPC_UNITY) != 0;
     const long long b = step / L.H;
@@ -170,6 +180,9 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
 #pragma unroll
     for (int c = 0; c < U; ++c) z[X + c] = (float)zb[L.H * X + t * U + c];
 
+    float lamf[X];
+#pragma unroll
+    for (int p = 0; p < X; ++p) lamf[p] = (HES && ar.lam) ? (float)ar.lam[b * L.m + t * X + p] : 0.f;
     float Rt[X][D];          // top X rows of R_s = I + a_s E dk_{s-1}; the lower U rows stay [0 I]
     float kprev[X], kacc[X], dkacc[X][D];
 #pragma unroll
@@ -285,7 +298,49 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
         // ---- layer-1 adjoint (per output) and its curvature ---------------------------------------------------------------
         // g2[q] = (g[2q], g[2q+1])[i] = sum_j s'(a2_j) * W23T[i][j][2q..2q+1]: scalar-broadcast x uniform pair (the FFMA2 form
         // of the layer-2 loop), four independent chains; s'(a2) stays in registers for the whole loop.
-        if (HES) {
+        const bool lastc = NEMPC_FAST_CONTRACT_LAST && HES && (s + 1 == st.S);
+        f2 Ml2[NSH];                                   // contracted layer-1 curvature of the last stage (pairs over e)
+#pragma unroll
+        for (int e = 0; e < NSH; ++e) Ml2[e] = pk(0.f, 0.f);
+        if (HES && lastc) {
+            // y_j = s'(a2_j) * (W3[j][.] . lambda): one adjoint row, contracted with the multipliers
+            f2 y2[H2 / 2];
+#pragma unroll
+            for (int h = 0; h < H2 / 2; ++h) {
+                float yv[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int j = 2 * h + r, jc = j / JC, jj = j - jc * JC;
+                    float wl = 0.f;
+#pragma unroll
+                    for (int p = 0; p < X; ++p) wl = fmaf(w.W3T[jc][jj][p], lamf[p], wl);
+                    yv[r] = scr[(SC::SP2_OFF + j) * sstride] * wl;
+                }
+                y2[h] = pk(yv[0], yv[1]);
+            }
+#pragma unroll 1
+            for (int i = 0; i < H1; ++i) {
+                const float t1 = scr[(SC::H1_OFF + i) * sstride];
+                const float sp = fmaf(-t1, t1, 1.f);
+                const float spp = -2.f * t1 * sp;
+                f2 g[2];
+                g[0] = pk(0.f, 0.f); g[1] = pk(0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < H2 / 2; ++h) {
+                    const int j = 2 * h, jc = j / JC, hh = (j - jc * JC) / 2;          // JC is even: a pair never straddles two chunks
+                    const nf4 wq = w.W2C[jc][i][hh / 2];
+                    g[h & 1] = fma2(y2[h], (hh & 1) ? pk(wq.z, wq.w) : pk(wq.x, wq.y), g[h & 1]);
+                }
+                const float gl = (f2lo(g[0]) + f2hi(g[0])) + (f2lo(g[1]) + f2hi(g[1]));
+                const float cf = spp * gl;
+#pragma unroll
+                for (int e = 0; e < NSH; ++e) {
+                    const nf4 pq = w.P1T[i][e / 2];
+                    Ml2[e] = fma2(pk(cf, cf), (e & 1) ? pk(pq.z, pq.w) : pk(pq.x, pq.y), Ml2[e]);
+                }
+            }
+        }
+        if (HES && !lastc) {
             float sp2[H2];
 #pragma unroll
             for (int j = 0; j < H2; ++j) sp2[j] = scr[(SC::SP2_OFF + j) * sstride];
@@ -342,7 +397,51 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
                     dkacc[p][c] = fmaf(c_s, a, dkacc[p][c]);
                 }
         }
-        if (HES) {
+        if (HES && lastc) {
+            // last stage, contracted: out = sum_p lambda_p hacc[p] + c_s (R^T M(lambda) R + a_s sum_k (lambda^T J)[k] h_{s-1}[k]),
+            // M(lambda) = sum_p lambda_p M_p (layer-2 curvature, per output above) + the contracted layer-1 curvature
+            float Ml[NS], jl[X];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) {
+                float a = (e & 1) ? f2hi(Ml2[e / 2]) : f2lo(Ml2[e / 2]);
+#pragma unroll
+                for (int p = 0; p < X; ++p) a = fmaf(lamf[p], M[p][e], a);
+                Ml[e] = a;
+            }
+#pragma unroll
+            for (int kk = 0; kk < X; ++kk) {
+                float a = 0.f;
+#pragma unroll
+                for (int p = 0; p < X; ++p) a = fmaf(lamf[p], J[p][kk], a);
+                jl[kk] = a_s * a;
+            }
+            float tm[D][D];
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int l2 = 0; l2 < D; ++l2) a = fmaf(Ml[l2 <= kk ? kk * (kk + 1) / 2 + l2 : l2 * (l2 + 1) / 2 + kk], NEMPC_RF(l2, c), a);
+                    tm[kk][c] = a;
+                }
+#pragma unroll
+            for (int a2 = 0; a2 < D; ++a2)
+#pragma unroll
+                for (int c = 0; c <= a2; ++c) {
+                    const int e = a2 * (a2 + 1) / 2 + c;
+                    float a = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) a = fmaf(NEMPC_RF(kk, a2), tm[kk][c], a);
+#pragma unroll
+                    for (int kk = 0; kk < X; ++kk) a = fmaf(jl[kk], scr[(SC::HPREV_OFF + kk * NS + e) * sstride], a);
+                    float o = c_s * a;
+#pragma unroll
+                    for (int p = 0; p < X; ++p) o = fmaf(lamf[p], scr[(SC::HACC_OFF + p * NS + e) * sstride], o);
+                    scr[(SC::HACC_OFF + e) * sstride] = o;         // e < NS: slot of output 0, read (p = 0, e) just above by this thread only
+                }
+        }
+        if (HES && !lastc) {
             float hs[X][NS];
 #pragma unroll
             for (int p = 0; p < X; ++p) {
@@ -433,8 +532,11 @@ NEMPC_HD void fast_step(const FastWeights<X, U, H1, H2, NCHUNK>& w, const StageT
             for (int c = 0; c <= a; ++c) {
                 if (t == 0 && c < X) continue;
                 float acc = 0.f;
+                if (NEMPC_FAST_CONTRACT_LAST) acc = scr[(SC::HACC_OFF + a * (a + 1) / 2 + c) * sstride];      // contracted by the last stage
+                else {
 #pragma unroll
-                for (int p = 0; p < X; ++p) acc = fmaf(lam[p], scr[(SC::HACC_OFF + p * NS + a * (a + 1) / 2 + c) * sstride], acc);
+                    for (int p = 0; p < X; ++p) acc = fmaf(lam[p], scr[(SC::HACC_OFF + p * NS + a * (a + 1) / 2 + c) * sstride], acc);
+                }
                 TW v = (TW)acc;
                 int slot;
                 if (a < X) {

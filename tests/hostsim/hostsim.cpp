@@ -118,7 +118,7 @@ extern "C" int hostsim_run(int x, int u, int H, int n_layers, const int* widths,
         if (what != 0 || compute_f64 || act != 0 || n_layers != 3 || x != 2 || u != 1) return -1;
         StageTable<float> st = make_stage_table<float>(rk4, dt);
         const int mode = out2 ? 2 : (out1 ? 1 : 0);
-        if (widths[0] == 30 && widths[1] == 30) run_fast<2, 1, 30, 30, 2>(wflat, st, L, ar, mode);
+        if (widths[0] == 30 && widths[1] == 30) run_fast<2, 1, 30, 30, 3>(wflat, st, L, ar, mode);       // three register chunks of ten neurons: the production instantiation
         else if (widths[0] == 32 && widths[1] == 32) run_fast<2, 1, 32, 32, 2>(wflat, st, L, ar, mode);
         else if (widths[0] == 16 && widths[1] == 16) run_fast<2, 1, 16, 16, 1>(wflat, st, L, ar, mode);
         else return -1;
