@@ -71,6 +71,9 @@ __device__ __forceinline__ void fast64_step(const Fast64Weights<X, U, H1, H2>& w
 #pragma unroll
     for (int c = 0; c < U; ++c) z[X + c] = (double)zb[L.H * X + t * U + c];
 
+    double lamd[X];          // multipliers of this step's rows: the LAST stage contracts them into its layer-1 adjoint (NEMPC_FAST_CONTRACT_LAST, nempc_fast.cuh)
+#pragma unroll
+    for (int p = 0; p < X; ++p) lamd[p] = (HES && ar.lam) ? (double)ar.lam[b * L.m + t * X + p] : 0.0;
     double Rt[X][D];         // top X rows of R_s = I + a_s E dk_{s-1}; the lower U rows stay [0 I]
     double kprev[X], kacc[X], dkacc[X][D];
 #pragma unroll
@@ -171,7 +174,33 @@ __device__ __forceinline__ void fast64_step(const Fast64Weights<X, U, H1, H2>& w
             }
         }
         // ---- layer-1 adjoint (per output) and its curvature: g[p][i] = sum_j s'(a2_j) W2[i][j] W3[j][p]
-        if (HES) {
+        const bool lastc = NEMPC_FAST_CONTRACT_LAST && HES && (s + 1 == st.S);
+        double Ml[NS];                                            // contracted layer-1 curvature of the last stage
+#pragma unroll
+        for (int e = 0; e < NS; ++e) Ml[e] = 0.0;
+        if (HES && lastc) {
+            // y_j = s'(a2_j) (W3[j][.] . lambda) replaces s'(a2_j) in the scratch: ONE adjoint row g[i] = sum_j y_j W2[i][j]
+#pragma unroll 2
+            for (int j = 0; j < H2; ++j) {
+                double wl = 0.0;
+#pragma unroll
+                for (int p = 0; p < X; ++p) wl = fma(w.W3[j][p], lamd[p], wl);
+                scr[(SC::SP2_OFF + j) * sstride] *= wl;
+            }
+#pragma unroll 1
+            for (int i = 0; i < H1; ++i) {
+                const double t1 = scr[(SC::H1_OFF + i) * sstride];
+                const double sp = fma(-t1, t1, 1.0);
+                const double spp = -2.0 * t1 * sp;
+                double g[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < H2; ++j) g[j & 3] = fma(scr[(SC::SP2_OFF + j) * sstride], w.W2[i][j], g[j & 3]);
+                const double cf = spp * ((g[0] + g[1]) + (g[2] + g[3]));
+#pragma unroll
+                for (int e = 0; e < NS; ++e) Ml[e] = fma(cf, w.P1[i][e], Ml[e]);
+            }
+        }
+        if (HES && !lastc) {
 #pragma unroll 1
             for (int i = 0; i < H1; ++i) {
                 const double t1 = scr[(SC::H1_OFF + i) * sstride];
@@ -209,7 +238,48 @@ __device__ __forceinline__ void fast64_step(const Fast64Weights<X, U, H1, H2>& w
                     dkacc[p][c] = fma(c_s, a, dkacc[p][c]);
                 }
         }
-        if (HES) {
+        if (HES && lastc) {
+            // out = sum_p lambda_p hacc[p] + c_s (R^T M(lambda) R + a_s sum_k (lambda^T J)[k] h_{s-1}[k]), M(lambda) = sum_p lambda_p M_p + Ml
+            double jl[X];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) {
+#pragma unroll
+                for (int p = 0; p < X; ++p) Ml[e] = fma(lamd[p], M[p][e], Ml[e]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < X; ++kk) {
+                double a = 0.0;
+#pragma unroll
+                for (int p = 0; p < X; ++p) a = fma(lamd[p], J[p][kk], a);
+                jl[kk] = a_s * a;
+            }
+            double tm[D][D];
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int l2 = 0; l2 < D; ++l2) a = fma(Ml[l2 <= kk ? kk * (kk + 1) / 2 + l2 : l2 * (l2 + 1) / 2 + kk], NEMPC_RF64(l2, c), a);
+                    tm[kk][c] = a;
+                }
+#pragma unroll
+            for (int a2 = 0; a2 < D; ++a2)
+#pragma unroll
+                for (int c = 0; c <= a2; ++c) {
+                    const int e = a2 * (a2 + 1) / 2 + c;
+                    double a = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) a = fma(NEMPC_RF64(kk, a2), tm[kk][c], a);
+#pragma unroll
+                    for (int kk = 0; kk < X; ++kk) a = fma(jl[kk], scr[(SC::HPREV_OFF + kk * NS + e) * sstride], a);
+                    double o = c_s * a;
+#pragma unroll
+                    for (int p = 0; p < X; ++p) o = fma(lamd[p], scr[(SC::HACC_OFF + p * NS + e) * sstride], o);
+                    scr[(SC::HACC_OFF + e) * sstride] = o;
+                }
+        }
+        if (HES && !lastc) {
             double hs[X][NS];
 #pragma unroll
             for (int p = 0; p < X; ++p) {
@@ -300,8 +370,11 @@ __device__ __forceinline__ void fast64_step(const Fast64Weights<X, U, H1, H2>& w
             for (int c = 0; c <= a; ++c) {
                 if (t == 0 && c < X) continue;
                 double v = 0.0;
+                if (NEMPC_FAST_CONTRACT_LAST) v = scr[(SC::HACC_OFF + a * (a + 1) / 2 + c) * sstride];          // contracted by the last stage
+                else {
 #pragma unroll
-                for (int p = 0; p < X; ++p) v = fma(lam[p], scr[(SC::HACC_OFF + p * NS + a * (a + 1) / 2 + c) * sstride], v);
+                    for (int p = 0; p < X; ++p) v = fma(lam[p], scr[(SC::HACC_OFF + p * NS + a * (a + 1) / 2 + c) * sstride], v);
+                }
                 int slot;
                 if (a < X) {
                     slot = hes_slot_xx(L, t, a, c);
@@ -345,11 +418,11 @@ nempc_fast64_kernel(const __grid_constant__ Fast64Weights<X, U, H1, H2> w, const
     const FW& ws = *reinterpret_cast<const FW*>(fast64_smem);
     double* scr = reinterpret_cast<double*>(fast64_smem + WB) + threadIdx.x;
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps; step += (long long)gridDim.x * blockDim.x)
-        fast64_step<X, U, H1, H2, JC, MODE, TIO>(ws, st, L, ar, step, scr, (int)blockDim.x);
+        fast64_step<X, U, H1, H2, JC, MODE, TIO>(ws, st, L, ar, step, scr, NEMPC_FAST64_THREADS);     // the launch uses exactly this block size
 #else
     double* scr = reinterpret_cast<double*>(fast64_smem) + threadIdx.x;
     for (long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x; step < ar.nsteps; step += (long long)gridDim.x * blockDim.x)
-        fast64_step<X, U, H1, H2, JC, MODE, TIO>(w, st, L, ar, step, scr, (int)blockDim.x);
+        fast64_step<X, U, H1, H2, JC, MODE, TIO>(w, st, L, ar, step, scr, NEMPC_FAST64_THREADS);
 #endif
 }
 #endif  // __CUDACC__
