@@ -48,7 +48,9 @@ class CudaIpm(Optimizer):
         z0 = initial_guess(problem, self)[None] if warm else None
         out = problem.ev.solve(np.asarray(problem.get_init_value(), np.float64)[None], lb, ub, z_init=z0, **self._options())
         status = int(out["status"][0].item())
-        self.last_info = dict(status=status, iterations=int(out["iterations"][0].item()), kkt_error=float(out["kkt_error"][0].item()))
+        self.last_info = dict(status=status, iterations=int(out["iterations"][0].item()), kkt_error=float(out["kkt_error"][0].item()),
+                              device_side_loop=out["used_graph"],            # the iteration loop ran as one CUDA graph (nempc_solve_stats)
+                              unaccepted_steps=out["unaccepted_steps"])      # steps taken although the line search ran out of halvings
         if status != 0:
             return Optimizer.FAIL
         self.prev_result = out["z"][0].cpu().numpy()
