@@ -370,6 +370,7 @@ struct nempc_handle {
     struct HostKey { int64_t B; const void* in[4]; void* out[5]; double sigma; bool operator==(const HostKey& o) const { return memcmp(this, &o, sizeof(HostKey)) == 0; } };
     HostKey hk{}; int hk_seen = 0; cudaGraphExec_t hk_exec = nullptr; long long hk_launches = 0; bool hk_disabled = false;
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_kern[3] = {nullptr, nullptr, nullptr};   // chunk pipeline: kernels of chunk c+1 wait for the kernels of chunk c when the evaluation kernels share a per-handle scratch
     // solver workspace
     void* sv_buf = nullptr; size_t sv_cap = 0; double *sv_lb = nullptr, *sv_ub = nullptr; int* sv_counts = nullptr; int* sv_counts_host = nullptr;
     // nempc_solve's iteration loop as a CUDA graph with two nested WHILE nodes, replayed while (batch, options, workspace) stay the same
@@ -561,6 +562,7 @@ static void free_device(nempc_handle* h) {
     if (h->sk_exec) cudaGraphExecDestroy(h->sk_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int i = 0; i < 3; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    for (int i = 0; i < 3; ++i) if (h->ev_kern[i]) cudaEventDestroy(h->ev_kern[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 3; ++i) if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
 }
@@ -1224,10 +1226,19 @@ static int eval_host_issue(nempc_handle* h, int64_t B, const void* const in[4], 
             if (sz[i]) CU(h, cudaMemcpyAsync(din[i], (const char*)in[i] + c0 * in_w[i], nb * in_w[i], cudaMemcpyHostToDevice, s));
         }
         for (int i = 0; i < 5; ++i) dout[i] = sz[4 + i] ? (char*)h->st_buf[4 + i] + c0 * out_w[i] : nullptr;
+        // The width-256 / adjoint-form kernels (per-CTA scratch indexed by blockIdx) and the float64 tensor-core path (network outputs + stage
+        // state of one chunk of steps) keep scratch in the HANDLE: the tail of chunk c's kernels must not overlap the head of chunk c+1's on
+        // another stream.  Their kernels are chained with an event; the copies on either side still overlap them.
+        const bool shared_scratch = h->use_wide || h->wide_hes || h->dmma_id >= 0;
+        if (shared_scratch && ci > 0) CU(h, cudaStreamWaitEvent(s, h->ev_kern[(ci - 1) % 3], 0));
         h->exo_base = c0;
         int rc = nempc_eval(h, nb, din[0], din[1], din[2], din[3], sigma, dout[0], dout[1], dout[2], dout[3], dout[4], (void*)s);
         h->exo_base = 0;
         if (rc) return rc;
+        if (shared_scratch) {
+            if (!h->ev_kern[ci % 3]) CU(h, cudaEventCreateWithFlags(&h->ev_kern[ci % 3], cudaEventDisableTiming));
+            CU(h, cudaEventRecord(h->ev_kern[ci % 3], s));
+        }
         for (int i = 0; i < 5; ++i)
             if (sz[4 + i]) CU(h, cudaMemcpyAsync((char*)outp[i] + c0 * out_w[i], dout[i], nb * out_w[i], cudaMemcpyDeviceToHost, s));
     }

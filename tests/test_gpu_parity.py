@@ -733,3 +733,26 @@ def test_float64_tensor_core_path_dispatch_and_chunks():
     with pytest.raises(NempcError):
         _evaluator(m2, "rk4", 5, "float64", "tc")
     assert "generic" in _evaluator(m2, "rk4", 5, "float64", "auto").kernel_name
+
+
+@pytest.mark.parametrize("compute,kind,dims,xd,ud,H,B,tag", [("float64", "rk4", [3, 64, 64, 2], 2, 1, 8, 1100, "nempc_dmma_net_kernel"),
+                                                           ("float32", "discrete", [16, 256, 256, 12], 12, 4, 3, 1100, "nempc_wide_kernel"),
+                                                           ("float32", "rk4", [5, 256, 256, 4], 4, 1, 4, 1300, "nempc_wide_kernel")])
+def test_host_chunk_pipeline_of_kernels_with_handle_scratch(compute, kind, dims, xd, ud, H, B, tag):
+    """nempc_eval_host cuts B >= 512 problems into chunks on three streams (H2D | kernels | D2H overlap).  The width-256 kernel and the
+    float64 tensor-core path keep scratch in the handle, so the kernels of consecutive chunks are chained with an event: the host call
+    must return the bits of the one-launch device call -- directly issued (first call), and replayed as the captured graph (third call)."""
+    mlp, obj, Z, X0, lam, sig = _problem(dims, xd, ud, H, B)
+    ev = _evaluator(mlp, kind, H, compute, "auto", obj)
+    assert tag in ev.kernel_name
+    got = _run(ev, Z, X0, lam, sig)
+    for rep in range(3):
+        host = ev.eval_host(Z, X0, lam, sig)
+        for _, kg in KEYS:
+            np.testing.assert_array_equal(host[kg], got[kg], err_msg=f"{kg} (call {rep})")
+    pick = np.array([0, 274, 275, 549, 550, B - 1])                       # both sides of the chunk boundaries (chunks of 275 / 325 problems)
+    ref = BlockEvaluator(mlp, kind, H, DT=0.1, objective=obj).evaluate(Z[pick], X0[pick], lam[pick], sig[pick])
+    tol = TOL64 if compute == "float64" else TOL32
+    for kr, kg in KEYS:
+        assert _relerr(host[kg][pick], ref[kr]) < tol, kg
+    ev.close()
